@@ -1,0 +1,216 @@
+"""Generate golden fixtures by executing the UNMODIFIED reference (/root/reference) on CPU.
+
+TEST INFRASTRUCTURE.  Run in the build container only (the reference cannot travel):
+
+    python oracle/gen_golden.py            # rewrites tests/golden/*.npz
+
+The reference's own classes are imported from /root/reference with the two import stubs of
+oracle/stubs/ (torch_sparse -> torch.sparse.mm, dgl -> unused) and fed
+seeded synthetic search logs written in the reference's on-disk format by
+ihgnn_b200.synth.write_reference_files, i.e. through the reference's own
+`GraphDataset.__init__` parsing and `PpsHyperGraph.from_interactions` Python loop.
+Each fixture stores inputs, the reference `state_dict`, and the reference's outputs and
+parameter gradients in fp32 and -- same modules cast to double -- fp64 (the arbiter).
+Nothing from the reference's sources is copied; only numbers it computed are stored.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE = "/root/reference"
+sys.dont_write_bytecode = True
+sys.path.insert(0, os.path.join(REPO, "oracle", "stubs"))
+sys.path.insert(0, REFERENCE)
+sys.path.insert(0, REPO)
+
+from ihgnn_b200 import synth  # noqa: E402
+
+with contextlib.redirect_stdout(io.StringIO()):
+    from Helpers.GlobalSettings import Gs, Gsv  # noqa: E402
+    Gs.graph_completeness = Gsv.graph_uqi
+    from Helpers.IOHelper import IOHelper  # noqa: E402
+    IOHelper.warned_about_cannot_log = True
+    from Helpers.Graph import PpsHyperGraph  # noqa: E402
+    from Dataset import GraphDataset  # noqa: E402
+    from Models import RawGnn, IHGNNLayer, HGCNLayer, HemPredictionLayer  # noqa: E402
+
+CPU = torch.device("cpu")
+
+CASES = {
+    # name: synthetic log + model config.  Tiny on purpose: each npz stays well under 1 MB.
+    "ihgnn_o3_L2_amazon": dict(U=60, Q=25, I=90, V=40, E=400, shape="amazon", seed=11,
+                               gnn="IHGNN", L=2, order=3, d=16, batch=24),
+    "ihgnn_o2_L1_cikm": dict(U=30, Q=12, I=50, V=25, E=220, shape="cikm", seed=12,
+                             gnn="IHGNN", L=1, order=2, d=8, batch=16),
+    "ihgnn_o1_L3_cikm": dict(U=45, Q=20, I=70, V=30, E=300, shape="cikm", seed=13,
+                             gnn="IHGNN", L=3, order=1, d=32, batch=20),
+    "hgcn_L2_amazon": dict(U=50, Q=20, I=80, V=30, E=350, shape="amazon", seed=14,
+                           gnn="HGCN", L=2, order=1, d=16, batch=20),
+    # d=64 / 3 layers at the smallest size that still has heavy (Zipf head) nodes
+    "ihgnn_o3_L3_d64": dict(U=100, Q=30, I=90, V=40, E=1200, shape="cikm", seed=15,
+                            gnn="IHGNN", L=3, order=3, d=64, batch=33),
+}
+
+
+def _np(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy()
+
+
+def _cast_model_to_double(model):
+    """fp64 arbiter: parameters AND the non-parameter graph tensors
+    (Dv_neg_1, incidence) are cast, not recomputed."""
+    model.double()
+    for gnn in model.gnns:
+        if hasattr(gnn, "Dv_neg_1"):
+            gnn.Dv_neg_1 = gnn.Dv_neg_1.double()
+        if hasattr(gnn, "Dv_neg_1_slash_2"):
+            gnn.Dv_neg_1_slash_2 = gnn.Dv_neg_1_slash_2.double()
+            gnn.De_neg_1 = gnn.De_neg_1.double()
+        for name in ("incidence", "incidence_t"):
+            if hasattr(gnn, name):
+                setattr(gnn, name, getattr(gnn, name).to(torch.float64))
+    return model
+
+
+def _layer_outputs(model):
+    """Per-layer outputs, computed the way RawGnn.forward does (RawGnn.py:112-118)."""
+    x = torch.cat(model.embeddings(None, None, None))
+    outs = [x]
+    h = x
+    for gnn in model.gnns:
+        h = gnn(h)
+        outs.append(h)
+    return outs
+
+
+def _run(model, users, queries, items, flags, prefix, out):
+    model.zero_grad()
+    scores = model(users, queries, items)
+    loss = torch.nn.BCEWithLogitsLoss()(scores, flags.to(scores.dtype))   # Main.py:191
+    loss.backward()
+    out[f"{prefix}.scores"] = _np(scores)
+    out[f"{prefix}.loss"] = _np(loss)
+    for k, p in model.named_parameters():
+        out[f"{prefix}.grad.{k}"] = _np(p.grad)
+    with torch.no_grad():
+        for li, o in enumerate(_layer_outputs(model)):
+            out[f"{prefix}.layer_out.{li}"] = _np(o)
+        # evaluation form (RawGnn.py:124-133, TestSearchLogDataLoader Dataset.py:324-329):
+        # one (u, q) against ALL items, item_indices None
+        model.save_features_for_test()
+        I = model.dataset.item_count
+        u0, q0 = int(users[0]), int(queries[0])
+        ev = model(u0 * torch.ones(I, dtype=torch.long), q0 * torch.ones(I, dtype=torch.long), None)
+        out[f"{prefix}.eval_scores"] = _np(ev)
+        model.clear_saved_feature()
+    # conv-only metric M1: loss = sum(cat(outs,1)) w.r.t. X
+    x = torch.cat(model.embeddings(None, None, None)).detach().clone().requires_grad_(True)
+    outs = [x]
+    h = x
+    for gnn in model.gnns:
+        h = gnn(h)
+        outs.append(h)
+    model.zero_grad()
+    torch.cat(outs, 1).sum().backward()
+    out[f"{prefix}.conv_dx"] = _np(x.grad)
+    for k, p in model.named_parameters():
+        if k.startswith("gnn_"):
+            out[f"{prefix}.conv_grad.{k}"] = _np(p.grad)
+
+
+def make_case(name: str, cfg: dict, outdir: str) -> None:
+    log = synth.make_search_log(cfg["U"], cfg["Q"], cfg["I"], cfg["E"], cfg["V"],
+                                shape=cfg["shape"], seed=cfg["seed"], with_negatives=True)
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        synth.write_reference_files(log, tmp)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ds = GraphDataset(os.path.join(tmp, "graph_info.txt"),
+                              os.path.join(tmp, "queries_multihot.txt"),
+                              os.path.join(tmp, "train_data.csv"),
+                              PpsHyperGraph, 10, 0, CPU)
+    # the reference's own parse must reproduce the generator's positives, in order
+    uqi = np.array([p.uqif()[:3] for p in ds.pos_interactions], dtype=np.int64)
+    assert np.array_equal(uqi[:, 0], log.pos_user) and np.array_equal(uqi[:, 1], log.pos_query) \
+        and np.array_equal(uqi[:, 2], log.pos_item), "generator/reference parse mismatch"
+
+    g = ds.hypergraph            # the reference's Python-loop builder, Graph.py:94-134
+    adj = g.Adjacency
+    csr = adj.to_sparse_csr()
+    out["counts"] = np.array([cfg["U"], cfg["Q"], cfg["I"], cfg["V"], cfg["E"]], dtype=np.int64)
+    out["pos_user"], out["pos_query"], out["pos_item"] = log.pos_user, log.pos_query, log.pos_item
+    out["bag_words"] = _np(ds.queries_for_embeddingbag)
+    out["bag_offsets"] = _np(ds.queries_offset_for_embeddingbag)
+    out["graph.I3"] = _np(g.I3)
+    out["graph.coo_indices"] = _np(adj.indices())
+    out["graph.coo_values"] = _np(adj.values())
+    out["graph.crow"] = _np(csr.crow_indices())
+    out["graph.col"] = _np(csr.col_indices())
+    out["graph.VertexDegrees"] = _np(g.VertexDegrees)
+    out["graph.EdgeDegrees"] = _np(g.EdgeDegrees)
+    out["graph.EdgeCount"] = np.array(g.EdgeCount, dtype=np.int64)
+
+    layer_type = IHGNNLayer if cfg["gnn"] == "IHGNN" else HGCNLayer
+    torch.manual_seed(1000 + cfg["seed"])
+    model = RawGnn(device=CPU, dataset=ds, embedding_size=cfg["d"], gnn_layer_type=layer_type,
+                   gnn_layer_count=cfg["L"], feature_interaction_order=cfg["order"],
+                   phase2_attention=False, predictions=HemPredictionLayer, lambda_muq=0.5)
+    for k, v in model.state_dict().items():
+        out[f"state.{k}"] = _np(v)
+    out["cfg.gnn"] = np.array(cfg["gnn"])
+    out["cfg.L"] = np.array(cfg["L"])
+    out["cfg.order"] = np.array(cfg["order"])
+    out["cfg.d"] = np.array(cfg["d"])
+    out["cfg.lambda_muq"] = np.array(0.5)
+
+    # a training batch in TrainTestHelper.py:126-129 form: positives then 10 negatives each
+    rng = np.random.default_rng(cfg["seed"] + 500)
+    b = cfg["batch"]
+    pick = rng.choice(cfg["E"], size=b, replace=False)
+    pu, pq, pi = log.pos_user[pick], log.pos_query[pick], log.pos_item[pick]
+    nu, nq = np.repeat(pu, 10), np.repeat(pq, 10)
+    ni = rng.integers(0, cfg["I"], size=b * 10)
+    users = torch.from_numpy(np.concatenate([pu, nu]))
+    queries = torch.from_numpy(np.concatenate([pq, nq]))
+    items = torch.from_numpy(np.concatenate([pi, ni]))
+    flags = torch.cat([torch.ones(b), torch.zeros(b * 10)])
+    out["batch.users"], out["batch.queries"], out["batch.items"] = _np(users), _np(queries), _np(items)
+    out["batch.flags"] = _np(flags)
+
+    _run(model, users, queries, items, flags, "ref32", out)
+
+    # indexed embedding lookups, the Srrl client form (Srrl.py:74-94)
+    with torch.no_grad():
+        qi = torch.from_numpy(rng.integers(0, cfg["Q"], size=9))
+        out["embed.query_indices"] = _np(qi)
+        out["ref32.embed_user_idx"] = _np(model.embeddings.embed_user(users[:9]))
+        out["ref32.embed_item_idx"] = _np(model.embeddings.embed_item(items[:9]))
+        out["ref32.embed_query_idx"] = _np(model.embeddings.embed_query(qi))
+
+    _cast_model_to_double(model)
+    _run(model, users, queries, items, flags, "ref64", out)
+
+    path = os.path.join(outdir, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB, E={g.EdgeCount}, "
+          f"zero-degree nodes={(np.diff(out['graph.crow']) == 0).sum()}, "
+          f"max degree={np.diff(out['graph.crow']).max()}")
+
+
+def main():
+    outdir = os.path.join(REPO, "tests", "golden")
+    os.makedirs(outdir, exist_ok=True)
+    for name, cfg in CASES.items():
+        make_case(name, cfg, outdir)
+
+
+if __name__ == "__main__":
+    main()

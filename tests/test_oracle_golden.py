@@ -1,0 +1,81 @@
+"""Pins the oracle (oracle/ihgnn_oracle.py) against outputs of the reference itself.
+
+The reference has no tests or golden vectors, so the fixtures under
+tests/golden/ were produced by oracle/gen_golden.py executing the unmodified reference
+classes on CPU.  Indices must agree bit-exactly; fp32 values must agree far inside the 1e-5
+parity budget (same ATen ops in the same order), and the fp64 arbiter to ~1e-12.
+"""
+import numpy as np
+import torch
+
+from helpers import batch_of, max_rel, oracle_graph, oracle_model, orc
+
+
+def test_graph_indices_bit_exact(golden):
+    g = oracle_graph(golden)
+    assert np.array_equal(g.I3.numpy(), golden["graph.I3"])
+    assert np.array_equal(g.rowptr.numpy(), golden["graph.crow"])
+    assert np.array_equal(g.col.numpy(), golden["graph.col"])
+    assert np.array_equal(torch.stack([g.row, g.col]).numpy(), golden["graph.coo_indices"])
+    assert np.array_equal(g.VertexDegrees.numpy(), golden["graph.VertexDegrees"])
+    assert np.array_equal(g.EdgeDegrees.numpy(), golden["graph.EdgeDegrees"])
+    assert g.EdgeCount == int(golden["graph.EdgeCount"])
+    assert np.all(golden["graph.coo_values"] == 1.0)
+
+
+def _check(golden, dtype, prefix, tol):
+    m = oracle_model(golden, dtype)
+    users, queries, items, flags = batch_of(golden)
+    scores = m.forward(users, queries, items)
+    loss = orc.bce_with_logits_mean(scores, flags.to(dtype))
+    loss.backward()
+    assert max_rel(scores.detach().numpy(), golden[f"{prefix}.scores"]) <= tol
+    assert max_rel(loss.detach().numpy(), golden[f"{prefix}.loss"]) <= tol
+    for k, gr in m.grads().items():
+        assert max_rel(gr.numpy(), golden[f"{prefix}.grad.{k}"]) <= tol, k
+    with torch.no_grad():
+        outs = m.conv_stack(m.input_features())
+        for li, o in enumerate(outs):
+            assert max_rel(o.numpy(), golden[f"{prefix}.layer_out.{li}"]) <= tol, li
+        I = m.I
+        ev = m.forward(users[0] * torch.ones(I, dtype=torch.long),
+                       queries[0] * torch.ones(I, dtype=torch.long), None)
+        assert max_rel(ev.numpy(), golden[f"{prefix}.eval_scores"]) <= tol
+    x = m.input_features().detach()
+    dx = orc.conv_fwd_bwd(m, x)
+    assert max_rel(dx.numpy(), golden[f"{prefix}.conv_dx"]) <= tol
+    for k, gr in m.grads().items():
+        if k.startswith("gnn_"):
+            assert max_rel(gr.numpy(), golden[f"{prefix}.conv_grad.{k}"]) <= tol, k
+
+
+def test_model_fp32_matches_reference(golden):
+    # same ops, same order: expect ~0; allow a few ulp for MKL threading differences
+    _check(golden, torch.float32, "ref32", 2e-6)
+
+
+def test_model_fp64_matches_reference(golden):
+    _check(golden, torch.float64, "ref64", 1e-12)
+
+
+def test_reference_fp32_noise_floor_is_inside_budget(golden):
+    """The reference's own fp32-vs-fp64 error bounds what 1e-5 parity can mean."""
+    worst = 0.0
+    for k in golden:
+        if k.startswith("ref32.") and k != "ref32.loss" and "ref64." + k[len("ref32."):] in golden:
+            worst = max(worst, max_rel(golden[k], golden["ref64." + k[len("ref32."):]]))
+    assert worst < 1e-5, worst
+
+
+def test_indexed_embedding_lookups(golden):
+    m = oracle_model(golden)
+    p = m.params
+    users, queries, items, _ = batch_of(golden)
+    with torch.no_grad():
+        eu = orc.embed_user(p["embeddings.embedding_user.weight"], users[:9])
+        ei = orc.embed_item(p["embeddings.embedding_item.weight"], items[:9])
+        eq = orc.embed_query(p["embeddings.embedding_bag_vocabulary.weight"], m.bag_words,
+                             m.bag_offsets, torch.from_numpy(golden["embed.query_indices"]))
+    assert np.array_equal(eu.numpy(), golden["ref32.embed_user_idx"])
+    assert np.array_equal(ei.numpy(), golden["ref32.embed_item_idx"])
+    assert max_rel(eq.numpy(), golden["ref32.embed_query_idx"]) <= 1e-7
