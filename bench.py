@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- hypergraph-conv throughput of the IHGNN hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload amazon-full|cikm|amazon-small]
+    python bench.py --impl reference ...      # the CPU arm: oracle port of the reference path
+
+One "step" = one fwd+bwd pass of the L-layer IHGNN stack over the whole hypergraph (metric M1,
+SURVEY.md section 8d: input X [N,d] requires grad, loss = sum(cat(outs,1)), order 3 on layer 0
+and order 1 after, as Models/RawGnn.py:76-78).  `value` = E*L / t in hyperedge-layers/s with
+everything resident in HBM; `e2e` = the same E*L divided by the time of a full training step
+through the public API (RawGnn.forward -> BCE -> backward -> Adam) with the batch indices
+coming from pinned host memory and the loss read back every step.
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+from ihgnn_b200 import synth  # noqa: E402
+
+METRIC = "hypergraph_conv_hyperedge_layers_per_sec_fwd_bwd"
+UNIT = "hyperedge-layers/s"
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def conv_algorithmic_bytes(E: int, N: int, d: int) -> int:
+    """bytes per IHGNN layer, fwd+bwd = E(60+76d) + N(28d+12)."""
+    return E * (60 + 76 * d) + N * (28 * d + 12)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class KernelProfiler:
+    """Collects CUDA-event timings of every C-ABI call (installed as ihgnn_b200._lib.profiler)."""
+
+    def __init__(self):
+        self.records = []
+
+    def add(self, name, tag, algo_bytes, start, end):
+        self.records.append((tag, algo_bytes, start, end))
+
+    def summary(self, steps: int):
+        agg = {}
+        for tag, nbytes, s, e in self.records:
+            ms = s.elapsed_time(e)
+            a = agg.setdefault(tag, {"ms": 0.0, "calls": 0, "bytes": 0})
+            a["ms"] += ms; a["calls"] += 1; a["bytes"] += nbytes
+        for a in agg.values():
+            a["avg_ms"] = a["ms"] / a["calls"]
+            a["gbs"] = (a["bytes"] / a["calls"]) / (a["avg_ms"] * 1e-3) / 1e9 if a["avg_ms"] > 0 else 0.0
+            a["ms_per_step"] = a["ms"] / steps
+        return agg
+
+
+# ----------------------------------------------------------------------------------------
+# the CPU arm: oracle port of the reference path, all host threads
+# ----------------------------------------------------------------------------------------
+def cpu_sample_model(log, layers: int, d: int, sample_edges: int):
+    """Oracle model over a bounded sample of the workload: the same node tables, the first
+    `sample_edges` positive interactions of the same log."""
+    from oracle import ihgnn_oracle as orc
+    Es = min(sample_edges, log.edge_count)
+    g = orc.build_hypergraph(log.pos_user[:Es], log.pos_query[:Es], log.pos_item[:Es],
+                             log.user_count, log.query_count, log.item_count)
+    gen = torch.Generator().manual_seed(0)
+    state = {}
+    for k in range(layers):
+        K = 7 if k == 0 else 3
+        state[f"gnn_{k}.feature_interactor.aggregation.weight"] = (torch.rand(d, K * d, generator=gen) - 0.5) * (2 / (K * d) ** 0.5)
+        state[f"gnn_{k}.feature_interactor.aggregation.bias"] = (torch.rand(d, generator=gen) - 0.5) * 0.1
+        state[f"gnn_{k}.feature_transform.weight"] = (torch.rand(d, d, generator=gen) - 0.5) * (2 / d ** 0.5)
+        state[f"gnn_{k}.feature_transform.bias"] = (torch.rand(d, generator=gen) - 0.5) * 0.1
+    words, offsets = log.bag_inputs()
+    m = orc.OracleModel(state, g, torch.from_numpy(words), torch.from_numpy(offsets),
+                        log.user_count, log.query_count, log.item_count, layer_type="IHGNN",
+                        layer_count=layers, order=3, dtype=torch.float32)
+    x = torch.randn(log.node_count, d, generator=gen) * 0.05
+    return orc, m, x, Es
+
+
+def time_cpu(log, layers, d, sample_edges, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    orc, m, x, Es = cpu_sample_model(log, layers, d, sample_edges)
+    for _ in range(warmup):
+        orc.conv_fwd_bwd(m, x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.conv_fwd_bwd(m, x)
+    dt = (time.perf_counter() - t0) / steps
+    return Es * layers / dt, dt, Es
+
+
+def run_reference_arm(args, log, layers, d):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, dt, Es = time_cpu(log, layers, d, args.cpu_sample_edges, args.steps, max(args.warmup, 1))
+    cores = os.cpu_count() or 1
+    sample = (f"first {Es} of {log.edge_count} hyperedges of '{args.workload}' over the full node set "
+              f"(N={log.node_count}), conv fwd+bwd, fp32, torch {torch.__version__} CPU")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "layers": layers, "dim": d, "hyperedges": log.edge_count,
+                   "nodes": log.node_count, "interaction_order": 3},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+# the GPU arm
+# ----------------------------------------------------------------------------------------
+def run_gpu_arm(args, log, layers, d):
+    from ihgnn_b200 import HemPredictionLayer, IHGNNLayer, RawGnn, _lib
+    from ihgnn_b200.dataset import GraphDataset
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: ihgnn_b200 has no CPU fallback "
+                           "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    # --- build: graph indices on the device, model with the reference's own initialisers
+    t_build0 = time.perf_counter()
+    ds = GraphDataset.from_search_log(log, dev)
+    graph = ds.hypergraph
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build0
+    torch.manual_seed(0)
+    model = RawGnn(device=dev, dataset=ds, embedding_size=d, gnn_layer_type=IHGNNLayer,
+                   gnn_layer_count=layers, feature_interaction_order=3, phase2_attention=False,
+                   predictions=HemPredictionLayer, lambda_muq=0.5).to(dev)
+    E, N = graph.EdgeCount, graph.node_count
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # --- M1: conv stack fwd+bwd, inputs resident in HBM -------------------------------
+    x = model.embeddings.embed_all().detach().clone().requires_grad_(True)
+
+    def conv_step():
+        x.grad = None
+        for p in model.parameters():
+            p.grad = None
+        outs = model.conv_stack(x)
+        torch.cat(outs, 1).sum().backward()
+
+    for _ in range(args.warmup):
+        conv_step()
+    prof = KernelProfiler()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    _lib.profiler = prof
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        conv_step()
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    _lib.profiler = None
+    t_conv = ev0.elapsed_time(ev1) * 1e-3 / args.steps
+    clocks = sampler.stop()
+    kern = prof.summary(args.steps)
+
+    # --- e2e: a full training step through the public API, host batch in, loss out -----
+    opt = torch.optim.Adam(model.parameters(), 1e-3)                      # Main.py:192
+    rng = np.random.default_rng(123)
+    B, NEG = 100, 10                                                      # GlobalSettings.py:26,39
+    n_batches = 8
+    host_batches = []
+    for _ in range(n_batches):
+        pick = rng.integers(0, E, size=B)
+        pu, pq, pi = log.pos_user[pick], log.pos_query[pick], log.pos_item[pick]
+        users = np.concatenate([pu, np.repeat(pu, NEG)])
+        queries = np.concatenate([pq, np.repeat(pq, NEG)])
+        items = np.concatenate([pi, rng.integers(0, log.item_count, size=B * NEG)])
+        flags = np.concatenate([np.ones(B, np.float32), np.zeros(B * NEG, np.float32)])
+        host_batches.append(tuple(torch.from_numpy(a).pin_memory() for a in (users, queries, items, flags)))
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_batches[0])
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def train_step(i):
+        users, queries, items, flags = (t.to(dev, non_blocking=True) for t in host_batches[i % n_batches])
+        scores = model(users, queries, items)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(scores, flags)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        loss_host.copy_(loss.detach().view(1), non_blocking=False)        # loss.item() of the reference
+        return loss_host
+
+    e2e_warm = max(3, min(args.warmup, 5))
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(e2e_warm):
+        train_step(i)
+    barrier()
+    ev0.record()
+    for i in range(e2e_steps):
+        train_step(i)
+    ev1.record()
+    barrier()
+    t_e2e = ev0.elapsed_time(ev1) * 1e-3 / e2e_steps
+
+    # --- max over ranks ---------------------------------------------------------------
+    if dist is not None:
+        tt = torch.tensor([t_conv, t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_conv, t_e2e = float(tt[0]), float(tt[1])
+    total_units = E * layers * world          # replicas: every rank convolves its own copy of the workload
+    value = total_units / t_conv
+    e2e_value = total_units / t_e2e
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    dom_tag = max(kern, key=lambda k: kern[k]["ms"])
+    dom = kern[dom_tag]
+    conv_bytes = layers * conv_algorithmic_bytes(E, N, d)
+    roofline = {
+        "bound": "hbm", "kernel": dom_tag, "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
+        "frac": dom["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+        "kernel_avg_ms": dom["avg_ms"], "kernel_share_of_step": dom["ms_per_step"] / (t_conv * 1e3),
+        "algorithmic_bytes_per_launch": dom["bytes"] / dom["calls"],
+        # whole conv step against SURVEY 8(d)'s E(60+76d)+N(28d+12) bytes per layer
+        "conv_step": {"algorithmic_bytes": conv_bytes, "achieved": conv_bytes / t_conv / 1e9,
+                      "frac": conv_bytes / t_conv / 1e9 / peak},
+    }
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt, Es = time_cpu(log, layers, d, args.cpu_sample_edges, 3, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"first {Es} of {E} hyperedges over the full node set, 3 timed conv fwd+bwd steps "
+                         f"({dt * 1e3:.0f} ms/step), oracle port (torch CPU ops), fp32"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_conv * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "layers": layers, "dim": d, "hyperedges": E, "nodes": N,
+                   "interaction_order": 3, "parallelism": f"replicas x{world}" if world > 1 else "single",
+                   "l2_policy": "inputs larger than L2 (no flush): per step the kernels stream "
+                                f"{conv_bytes / 1e9:.1f} GB algorithmic vs 126 MB L2",
+                   "graph_build_s": t_build},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
+                "train_samples_per_s": B * (1 + NEG) * world / t_e2e,
+                "what": "RawGnn.forward(batch) -> BCEWithLogits -> backward -> Adam.step, batch indices "
+                        "from pinned host memory, loss copied back every step"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "kernels": {k: {"ms_per_step": round(v["ms_per_step"], 4), "calls_per_step": v["calls"] / args.steps,
+                        "GBps": round(v["gbs"], 1)} for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])},
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="amazon-full", choices=sorted(synth.WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="multiply every workload count")
+    ap.add_argument("--cpu-sample-edges", type=int, default=200_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    w = synth.WORKLOADS[args.workload]
+    layers, d = w["layers"], w["dim"]
+    log = synth.make_workload(args.workload, scale=args.scale)
+    if args.impl == "reference":
+        run_reference_arm(args, log, layers, d)
+    else:
+        run_gpu_arm(args, log, layers, d)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,26 @@
+"""ihgnn_b200 -- B200-native (sm_100a) implementation of IHGNN's interactive hypergraph
+convolution hot path behind the reference's own layer API.
+
+Importing the package does not load the CUDA library; the first kernel call does, and fails
+loudly if libihgnn_b200.so is missing (there is no CPU or PyTorch fallback).
+"""
+from . import synth  # noqa: F401  (numpy-only)
+
+__all__ = ["synth", "PpsHyperGraph", "GraphDataset", "EmbeddingLayer", "FeatureInteractor",
+           "IHGNNLayer", "HGCNLayer", "HemPredictionLayer", "RawGnn"]
+
+
+def __getattr__(name):
+    if name == "PpsHyperGraph":
+        from .graph import PpsHyperGraph
+        return PpsHyperGraph
+    if name == "GraphDataset":
+        from .dataset import GraphDataset
+        return GraphDataset
+    if name in ("EmbeddingLayer", "FeatureInteractor", "IHGNNLayer", "HGCNLayer", "HemPredictionLayer"):
+        from . import layers
+        return getattr(layers, name)
+    if name == "RawGnn":
+        from .model import RawGnn
+        return RawGnn
+    raise AttributeError(name)

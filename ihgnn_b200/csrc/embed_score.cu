@@ -1,0 +1,250 @@
+// K-C / K-D: embedding row movement and the fused HEM scorer.
+//
+//   ihg_copy_rows / ihg_gather_rows / ihg_scatter_add_rows
+//        EmbeddingLayer.embed_user / embed_item (/root/reference/Models/EmbeddingLayers.py:70-74)
+//        and RawGnn's batch row selects (Models/RawGnn.py:128-133) with their backward.
+//        (EmbeddingBag(mean), EmbeddingLayers.py:79, is ihg_segment_reduce over the bag CSR.)
+//   ihg_hem_score_fwd / bwd
+//        HemPredictionLayer.forward (Models/PredictionLayers.py:21-44): replaces ~8 elementwise
+//        launches (2 mul, add, mul, sum, index, add) by one warp-per-row kernel.
+//
+// All HBM/latency-bound: 128-bit accesses, one warp (or lane group) per row, reductions by
+// fixed shuffle trees and ordered loops -- no float atomics.
+#include "common.cuh"
+
+namespace ihg {
+
+__global__ void __launch_bounds__(256)
+copy_rows_kernel(const float* __restrict__ src, int64_t src_ld, float* __restrict__ dst,
+                 int64_t dst_ld, int64_t n_rows, int nvec) {
+    const int64_t total = n_rows * nvec;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / nvec;
+        const int c = (int)(idx % nvec);
+        stg4(dst + r * dst_ld + 4 * c, ldg4_stream(src + r * src_ld + 4 * c));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ table, int64_t table_ld,
+                   const int64_t* __restrict__ idx, int64_t idx_offset, int64_t count,
+                   float* __restrict__ out, int64_t out_ld, int nvec) {
+    const int64_t total = count * nvec;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = t / nvec;
+        const int c = (int)(t % nvec);
+        const int64_t row = __ldg(idx + b) + idx_offset;
+        stg4(out + b * out_ld + 4 * c, ldg4(table + row * table_ld + 4 * c));
+    }
+}
+
+// One block per source row b.  The first occurrence of an index ("leader") sums every later
+// duplicate in ascending b and adds the total to the destination row once => deterministic.
+__global__ void __launch_bounds__(128)
+scatter_add_rows_kernel(const float* __restrict__ g, int64_t g_ld, const int64_t* __restrict__ idx,
+                        int64_t idx_offset, int64_t count, float* __restrict__ out,
+                        int64_t out_ld, int nvec) {
+    __shared__ int dup_before;
+    const int64_t b = blockIdx.x;
+    const int64_t my = __ldg(idx + b);
+    if (threadIdx.x == 0) dup_before = 0;
+    __syncthreads();
+    int found = 0;
+    for (int64_t j = threadIdx.x; j < b; j += blockDim.x) found |= (__ldg(idx + j) == my);
+    if (found) dup_before = 1;   // benign race: every writer stores 1
+    __syncthreads();
+    if (dup_before) return;
+    for (int c = threadIdx.x; c < nvec; c += blockDim.x) {
+        float4 acc = ldg4(g + b * g_ld + 4 * c);
+        for (int64_t j = b + 1; j < count; ++j)
+            if (__ldg(idx + j) == my) f4_add(acc, ldg4(g + j * g_ld + 4 * c));
+        float* o = out + (my + idx_offset) * out_ld + 4 * c;
+        float4 base = *reinterpret_cast<const float4*>(o);
+        f4_add(base, acc);
+        stg4(o, base);
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+hem_score_fwd_kernel(const float* __restrict__ uf, int64_t u_ld, const float* __restrict__ qf,
+                     int64_t q_ld, const float* __restrict__ itf, int64_t i_ld,
+                     const float* __restrict__ items_bias, const int64_t* __restrict__ item_idx,
+                     float lam, int64_t count, int nvec, float* __restrict__ score) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const float oml = 1.0f - lam;
+    for (int64_t b = warp; b < count; b += nwarps) {
+        float s = 0.f;
+        for (int c = lane; c < nvec; c += 32) {
+            const float4 q = ldg4(qf + b * q_ld + 4 * c);
+            const float4 it = ldg4(itf + b * i_ld + 4 * c);
+            float4 m = q;
+            if (uf) {
+                const float4 u = ldg4(uf + b * u_ld + 4 * c);
+                m = make_float4(lam * q.x + oml * u.x, lam * q.y + oml * u.y,
+                                lam * q.z + oml * u.z, lam * q.w + oml * u.w);
+            }
+            s += it.x * m.x + it.y * m.y + it.z * m.z + it.w * m.w;
+        }
+        s = warp_sum(s);
+        if (lane == 0) {
+            const int64_t bi = item_idx ? __ldg(item_idx + b) : b;
+            score[b] = s + __ldg(items_bias + bi);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hem_score_bwd_kernel(const float* __restrict__ dscore, const float* __restrict__ uf, int64_t u_ld,
+                     const float* __restrict__ qf, int64_t q_ld, const float* __restrict__ itf,
+                     int64_t i_ld, float lam, int64_t count, int nvec, float* __restrict__ d_user,
+                     float* __restrict__ d_query, float* __restrict__ d_item) {
+    const int64_t total = count * nvec;
+    const float oml = 1.0f - lam;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = t / nvec;
+        const int c = (int)(t % nvec);
+        const float gsc = __ldg(dscore + b);
+        const float4 q = ldg4(qf + b * q_ld + 4 * c);
+        const float4 it = ldg4(itf + b * i_ld + 4 * c);
+        float4 m = q;
+        if (uf) {
+            const float4 u = ldg4(uf + b * u_ld + 4 * c);
+            m = make_float4(lam * q.x + oml * u.x, lam * q.y + oml * u.y,
+                            lam * q.z + oml * u.z, lam * q.w + oml * u.w);
+        }
+        const int64_t o = b * (int64_t)nvec * 4 + 4 * c;   // gradients are dense [count, dim]
+        if (d_item) stg4(d_item + o, f4_scale(gsc, m));
+        if (uf) {
+            if (d_query) stg4(d_query + o, f4_scale(gsc * lam, it));
+            if (d_user) stg4(d_user + o, f4_scale(gsc * oml, it));
+        } else {
+            if (d_query) stg4(d_query + o, f4_scale(gsc, it));
+        }
+    }
+}
+
+// d_bias[i] = sum of dscore[b] over b with item_idx[b] == i, ascending b (leader scheme)
+__global__ void __launch_bounds__(256)
+hem_bias_grad_kernel(const float* __restrict__ dscore, const int64_t* __restrict__ item_idx,
+                     int64_t count, float* __restrict__ d_bias) {
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < count;
+         b += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t my = __ldg(item_idx + b);
+        bool leader = true;
+        for (int64_t j = 0; j < b; ++j)
+            if (__ldg(item_idx + j) == my) { leader = false; break; }
+        if (!leader) continue;
+        float s = __ldg(dscore + b);
+        for (int64_t j = b + 1; j < count; ++j)
+            if (__ldg(item_idx + j) == my) s += __ldg(dscore + j);
+        d_bias[my] = s;
+    }
+}
+
+static unsigned blocks_for(int64_t n, int threads) {
+    int64_t b = ceil_div(n > 0 ? n : 1, threads);
+    const int64_t cap = (int64_t)kNumSMs * 32;
+    return (unsigned)(b < cap ? b : cap);
+}
+
+}  // namespace ihg
+
+using namespace ihg;
+
+extern "C" {
+
+int ihg_copy_rows(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t n_rows,
+                  int32_t dim, void* stream) {
+    IHG_REQUIRE(src && dst, "copy_rows: null pointer");
+    IHG_REQUIRE(dim > 0 && dim % 4 == 0 && src_ld % 4 == 0 && dst_ld % 4 == 0,
+                "copy_rows: dim and leading dimensions must be multiples of 4");
+    if (n_rows <= 0) return IHG_OK;
+    copy_rows_kernel<<<blocks_for(n_rows * (dim / 4), 256), 256, 0, as_stream(stream)>>>(
+        src, src_ld, dst, dst_ld, n_rows, dim / 4);
+    IHG_LAUNCH_CHECK();
+    return IHG_OK;
+}
+
+int ihg_gather_rows(const float* table, int64_t table_ld, const int64_t* idx, int64_t idx_offset,
+                    int64_t count, float* out, int64_t out_ld, int32_t dim, void* stream) {
+    IHG_REQUIRE(table && idx && out, "gather_rows: null pointer");
+    IHG_REQUIRE(dim > 0 && dim % 4 == 0 && table_ld % 4 == 0 && out_ld % 4 == 0,
+                "gather_rows: dim and leading dimensions must be multiples of 4");
+    if (count <= 0) return IHG_OK;
+    gather_rows_kernel<<<blocks_for(count * (dim / 4), 256), 256, 0, as_stream(stream)>>>(
+        table, table_ld, idx, idx_offset, count, out, out_ld, dim / 4);
+    IHG_LAUNCH_CHECK();
+    return IHG_OK;
+}
+
+int ihg_scatter_add_rows(const float* g, int64_t g_ld, const int64_t* idx, int64_t idx_offset,
+                         int64_t count, float* out, int64_t out_ld, int32_t dim, void* stream) {
+    IHG_REQUIRE(g && idx && out, "scatter_add_rows: null pointer");
+    IHG_REQUIRE(dim > 0 && dim % 4 == 0 && g_ld % 4 == 0 && out_ld % 4 == 0,
+                "scatter_add_rows: dim and leading dimensions must be multiples of 4");
+    IHG_REQUIRE(count <= 65536, "scatter_add_rows: count=%lld exceeds the 65536-row batch limit", (long long)count);
+    if (count <= 0) return IHG_OK;
+    scatter_add_rows_kernel<<<(unsigned)count, 128, 0, as_stream(stream)>>>(g, g_ld, idx, idx_offset,
+                                                                            count, out, out_ld, dim / 4);
+    IHG_LAUNCH_CHECK();
+    return IHG_OK;
+}
+
+int ihg_hem_score_fwd(const float* user_f, int64_t user_ld, const float* query_f, int64_t query_ld,
+                      const float* item_f, int64_t item_ld, const float* items_bias,
+                      const int64_t* item_idx, float lambda_muq, int64_t count, int32_t dim,
+                      float* score, void* stream) {
+    IHG_REQUIRE(query_f && item_f && items_bias && score, "hem_score_fwd: null pointer");
+    IHG_REQUIRE(dim > 0 && dim % 4 == 0 && query_ld % 4 == 0 && item_ld % 4 == 0 && (!user_f || user_ld % 4 == 0),
+                "hem_score_fwd: dim and leading dimensions must be multiples of 4");
+    if (count <= 0) return IHG_OK;
+    hem_score_fwd_kernel<<<blocks_for(count, 8), 256, 0, as_stream(stream)>>>(
+        user_f, user_ld, query_f, query_ld, item_f, item_ld, items_bias, item_idx, lambda_muq, count,
+        dim / 4, score);
+    IHG_LAUNCH_CHECK();
+    return IHG_OK;
+}
+
+int ihg_hem_score_bwd(const float* dscore, const float* user_f, int64_t user_ld,
+                      const float* query_f, int64_t query_ld, const float* item_f, int64_t item_ld,
+                      const int64_t* item_idx, float lambda_muq, int64_t count, int32_t dim,
+                      float* d_user, float* d_query, float* d_item, float* d_bias,
+                      int64_t item_count, void* stream) {
+    IHG_REQUIRE(dscore && query_f && item_f, "hem_score_bwd: null pointer");
+    IHG_REQUIRE(dim > 0 && dim % 4 == 0 && query_ld % 4 == 0 && item_ld % 4 == 0 && (!user_f || user_ld % 4 == 0),
+                "hem_score_bwd: dim and leading dimensions must be multiples of 4");
+    cudaStream_t st = as_stream(stream);
+    if (d_bias) {
+        IHG_REQUIRE(item_count > 0, "hem_score_bwd: item_count must be given with d_bias");
+        if (item_idx) {
+            IHG_REQUIRE(count <= 65536, "hem_score_bwd: count=%lld exceeds the 65536-row batch limit", (long long)count);
+            IHG_CUDA(cudaMemsetAsync(d_bias, 0, (size_t)item_count * 4, st));
+            if (count > 0) {
+                hem_bias_grad_kernel<<<blocks_for(count, 256), 256, 0, st>>>(dscore, item_idx, count, d_bias);
+                IHG_LAUNCH_CHECK();
+            }
+        } else {
+            IHG_REQUIRE(count == item_count, "hem_score_bwd: all-items form needs count == item_count");
+            IHG_CUDA(cudaMemcpyAsync(d_bias, dscore, (size_t)count * 4, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    if (count <= 0) return IHG_OK;
+    hem_score_bwd_kernel<<<blocks_for(count * (dim / 4), 256), 256, 0, st>>>(
+        dscore, user_f, user_ld, query_f, query_ld, item_f, item_ld, lambda_muq, count, dim / 4,
+        d_user, d_query, d_item);
+    IHG_LAUNCH_CHECK();
+    return IHG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+"""Mirror of the `GraphDataset` attributes the hot-path layers consume
+(/root/reference/Dataset.py:141-186 and the lazy `.graph` / `.hypergraph` properties :78-96).
+
+The reference parses CSV search logs in Python; this container is filled either from a
+`synth.SearchLogSet` (arrays) or from the reference's on-disk files, and builds its
+hypergraph on the device through `ihgnn_b200.graph.PpsHyperGraph`.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .graph import PpsHyperGraph
+from .synth import SearchLogSet
+
+
+class GraphDataset:
+    """Holds counts, index tensors and the lazily built hypergraph, attribute-compatible with
+    the reference's GraphDataset for everything RawGnn and the layers read."""
+
+    device: torch.device
+
+    def __init__(self, user_count: int, query_count: int, item_count: int, vocab_size: int,
+                 bag_words: np.ndarray, bag_offsets: np.ndarray,
+                 pos_user: np.ndarray, pos_query: np.ndarray, pos_item: np.ndarray,
+                 device, graph_type=PpsHyperGraph):
+        device = torch.device(device)
+        GraphDataset.device = device                       # Dataset.py:135
+        self.graph_type = graph_type
+        self.user_count, self.query_count = int(user_count), int(query_count)
+        self.item_count, self.vocab_size = int(item_count), int(vocab_size)
+        self.node_count = self.user_count + self.query_count + self.item_count   # Dataset.py:145
+        self.query_start_index_in_graph = self.user_count                         # :146
+        self.item_start_index_in_graph = self.user_count + self.query_count       # :147
+        # one-hot value == index + 1 (row 0 of every table is padding)   Dataset.py:149-155
+        self.users_onehot = torch.arange(1, 1 + self.user_count, device=device)
+        self.items_onehot = torch.arange(1, 1 + self.item_count, device=device)
+        self.vocabulary_onehot = torch.arange(1, 1 + self.vocab_size, device=device)
+        # EmbeddingBag inputs: flat word ids (+1) and per-query start offsets   Dataset.py:165-186
+        self.queries_for_embeddingbag = torch.as_tensor(np.asarray(bag_words, dtype=np.int64), device=device)
+        self.queries_offset_for_embeddingbag = torch.as_tensor(np.asarray(bag_offsets, dtype=np.int64), device=device)
+        self.queries_multihot = None       # legacy sparse view of the reference; never read
+        self.pos_user = np.asarray(pos_user, dtype=np.int64)
+        self.pos_query = np.asarray(pos_query, dtype=np.int64)
+        self.pos_item = np.asarray(pos_item, dtype=np.int64)
+        self._hgraph: Optional[PpsHyperGraph] = None
+
+    def __len__(self) -> int:
+        return int(self.pos_user.shape[0])
+
+    @property
+    def hypergraph(self) -> PpsHyperGraph:                  # Dataset.py:91-96
+        if self._hgraph is None:
+            self._hgraph = PpsHyperGraph.from_tensors(
+                self.pos_user, self.pos_query, self.pos_item,
+                self.user_count, self.query_count, self.item_count, GraphDataset.device)
+        return self._hgraph
+
+    @property
+    def graph(self) -> PpsHyperGraph:                       # Dataset.py:79-82
+        return self.hypergraph
+
+    @classmethod
+    def from_search_log(cls, log: SearchLogSet, device) -> "GraphDataset":
+        words, offsets = log.bag_inputs()
+        return cls(log.user_count, log.query_count, log.item_count, log.vocab_size, words, offsets,
+                   log.pos_user, log.pos_query, log.pos_item, device)
+
+    @classmethod
+    def from_files(cls, directory: str, device, train_file: str = "train_data.csv") -> "GraphDataset":
+        """Read the reference's on-disk format (graph_info.txt, queries_multihot.txt,
+        train_data.csv; Dataset.py:141-200, Helpers/SearchLog.py:63-71)."""
+        with open(os.path.join(directory, "graph_info.txt"), encoding="utf-8") as f:
+            U, Q, I, V = (int(p) for p in f.readline().split())
+        words, offsets = [], []
+        with open(os.path.join(directory, "queries_multihot.txt"), encoding="utf-8") as f:
+            for line in f:
+                offsets.append(len(words))
+                words.extend(int(p) + 1 for p in line.split())
+        pu, pq, pi = [], [], []
+        with open(os.path.join(directory, train_file), encoding="utf-8") as f:
+            f.readline()
+            for line in f:
+                u, q, _t, items, _pages, _pos, flags, _times = line.strip().split(",")
+                for it, fl in zip(items.split(), flags.split()):
+                    if int(fl) > 0:
+                        pu.append(int(u)); pq.append(int(q)); pi.append(int(it))
+        return cls(U, Q, I, V, np.asarray(words, dtype=np.int64), np.asarray(offsets, dtype=np.int64),
+                   np.asarray(pu), np.asarray(pq), np.asarray(pi), device)

@@ -1,0 +1,272 @@
+"""Raw kernel wrappers and the custom autograd Functions built on them.
+
+Everything here calls the C ABI of libihgnn_b200.so through `_lib`; there is no torch-op
+fallback for any of the hot-path computations.  torch supplies device memory (the caching
+allocator), the current stream and the autograd tape.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from .graph import INT64_MAX, CsrPlan, PpsHyperGraph
+
+_F32 = torch.float32
+
+
+def _empty(shape, like: torch.Tensor) -> torch.Tensor:
+    return torch.empty(shape, dtype=_F32, device=like.device)
+
+
+def _ws(nbytes: int, like: torch.Tensor) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=like.device)
+
+
+# --------------------------------------------------------------------------------------
+# raw ops (no autograd)
+# --------------------------------------------------------------------------------------
+def segment_reduce(plan: CsrPlan, src: torch.Tensor, dim: int, *, src_row_mul: int = 1,
+                   bounds: Tuple[int, int] = (INT64_MAX, INT64_MAX),
+                   src_scale: Optional[torch.Tensor] = None,
+                   row_scale: Optional[torch.Tensor] = None,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r] = row_scale[r] * sum_{j in row r} src_scale[col j] * src[col[j]*mul + slot(r)]."""
+    _lib.require_cuda(src, src_scale, row_scale, out)
+    if src_row_mul == 1:
+        src = _lib.rows_f32(src)
+        src_ld = _lib.ld(src)
+    else:
+        assert src.is_contiguous() and src.dtype == _F32
+        src_ld = dim
+    if out is None:
+        out = _empty((plan.n_rows, dim), src)
+    _lib.call("ihg_segment_reduce", plan.ref(), _lib.ptr(src), src_ld, src_row_mul, bounds[0],
+              bounds[1], _lib.ptr(src_scale), _lib.ptr(row_scale), _lib.ptr(plan.partial(dim)),
+              _lib.ptr(out), _lib.ld(out), dim, _lib.stream_ptr(),
+              tag=f"segment_reduce[mul={src_row_mul}]",
+              algo_bytes=plan.nnz * (4 + 4 * dim) + plan.n_rows * (4 * dim + 16))
+    return out
+
+
+def edge_gather_sum(src: torch.Tensor, i3: torch.Tensor, *, node_scale: Optional[torch.Tensor] = None,
+                    alpha: float = 1.0, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[e] = alpha * sum_s node_scale[i3[e,s]] * src[i3[e,s]] (+ bias)."""
+    _lib.require_cuda(src, i3, node_scale, bias)
+    src = _lib.rows_f32(src)
+    E, dim = int(i3.shape[0]), int(src.shape[1])
+    out = _empty((E, dim), src)
+    _lib.call("ihg_edge_gather_sum", _lib.ptr(src), _lib.ld(src), _lib.ptr(node_scale), float(alpha),
+              _lib.ptr(bias), _lib.ptr(i3), E, _lib.ptr(out), dim, dim, _lib.stream_ptr(),
+              tag="edge_gather_sum", algo_bytes=E * (12 + 16 * dim + (12 if node_scale is not None else 0)))
+    return out
+
+
+def node_linear(x: torch.Tensor, w: torch.Tensor, *, transpose_w: bool = False,
+                bias: Optional[torch.Tensor] = None, addend: Optional[torch.Tensor] = None,
+                bounds: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """Typed Linear.  w: [T, n_out, n_in] (transpose_w False) -> y = x W[t]^T + bias[t] + addend;
+    transpose_w True -> y = x W[t] (n_out = w.shape[2])."""
+    _lib.require_cuda(x, w, bias, addend)
+    x = _lib.rows_f32(x)
+    w = w.contiguous()
+    assert w.dim() == 3 and w.dtype == _F32
+    T, r, c = (int(s) for s in w.shape)
+    n_out, n_in = (c, r) if transpose_w else (r, c)
+    assert x.shape[1] == n_in, (x.shape, w.shape, transpose_w)
+    n_rows = int(x.shape[0])
+    if T == 1:
+        b0 = b1 = n_rows
+    else:
+        assert T == 3 and bounds is not None
+        b0, b1 = bounds
+    if bias is not None:
+        bias = bias.contiguous()
+    if addend is not None:
+        addend = _lib.rows_f32(addend)
+    y = _empty((n_rows, n_out), x)
+    _lib.call("ihg_node_linear", _lib.ptr(x), _lib.ld(x), _lib.ptr(w), T, n_out, n_in,
+              1 if transpose_w else 0, _lib.ptr(bias), _lib.ptr(addend),
+              _lib.ld(addend) if addend is not None else 0, n_rows, b0, b1, _lib.ptr(y), n_out,
+              _lib.stream_ptr(), tag="node_linear",
+              algo_bytes=n_rows * 4 * (n_in + n_out + (n_out if addend is not None else 0)))
+    return y
+
+
+def node_linear_wgrad(dy: torch.Tensor, x: torch.Tensor, n_types: int,
+                      bounds: Optional[Tuple[int, int]], want_bias: bool):
+    """dw[t] = sum_{r in t} dy[r]^T x[r] -> [T, n_out, n_in]; db[t] = sum dy[r] -> [T, n_out]."""
+    dy = _lib.rows_f32(dy)
+    x = _lib.rows_f32(x)
+    n_rows, n_out, n_in = int(x.shape[0]), int(dy.shape[1]), int(x.shape[1])
+    b0, b1 = (n_rows, n_rows) if n_types == 1 else bounds
+    dw = _empty((n_types, n_out, n_in), x)
+    db = _empty((n_types, n_out), x) if want_bias else None
+    ws_bytes = _lib.lib().ihg_node_linear_wgrad_workspace_bytes(n_types, n_out, n_in)
+    ws = _ws(ws_bytes, x)
+    _lib.call("ihg_node_linear_wgrad", _lib.ptr(dy), _lib.ld(dy), _lib.ptr(x), _lib.ld(x), n_rows,
+              b0, b1, n_types, n_out, n_in, _lib.ptr(dw), _lib.ptr(db), _lib.ptr(ws), ws_bytes,
+              _lib.stream_ptr(), tag="node_linear_wgrad", algo_bytes=n_rows * 4 * (n_in + n_out))
+    return dw, db
+
+
+# --------------------------------------------------------------------------------------
+# autograd Functions
+# --------------------------------------------------------------------------------------
+class TypedLinearFn(torch.autograd.Function):
+    """y = x W[type(row)]^T + b[type(row)];  w [T, n_out, n_in], b [T, n_out] or None."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, bounds):
+        ctx.bounds = bounds
+        ctx.has_bias = b is not None
+        x = _lib.rows_f32(x)
+        w = w.contiguous()
+        ctx.save_for_backward(x, w)
+        return node_linear(x, w, bias=b, bounds=bounds)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _lib.rows_f32(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = node_linear(dy, w, transpose_w=True, bounds=ctx.bounds)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = node_linear_wgrad(dy, x, int(w.shape[0]), ctx.bounds, ctx.has_bias)
+        return dx, dw, db, None
+
+
+def typed_linear(x, w, b=None, bounds=None):
+    return TypedLinearFn.apply(x, w, b, bounds)
+
+
+class EmbedAllFn(torch.autograd.Function):
+    """EmbeddingLayer.forward(None, None, None) fused with RawGnn's cat
+    (/root/reference/Models/EmbeddingLayers.py:63-81, Models/RawGnn.py:112):
+        X = [ weight_user[1:] ; bag_mean(weight_vocab) ; weight_item[1:] ]      [N, d]
+    Backward: dense table gradients with the padding row 0 zero; the vocabulary gradient is a
+    segmented reduce over the word -> query transpose (deterministic)."""
+
+    @staticmethod
+    def forward(ctx, w_user, w_vocab, w_item, tables):
+        _lib.require_cuda(w_user, w_vocab, w_item)
+        U, Q, I = tables.user_count, tables.query_count, tables.item_count
+        d = int(w_user.shape[1])
+        w_user, w_vocab, w_item = (_lib.rows_f32(t) for t in (w_user, w_vocab, w_item))
+        x = _empty((U + Q + I, d), w_user)
+        st = _lib.stream_ptr()
+        _lib.call("ihg_copy_rows", w_user.data_ptr() + 4 * _lib.ld(w_user), _lib.ld(w_user),
+                  _lib.ptr(x), d, U, d, st)
+        segment_reduce(tables.bag_plan, w_vocab, d, row_scale=tables.bag_inv_len, out=x[U:U + Q])
+        _lib.call("ihg_copy_rows", w_item.data_ptr() + 4 * _lib.ld(w_item), _lib.ld(w_item),
+                  x.data_ptr() + 4 * d * (U + Q), d, I, d, st)
+        ctx.tables = tables
+        ctx.shapes = (tuple(w_user.shape), tuple(w_vocab.shape), tuple(w_item.shape))
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        t = ctx.tables
+        U, Q, I = t.user_count, t.query_count, t.item_count
+        dx = _lib.rows_f32(dx)
+        d = int(dx.shape[1])
+        ldx = _lib.ld(dx)
+        st = _lib.stream_ptr()
+        su, sv, si = ctx.shapes
+        dwu = dwv = dwi = None
+        if ctx.needs_input_grad[0]:
+            dwu = _empty(su, dx)
+            dwu[0].zero_()                                   # padding_idx=0 row: zero gradient
+            _lib.call("ihg_copy_rows", _lib.ptr(dx), ldx, dwu.data_ptr() + 4 * d, d, U, d, st)
+        if ctx.needs_input_grad[1]:
+            # dW_vocab[w] = sum over occurrences (q, w) of dX[U+q] / len(q)
+            dwv = segment_reduce(t.word_plan, dx[U:U + Q], d, src_scale=t.bag_inv_len)
+        if ctx.needs_input_grad[2]:
+            dwi = _empty(si, dx)
+            dwi[0].zero_()
+            _lib.call("ihg_copy_rows", dx.data_ptr() + 4 * ldx * (U + Q), ldx,
+                      dwi.data_ptr() + 4 * d, d, I, d, st)
+        return dwu, dwv, dwi, None
+
+
+class GatherRowsFn(torch.autograd.Function):
+    """out[b] = table[idx[b] + offset]; backward is a deterministic scatter-add into a dense
+    gradient (the reference's `index` / `embedding` backward)."""
+
+    @staticmethod
+    def forward(ctx, table, idx, offset: int):
+        _lib.require_cuda(table, idx)
+        table = _lib.rows_f32(table)
+        idx = idx.to(torch.int64).contiguous()
+        B, d = int(idx.numel()), int(table.shape[1])
+        out = _empty((B, d), table)
+        _lib.call("ihg_gather_rows", _lib.ptr(table), _lib.ld(table), _lib.ptr(idx), offset, B,
+                  _lib.ptr(out), d, d, _lib.stream_ptr())
+        ctx.save_for_backward(idx)
+        ctx.offset, ctx.shape = offset, tuple(table.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        g = _lib.rows_f32(g)
+        d = int(g.shape[1])
+        dt = torch.zeros(ctx.shape, dtype=_F32, device=g.device)
+        _lib.call("ihg_scatter_add_rows", _lib.ptr(g), _lib.ld(g), _lib.ptr(idx), ctx.offset,
+                  int(idx.numel()), _lib.ptr(dt), d, d, _lib.stream_ptr())
+        return dt, None, None
+
+
+def gather_rows(table, idx, offset: int = 0):
+    return GatherRowsFn.apply(table, idx, offset)
+
+
+class HemScoreFn(torch.autograd.Function):
+    """HemPredictionLayer.forward, dot-product branch
+    (/root/reference/Models/PredictionLayers.py:21-44)."""
+
+    @staticmethod
+    def forward(ctx, user_f, query_f, item_f, items_bias, item_idx, lam: float):
+        _lib.require_cuda(user_f, query_f, item_f, items_bias, item_idx)
+        query_f, item_f = _lib.rows_f32(query_f), _lib.rows_f32(item_f)
+        if user_f is not None:
+            user_f = _lib.rows_f32(user_f)
+        if item_idx is not None:
+            item_idx = item_idx.to(torch.int64).contiguous()
+        items_bias = items_bias.contiguous()
+        B, D = int(item_f.shape[0]), int(item_f.shape[1])
+        score = torch.empty(B, dtype=_F32, device=item_f.device)
+        _lib.call("ihg_hem_score_fwd", _lib.ptr(user_f), _lib.ld(user_f) if user_f is not None else 0,
+                  _lib.ptr(query_f), _lib.ld(query_f), _lib.ptr(item_f), _lib.ld(item_f),
+                  _lib.ptr(items_bias), _lib.ptr(item_idx), float(lam), B, D, _lib.ptr(score),
+                  _lib.stream_ptr())
+        ctx.lam, ctx.n_items = float(lam), int(items_bias.numel())
+        ctx.has_user, ctx.has_idx = user_f is not None, item_idx is not None
+        ctx.save_for_backward(*(t for t in (user_f, query_f, item_f, item_idx) if t is not None))
+        return score
+
+    @staticmethod
+    def backward(ctx, dscore):
+        saved = list(ctx.saved_tensors)
+        user_f = saved.pop(0) if ctx.has_user else None
+        query_f, item_f = saved.pop(0), saved.pop(0)
+        item_idx = saved.pop(0) if ctx.has_idx else None
+        dscore = dscore.contiguous()
+        B, D = int(item_f.shape[0]), int(item_f.shape[1])
+        need = ctx.needs_input_grad
+        d_user = _empty((B, D), item_f) if (ctx.has_user and need[0]) else None
+        d_query = _empty((B, D), item_f) if need[1] else None
+        d_item = _empty((B, D), item_f) if need[2] else None
+        d_bias = torch.empty(ctx.n_items, dtype=_F32, device=item_f.device) if need[3] else None
+        _lib.call("ihg_hem_score_bwd", _lib.ptr(dscore), _lib.ptr(user_f),
+                  _lib.ld(user_f) if user_f is not None else 0, _lib.ptr(query_f), _lib.ld(query_f),
+                  _lib.ptr(item_f), _lib.ld(item_f), _lib.ptr(item_idx), ctx.lam, B, D,
+                  _lib.ptr(d_user), _lib.ptr(d_query), _lib.ptr(d_item), _lib.ptr(d_bias),
+                  ctx.n_items, _lib.stream_ptr())
+        return d_user, d_query, d_item, d_bias, None, None
+
+
+def hem_score(user_f, query_f, item_f, items_bias, item_idx, lam):
+    return HemScoreFn.apply(user_f, query_f, item_f, items_bias, item_idx, lam)

@@ -1,0 +1,205 @@
+/*
+ * ihgnn_b200.h -- C ABI of libihgnn_b200.so: the B200 (sm_100a) implementation of IHGNN's
+ * interactive hypergraph-convolution hot path.
+ *
+ * Conventions (last row):
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *   - the caller owns every buffer, the library allocates nothing and keeps no state
+ *     (workspaces are caller-provided, their sizes come from the *_workspace_bytes calls);
+ *   - every launch is asynchronous on `stream` (a cudaStream_t passed as void*); there is no
+ *     hidden synchronisation, so the calls can be captured in a CUDA graph;
+ *   - fp32 values, row-major, leading dimensions (`*_ld`) in elements; int32 indices inside
+ *     the library, int64 where the reference hands int64 tensors in (graph input, batch
+ *     indices);
+ *   - return value 0 = ok, non-zero = error (IHG_ERR_*), text via ihg_last_error();
+ *   - results are deterministic: no floating-point atomics anywhere.
+ *
+ * The reference is pure PyTorch, so it has no FFI of its own; each entry point below names
+ * the reference Python code (file:line under /root/reference) whose computation it replaces.
+ * The reference-side binding (a ctypes stub + autograd.Function) is shown in INTEGRATION.md
+ * and implemented in ihgnn_b200/_lib.py and ihgnn_b200/functional.py.
+ */
+#ifndef IHGNN_B200_H
+#define IHGNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IHG_ABI_VERSION 1
+
+#define IHG_OK 0
+#define IHG_ERR_INVALID_ARGUMENT 1   /* bad shape / null pointer / unsupported dimension   */
+#define IHG_ERR_CUDA 2               /* a CUDA runtime call or launch failed              */
+#define IHG_ERR_WORKSPACE 3          /* caller workspace too small                        */
+
+int ihg_abi_version(void);
+/* Thread-local text of the last error raised on the calling thread ("" if none). */
+const char* ihg_last_error(void);
+/* Number of CUDA kernels this library has launched in the process so far (all threads). */
+int64_t ihg_launch_count(void);
+
+/* Host-side struct describing a CSR matrix with unit values plus its deterministic
+ * load-balancing plan (rows longer than `chunk_len` are split into chunks whose partial
+ * sums are combined in fixed order).  All pointers are device pointers. */
+typedef struct ihg_csr {
+    int64_t n_rows;
+    int64_t nnz;
+    const int32_t* rowptr;     /* [n_rows+1]                                             */
+    const int32_t* col;        /* [nnz]                                                  */
+    int32_t chunk_len;
+    int64_t n_seg;             /* work items: one per row chunk (>= n_rows)              */
+    int64_t n_split;           /* rows that were split into more than one chunk          */
+    int64_t n_part;            /* partial-sum rows needed by split rows                  */
+    const int32_t* seg_row;    /* [n_seg]  row of the chunk                              */
+    const int32_t* seg_begin;  /* [n_seg]  first nnz position of the chunk               */
+    const int32_t* seg_part;   /* [n_seg]  partial slot, or -1 when the row is not split */
+    const int32_t* split_row;  /* [n_split]                                              */
+    const int32_t* split_ptr;  /* [n_split+1] range of partial slots of each split row   */
+} ihg_csr;
+
+/* ------------------------------------------------------------------------------------
+ * a1  PpsHyperGraph.from_interactions            Helpers/Graph.py:94-134
+ *     (+ the coalesce() of GnnLayers.py:190).  Replaces the per-edge Python loop and the
+ *     COO sort by a device histogram + scan + stable LSD radix sort.
+ * in : user/query/item  int64 [E], 0-based per-type ids, in file (= hyperedge) order
+ * out: i3      int32 [E,3]   global node ids (u, q+U, i+U+Q)            Graph.py:110-117,129
+ *      rowptr  int32 [N+1], col int32 [3E]: CSR of Adjacency.coalesce() (edge ids ascending
+ *              inside a node)                                            Graph.py:123-128
+ *      vertex_degrees fp32 [N] with 0 stored as 1e-8                     Graph.py:112,120
+ *      dv_inv = vertex_degrees^-1 (GnnLayers.py:187), dv_inv_sqrt = ^-1/2 (GnnLayers.py:133)
+ *      error_flag int32 [1]: set non-zero if any id is out of range
+ * ------------------------------------------------------------------------------------ */
+int64_t ihg_graph_workspace_bytes(int64_t edge_count, int64_t node_count);
+int ihg_graph_build(const int64_t* user, const int64_t* query, const int64_t* item,
+                    int64_t edge_count, int64_t user_count, int64_t query_count,
+                    int64_t item_count, int32_t* i3, int32_t* rowptr, int32_t* col,
+                    float* vertex_degrees, float* dv_inv, float* dv_inv_sqrt,
+                    int32_t* error_flag, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+
+/* Stable CSR of a key array: rowptr[k] = #keys < k, perm = positions sorted by key with
+ * ascending position inside a key.  Used for the vocabulary->query transpose that the
+ * EmbeddingBag backward needs (EmbeddingLayers.py:79; torch _embedding_bag_dense_backward).
+ * `values` (nullable, int32 [n]) is permuted along: out_values[j] = values[perm[j]]. */
+int64_t ihg_csr_from_keys_workspace_bytes(int64_t n, int64_t num_keys);
+int ihg_csr_from_keys(const int32_t* keys, const int32_t* values, int64_t n, int64_t num_keys,
+                      int32_t* rowptr, int32_t* perm, int32_t* out_values,
+                      int32_t* error_flag, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+
+/* Load-balancing plan for ihg_segment_reduce.  Capacities the caller must provide:
+ *   seg_*      : n_rows + nnz/chunk_len + 1 entries
+ *   split_row  : nnz/chunk_len + 1,  split_ptr: nnz/chunk_len + 2
+ * counts (device int64 [3]) receives n_seg, n_split, n_part. */
+int64_t ihg_segment_plan_workspace_bytes(int64_t n_rows);
+int ihg_segment_plan_build(const int32_t* rowptr, int64_t n_rows, int32_t chunk_len,
+                           int32_t* seg_row, int32_t* seg_begin, int32_t* seg_part,
+                           int32_t* split_row, int32_t* split_ptr, int64_t* counts,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * a7  torch_sparse.matmul(incidence, Ef) * Dv^-1     Models/GnnLayers.py:233-234
+ *     (and its transpose products in backward; EmbeddingBag(mean) EmbeddingLayers.py:79).
+ * Deterministic segmented reduction over CSR rows:
+ *   out[r, 0:dim] = row_scale[r] * sum_{j in row r, ascending}
+ *                       src_scale[s(j)] * src[s(j), 0:dim],
+ *   s(j) = col[j] * src_row_mul + slot(r),  slot(r) = (r >= bound0) + (r >= bound1)
+ * (src_row_mul = 3 with the node-type bounds reads the per-slot gradient rows [E,3,dim];
+ * src_row_mul = 1 with bounds = INT64_MAX is the plain SpMM).  row_scale / src_scale may be
+ * null (= 1).  `partial` is scratch of csr->n_part * dim floats.  dim % 4 == 0, dim <= 256.
+ * ------------------------------------------------------------------------------------ */
+int ihg_segment_reduce(const ihg_csr* csr_host, const float* src, int64_t src_ld,
+                       int32_t src_row_mul, int64_t bound0, int64_t bound1,
+                       const float* src_scale, const float* row_scale, float* partial,
+                       float* out, int64_t out_ld, int32_t dim, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * a6/a8  node -> hyperedge gather-sum.
+ *   out[e,:] = alpha * sum_{s<3} node_scale[i3[e,s]] * src[i3[e,s], :]  (+ bias)
+ * Order-1 FeatureInteractor after hoisting the aggregation Linear to node level
+ * (CommonLayers.py:58-66), HGCN's incidence_t SpMM (GnnLayers.py:148-149), and the
+ * backward of the edge->node SpMM (dEf = H^T (Dv^-1 dOut)).  node_scale / bias nullable.
+ * ------------------------------------------------------------------------------------ */
+int ihg_edge_gather_sum(const float* src, int64_t src_ld, const float* node_scale,
+                        float alpha, const float* bias, const int32_t* i3, int64_t edge_count,
+                        float* out, int64_t out_ld, int32_t dim, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * a6  FeatureInteractor.forward, order 2/3          Models/CommonLayers.py:68-85
+ *   ef[e,:] = p[u]+p[q]+p[i]                      (first-order blocks, hoisted: p = X' Wa_s^T
+ *                                                  per node type, bias folded into p)
+ *           + W_hi . cat(u*q, q*i, i*u [, u*q*i])  u,q,i = xp rows of the edge's nodes
+ * w_hi = aggregation.weight[:, 3*dim:] ([dim, nb*dim], row stride w_ld), nb = order+... 3 or 4.
+ * Backward: given def = dL/def [E,dim] writes slot_grad[e,s,:] = dL/d(xp row of slot s)
+ * through the products only, and dw_hi [dim, nb*dim] (dense, deterministic two-pass sum).
+ * dim % 4 == 0, dim <= 128.
+ * ------------------------------------------------------------------------------------ */
+int ihg_edge_interact_fwd(const float* xp, int64_t xp_ld, const float* p, int64_t p_ld,
+                          const float* w_hi, int64_t w_ld, int32_t order, const int32_t* i3,
+                          int64_t edge_count, float* ef, int64_t ef_ld, int32_t dim,
+                          void* stream);
+int64_t ihg_edge_interact_bwd_workspace_bytes(int32_t dim, int32_t order);
+int ihg_edge_interact_bwd(const float* xp, int64_t xp_ld, const float* def, int64_t def_ld,
+                          const float* w_hi, int64_t w_ld, int32_t order, const int32_t* i3,
+                          int64_t edge_count, float* slot_grad, float* dw_hi, int32_t dim,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * a5  feature_transform / hoisted aggregation Linear  GnnLayers.py:224, CommonLayers.py:66
+ * Node-level typed Linear: rows [0,bound0) use weight 0, [bound0,bound1) weight 1, the rest
+ * weight 2 (n_types = 1: one weight for all rows).
+ *   transpose_w = 0:  y[r,:] = x[r,:] . W[t]^T (+ bias[t]) (+ addend[r,:]),  W[t]: [n_out, n_in]
+ *   transpose_w = 1:  y[r,:] = x[r,:] . W[t]   (+ ...),                      W[t]: [n_in, n_out]
+ * wgrad: dw[t] = sum_{r in type t} dy[r]^T x[r]  ([n_out, n_in]), db[t] = sum dy[r]
+ * (deterministic two-pass).  n_in, n_out multiples of 4, <= 128.
+ * ------------------------------------------------------------------------------------ */
+int ihg_node_linear(const float* x, int64_t x_ld, const float* w, int32_t n_types,
+                    int32_t n_out, int32_t n_in, int32_t transpose_w, const float* bias,
+                    const float* addend, int64_t addend_ld, int64_t n_rows, int64_t bound0,
+                    int64_t bound1, float* y, int64_t y_ld, void* stream);
+int64_t ihg_node_linear_wgrad_workspace_bytes(int32_t n_types, int32_t n_out, int32_t n_in);
+int ihg_node_linear_wgrad(const float* dy, int64_t dy_ld, const float* x, int64_t x_ld,
+                          int64_t n_rows, int64_t bound0, int64_t bound1, int32_t n_types,
+                          int32_t n_out, int32_t n_in, float* dw, float* db, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * a3  EmbeddingLayer lookups                       Models/EmbeddingLayers.py:70-81
+ * copy_rows   : dst[r,:] = src[r,:] for a row range (the identity-index lookup of all
+ *               users / items: weight[1:], 128-bit vectorised)
+ * gather_rows : out[b,:] = table[idx[b] + idx_offset, :]   (indexed form; RawGnn.py:128-133)
+ * scatter_add_rows: out[idx[b]+idx_offset,:] += g[b,:], duplicates summed in ascending b
+ *               (backward of gather_rows; `out` must hold the base values, e.g. zeros).
+ * ------------------------------------------------------------------------------------ */
+int ihg_copy_rows(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t n_rows,
+                  int32_t dim, void* stream);
+int ihg_gather_rows(const float* table, int64_t table_ld, const int64_t* idx,
+                    int64_t idx_offset, int64_t count, float* out, int64_t out_ld, int32_t dim,
+                    void* stream);
+int ihg_scatter_add_rows(const float* g, int64_t g_ld, const int64_t* idx, int64_t idx_offset,
+                         int64_t count, float* out, int64_t out_ld, int32_t dim, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * a10 HemPredictionLayer.forward                   Models/PredictionLayers.py:21-44
+ *   m = lambda*q + (1-lambda)*u   (u null: m = q);  score[b] = sum_D item[b]*m[b] + bias[b']
+ *   b' = item_idx[b] (item_idx null: b' = b, "all items").  Dot-product branch only.
+ * bwd: d_item = g*m, d_query = g*lambda*item, d_user = g*(1-lambda)*item (null = skip),
+ *      d_bias[i] = sum_{b: idx[b]==i} g[b] in ascending b (d_bias pre-zeroed by the callee).
+ * ------------------------------------------------------------------------------------ */
+int ihg_hem_score_fwd(const float* user_f, int64_t user_ld, const float* query_f,
+                      int64_t query_ld, const float* item_f, int64_t item_ld,
+                      const float* items_bias, const int64_t* item_idx, float lambda_muq,
+                      int64_t count, int32_t dim, float* score, void* stream);
+int ihg_hem_score_bwd(const float* dscore, const float* user_f, int64_t user_ld,
+                      const float* query_f, int64_t query_ld, const float* item_f,
+                      int64_t item_ld, const int64_t* item_idx, float lambda_muq, int64_t count,
+                      int32_t dim, float* d_user, float* d_query, float* d_item, float* d_bias,
+                      int64_t item_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IHGNN_B200_H */

@@ -1,0 +1,235 @@
+"""GPU parity tests (run on the B200 with `-m gpu`): the CUDA path, called through the C ABI
+of libihgnn_b200.so, against (a) the golden vectors the unmodified reference produced
+(tests/golden/, see oracle/gen_golden.py) and (b) the pinned CPU oracle on seeded inputs.
+
+Bar (BASELINE.json north_star): indices bit-exact; fp32 outputs and gradients within 1e-5
+max-norm relative of the reference path (the fp64 arbiter run of the reference itself).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import REL_TOL, batch_of, max_rel, oracle_model, orc, state_of
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _dataset(golden):
+    from ihgnn_b200.dataset import GraphDataset
+    U, Q, I, V, E = (int(x) for x in golden["counts"])
+    return GraphDataset(U, Q, I, V, golden["bag_words"], golden["bag_offsets"],
+                        golden["pos_user"], golden["pos_query"], golden["pos_item"], DEV)
+
+
+def _model(golden, ds=None):
+    from ihgnn_b200 import HGCNLayer, HemPredictionLayer, IHGNNLayer, RawGnn
+    ds = ds or _dataset(golden)
+    layer = IHGNNLayer if str(golden["cfg.gnn"]) == "IHGNN" else HGCNLayer
+    m = RawGnn(device=torch.device(DEV), dataset=ds, embedding_size=int(golden["cfg.d"]),
+               gnn_layer_type=layer, gnn_layer_count=int(golden["cfg.L"]),
+               feature_interaction_order=int(golden["cfg.order"]), phase2_attention=False,
+               predictions=HemPredictionLayer, lambda_muq=float(golden["cfg.lambda_muq"]))
+    m.load_state_dict(state_of(golden), strict=True)      # state_dict key/shape parity
+    return m.to(DEV)
+
+
+def test_library_loaded():
+    from ihgnn_b200 import _lib
+    assert _lib.lib().ihg_abi_version() == 1
+
+
+def test_graph_build_matches_reference_bit_exact(golden):
+    g = _dataset(golden).hypergraph
+    assert np.array_equal(g.i3.cpu().numpy().astype(np.int64), golden["graph.I3"])
+    assert np.array_equal(g.I3.cpu().numpy(), golden["graph.I3"])
+    assert np.array_equal(g.rowptr.cpu().numpy().astype(np.int64), golden["graph.crow"])
+    assert np.array_equal(g.col.cpu().numpy().astype(np.int64), golden["graph.col"])
+    assert np.array_equal(g.VertexDegrees.cpu().numpy(), golden["graph.VertexDegrees"])
+    assert np.array_equal(g.EdgeDegrees.cpu().numpy(), golden["graph.EdgeDegrees"])
+    assert g.EdgeCount == int(golden["graph.EdgeCount"])
+    adj = g.Adjacency
+    assert np.array_equal(adj.indices().cpu().numpy(), golden["graph.coo_indices"])
+    assert np.array_equal(adj.values().cpu().numpy(), golden["graph.coo_values"])
+    dv = torch.from_numpy(golden["graph.VertexDegrees"]).pow(-1).view(-1).numpy()
+    assert np.array_equal(g.dv_inv.cpu().numpy(), dv)      # GnnLayers.py:187, bit-exact reciprocal
+
+
+@pytest.mark.parametrize("shape,U,Q,I,E,zipf", [
+    ("amazon", 3000, 40, 900, 60_000, 1.1),     # heavy head: rows far above chunk_len (split path)
+    ("cikm", 20_000, 5_000, 15_000, 250_000, 0.8),
+    ("amazon", 7, 3, 5, 1, 0.0),                # a single hyperedge
+    ("amazon", 300_000, 70_000, 200_000, 50_000, 0.0),   # mostly isolated nodes, > 2^16 keys
+])
+def test_graph_build_matches_oracle(shape, U, Q, I, E, zipf):
+    from ihgnn_b200 import synth
+    from ihgnn_b200.graph import PpsHyperGraph
+    log = synth.make_search_log(U, Q, I, E, 50, shape=shape, seed=E % 97, zipf=zipf)
+    ref = orc.build_hypergraph(log.pos_user, log.pos_query, log.pos_item, U, Q, I)
+    g = PpsHyperGraph.from_tensors(log.pos_user, log.pos_query, log.pos_item, U, Q, I, DEV)
+    assert torch.equal(g.i3.cpu().to(torch.int64), ref.I3)
+    assert torch.equal(g.rowptr.cpu().to(torch.int64), ref.rowptr)
+    assert torch.equal(g.col.cpu().to(torch.int64), ref.col)
+    assert torch.equal(g.VertexDegrees.cpu(), ref.VertexDegrees)
+    assert torch.equal(g.dv_inv.cpu(), ref.VertexDegrees.pow(-1).view(-1))
+    assert max_rel(g.dv_inv_sqrt.cpu().numpy(), ref.VertexDegrees.pow(-0.5).view(-1).numpy()) < 1e-7
+    # plan invariants: every incidence covered exactly once, in order
+    p = g.plan
+    seg_row, seg_begin = p.seg_row.cpu().numpy(), p.seg_begin.cpu().numpy()
+    rowptr = ref.rowptr.numpy()
+    ends = np.minimum(seg_begin + p.chunk_len, rowptr[seg_row + 1])
+    assert (ends - seg_begin).sum() == 3 * E
+    assert np.all(np.diff(seg_row) >= 0)
+    assert p.n_split == int((np.diff(rowptr) > p.chunk_len).sum())
+
+
+def test_graph_build_rejects_out_of_range():
+    from ihgnn_b200.graph import PpsHyperGraph
+    with pytest.raises(ValueError):
+        PpsHyperGraph.from_tensors([0, 5], [0, 0], [0, 0], 3, 2, 2, DEV)
+
+
+def test_cpu_device_fails_loudly():
+    from ihgnn_b200.graph import PpsHyperGraph
+    with pytest.raises(RuntimeError):
+        PpsHyperGraph.from_tensors([0], [0], [0], 3, 2, 2, "cpu")
+
+
+@pytest.mark.parametrize("dim", [4, 8, 16, 32, 64, 128, 192, 256])
+def test_segment_reduce_and_gather_sum_vs_oracle(dim):
+    from ihgnn_b200 import functional as F_
+    from ihgnn_b200 import synth
+    from ihgnn_b200.graph import PpsHyperGraph
+    U, Q, I, E = 400, 30, 200, 9000
+    log = synth.make_search_log(U, Q, I, E, 50, shape="cikm", seed=dim, zipf=1.0)
+    ref = orc.build_hypergraph(log.pos_user, log.pos_query, log.pos_item, U, Q, I)
+    g = PpsHyperGraph.from_tensors(log.pos_user, log.pos_query, log.pos_item, U, Q, I, DEV, chunk_len=64)
+    assert g.plan.n_split > 0
+    gen = torch.Generator().manual_seed(dim)
+    ef = torch.randn(E, dim, generator=gen)
+    x = torch.randn(U + Q + I, dim, generator=gen)
+    dv = ref.VertexDegrees.pow(-1)
+    want = (dv.double() * torch.sparse.mm(ref.adjacency(torch.float64), ef.double())).numpy()
+    got = F_.segment_reduce(g.plan, ef.to(DEV), dim, row_scale=g.dv_inv).cpu().numpy()
+    assert max_rel(got, want) < 2e-6
+    # isolated nodes produce exact zeros (1e8 * 0)
+    iso = (np.diff(ref.rowptr.numpy()) == 0)
+    assert iso.any() and np.all(got[iso] == 0.0)
+    want_e = (x.double() * dv.double())[ref.I3].sum(1).numpy()
+    got_e = F_.edge_gather_sum(x.to(DEV), g.i3, node_scale=g.dv_inv).cpu().numpy()
+    assert max_rel(got_e, want_e) < 2e-6
+    # per-slot gradient layout [E,3,dim] reduced by node type
+    sg = torch.randn(E, 3, dim, generator=gen)
+    want_s = torch.zeros(U + Q + I, dim, dtype=torch.float64)
+    for s in range(3):
+        want_s.index_add_(0, ref.I3[:, s], sg[:, s].double())
+    got_s = F_.segment_reduce(g.plan, sg.to(DEV), dim, src_row_mul=3, bounds=g.type_bounds).cpu().numpy()
+    assert max_rel(got_s, want_s.numpy()) < 2e-6
+
+
+def _run_model(m, golden):
+    users, queries, items, flags = (t.to(DEV) for t in batch_of(golden))
+    m.zero_grad()
+    scores = m(users, queries, items)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(scores, flags.float())
+    loss.backward()
+    grads = {k: p.grad.detach().cpu().numpy() for k, p in m.named_parameters()}
+    return scores.detach().cpu().numpy(), float(loss), grads
+
+
+def test_model_forward_backward_matches_reference(golden):
+    m = _model(golden)
+    scores, loss, grads = _run_model(m, golden)
+    worst = {}
+    worst["scores"] = max_rel(scores, golden["ref64.scores"])
+    worst["loss"] = abs(loss - float(golden["ref64.loss"])) / abs(float(golden["ref64.loss"]))
+    for k, g in grads.items():
+        worst["grad." + k] = max_rel(g, golden[f"ref64.grad.{k}"])
+    with torch.no_grad():
+        outs = m.conv_stack(m.embeddings.embed_all())
+        for li, o in enumerate(outs):
+            worst[f"layer_out.{li}"] = max_rel(o.cpu().numpy(), golden[f"ref64.layer_out.{li}"])
+        m.save_features_for_test()
+        I = m.dataset.item_count
+        u0, q0 = int(golden["batch.users"][0]), int(golden["batch.queries"][0])
+        ev = m(u0 * torch.ones(I, dtype=torch.long, device=DEV), q0 * torch.ones(I, dtype=torch.long, device=DEV), None)
+        worst["eval_scores"] = max_rel(ev.cpu().numpy(), golden["ref64.eval_scores"])
+        m.clear_saved_feature()
+    bad = {k: v for k, v in worst.items() if not v <= REL_TOL}
+    assert not bad, f"beyond {REL_TOL}: {bad}"
+
+
+def test_conv_stack_gradients_match_reference(golden):
+    """Metric M1's unit of work: loss = sum(cat(outs, 1)), gradient w.r.t. X and conv weights."""
+    m = _model(golden)
+    x = m.embeddings.embed_all().detach().clone().requires_grad_(True)
+    m.zero_grad()
+    torch.cat(m.conv_stack(x), 1).sum().backward()
+    assert max_rel(x.grad.cpu().numpy(), golden["ref64.conv_dx"]) <= REL_TOL
+    for k, p in m.named_parameters():
+        if k.startswith("gnn_"):
+            assert max_rel(p.grad.cpu().numpy(), golden[f"ref64.conv_grad.{k}"]) <= REL_TOL, k
+
+
+def test_results_are_bitwise_deterministic(golden):
+    m = _model(golden)
+    a = _run_model(m, golden)
+    b = _run_model(m, golden)
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1]
+    for k in a[2]:
+        assert np.array_equal(a[2][k], b[2][k]), k
+
+
+def test_indexed_embedding_lookups(golden):
+    m = _model(golden)
+    users, queries, items, _ = (t.to(DEV) for t in batch_of(golden))
+    e = m.embeddings
+    with torch.no_grad():
+        assert np.array_equal(e.embed_user(users[:9]).cpu().numpy(), golden["ref32.embed_user_idx"])
+        assert np.array_equal(e.embed_item(items[:9]).cpu().numpy(), golden["ref32.embed_item_idx"])
+        qi = torch.from_numpy(golden["embed.query_indices"]).to(DEV)
+        assert max_rel(e.embed_query(qi).cpu().numpy(), golden["ref32.embed_query_idx"]) < 1e-6
+        u, q, i = e(None, None, None)
+        assert np.array_equal(u.cpu().numpy(), golden["state.embeddings.embedding_user.weight"][1:])
+        assert np.array_equal(i.cpu().numpy(), golden["state.embeddings.embedding_item.weight"][1:])
+
+
+@pytest.mark.parametrize("order,dim,layers", [(3, 64, 2), (3, 128, 2), (2, 32, 1), (1, 128, 3), (3, 48, 1)])
+def test_medium_graph_vs_oracle(order, dim, layers):
+    """Seeded medium-size case (heavy Zipf head, split rows, ragged tiles) against the oracle
+    in fp64, through the whole RawGnn stack: forward scores, loss and every gradient."""
+    from ihgnn_b200 import HemPredictionLayer, IHGNNLayer, RawGnn, synth
+    from ihgnn_b200.dataset import GraphDataset
+    U, Q, I, E, V = 1500, 200, 700, 20_011, 300
+    log = synth.make_search_log(U, Q, I, E, V, shape="cikm", seed=order * 1000 + dim, zipf=1.0)
+    ds = GraphDataset.from_search_log(log, DEV)
+    torch.manual_seed(dim + order)
+    m = RawGnn(device=torch.device(DEV), dataset=ds, embedding_size=dim, gnn_layer_type=IHGNNLayer,
+               gnn_layer_count=layers, feature_interaction_order=order, phase2_attention=False,
+               predictions=HemPredictionLayer, lambda_muq=0.5).to(DEV)
+    state = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    words, offsets = log.bag_inputs()
+    g = orc.build_hypergraph(log.pos_user, log.pos_query, log.pos_item, U, Q, I)
+    om = orc.OracleModel(state, g, torch.from_numpy(words), torch.from_numpy(offsets), U, Q, I,
+                         layer_type="IHGNN", layer_count=layers, order=order, dtype=torch.float64)
+    rng = np.random.default_rng(7)
+    b = 100
+    pick = rng.choice(E, size=b, replace=False)
+    users = torch.from_numpy(np.concatenate([log.pos_user[pick], np.repeat(log.pos_user[pick], 10)]))
+    queries = torch.from_numpy(np.concatenate([log.pos_query[pick], np.repeat(log.pos_query[pick], 10)]))
+    items = torch.from_numpy(np.concatenate([log.pos_item[pick], rng.integers(0, I, size=10 * b)]))
+    flags = torch.cat([torch.ones(b), torch.zeros(10 * b)])
+    so = om.forward(users, queries, items)
+    lo = orc.bce_with_logits_mean(so, flags.double())
+    lo.backward()
+    sg = m(users.to(DEV), queries.to(DEV), items.to(DEV))
+    lg = torch.nn.functional.binary_cross_entropy_with_logits(sg, flags.to(DEV))
+    lg.backward()
+    worst = {"scores": max_rel(sg.detach().cpu().numpy(), so.detach().numpy()),
+             "loss": abs(float(lg) - float(lo)) / abs(float(lo))}
+    og = om.grads()
+    for k, p in m.named_parameters():
+        worst["grad." + k] = max_rel(p.grad.cpu().numpy(), og[k].numpy())
+    bad = {k: v for k, v in worst.items() if not v <= REL_TOL}
+    assert not bad, f"beyond {REL_TOL}: {bad}"
