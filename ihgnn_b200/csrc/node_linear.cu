@@ -10,6 +10,7 @@
 // Roofline: HBM for realistic d (arithmetic intensity d/4 flop/B at fp32): bytes per row =
 // 4*(n_in + n_out) (+ addend), flops per row = 2*n_in*n_out.
 #include "gemm_tile.cuh"
+#include "tc_linear.h"
 
 namespace ihg {
 
@@ -179,9 +180,12 @@ int ihg_node_linear(const float* x, int64_t x_ld, const float* w, int32_t n_type
     IHG_REQUIRE(n_rows > 0 && x_ld >= n_in && y_ld >= n_out, "node_linear: bad shapes");
     if (n_types == 1) bound0 = bound1 = n_rows;
     IHG_REQUIRE(0 <= bound0 && bound0 <= bound1 && bound1 <= n_rows, "node_linear: bad type bounds");
+    cudaStream_t st = as_stream(stream);
+    if (node_linear_tc_eligible(n_out, n_in, x_ld, y_ld, addend, addend_ld))
+        return launch_node_linear_tc(x, x_ld, w, n_types, n_out, n_in, transpose_w, bias, addend,
+                                     addend_ld, n_rows, bound0, bound1, y, y_ld, st);
     TypeTiles tt{bound0, bound1, n_rows};
     const int64_t blocks = tt.tiles(0) + tt.tiles(1) + tt.tiles(2);
-    cudaStream_t st = as_stream(stream);
 #define IHG_NL_CASE(D)                                                                              \
     node_linear_kernel<D><<<(unsigned)blocks, kGemmThreads, 0, st>>>(x, x_ld, w, n_types, n_out, n_in, \
         transpose_w, bias, addend, addend_ld, tt, y, y_ld)

@@ -1,0 +1,152 @@
+// Blackwell (sm_100a) tensor-core primitives used by the fp32-accurate contraction kernels:
+// tcgen05.mma kind::tf32 with accumulators in TMEM, operands in shared memory in the UMMA
+// K-major / 128-byte-swizzle canonical layout, mbarrier completion, tcgen05.ld epilogues.
+//
+// Precision: every fp32 operand x is split as x = hi + lo with hi = rna_tf32(x),
+// lo = rna_tf32(x - hi); a product a*b is evaluated as a_hi*b_hi + a_lo*b_hi + a_hi*b_lo
+// ("3xTF32") with fp32 accumulation in TMEM.  The dropped a_lo*b_lo term and the roundings are
+// <= 2^-22 relative per product -- inside the 1e-5 parity budget with two orders of margin.
+#pragma once
+
+#include "common.cuh"
+
+namespace ihg {
+namespace tc {
+
+constexpr int kTileM = 128;          // rows per UMMA tile (M = 128, cta_group::1)
+constexpr int kChunkK = 32;          // fp32 elements per 128-byte swizzle row (one K chunk)
+constexpr int kChunkBytesPerRow = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- operand split ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = rna_tf32(x);
+    lo = rna_tf32(x - __uint_as_float(hi));
+}
+
+// Byte offset of element (row, 16-byte chunk c in [0,8)) inside one [rows x 128 B] operand
+// tile in the K-major SWIZZLE_128B canonical layout (tile base 1024-byte aligned): rows are
+// grouped by 8 (1024 B per group, SBO), the 16-byte chunk index is XORed with row % 8.
+__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk16) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk16 ^ (row & 7)) << 4));
+}
+
+// Store 4 consecutive K elements (one 16-byte chunk) of a row, split into hi / lo tiles.
+__device__ __forceinline__ void store_split_chunk(uint32_t hi_tile, uint32_t lo_tile, int row,
+                                                  int chunk16, const float4& v) {
+    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+    split_tf32(v.x, h0, l0);
+    split_tf32(v.y, h1, l1);
+    split_tf32(v.z, h2, l2);
+    split_tf32(v.w, h3, l3);
+    const uint32_t off = sw128_offset(row, chunk16);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(hi_tile + off), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(lo_tile + off), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
+}
+
+// ---- descriptors -----------------------------------------------------------------------
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B, 8-row groups 1024 B apart.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1
+//  [46,48), layout_type=2 [61,64).)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                 // LBO (unused for swizzled K-major): 16 B
+    d |= (uint64_t)(1024 >> 4) << 32;       // SBO: 1024 B between 8-row groups
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// Advance a K-major SW128 descriptor by `k_elems` fp32 elements inside the 128-byte row.
+__device__ __forceinline__ uint64_t advance_desc_k(uint64_t desc, int k_elems) {
+    return desc + (uint64_t)((k_elems * 4) >> 4);
+}
+
+// Instruction descriptor for kind::tf32, fp32 accumulate, A and B K-major, M = 128.
+// (cute::UMMA::InstrDescriptor: c_format [4,6)=1 F32, a_format [7,10)=2 TF32, b_format
+//  [10,13)=2, a_major [15]=0, b_major [16]=0, n_dim [17,23)=N>>3, m_dim [24,29)=M>>4.)
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+// ---- tcgen05 wrappers -------------------------------------------------------------------
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo for one K step of 8
+__device__ __forceinline__ void mma_3xtf32(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo,
+                                           uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
+                                           uint32_t accumulate) {
+    mma_tf32(tmem_d, a_lo, b_hi, idesc, accumulate);   // small terms first
+    mma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
+    mma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
+}
+__device__ __forceinline__ void mma_commit(uint32_t mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (tensor core reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_result_addr, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result_addr), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__host__ __device__ constexpr uint32_t tmem_cols_pow2(uint32_t n) {
+    return n <= 32 ? 32u : (n <= 64 ? 64u : (n <= 128 ? 128u : (n <= 256 ? 256u : 512u)));
+}
+
+// 32 lanes (this warp's TMEM quadrant) x 16 consecutive fp32 columns -> 16 registers/thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- mbarrier ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(mbar),
+        "r"(parity)
+        : "memory");
+}
+
+}  // namespace tc
+}  // namespace ihg

@@ -1,0 +1,16 @@
+// Host-side entry points of the tensor-core (tcgen05) kernels, called from the C-ABI wrappers.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ihg {
+
+bool node_linear_tc_eligible(int n_out, int n_in, int64_t x_ld, int64_t y_ld, const float* addend,
+                             int64_t addend_ld);
+int launch_node_linear_tc(const float* x, int64_t x_ld, const float* w, int n_types, int n_out,
+                          int n_in, int transpose_w, const float* bias, const float* addend,
+                          int64_t addend_ld, int64_t n_rows, int64_t bound0, int64_t bound1,
+                          float* y, int64_t y_ld, cudaStream_t st);
+
+}  // namespace ihg

@@ -233,3 +233,31 @@ def test_medium_graph_vs_oracle(order, dim, layers):
         worst["grad." + k] = max_rel(p.grad.cpu().numpy(), og[k].numpy())
     bad = {k: v for k, v in worst.items() if not v <= REL_TOL}
     assert not bad, f"beyond {REL_TOL}: {bad}"
+
+
+@pytest.mark.parametrize("n_in,n_out", [(32, 16), (32, 32), (64, 64), (128, 128), (64, 48), (128, 16), (96, 80)])
+@pytest.mark.parametrize("typed", [False, True])
+def test_node_linear_tensor_core_path(n_in, n_out, typed):
+    """tcgen05 3xTF32 typed Linear (and its transposed form) against fp64: the split-precision
+    contraction must stay ~1e-6 of exact, two orders inside the 1e-5 budget."""
+    from ihgnn_b200 import functional as F_
+    gen = torch.Generator().manual_seed(n_in * 1000 + n_out)
+    rows, b0, b1 = 1000, 333, 590           # ragged tiles, type bounds not multiples of 128
+    T = 3 if typed else 1
+    x = torch.randn(rows, n_in, generator=gen)
+    w = torch.randn(T, n_out, n_in, generator=gen) / n_in ** 0.5
+    b = torch.randn(T, n_out, generator=gen)
+    add = torch.randn(rows, n_out, generator=gen)
+    tid = torch.zeros(rows, dtype=torch.long)
+    if typed:
+        tid[b0:] = 1
+        tid[b1:] = 2
+    want = torch.einsum("rk,rnk->rn", x.double(), w.double()[tid]) + b.double()[tid] + add.double()
+    got = F_.node_linear(x.to(DEV), w.to(DEV), bias=b.to(DEV), addend=add.to(DEV),
+                         bounds=(b0, b1) if typed else None).cpu()
+    assert max_rel(got.numpy(), want.numpy()) < 3e-6
+    # transposed form: dy [rows, n_out] . W[t] -> [rows, n_in]
+    dy = torch.randn(rows, n_out, generator=gen)
+    want_t = torch.einsum("rn,rnk->rk", dy.double(), w.double()[tid])
+    got_t = F_.node_linear(dy.to(DEV), w.to(DEV), transpose_w=True, bounds=(b0, b1) if typed else None).cpu()
+    assert max_rel(got_t.numpy(), want_t.numpy()) < 3e-6
