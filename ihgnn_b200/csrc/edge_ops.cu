@@ -15,6 +15,7 @@
 // The contraction here runs on fp32 FFMA so that results stay within ~1e-7 of the reference;
 // flops per hyperedge = 2*nb*d^2 (nb = 3 or 4 product blocks) forward, 2x that backward.
 #include "gemm_tile.cuh"
+#include "tc_linear.h"
 
 namespace ihg {
 
@@ -375,14 +376,25 @@ static int check_interact(const char* what, int32_t order, int32_t dim) {
     return IHG_OK;
 }
 
+int64_t ihg_edge_interact_fwd_workspace_bytes(int32_t dim, int32_t order) {
+    const int nb = order == 3 ? 4 : 3;
+    return interact_tc_eligible(dim) ? interact_fwd_tc_workspace_bytes(dim, nb) : 0;
+}
+
 int ihg_edge_interact_fwd(const float* xp, int64_t xp_ld, const float* p, int64_t p_ld,
                           const float* w_hi, int64_t w_ld, int32_t order, const int32_t* i3,
-                          int64_t E, float* ef, int64_t ef_ld, int32_t dim, void* stream) {
+                          int64_t E, float* ef, int64_t ef_ld, int32_t dim, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
     IHG_REQUIRE(xp && p && w_hi && i3 && ef, "edge_interact_fwd: null pointer");
     if (int rc = check_interact("edge_interact_fwd", order, dim)) return rc;
     if (E == 0) return IHG_OK;
     const int nb = order == 3 ? 4 : 3;
     cudaStream_t st = as_stream(stream);
+    if (interact_tc_eligible(dim) && xp_ld % 4 == 0 && p_ld % 4 == 0 && ef_ld % 4 == 0) {
+        IHG_REQUIRE(workspace && workspace_bytes >= ihg_edge_interact_fwd_workspace_bytes(dim, order),
+                    "edge_interact_fwd: workspace too small");
+        return launch_interact_fwd_tc(xp, xp_ld, p, p_ld, w_hi, w_ld, nb, i3, E, ef, ef_ld, dim, workspace, st);
+    }
     const unsigned blocks = (unsigned)ceil_div(E, kTileRows);
 #define IHG_IF_CASE(D) edge_interact_fwd_kernel<D><<<blocks, kGemmThreads, 0, st>>>(xp, xp_ld, p, p_ld, w_hi, w_ld, nb, i3, E, ef, ef_ld, dim)
     if (dim <= 16) IHG_IF_CASE(1);

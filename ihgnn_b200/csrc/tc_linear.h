@@ -13,4 +13,12 @@ int launch_node_linear_tc(const float* x, int64_t x_ld, const float* w, int n_ty
                           int64_t addend_ld, int64_t n_rows, int64_t bound0, int64_t bound1,
                           float* y, int64_t y_ld, cudaStream_t st);
 
+bool interact_tc_eligible(int dim);
+int64_t interact_fwd_tc_workspace_bytes(int dim, int nb);
+int launch_interact_prep(const float* w_hi, int64_t w_ld, int nb, int dim, int transposed,
+                         void* wprep, cudaStream_t st);
+int launch_interact_fwd_tc(const float* xp, int64_t xp_ld, const float* p, int64_t p_ld,
+                           const float* w_hi, int64_t w_ld, int nb, const int32_t* i3, int64_t E,
+                           float* ef, int64_t ef_ld, int dim, void* workspace, cudaStream_t st);
+
 }  // namespace ihg

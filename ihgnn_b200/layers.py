@@ -177,9 +177,12 @@ class _EdgeInteractFn(torch.autograd.Function):
         xp, p, w_hi = _lib.rows_f32(xp), _lib.rows_f32(p), _lib.rows_f32(w_hi)
         dim, E = int(xp.shape[1]), graph.EdgeCount
         ef = torch.empty((E, dim), dtype=torch.float32, device=xp.device)
+        ws_bytes = _lib.lib().ihg_edge_interact_fwd_workspace_bytes(dim, order)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=xp.device)
         _lib.call("ihg_edge_interact_fwd", _lib.ptr(xp), _lib.ld(xp), _lib.ptr(p), _lib.ld(p),
                   _lib.ptr(w_hi), _lib.ld(w_hi), order, _lib.ptr(graph.i3), E, _lib.ptr(ef), dim,
-                  dim, _lib.stream_ptr(), tag="edge_interact_fwd", algo_bytes=E * (12 + 28 * dim))
+                  dim, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(),
+                  tag="edge_interact_fwd", algo_bytes=E * (12 + 28 * dim))
         ctx.graph, ctx.order = graph, order
         ctx.save_for_backward(xp, w_hi)
         return ef

@@ -135,12 +135,14 @@ int ihg_edge_gather_sum(const float* src, int64_t src_ld, const float* node_scal
  * w_hi = aggregation.weight[:, 3*dim:] ([dim, nb*dim], row stride w_ld), nb = order+... 3 or 4.
  * Backward: given def = dL/def [E,dim] writes slot_grad[e,s,:] = dL/d(xp row of slot s)
  * through the products only, and dw_hi [dim, nb*dim] (dense, deterministic two-pass sum).
- * dim % 4 == 0, dim <= 128.
+ * dim % 4 == 0, dim <= 128.  dim % 32 == 0 runs on the tensor cores (tcgen05, 3xTF32 split
+ * precision, fp32 accumulate); other dims on fp32 FFMA.
  * ------------------------------------------------------------------------------------ */
+int64_t ihg_edge_interact_fwd_workspace_bytes(int32_t dim, int32_t order);
 int ihg_edge_interact_fwd(const float* xp, int64_t xp_ld, const float* p, int64_t p_ld,
                           const float* w_hi, int64_t w_ld, int32_t order, const int32_t* i3,
                           int64_t edge_count, float* ef, int64_t ef_ld, int32_t dim,
-                          void* stream);
+                          void* workspace, int64_t workspace_bytes, void* stream);
 int64_t ihg_edge_interact_bwd_workspace_bytes(int32_t dim, int32_t order);
 int ihg_edge_interact_bwd(const float* xp, int64_t xp_ld, const float* def, int64_t def_ld,
                           const float* w_hi, int64_t w_ld, int32_t order, const int32_t* i3,

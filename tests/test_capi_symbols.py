@@ -40,7 +40,7 @@ def test_abi_version_and_error_channel(lib):
     # argument validation happens before any CUDA call, so it can be exercised without a GPU
     rc = lib.ihg_node_linear(None, 0, None, 1, 64, 64, 0, None, None, 0, 10, 0, 0, None, 0, None)
     assert rc == 1 and b"null pointer" in lib.ihg_last_error()
-    rc = lib.ihg_edge_interact_fwd(1, 64, 1, 64, 1, 64, 5, 1, 10, 1, 64, 64, None)
+    rc = lib.ihg_edge_interact_fwd(1, 64, 1, 64, 1, 64, 5, 1, 10, 1, 64, 64, None, 0, None)
     assert rc == 1 and b"order" in lib.ihg_last_error()
 
 
