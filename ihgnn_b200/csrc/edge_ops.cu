@@ -408,7 +408,9 @@ int ihg_edge_interact_fwd(const float* xp, int64_t xp_ld, const float* p, int64_
 
 int64_t ihg_edge_interact_bwd_workspace_bytes(int32_t dim, int32_t order) {
     const int nb = order == 3 ? 4 : 3;
-    return ws_slice((int64_t)kInteractWgradG * nb * dim * dim, 4) + 1024;
+    const int64_t simt = ws_slice((int64_t)kInteractWgradG * nb * dim * dim, 4) + 1024;
+    const int64_t tcb = interact_tc_eligible(dim) ? interact_bwd_tc_workspace_bytes(dim, nb) : 0;
+    return simt > tcb ? simt : tcb;
 }
 
 int ihg_edge_interact_bwd(const float* xp, int64_t xp_ld, const float* def, int64_t def_ld,
@@ -426,6 +428,8 @@ int ihg_edge_interact_bwd(const float* xp, int64_t xp_ld, const float* def, int6
         IHG_CUDA(cudaMemsetAsync(dw_hi, 0, (size_t)nb * dim * dim * 4, st));
         return IHG_OK;
     }
+    if (interact_tc_eligible(dim) && xp_ld % 4 == 0)
+        return launch_interact_bwd_tc(xp, xp_ld, def, def_ld, w_hi, w_ld, nb, i3, E, slot_grad, dw_hi, dim, workspace, st);
     const unsigned blocks = (unsigned)ceil_div(E, kTileRows);
     // (a) slot gradients; column groups of at most 64 features per pass
 #define IHG_IB_CASE(D) edge_interact_bwd_slot_kernel<D><<<blocks, kGemmThreads, 0, st>>>(xp, xp_ld, def, def_ld, w_hi, w_ld, nb, i3, E, slot_grad, dim)

@@ -266,6 +266,427 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
     if (warp == kMmaWarp) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+
+// =========================================================================================
+// backward (a): per-slot input gradients on tensor cores
+//   dz_b[e][k] = sum_n def[e][n] * W_b[n][k]        (A = def tile, B = W_b^T chunks)
+//   du = dz_uq*q + dz_iu*i + dz_uqi*q*i, ... written as slot_grad[e][slot][k]
+// Work unit = (tile of 128 hyperedges, column half h): NU = dim (dim <= 64) or dim/2 output
+// columns per unit, so that nb accumulators of NU columns fit TMEM twice (double buffering).
+// =========================================================================================
+constexpr int kSlotAStages = 2;
+
+__global__ void __launch_bounds__(kInteractThreads, 1)
+edge_interact_bwd_slot_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
+                                 const float* __restrict__ def, int64_t def_ld,
+                                 const uint8_t* __restrict__ wprep_t, int nb,
+                                 const int32_t* __restrict__ i3, int64_t E,
+                                 float* __restrict__ slot_grad, int dim, int nu, int b_stages) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_afull[kSlotAStages], bar_aempty[kSlotAStages];
+    __shared__ __align__(8) uint64_t bar_bfull[8], bar_bempty[8], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_base_slot;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KC = dim / kChunkK;                 // chunks along the contraction (n)
+    const int UH = dim / nu;                      // units per tile
+    const uint32_t b_tile_bytes = (uint32_t)nu * kChunkBytesPerRow;
+    const uint32_t a_stage_bytes = 2 * kATileBytes;
+    const uint32_t b_base = smem_base + kSlotAStages * a_stage_bytes;
+    const uint32_t b_stage_bytes = 2 * b_tile_bytes;
+    const int64_t n_tiles = (E + kTileM - 1) / kTileM;
+    const int64_t n_units = n_tiles * UH;
+    const uint32_t acc_cols = (uint32_t)(nb * nu);
+    const uint32_t tmem_cols = tmem_cols_pow2(2 * acc_cols);
+
+    if (tid == 0) {
+        for (int s = 0; s < kSlotAStages; ++s) {
+            mbar_init(smem_u32(&bar_afull[s]), kProducerWarps);
+            mbar_init(smem_u32(&bar_aempty[s]), 1);
+        }
+        for (int s = 0; s < b_stages; ++s) {
+            mbar_init(smem_u32(&bar_bfull[s]), 1);
+            mbar_init(smem_u32(&bar_bempty[s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&bar_tfull[s]), 1);
+            mbar_init(smem_u32(&bar_tempty[s]), 4);
+        }
+        mbar_init_fence();
+    }
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp < kProducerWarps) {
+        // ---- A producer: def tile rows, split to tf32 hi/lo
+        const int row = tid & 127, half = tid >> 7;
+        uint32_t it = 0;
+        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int64_t e = (u / UH) * kTileM + row;
+            const bool ok = e < E;
+            const float* src = def + e * def_ld + 16 * half;
+            for (int nc = 0; nc < KC; ++nc, ++it) {
+                float4 v[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[c] = ok ? ldg4(src + nc * kChunkK + 4 * c) : f4_zero();
+                const int s = it % kSlotAStages;
+                mbar_wait(smem_u32(&bar_aempty[s]), ((it / kSlotAStages) & 1u) ^ 1u);
+                const uint32_t a_hi = smem_base + (uint32_t)s * a_stage_bytes;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) store_split_chunk(a_hi, a_hi + kATileBytes, row, 4 * half + c, v[c]);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_afull[s]));
+            }
+        }
+    } else if (warp == kLoadWarp) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int h = (int)(u % UH);
+                for (int nc = 0; nc < KC; ++nc)
+                    for (int b = 0; b < nb; ++b, ++it) {
+                        const int s = it % b_stages;
+                        mbar_wait(smem_u32(&bar_bempty[s]), ((it / b_stages) & 1u) ^ 1u);
+                        const uint32_t full = smem_u32(&bar_bfull[s]);
+                        mbar_expect_tx(full, b_stage_bytes);
+                        bulk_g2s(b_base + (uint32_t)s * b_stage_bytes,
+                                 wprep_t + ((int64_t)(b * KC + nc) * UH + h) * b_stage_bytes, b_stage_bytes, full);
+                    }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(nu);
+            uint32_t ita = 0, itb = 0, t = 0;
+            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++t) {
+                const uint32_t buf = t & 1u;
+                mbar_wait(smem_u32(&bar_tempty[buf]), ((t >> 1) & 1u) ^ 1u);
+                fence_after_sync();
+                for (int nc = 0; nc < KC; ++nc, ++ita) {
+                    const int sa = ita % kSlotAStages;
+                    mbar_wait(smem_u32(&bar_afull[sa]), (ita / kSlotAStages) & 1u);
+                    fence_after_sync();
+                    const uint32_t a_hi = smem_base + (uint32_t)sa * a_stage_bytes;
+                    const uint64_t dah = make_kmajor_sw128_desc(a_hi);
+                    const uint64_t dal = make_kmajor_sw128_desc(a_hi + kATileBytes);
+                    for (int b = 0; b < nb; ++b, ++itb) {
+                        const int sb = itb % b_stages;
+                        mbar_wait(smem_u32(&bar_bfull[sb]), (itb / b_stages) & 1u);
+                        fence_after_sync();
+                        const uint32_t bh = b_base + (uint32_t)sb * b_stage_bytes;
+                        const uint64_t dbh = make_kmajor_sw128_desc(bh);
+                        const uint64_t dbl = make_kmajor_sw128_desc(bh + b_tile_bytes);
+                        const uint32_t tmem_d = tmem_base + buf * acc_cols + (uint32_t)(b * nu);
+#pragma unroll
+                        for (int ks = 0; ks < kChunkK / 8; ++ks)
+                            mma_3xtf32(tmem_d, advance_desc_k(dah, 8 * ks), advance_desc_k(dal, 8 * ks),
+                                       advance_desc_k(dbh, 8 * ks), advance_desc_k(dbl, 8 * ks), idesc,
+                                       (nc > 0 || ks > 0) ? 1u : 0u);
+                        mma_commit(smem_u32(&bar_bempty[sb]));
+                    }
+                    mma_commit(smem_u32(&bar_aempty[sa]));
+                }
+                mma_commit(smem_u32(&bar_tfull[buf]));
+            }
+        }
+    } else {
+        // ---- epilogue: product rule, thread = hyperedge row
+        const int q4 = warp - kEpilogueWarp0;
+        const int row = q4 * 32 + lane;
+        uint32_t t = 0;
+        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++t) {
+            const uint32_t buf = t & 1u;
+            const int h = (int)(u % UH);
+            const int64_t e = (u / UH) * kTileM + row;
+            const bool ok = e < E;
+            int nu_ = 0, nq = 0, ni = 0;
+            if (ok) {
+                nu_ = __ldg(i3 + 3 * e);
+                nq = __ldg(i3 + 3 * e + 1);
+                ni = __ldg(i3 + 3 * e + 2);
+            }
+            const float* pu = xp + (int64_t)nu_ * xp_ld + h * nu;
+            const float* pq = xp + (int64_t)nq * xp_ld + h * nu;
+            const float* pi = xp + (int64_t)ni * xp_ld + h * nu;
+            float* out = slot_grad + e * 3 * (int64_t)dim + h * nu;
+            const uint32_t taddr = tmem_base + buf * acc_cols + ((uint32_t)(q4 * 32) << 16);
+            bool waited = false;
+            for (int c0 = 0; c0 < nu; c0 += 16) {
+                float uu[16], qq[16], ii[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 a = ok ? ldg4(pu + c0 + 4 * j) : f4_zero();
+                    const float4 bq = ok ? ldg4(pq + c0 + 4 * j) : f4_zero();
+                    const float4 ci = ok ? ldg4(pi + c0 + 4 * j) : f4_zero();
+                    uu[4 * j] = a.x; uu[4 * j + 1] = a.y; uu[4 * j + 2] = a.z; uu[4 * j + 3] = a.w;
+                    qq[4 * j] = bq.x; qq[4 * j + 1] = bq.y; qq[4 * j + 2] = bq.z; qq[4 * j + 3] = bq.w;
+                    ii[4 * j] = ci.x; ii[4 * j + 1] = ci.y; ii[4 * j + 2] = ci.z; ii[4 * j + 3] = ci.w;
+                }
+                if (!waited) {
+                    mbar_wait(smem_u32(&bar_tfull[buf]), (t >> 1) & 1u);
+                    fence_after_sync();
+                    waited = true;
+                }
+                float du[16], dq[16], di[16], dz[16];
+                tmem_ld16(taddr + (uint32_t)c0, dz);                         // b = 0: u*q
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { du[j] = dz[j] * qq[j]; dq[j] = dz[j] * uu[j]; }
+                tmem_ld16(taddr + (uint32_t)(nu + c0), dz);                  // b = 1: q*i
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { dq[j] = fmaf(dz[j], ii[j], dq[j]); di[j] = dz[j] * qq[j]; }
+                tmem_ld16(taddr + (uint32_t)(2 * nu + c0), dz);              // b = 2: i*u
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { di[j] = fmaf(dz[j], uu[j], di[j]); du[j] = fmaf(dz[j], ii[j], du[j]); }
+                if (nb == 4) {
+                    tmem_ld16(taddr + (uint32_t)(3 * nu + c0), dz);          // b = 3: u*q*i
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        du[j] = fmaf(dz[j], qq[j] * ii[j], du[j]);
+                        dq[j] = fmaf(dz[j], uu[j] * ii[j], dq[j]);
+                        di[j] = fmaf(dz[j], uu[j] * qq[j], di[j]);
+                    }
+                }
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        stg4(out + c0 + 4 * j, make_float4(du[4 * j], du[4 * j + 1], du[4 * j + 2], du[4 * j + 3]));
+                        stg4(out + dim + c0 + 4 * j, make_float4(dq[4 * j], dq[4 * j + 1], dq[4 * j + 2], dq[4 * j + 3]));
+                        stg4(out + 2 * dim + c0 + 4 * j, make_float4(di[4 * j], di[4 * j + 1], di[4 * j + 2], di[4 * j + 3]));
+                    }
+                }
+            }
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[buf]));
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// Weight chunks for the slot kernel: tile (b, nc, h) = rows k in [h*nu, (h+1)*nu) of
+//   W_b^T[k][nc*32 .. +32) = w_hi[(nc*32 + n)*w_ld + b*dim + k], hi tile then lo tile.
+__global__ void __launch_bounds__(256)
+interact_prep_weights_t_kernel(const float* __restrict__ w_hi, int64_t w_ld, int nb, int dim, int nu,
+                               uint8_t* __restrict__ wprep) {
+    const int KC = dim / kChunkK, UH = dim / nu;
+    const int tile_bytes = nu * kChunkBytesPerRow;
+    const int64_t total = (int64_t)nb * KC * dim * 8;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c = idx & 7;
+        const int k = (idx >> 3) % dim;                 // output column == B-tile row
+        const int nc = (idx / (8 * dim)) % KC;
+        const int b = idx / ((int64_t)8 * dim * KC);
+        const int h = k / nu, r = k % nu;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = nc * kChunkK + 4 * c + j;
+            split_tf32(__ldg(w_hi + (int64_t)n * w_ld + (int64_t)b * dim + k), hi[j], lo[j]);
+        }
+        uint8_t* tile = wprep + ((int64_t)(b * KC + nc) * UH + h) * 2 * tile_bytes;
+        const uint32_t off = sw128_offset(r, c);
+        *reinterpret_cast<uint4*>(tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(tile + tile_bytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// =========================================================================================
+// backward (b): weight gradient on tensor cores, MN-major operands
+//   dw_b^T[k][n] = sum_e z_b[e][k] * def[e][n]
+// Both operands are stored as [edge rows x 32 features] sub-tiles in the same SW128 layout the
+// K-major kernels use; read through MN-major descriptors the edge index becomes the MMA K
+// dimension.  A = 128 product features (a "group": 4 sub-tiles), B = def (dim/32 sub-tiles).
+// The accumulators (G groups x dim columns) stay in TMEM across all tiles of the CTA; one
+// partial [G*128, dim] per CTA goes to the workspace and a second kernel sums them in order.
+// =========================================================================================
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;   // stride between 32-feature MN blocks
+    d |= (uint64_t)(1024 >> 4) << 32;                    // stride between 8-edge K groups
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t make_idesc_tf32_mn(int n) {
+    return make_idesc_tf32(n) | (1u << 15) | (1u << 16);  // a_major = b_major = MN
+}
+
+constexpr int kWgProducerThreads = kProducerWarps * 32;
+
+__global__ void __launch_bounds__(kInteractThreads, 1)
+edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
+                                  const float* __restrict__ def, int64_t def_ld, int nb,
+                                  const int32_t* __restrict__ i3, int64_t E, int dim, int te,
+                                  float* __restrict__ ws_dw) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_afull[2], bar_aempty[2], bar_bfull[2], bar_bempty[2], bar_done;
+    __shared__ uint32_t tmem_base_slot;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KC = dim / kChunkK;                          // 32-feature blocks of def / of one product
+    const int G = (nb * dim + 127) / 128;                  // groups of 128 product features
+    const uint32_t sub_bytes = (uint32_t)te * kChunkBytesPerRow;   // one [te x 128 B] sub-tile
+    const uint32_t a_stage_bytes = 8 * sub_bytes;          // 4 sub-tiles hi + 4 lo
+    const uint32_t b_stage_bytes = 2 * KC * sub_bytes;     // KC sub-tiles hi + KC lo
+    const uint32_t b_base = smem_base + 2 * a_stage_bytes;
+    const int64_t n_tiles = (E + te - 1) / te;
+    const uint32_t tmem_cols = tmem_cols_pow2((uint32_t)(G * dim));
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&bar_afull[s]), kProducerWarps);
+            mbar_init(smem_u32(&bar_aempty[s]), 1);
+            mbar_init(smem_u32(&bar_bfull[s]), kProducerWarps);
+            mbar_init(smem_u32(&bar_bempty[s]), 1);
+        }
+        mbar_init(smem_u32(&bar_done), 1);
+        mbar_init_fence();
+    }
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = tmem_base_slot;
+    const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
+    if (warp < kProducerWarps) {
+        const int parts = kWgProducerThreads / te;         // threads per edge row
+        const int row = tid % te, part = tid / te;
+        uint32_t ita = 0, itb = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++itb) {
+            const int64_t e = tile * te + row;
+            const bool ok = e < E;
+            int nu_ = 0, nq = 0, ni = 0;
+            if (ok) {
+                nu_ = __ldg(i3 + 3 * e);
+                nq = __ldg(i3 + 3 * e + 1);
+                ni = __ldg(i3 + 3 * e + 2);
+            }
+            const float* pu = xp + (int64_t)nu_ * xp_ld;
+            const float* pq = xp + (int64_t)nq * xp_ld;
+            const float* pi = xp + (int64_t)ni * xp_ld;
+            // ---- B stage: def tile
+            {
+                const int sb = itb & 1;
+                mbar_wait(smem_u32(&bar_bempty[sb]), ((itb >> 1) & 1u) ^ 1u);
+                const uint32_t bh = b_base + (uint32_t)sb * b_stage_bytes;
+                for (int blk = 0; blk < KC; ++blk)
+                    for (int c = part; c < 8; c += parts) {
+                        const float4 v = ok ? ldg4(def + e * def_ld + blk * kChunkK + 4 * c) : f4_zero();
+                        store_split_chunk(bh + (uint32_t)blk * sub_bytes, bh + (uint32_t)(KC + blk) * sub_bytes, row, c, v);
+                    }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_bfull[sb]));
+            }
+            // ---- A stages: one group of 128 product features each
+            for (int g = 0; g < G; ++g, ++ita) {
+                const int sa = ita & 1;
+                mbar_wait(smem_u32(&bar_aempty[sa]), ((ita >> 1) & 1u) ^ 1u);
+                const uint32_t ah = smem_base + (uint32_t)sa * a_stage_bytes;
+                for (int j = 0; j < 4; ++j) {
+                    const int f0 = g * 128 + j * kChunkK;          // first product feature of the sub-tile
+                    const int b = f0 / dim, k0 = f0 % dim;
+                    for (int c = part; c < 8; c += parts) {
+                        float4 z = f4_zero();
+                        if (ok && b < nb) {
+                            const float4 u = ldg4(pu + k0 + 4 * c), q = ldg4(pq + k0 + 4 * c), v = ldg4(pi + k0 + 4 * c);
+                            if (b == 0) z = f4_mul(u, q);
+                            else if (b == 1) z = f4_mul(q, v);
+                            else if (b == 2) z = f4_mul(v, u);
+                            else z = f4_mul(f4_mul(u, q), v);
+                        }
+                        store_split_chunk(ah + (uint32_t)j * sub_bytes, ah + (uint32_t)(4 + j) * sub_bytes, row, c, z);
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_afull[sa]));
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32_mn(dim);
+            uint32_t ita = 0, itb = 0;
+            bool first = true;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++itb) {
+                const int sb = itb & 1;
+                mbar_wait(smem_u32(&bar_bfull[sb]), (itb >> 1) & 1u);
+                fence_after_sync();
+                const uint32_t bh = b_base + (uint32_t)sb * b_stage_bytes;
+                for (int g = 0; g < G; ++g, ++ita) {
+                    const int sa = ita & 1;
+                    mbar_wait(smem_u32(&bar_afull[sa]), (ita >> 1) & 1u);
+                    fence_after_sync();
+                    const uint32_t ah = smem_base + (uint32_t)sa * a_stage_bytes;
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(g * dim);
+                    for (int ks = 0; ks < te / 8; ++ks) {
+                        const uint32_t koff = (uint32_t)ks * 1024u;   // 8 edge rows x 128 B
+                        const uint64_t dah = make_mnmajor_sw128_desc(ah + koff, sub_bytes);
+                        const uint64_t dal = make_mnmajor_sw128_desc(ah + 4 * sub_bytes + koff, sub_bytes);
+                        const uint64_t dbh = make_mnmajor_sw128_desc(bh + koff, sub_bytes);
+                        const uint64_t dbl = make_mnmajor_sw128_desc(bh + (uint32_t)KC * sub_bytes + koff, sub_bytes);
+                        mma_3xtf32(tmem_d, dah, dal, dbh, dbl, idesc, (first && ks == 0) ? 0u : 1u);
+                    }
+                    mma_commit(smem_u32(&bar_aempty[sa]));
+                }
+                mma_commit(smem_u32(&bar_bempty[sb]));
+                first = false;
+            }
+            mma_commit(smem_u32(&bar_done));
+        }
+    } else if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + 4) {
+        // ---- final epilogue: dump this CTA's partial dw^T [G*128, dim]
+        const int q4 = warp - kEpilogueWarp0;
+        const int r = q4 * 32 + lane;                               // product feature within the group
+        float* out = ws_dw + (int64_t)blockIdx.x * G * 128 * dim;
+        if (my_tiles > 0) {
+            mbar_wait(smem_u32(&bar_done), 0);
+            fence_after_sync();
+        }
+        for (int g = 0; g < G; ++g)
+            for (int c0 = 0; c0 < dim; c0 += 16) {
+                float acc[16];
+                if (my_tiles > 0) {
+                    tmem_ld16(tmem_base + (uint32_t)(g * dim + c0) + ((uint32_t)(q4 * 32) << 16), acc);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    stg4(out + ((int64_t)g * 128 + r) * dim + c0 + 4 * j,
+                         make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
+            }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// dw_hi[n][b*dim + k] = sum_cta ws[cta][b*dim + k][n]   (ascending cta: deterministic)
+__global__ void __launch_bounds__(256)
+interact_wgrad_tc_reduce_kernel(const float* __restrict__ ws, int n_cta, int G, int nb, int dim,
+                                float* __restrict__ dw_hi) {
+    const int64_t total = (int64_t)nb * dim * dim;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int n = idx % dim;                 // fastest: coalesced reads of ws rows
+        const int f = idx / dim;                 // product feature b*dim + k
+        float s = 0.f;
+        for (int c = 0; c < n_cta; ++c) s += ws[((int64_t)c * G * 128 + f) * dim + n];
+        dw_hi[(int64_t)n * nb * dim + f] = s;
+    }
+}
+
 bool interact_tc_eligible(int dim) {
     static const bool disabled = getenv("IHG_DISABLE_TC") != nullptr;
     return !disabled && dim % 32 == 0 && dim >= 32 && dim <= 128;
@@ -302,6 +723,65 @@ int launch_interact_fwd_tc(const float* xp, int64_t xp_ld, const float* p, int64
     edge_interact_fwd_tc_kernel<<<grid, kInteractThreads, smem, st>>>(xp, xp_ld, p, p_ld, wprep, nb, i3, E, ef,
                                                                       ef_ld, dim, cfg.stages, cfg.stage_bytes);
     IHG_LAUNCH_CHECK();
+    return IHG_OK;
+}
+
+static int slot_nu(int dim) { return dim > 64 ? dim / 2 : dim; }
+static int wgrad_te(int dim) { return dim > 64 ? 32 : 64; }
+static int wgrad_groups(int dim, int nb) { return (nb * dim + 127) / 128; }
+
+int64_t interact_bwd_tc_workspace_bytes(int dim, int nb) {
+    const int64_t wprep = (int64_t)nb * (dim / kChunkK) * 2 * dim * kChunkBytesPerRow + 1024;
+    const int64_t partial = (int64_t)kNumSMs * wgrad_groups(dim, nb) * 128 * dim * 4;
+    return wprep + partial + 1024;
+}
+
+int launch_interact_bwd_tc(const float* xp, int64_t xp_ld, const float* def, int64_t def_ld,
+                           const float* w_hi, int64_t w_ld, int nb, const int32_t* i3, int64_t E,
+                           float* slot_grad, float* dw_hi, int dim, void* workspace, cudaStream_t st) {
+    uint8_t* wprep = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    const int64_t wprep_bytes = (int64_t)nb * (dim / kChunkK) * 2 * dim * kChunkBytesPerRow;
+    float* partial = reinterpret_cast<float*>(wprep + ((wprep_bytes + 1023) & ~(int64_t)1023));
+    // ---- (a) slot gradients
+    const int nu = slot_nu(dim);
+    {
+        const int64_t total = (int64_t)nb * (dim / kChunkK) * dim * 8;
+        interact_prep_weights_t_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w_hi, w_ld, nb, dim, nu, wprep);
+        IHG_LAUNCH_CHECK();
+        const uint32_t b_stage = 2u * (uint32_t)nu * kChunkBytesPerRow;
+        int b_stages = (int)((200 * 1024 - kSlotAStages * 2 * kATileBytes) / b_stage);
+        if (b_stages > 8) b_stages = 8;
+        const int smem = kSlotAStages * 2 * kATileBytes + b_stages * (int)b_stage + 1024;
+        static int attr_smem = 0;
+        if (attr_smem < smem) {
+            IHG_CUDA(cudaFuncSetAttribute(edge_interact_bwd_slot_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_smem = smem;
+        }
+        const int64_t n_units = ((E + kTileM - 1) / kTileM) * (dim / nu);
+        const unsigned grid = (unsigned)(n_units < kNumSMs ? n_units : kNumSMs);
+        edge_interact_bwd_slot_tc_kernel<<<grid, kInteractThreads, smem, st>>>(xp, xp_ld, def, def_ld, wprep, nb, i3, E,
+                                                                               slot_grad, dim, nu, b_stages);
+        IHG_LAUNCH_CHECK();
+    }
+    // ---- (b) weight gradient
+    {
+        const int te = wgrad_te(dim);
+        const int G = wgrad_groups(dim, nb);
+        const int KC = dim / kChunkK;
+        const int smem = 2 * 8 * te * kChunkBytesPerRow + 2 * 2 * KC * te * kChunkBytesPerRow + 1024;
+        static int attr_smem = 0;
+        if (attr_smem < smem) {
+            IHG_CUDA(cudaFuncSetAttribute(edge_interact_bwd_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_smem = smem;
+        }
+        const int64_t n_tiles = (E + te - 1) / te;
+        const unsigned grid = (unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+        edge_interact_bwd_wgrad_tc_kernel<<<grid, kInteractThreads, smem, st>>>(xp, xp_ld, def, def_ld, nb, i3, E, dim, te, partial);
+        IHG_LAUNCH_CHECK();
+        const int64_t total = (int64_t)nb * dim * dim;
+        interact_wgrad_tc_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, (int)grid, G, nb, dim, dw_hi);
+        IHG_LAUNCH_CHECK();
+    }
     return IHG_OK;
 }
 
