@@ -500,19 +500,35 @@ interact_prep_weights_t_kernel(const float* __restrict__ w_hi, int64_t w_ld, int
 // =========================================================================================
 // backward (b): weight gradient on tensor cores, MN-major operands
 //   dw_b^T[k][n] = sum_e z_b[e][k] * def[e][n]
-// Both operands are stored as [edge rows x 32 features] sub-tiles in the same SW128 layout the
-// K-major kernels use; read through MN-major descriptors the edge index becomes the MMA K
-// dimension.  A = 128 product features (a "group": 4 sub-tiles), B = def (dim/32 sub-tiles).
+// Both operands are stored as [edge rows x 32 features] sub-tiles (128 B per edge row) in the
+// MN-major SWIZZLE_128B_BASE32B layout; the edge index is the MMA K dimension.  A = 128 product features (a "group": 4 sub-tiles), B = def (dim/32 sub-tiles).
 // The accumulators (G groups x dim columns) stay in TMEM across all tiles of the CTA; one
 // partial [G*128, dim] per CTA goes to the workspace and a second kernel sums them in order.
 // =========================================================================================
+// MN-major tf32 operands must use the SWIZZLE_128B_BASE32B canonical layout (the only MN-major
+// layout the tensor core accepts for 32-bit types): rows of 128 B (32 consecutive MN elements)
+// per K index, K atoms of 4 rows (512 B), the 32-byte chunk index XORed with row % 4.
+__device__ __forceinline__ uint32_t sw128b32_offset(int row, int chunk16) {
+    return (uint32_t)(row * 128 + ((((chunk16 >> 1) ^ (row & 3)) << 5) | ((chunk16 & 1) << 4)));
+}
+__device__ __forceinline__ void store_split_chunk_mn(uint32_t hi_tile, uint32_t lo_tile, int row,
+                                                     int chunk16, const float4& v) {
+    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+    split_tf32(v.x, h0, l0);
+    split_tf32(v.y, h1, l1);
+    split_tf32(v.z, h2, l2);
+    split_tf32(v.w, h3, l3);
+    const uint32_t off = sw128b32_offset(row, chunk16);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(hi_tile + off), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(lo_tile + off), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
+}
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;   // stride between 32-feature MN blocks
-    d |= (uint64_t)(1024 >> 4) << 32;                    // stride between 8-edge K groups
+    d |= (uint64_t)(512 >> 4) << 32;                     // stride between 4-edge K atoms
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;                              // SWIZZLE_128B_BASE32B
     return d;
 }
 __device__ __forceinline__ uint32_t make_idesc_tf32_mn(int n) {
@@ -581,7 +597,7 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                 for (int blk = 0; blk < KC; ++blk)
                     for (int c = part; c < 8; c += parts) {
                         const float4 v = ok ? ldg4(def + e * def_ld + blk * kChunkK + 4 * c) : f4_zero();
-                        store_split_chunk(bh + (uint32_t)blk * sub_bytes, bh + (uint32_t)(KC + blk) * sub_bytes, row, c, v);
+                        store_split_chunk_mn(bh + (uint32_t)blk * sub_bytes, bh + (uint32_t)(KC + blk) * sub_bytes, row, c, v);
                     }
                 fence_async_smem();
                 __syncwarp();
@@ -604,7 +620,7 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                             else if (b == 2) z = f4_mul(v, u);
                             else z = f4_mul(f4_mul(u, q), v);
                         }
-                        store_split_chunk(ah + (uint32_t)j * sub_bytes, ah + (uint32_t)(4 + j) * sub_bytes, row, c, z);
+                        store_split_chunk_mn(ah + (uint32_t)j * sub_bytes, ah + (uint32_t)(4 + j) * sub_bytes, row, c, z);
                     }
                 }
                 fence_async_smem();
