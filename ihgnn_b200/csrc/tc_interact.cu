@@ -40,6 +40,38 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
+// Per-warp staging tile for the epilogues: 32 rows x 128 B, 16-byte chunks XOR-swizzled by
+// row & 7.  Written thread-per-row (TMEM order), read with 8 lanes per row (coalesced global
+// access: one full 128-byte line per row instead of 32 partial lines per request).
+constexpr int kEpiStageBytes = 32 * 128;
+__device__ __forceinline__ uint32_t epi_off(int row, int chunk) {
+    return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ void sts4(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+// 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // wprep[(b*KC + kc)] = { hi tile [dim rows x 128 B, SW128], lo tile } of
 //   W_b[n][kc*32 .. kc*32+32) = w_hi[n*w_ld + b*dim + kc*32 + k]           (transposed == 0)
 //   W_b^T[k][nc*32 .. +32)    = w_hi[(nc*32 + n)*w_ld + b*dim + k]         (transposed == 1)
@@ -81,7 +113,7 @@ static inline InteractSmem interact_smem(int dim) {
     InteractSmem s;
     s.b_tile_bytes = (uint32_t)dim * kChunkBytesPerRow;
     s.stage_bytes = 2 * kATileBytes + 2 * s.b_tile_bytes;
-    s.stages = (int)((200 * 1024) / s.stage_bytes);
+    s.stages = (int)((200 * 1024) / s.stage_bytes);   // + 16 KB epilogue staging stays < 227 KB
     if (s.stages > 6) s.stages = 6;
     return s;
 }
@@ -101,6 +133,7 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
     const uint32_t b_tile_bytes = (uint32_t)dim * kChunkBytesPerRow;
     const int64_t n_tiles = (E + kTileM - 1) / kTileM;
     const uint32_t tmem_cols = tmem_cols_pow2((uint32_t)(2 * dim));
+    const uint32_t epi_base = smem_base + (uint32_t)stages * stage_bytes;   // 4 x 4 KB staging tiles
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -121,28 +154,34 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
 
     if (warp < kProducerWarps) {
         // ======================= producers =======================
-        const int row = tid & 127;          // hyperedge row of the tile
-        const int half = tid >> 7;          // which 64-byte half of the 128-byte slice
+        // lane mapping (row, chunk): 8 consecutive lanes read one row's 128-byte slice, so a warp
+        // request touches 4 full lines; thread owns chunk c of rows r0, r0+32, r0+64, r0+96.
+        const int c = tid & 7, r0 = tid >> 3;
         uint32_t it = 0;                    // global chunk counter (stage ring position)
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t e = tile * kTileM + row;
-            const bool ok = e < E;
-            int nu = 0, nq = 0, ni = 0;
-            if (ok) {
-                nu = __ldg(i3 + 3 * e);
-                nq = __ldg(i3 + 3 * e + 1);
-                ni = __ldg(i3 + 3 * e + 2);
+            const float *pu[4], *pq[4], *pi[4];
+            bool ok[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t e = tile * kTileM + r0 + 32 * j;
+                ok[j] = e < E;
+                int nu = 0, nq = 0, ni = 0;
+                if (ok[j]) {
+                    nu = __ldg(i3 + 3 * e);
+                    nq = __ldg(i3 + 3 * e + 1);
+                    ni = __ldg(i3 + 3 * e + 2);
+                }
+                pu[j] = xp + (int64_t)nu * xp_ld + 4 * c;
+                pq[j] = xp + (int64_t)nq * xp_ld + 4 * c;
+                pi[j] = xp + (int64_t)ni * xp_ld + 4 * c;
             }
-            const float* pu = xp + (int64_t)nu * xp_ld + 16 * half;
-            const float* pq = xp + (int64_t)nq * xp_ld + 16 * half;
-            const float* pi = xp + (int64_t)ni * xp_ld + 16 * half;
             for (int kc = 0; kc < KC; ++kc) {
                 float4 u[4], q[4], v[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    u[c] = ok ? ldg4(pu + kc * kChunkK + 4 * c) : f4_zero();
-                    q[c] = ok ? ldg4(pq + kc * kChunkK + 4 * c) : f4_zero();
-                    v[c] = ok ? ldg4(pi + kc * kChunkK + 4 * c) : f4_zero();
+                for (int j = 0; j < 4; ++j) {
+                    u[j] = ok[j] ? ldg4(pu[j] + kc * kChunkK) : f4_zero();
+                    q[j] = ok[j] ? ldg4(pq[j] + kc * kChunkK) : f4_zero();
+                    v[j] = ok[j] ? ldg4(pi[j] + kc * kChunkK) : f4_zero();
                 }
                 for (int b = 0; b < nb; ++b, ++it) {
                     const int s = it % stages;
@@ -151,13 +190,13 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
                     const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes;
                     const uint32_t a_lo = a_hi + kATileBytes;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int j = 0; j < 4; ++j) {
                         float4 z;
-                        if (b == 0) z = f4_mul(u[c], q[c]);
-                        else if (b == 1) z = f4_mul(q[c], v[c]);
-                        else if (b == 2) z = f4_mul(v[c], u[c]);
-                        else z = f4_mul(f4_mul(u[c], q[c]), v[c]);
-                        store_split_chunk(a_hi, a_lo, row, 4 * half + c, z);
+                        if (b == 0) z = f4_mul(u[j], q[j]);
+                        else if (b == 1) z = f4_mul(q[j], v[j]);
+                        else if (b == 2) z = f4_mul(v[j], u[j]);
+                        else z = f4_mul(f4_mul(u[j], q[j]), v[j]);
+                        store_split_chunk(a_hi, a_lo, r0 + 32 * j, c, z);
                     }
                     fence_async_smem();
                     __syncwarp();
@@ -215,44 +254,54 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
     } else {
         // ======================= epilogue =======================
         const int q4 = warp - kEpilogueWarp0;           // TMEM lane quadrant == warp % 4
-        const int row = q4 * 32 + lane;
+        const uint32_t stg = epi_base + (uint32_t)q4 * kEpiStageBytes;
+        const int c = lane & 7, rs = lane >> 3;         // (row-in-group, chunk) mapping for global access
         uint32_t t = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
             const uint32_t buf = t & 1u;
-            const int64_t e = tile * kTileM + row;
-            const bool ok = e < E;
-            int nu = 0, nq = 0, ni = 0;
-            if (ok) {
-                nu = __ldg(i3 + 3 * e);
-                nq = __ldg(i3 + 3 * e + 1);
-                ni = __ldg(i3 + 3 * e + 2);
+            const int64_t e0 = tile * kTileM + q4 * 32;
+            // node ids of the 8 rows this lane serves in the coalesced phase (rows rs, rs+4, ...)
+            int nu[8], nq[8], ni[8];
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) {
+                const int64_t e = e0 + itr * 4 + rs;
+                const bool ok = e < E;
+                nu[itr] = ok ? __ldg(i3 + 3 * e) : -1;
+                nq[itr] = ok ? __ldg(i3 + 3 * e + 1) : 0;
+                ni[itr] = ok ? __ldg(i3 + 3 * e + 2) : 0;
             }
-            const float* pu = p + (int64_t)nu * p_ld;
-            const float* pq = p + (int64_t)nq * p_ld;
-            const float* pi = p + (int64_t)ni * p_ld;
             mbar_wait(smem_u32(&bar_tfull[buf]), (t >> 1) & 1u);
             fence_after_sync();
             const uint32_t taddr = tmem_base + buf * (uint32_t)dim + ((uint32_t)(q4 * 32) << 16);
-            for (int c0 = 0; c0 < dim; c0 += 16) {
-                float4 base[4];
+            for (int c0 = 0; c0 < dim; c0 += 32) {
+                float acc[32];
+                tmem_ld32(taddr + (uint32_t)c0, acc);
+                __syncwarp();                             // previous slab fully read back
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (ok) {
-                        base[j] = ldg4(pu + c0 + 4 * j);
-                        f4_add(base[j], ldg4(pq + c0 + 4 * j));
-                        f4_add(base[j], ldg4(pi + c0 + 4 * j));
-                    } else {
-                        base[j] = f4_zero();
+                for (int j = 0; j < 8; ++j)
+                    sts4(stg + epi_off(lane, j), make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    float4 base[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int itr = hb * 4 + k;
+                        if (nu[itr] >= 0) {
+                            base[k] = ldg4(p + (int64_t)nu[itr] * p_ld + c0 + 4 * c);
+                            f4_add(base[k], ldg4(p + (int64_t)nq[itr] * p_ld + c0 + 4 * c));
+                            f4_add(base[k], ldg4(p + (int64_t)ni[itr] * p_ld + c0 + 4 * c));
+                        }
                     }
-                }
-                float acc[16];
-                tmem_ld16(taddr + (uint32_t)c0, acc);
-                if (ok) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float4 o = make_float4(base[j].x + acc[4 * j], base[j].y + acc[4 * j + 1],
-                                               base[j].z + acc[4 * j + 2], base[j].w + acc[4 * j + 3]);
-                        stg4(ef + e * ef_ld + c0 + 4 * j, o);
+                    for (int k = 0; k < 4; ++k) {
+                        const int itr = hb * 4 + k;
+                        if (nu[itr] >= 0) {
+                            const int r = itr * 4 + rs;
+                            float4 o = lds4(stg + epi_off(r, c));
+                            f4_add(o, base[k]);
+                            stg4(ef + (e0 + r) * ef_ld + c0 + 4 * c, o);
+                        }
                     }
                 }
             }
@@ -728,7 +777,7 @@ int launch_interact_fwd_tc(const float* xp, int64_t xp_ld, const float* p, int64
     uint8_t* wprep = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
     if (int rc = launch_interact_prep(w_hi, w_ld, nb, dim, 0, wprep, st)) return rc;
     const InteractSmem cfg = interact_smem(dim);
-    const int smem = cfg.stages * (int)cfg.stage_bytes + 1024;
+    const int smem = cfg.stages * (int)cfg.stage_bytes + 4 * kEpiStageBytes + 1024;
     static int attr_smem = 0;
     if (attr_smem < smem) {
         IHG_CUDA(cudaFuncSetAttribute(edge_interact_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
