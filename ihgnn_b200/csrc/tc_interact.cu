@@ -335,6 +335,7 @@ edge_interact_bwd_slot_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
     __shared__ __align__(8) uint64_t bar_afull[kSlotAStages], bar_aempty[kSlotAStages];
     __shared__ __align__(8) uint64_t bar_bfull[8], bar_bempty[8], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ int32_t slot_ids[4][3][32];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KC = dim / kChunkK;                 // chunks along the contraction (n)
@@ -343,6 +344,7 @@ edge_interact_bwd_slot_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
     const uint32_t a_stage_bytes = 2 * kATileBytes;
     const uint32_t b_base = smem_base + kSlotAStages * a_stage_bytes;
     const uint32_t b_stage_bytes = 2 * b_tile_bytes;
+    const uint32_t epi_base = b_base + (uint32_t)b_stages * b_stage_bytes;   // 12 x 4 KB staging tiles
     const int64_t n_tiles = (E + kTileM - 1) / kTileM;
     const int64_t n_units = n_tiles * UH;
     const uint32_t acc_cols = (uint32_t)(nb * nu);
@@ -370,22 +372,23 @@ edge_interact_bwd_slot_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
     const uint32_t tmem_base = tmem_base_slot;
 
     if (warp < kProducerWarps) {
-        // ---- A producer: def tile rows, split to tf32 hi/lo
-        const int row = tid & 127, half = tid >> 7;
+        // ---- A producer: def tile rows, split to tf32 hi/lo; (row, chunk) lane mapping
+        const int c = tid & 7, r0 = tid >> 3;
         uint32_t it = 0;
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const int64_t e = (u / UH) * kTileM + row;
-            const bool ok = e < E;
-            const float* src = def + e * def_ld + 16 * half;
+            const int64_t e0 = (u / UH) * kTileM;
             for (int nc = 0; nc < KC; ++nc, ++it) {
                 float4 v[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) v[c] = ok ? ldg4(src + nc * kChunkK + 4 * c) : f4_zero();
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t e = e0 + r0 + 32 * j;
+                    v[j] = e < E ? ldg4(def + e * def_ld + nc * kChunkK + 4 * c) : f4_zero();
+                }
                 const int s = it % kSlotAStages;
                 mbar_wait(smem_u32(&bar_aempty[s]), ((it / kSlotAStages) & 1u) ^ 1u);
                 const uint32_t a_hi = smem_base + (uint32_t)s * a_stage_bytes;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) store_split_chunk(a_hi, a_hi + kATileBytes, row, 4 * half + c, v[c]);
+                for (int j = 0; j < 4; ++j) store_split_chunk(a_hi, a_hi + kATileBytes, r0 + 32 * j, c, v[j]);
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bar_afull[s]));
@@ -443,68 +446,104 @@ edge_interact_bwd_slot_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
             }
         }
     } else {
-        // ---- epilogue: product rule, thread = hyperedge row
+        // ---- epilogue: product rule.  Global traffic (u,q,i gathers, slot_grad stores) uses the
+        // coalesced (row, chunk) mapping; the math runs thread-per-row (TMEM order); three per-warp
+        // staging tiles transpose between the two.
         const int q4 = warp - kEpilogueWarp0;
-        const int row = q4 * 32 + lane;
+        const uint32_t su = epi_base + (uint32_t)(q4 * 3) * kEpiStageBytes;
+        const uint32_t sq = su + kEpiStageBytes, si = sq + kEpiStageBytes;
+        const int c = lane & 7, rs = lane >> 3;
         uint32_t t = 0;
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++t) {
             const uint32_t buf = t & 1u;
             const int h = (int)(u % UH);
-            const int64_t e = (u / UH) * kTileM + row;
-            const bool ok = e < E;
-            int nu_ = 0, nq = 0, ni = 0;
-            if (ok) {
-                nu_ = __ldg(i3 + 3 * e);
-                nq = __ldg(i3 + 3 * e + 1);
-                ni = __ldg(i3 + 3 * e + 2);
+            const int64_t e0 = (u / UH) * kTileM + q4 * 32;
+            // node ids of this warp's 32 rows, kept in shared memory (registers are needed by the
+            // product-rule math): ids[s][row], -1 marks rows beyond E
+            __syncwarp();
+            {
+                const int64_t e = e0 + lane;
+                const bool ok = e < E;
+                slot_ids[q4][0][lane] = ok ? __ldg(i3 + 3 * e) : -1;
+                slot_ids[q4][1][lane] = ok ? __ldg(i3 + 3 * e + 1) : 0;
+                slot_ids[q4][2][lane] = ok ? __ldg(i3 + 3 * e + 2) : 0;
             }
-            const float* pu = xp + (int64_t)nu_ * xp_ld + h * nu;
-            const float* pq = xp + (int64_t)nq * xp_ld + h * nu;
-            const float* pi = xp + (int64_t)ni * xp_ld + h * nu;
-            float* out = slot_grad + e * 3 * (int64_t)dim + h * nu;
+            __syncwarp();
             const uint32_t taddr = tmem_base + buf * acc_cols + ((uint32_t)(q4 * 32) << 16);
             bool waited = false;
-            for (int c0 = 0; c0 < nu; c0 += 16) {
-                float uu[16], qq[16], ii[16];
+            for (int c0 = 0; c0 < nu; c0 += 32) {
+                const int col = h * nu + c0;
+                const int ncol = min(32, nu - c0);           // 32, or 16 for nu = 48
+                __syncwarp();
+                // load phase: coalesced gathers into the staging tiles
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 a = ok ? ldg4(pu + c0 + 4 * j) : f4_zero();
-                    const float4 bq = ok ? ldg4(pq + c0 + 4 * j) : f4_zero();
-                    const float4 ci = ok ? ldg4(pi + c0 + 4 * j) : f4_zero();
-                    uu[4 * j] = a.x; uu[4 * j + 1] = a.y; uu[4 * j + 2] = a.z; uu[4 * j + 3] = a.w;
-                    qq[4 * j] = bq.x; qq[4 * j + 1] = bq.y; qq[4 * j + 2] = bq.z; qq[4 * j + 3] = bq.w;
-                    ii[4 * j] = ci.x; ii[4 * j + 1] = ci.y; ii[4 * j + 2] = ci.z; ii[4 * j + 3] = ci.w;
+                for (int itr = 0; itr < 8; ++itr) {
+                    const int r = itr * 4 + rs;
+                    float4 a = f4_zero(), b = f4_zero(), d = f4_zero();
+                    const int n0 = slot_ids[q4][0][r];
+                    if (n0 >= 0 && 4 * c < ncol) {
+                        a = ldg4(xp + (int64_t)n0 * xp_ld + col + 4 * c);
+                        b = ldg4(xp + (int64_t)slot_ids[q4][1][r] * xp_ld + col + 4 * c);
+                        d = ldg4(xp + (int64_t)slot_ids[q4][2][r] * xp_ld + col + 4 * c);
+                    }
+                    sts4(su + epi_off(r, c), a);
+                    sts4(sq + epi_off(r, c), b);
+                    sts4(si + epi_off(r, c), d);
                 }
+                __syncwarp();
                 if (!waited) {
                     mbar_wait(smem_u32(&bar_tfull[buf]), (t >> 1) & 1u);
                     fence_after_sync();
                     waited = true;
                 }
-                float du[16], dq[16], di[16], dz[16];
-                tmem_ld16(taddr + (uint32_t)c0, dz);                         // b = 0: u*q
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { du[j] = dz[j] * qq[j]; dq[j] = dz[j] * uu[j]; }
-                tmem_ld16(taddr + (uint32_t)(nu + c0), dz);                  // b = 1: q*i
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { dq[j] = fmaf(dz[j], ii[j], dq[j]); di[j] = dz[j] * qq[j]; }
-                tmem_ld16(taddr + (uint32_t)(2 * nu + c0), dz);              // b = 2: i*u
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { di[j] = fmaf(dz[j], uu[j], di[j]); du[j] = fmaf(dz[j], ii[j], du[j]); }
-                if (nb == 4) {
-                    tmem_ld16(taddr + (uint32_t)(3 * nu + c0), dz);          // b = 3: u*q*i
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        du[j] = fmaf(dz[j], qq[j] * ii[j], du[j]);
-                        dq[j] = fmaf(dz[j], uu[j] * ii[j], dq[j]);
-                        di[j] = fmaf(dz[j], uu[j] * qq[j], di[j]);
-                    }
-                }
-                if (ok) {
+                // compute phase: thread = row `lane`, 16 columns at a time, results overwrite inputs
+                for (int hc = 0; hc < ncol; hc += 16) {
+                    float uu[16], qq[16], ii[16];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        stg4(out + c0 + 4 * j, make_float4(du[4 * j], du[4 * j + 1], du[4 * j + 2], du[4 * j + 3]));
-                        stg4(out + dim + c0 + 4 * j, make_float4(dq[4 * j], dq[4 * j + 1], dq[4 * j + 2], dq[4 * j + 3]));
-                        stg4(out + 2 * dim + c0 + 4 * j, make_float4(di[4 * j], di[4 * j + 1], di[4 * j + 2], di[4 * j + 3]));
+                        const float4 a = lds4(su + epi_off(lane, hc / 4 + j));
+                        const float4 b = lds4(sq + epi_off(lane, hc / 4 + j));
+                        const float4 d = lds4(si + epi_off(lane, hc / 4 + j));
+                        uu[4 * j] = a.x; uu[4 * j + 1] = a.y; uu[4 * j + 2] = a.z; uu[4 * j + 3] = a.w;
+                        qq[4 * j] = b.x; qq[4 * j + 1] = b.y; qq[4 * j + 2] = b.z; qq[4 * j + 3] = b.w;
+                        ii[4 * j] = d.x; ii[4 * j + 1] = d.y; ii[4 * j + 2] = d.z; ii[4 * j + 3] = d.w;
+                    }
+                    float du[16], dq[16], di[16], dz[16];
+                    tmem_ld16(taddr + (uint32_t)(c0 + hc), dz);                       // b = 0: u*q
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { du[j] = dz[j] * qq[j]; dq[j] = dz[j] * uu[j]; }
+                    tmem_ld16(taddr + (uint32_t)(nu + c0 + hc), dz);                  // b = 1: q*i
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { dq[j] = fmaf(dz[j], ii[j], dq[j]); di[j] = dz[j] * qq[j]; }
+                    tmem_ld16(taddr + (uint32_t)(2 * nu + c0 + hc), dz);              // b = 2: i*u
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { di[j] = fmaf(dz[j], uu[j], di[j]); du[j] = fmaf(dz[j], ii[j], du[j]); }
+                    if (nb == 4) {
+                        tmem_ld16(taddr + (uint32_t)(3 * nu + c0 + hc), dz);          // b = 3: u*q*i
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            du[j] = fmaf(dz[j], qq[j] * ii[j], du[j]);
+                            dq[j] = fmaf(dz[j], uu[j] * ii[j], dq[j]);
+                            di[j] = fmaf(dz[j], uu[j] * qq[j], di[j]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        sts4(su + epi_off(lane, hc / 4 + j), make_float4(du[4 * j], du[4 * j + 1], du[4 * j + 2], du[4 * j + 3]));
+                        sts4(sq + epi_off(lane, hc / 4 + j), make_float4(dq[4 * j], dq[4 * j + 1], dq[4 * j + 2], dq[4 * j + 3]));
+                        sts4(si + epi_off(lane, hc / 4 + j), make_float4(di[4 * j], di[4 * j + 1], di[4 * j + 2], di[4 * j + 3]));
+                    }
+                }
+                __syncwarp();
+                // store phase: coalesced slot_grad rows
+#pragma unroll
+                for (int itr = 0; itr < 8; ++itr) {
+                    const int r = itr * 4 + rs;
+                    if (slot_ids[q4][0][r] >= 0 && 4 * c < ncol) {
+                        float* out = slot_grad + (e0 + r) * 3 * (int64_t)dim + col + 4 * c;
+                        stg4(out, lds4(su + epi_off(r, c)));
+                        stg4(out + dim, lds4(sq + epi_off(r, c)));
+                        stg4(out + 2 * dim, lds4(si + epi_off(r, c)));
                     }
                 }
             }
@@ -623,55 +662,74 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
     const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
     if (warp < kProducerWarps) {
-        const int parts = kWgProducerThreads / te;         // threads per edge row
-        const int row = tid % te, part = tid / te;
+        // (row, chunk) lane mapping: 8 consecutive lanes cover one row's 128-byte slice
+        const int c = tid & 7, r0 = tid >> 3;              // rows r0, r0+32 (, ...) of the tile
+        const int nrow = te / 32;                          // rows per thread: 1 (te=32) or 2 (te=64)
         uint32_t ita = 0, itb = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++itb) {
-            const int64_t e = tile * te + row;
-            const bool ok = e < E;
-            int nu_ = 0, nq = 0, ni = 0;
-            if (ok) {
-                nu_ = __ldg(i3 + 3 * e);
-                nq = __ldg(i3 + 3 * e + 1);
-                ni = __ldg(i3 + 3 * e + 2);
+            bool ok[2];
+            const float *pu[2], *pq[2], *pi[2], *pd[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int64_t e = tile * te + r0 + 32 * j;
+                ok[j] = j < nrow && e < E;
+                int nu_ = 0, nq = 0, ni = 0;
+                if (ok[j]) {
+                    nu_ = __ldg(i3 + 3 * e);
+                    nq = __ldg(i3 + 3 * e + 1);
+                    ni = __ldg(i3 + 3 * e + 2);
+                }
+                pu[j] = xp + (int64_t)nu_ * xp_ld + 4 * c;
+                pq[j] = xp + (int64_t)nq * xp_ld + 4 * c;
+                pi[j] = xp + (int64_t)ni * xp_ld + 4 * c;
+                pd[j] = def + (ok[j] ? e : 0) * def_ld + 4 * c;
             }
-            const float* pu = xp + (int64_t)nu_ * xp_ld;
-            const float* pq = xp + (int64_t)nq * xp_ld;
-            const float* pi = xp + (int64_t)ni * xp_ld;
             // ---- B stage: def tile
             {
                 const int sb = itb & 1;
                 mbar_wait(smem_u32(&bar_bempty[sb]), ((itb >> 1) & 1u) ^ 1u);
                 const uint32_t bh = b_base + (uint32_t)sb * b_stage_bytes;
                 for (int blk = 0; blk < KC; ++blk)
-                    for (int c = part; c < 8; c += parts) {
-                        const float4 v = ok ? ldg4(def + e * def_ld + blk * kChunkK + 4 * c) : f4_zero();
-                        store_split_chunk_mn(bh + (uint32_t)blk * sub_bytes, bh + (uint32_t)(KC + blk) * sub_bytes, row, c, v);
-                    }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        if (j < nrow) {
+                            const float4 v = ok[j] ? ldg4(pd[j] + blk * kChunkK) : f4_zero();
+                            store_split_chunk_mn(bh + (uint32_t)blk * sub_bytes, bh + (uint32_t)(KC + blk) * sub_bytes,
+                                                 r0 + 32 * j, c, v);
+                        }
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bar_bfull[sb]));
             }
             // ---- A stages: one group of 128 product features each
             for (int g = 0; g < G; ++g, ++ita) {
+                float4 z[4][2];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const int f0 = g * 128 + j4 * kChunkK;         // first product feature of the sub-tile
+                    const int b = f0 / dim, k0 = f0 % dim;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        z[j4][j] = f4_zero();
+                        if (ok[j] && b < nb) {
+                            const float4 u = ldg4(pu[j] + k0), q = ldg4(pq[j] + k0), v = ldg4(pi[j] + k0);
+                            if (b == 0) z[j4][j] = f4_mul(u, q);
+                            else if (b == 1) z[j4][j] = f4_mul(q, v);
+                            else if (b == 2) z[j4][j] = f4_mul(v, u);
+                            else z[j4][j] = f4_mul(f4_mul(u, q), v);
+                        }
+                    }
+                }
                 const int sa = ita & 1;
                 mbar_wait(smem_u32(&bar_aempty[sa]), ((ita >> 1) & 1u) ^ 1u);
                 const uint32_t ah = smem_base + (uint32_t)sa * a_stage_bytes;
-                for (int j = 0; j < 4; ++j) {
-                    const int f0 = g * 128 + j * kChunkK;          // first product feature of the sub-tile
-                    const int b = f0 / dim, k0 = f0 % dim;
-                    for (int c = part; c < 8; c += parts) {
-                        float4 z = f4_zero();
-                        if (ok && b < nb) {
-                            const float4 u = ldg4(pu + k0 + 4 * c), q = ldg4(pq + k0 + 4 * c), v = ldg4(pi + k0 + 4 * c);
-                            if (b == 0) z = f4_mul(u, q);
-                            else if (b == 1) z = f4_mul(q, v);
-                            else if (b == 2) z = f4_mul(v, u);
-                            else z = f4_mul(f4_mul(u, q), v);
-                        }
-                        store_split_chunk_mn(ah + (uint32_t)j * sub_bytes, ah + (uint32_t)(4 + j) * sub_bytes, row, c, z);
-                    }
-                }
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        if (j < nrow)
+                            store_split_chunk_mn(ah + (uint32_t)j4 * sub_bytes, ah + (uint32_t)(4 + j4) * sub_bytes,
+                                                 r0 + 32 * j, c, z[j4][j]);
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bar_afull[sa]));
@@ -814,9 +872,9 @@ int launch_interact_bwd_tc(const float* xp, int64_t xp_ld, const float* def, int
         interact_prep_weights_t_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w_hi, w_ld, nb, dim, nu, wprep);
         IHG_LAUNCH_CHECK();
         const uint32_t b_stage = 2u * (uint32_t)nu * kChunkBytesPerRow;
-        int b_stages = (int)((200 * 1024 - kSlotAStages * 2 * kATileBytes) / b_stage);
+        int b_stages = (int)((172 * 1024 - kSlotAStages * 2 * kATileBytes) / b_stage);
         if (b_stages > 8) b_stages = 8;
-        const int smem = kSlotAStages * 2 * kATileBytes + b_stages * (int)b_stage + 1024;
+        const int smem = kSlotAStages * 2 * kATileBytes + b_stages * (int)b_stage + 12 * kEpiStageBytes + 1024;
         static int attr_smem = 0;
         if (attr_smem < smem) {
             IHG_CUDA(cudaFuncSetAttribute(edge_interact_bwd_slot_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
