@@ -1,0 +1,87 @@
+"""Drop-in installation into the (unmodified) reference tree.
+
+    import ihgnn_b200.install as inst
+    inst.patch_reference("/path/to/IHGNN")     # before Main.py's imports run
+
+or, as a launcher that leaves the reference untouched on disk:
+
+    python -m ihgnn_b200.install /path/to/IHGNN/Main.py --device 0 --gnn IHGNN ...
+
+`patch_reference` imports the reference's `Helpers.Graph`, `Models.*` and `Dataset` modules and
+rebinds the hot-path classes -- PpsHyperGraph, EmbeddingLayer, FeatureInteractor, IHGNNLayer,
+HGCNLayer, HemPredictionLayer -- to the CUDA-backed ones in every namespace that holds a
+reference to them (`Models/__init__.py:12-24` name maps included), so `Main.py`, `RawGnn` and
+`Srrl` run on top unchanged.  The reference imports `torch_sparse` and `dgl` unconditionally
+(`Helpers/Torches.py:13-18`); they must be importable (the real packages, or the stubs under
+oracle/stubs/ that the test-suite uses).
+"""
+from __future__ import annotations
+
+import importlib
+import runpy
+import sys
+from typing import Dict
+
+_REPLACED = ("PpsHyperGraph", "EmbeddingLayer", "FeatureInteractor", "IHGNNLayer", "HGCNLayer",
+             "HemPredictionLayer")
+
+
+def replacement_classes() -> Dict[str, type]:
+    from . import layers
+    from .graph import PpsHyperGraph
+    out = {"PpsHyperGraph": PpsHyperGraph}
+    for name in _REPLACED[1:]:
+        out[name] = getattr(layers, name)
+    return out
+
+
+def patch_reference(reference_dir: str = None) -> Dict[str, int]:
+    """Rebind the hot-path classes inside the imported reference modules.  Returns, per class
+    name, how many module attributes were rebound."""
+    if reference_dir and reference_dir not in sys.path:
+        sys.path.insert(0, reference_dir)
+    mods = [importlib.import_module(m) for m in (
+        "Helpers.Graph", "Dataset", "Models.CommonLayers", "Models.EmbeddingLayers",
+        "Models.GnnLayers", "Models.PredictionLayers", "Models.RawGnn", "Models.Srrl", "Models")]
+    new = replacement_classes()
+    old = {}
+    for m in mods:
+        for name in _REPLACED:
+            cls = getattr(m, name, None)
+            if isinstance(cls, type) and cls is not new[name]:
+                old.setdefault(name, set()).add(cls)
+    counts = {name: 0 for name in _REPLACED}
+    for m in mods:
+        for name in _REPLACED:
+            if getattr(m, name, None) in old.get(name, ()):
+                setattr(m, name, new[name])
+                counts[name] += 1
+        # dict/list registries built at import time (Models/__init__.py:15-24)
+        for attr in ("parse_gnn_layer", "GnnLayerTypes"):
+            reg = getattr(m, attr, None)
+            if isinstance(reg, dict):
+                for k, v in list(reg.items()):
+                    for name in _REPLACED:
+                        if v in old.get(name, ()):
+                            reg[k] = new[name]
+            elif isinstance(reg, list):
+                for i, v in enumerate(reg):
+                    for name in _REPLACED:
+                        if v in old.get(name, ()):
+                            reg[i] = new[name]
+    return counts
+
+
+def main(argv=None) -> None:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if not argv:
+        raise SystemExit("usage: python -m ihgnn_b200.install /path/to/IHGNN/Main.py [Main.py args...]")
+    script = argv[0]
+    import os
+    patch_reference(os.path.dirname(os.path.abspath(script)))
+    sys.argv = [script] + argv[1:]
+    runpy.run_path(script, run_name="__main__")
+
+
+if __name__ == "__main__":
+    main()

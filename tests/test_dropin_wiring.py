@@ -1,0 +1,60 @@
+"""Drop-in wiring against the live reference tree (build container only: skipped where
+/root/reference is absent).  No kernels run here -- the check is that, after
+`patch_reference`, every name the reference's Main.py / RawGnn / Srrl resolves for the hot
+path is bound to the CUDA-backed class, and that signatures still match."""
+import inspect
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import REPO
+
+REFERENCE = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference tree not present")
+
+CODE = r'''
+import sys, inspect
+sys.dont_write_bytecode = True
+sys.path.insert(0, "%(repo)s/oracle/stubs"); sys.path.insert(0, "%(ref)s"); sys.path.insert(0, "%(repo)s")
+from Helpers.GlobalSettings import Gs, Gsv
+Gs.graph_completeness = Gsv.graph_uqi
+import Models, Models.GnnLayers as G, Models.CommonLayers as C, Models.EmbeddingLayers as Em, Models.PredictionLayers as P
+import Helpers.Graph as HG
+ref = {"IHGNNLayer": G.IHGNNLayer, "HGCNLayer": G.HGCNLayer, "FeatureInteractor": C.FeatureInteractor,
+       "EmbeddingLayer": Em.EmbeddingLayer, "HemPredictionLayer": P.HemPredictionLayer,
+       "PpsHyperGraph": HG.PpsHyperGraph}
+import ihgnn_b200.install as inst
+new = inst.replacement_classes()
+# identical constructor / forward signatures (parameter names and order)
+for name, cls in ref.items():
+    a = list(inspect.signature(cls.__init__).parameters)
+    b = list(inspect.signature(new[name].__init__).parameters)
+    assert a == b, (name, a, b)
+    if hasattr(cls, "forward"):
+        a = list(inspect.signature(cls.forward).parameters); b = list(inspect.signature(new[name].forward).parameters)
+        assert a == b, (name, a, b)
+a = list(inspect.signature(HG.PpsHyperGraph.from_interactions).parameters)
+b = list(inspect.signature(new["PpsHyperGraph"].from_interactions).parameters)
+assert a == b, (a, b)
+counts = inst.patch_reference()
+assert all(v >= 1 for v in counts.values()), counts
+import Dataset as D
+R = sys.modules['Models.RawGnn']
+assert R.IHGNNLayer is new["IHGNNLayer"] and R.HGCNLayer is new["HGCNLayer"]
+assert R.EmbeddingLayer is new["EmbeddingLayer"] and R.HemPredictionLayer is new["HemPredictionLayer"]
+assert D.PpsHyperGraph is new["PpsHyperGraph"] and G.FeatureInteractor is new["FeatureInteractor"]
+assert Models.parse_gnn_layer["IHGNN"] is new["IHGNNLayer"] and Models.parse_gnn_layer["ihgnn"] is new["IHGNNLayer"]
+assert Models.parse_gnn_layer["HGCN"] is new["HGCNLayer"]
+# the layers read the reference's own settings object once it is importable
+from ihgnn_b200 import settings
+assert settings.Gs is Gs
+print("WIRING-OK")
+'''
+
+
+def test_patch_reference_rebinds_every_hot_path_name():
+    code = CODE % {"repo": REPO, "ref": REFERENCE}
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert res.returncode == 0 and "WIRING-OK" in res.stdout, res.stdout + res.stderr
