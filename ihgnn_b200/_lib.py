@@ -28,8 +28,7 @@ class IhgCsr(Structure):
         ("rowptr", c_void_p), ("col", c_void_p),
         ("chunk_len", c_int32),
         ("n_seg", c_int64), ("n_split", c_int64), ("n_part", c_int64),
-        ("seg_row", c_void_p), ("seg_begin", c_void_p), ("seg_part", c_void_p),
-        ("split_row", c_void_p), ("split_ptr", c_void_p),
+        ("seg", c_void_p), ("split_row", c_void_p), ("split_ptr", c_void_p),
     ]
 
 
@@ -46,7 +45,7 @@ SIGNATURES = {
     "ihg_csr_from_keys_workspace_bytes": (I64, [I64, I64]),
     "ihg_csr_from_keys": (c_int32, [P, P, I64, I64, P, P, P, P, P, I64, P]),
     "ihg_segment_plan_workspace_bytes": (I64, [I64]),
-    "ihg_segment_plan_build": (c_int32, [P, I64, I32, P, P, P, P, P, P, P, I64, P]),
+    "ihg_segment_plan_build": (c_int32, [P, I64, I32, P, P, P, P, P, I64, P]),
     "ihg_segment_reduce": (c_int32, [POINTER(IhgCsr), P, I64, I32, I64, I64, P, P, P, P, I64, I32, P]),
     "ihg_edge_gather_sum": (c_int32, [P, I64, P, F32, P, P, I64, P, I64, I32, P]),
     "ihg_edge_interact_fwd_workspace_bytes": (I64, [I32, I32]),

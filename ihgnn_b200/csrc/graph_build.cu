@@ -326,8 +326,7 @@ plan_count_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, int32_t ch
 __global__ void __launch_bounds__(256)
 plan_fill_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, int32_t chunk_len,
                  const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ split_idx,
-                 const int32_t* __restrict__ part_ptr, int32_t* __restrict__ seg_row,
-                 int32_t* __restrict__ seg_begin, int32_t* __restrict__ seg_part,
+                 const int32_t* __restrict__ part_ptr, int4* __restrict__ seg,
                  int32_t* __restrict__ split_row, int32_t* __restrict__ split_ptr,
                  int64_t* __restrict__ counts) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
@@ -335,12 +334,11 @@ plan_fill_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, int32_t chu
         const int32_t s0 = seg_ptr[r];
         const int32_t nch = seg_ptr[r + 1] - s0;
         const int32_t p0 = part_ptr[r];
-        const int32_t begin = rowptr[r];
+        const int32_t begin = rowptr[r], row_end = rowptr[r + 1];
         const bool split = nch > 1;
         for (int32_t c = 0; c < nch; ++c) {
-            seg_row[s0 + c] = (int32_t)r;
-            seg_begin[s0 + c] = begin + c * chunk_len;
-            seg_part[s0 + c] = split ? p0 + c : -1;
+            const int32_t b = begin + c * chunk_len;
+            seg[s0 + c] = make_int4(b, min(b + chunk_len, row_end), (int32_t)r, split ? p0 + c : -1);
         }
         if (split) {
             split_row[split_idx[r]] = (int32_t)r;
@@ -453,13 +451,12 @@ int64_t ihg_segment_plan_workspace_bytes(int64_t n_rows) {
 }
 
 int ihg_segment_plan_build(const int32_t* rowptr, int64_t n_rows, int32_t chunk_len,
-                           int32_t* seg_row, int32_t* seg_begin, int32_t* seg_part,
-                           int32_t* split_row, int32_t* split_ptr, int64_t* counts,
+                           int32_t* seg, int32_t* split_row, int32_t* split_ptr, int64_t* counts,
                            void* workspace, int64_t workspace_bytes, void* stream) {
     IHG_REQUIRE(n_rows > 0 && chunk_len >= 32 && n_rows < (int64_t)INT32_MAX,
                 "segment_plan: bad arguments n_rows=%lld chunk_len=%d", (long long)n_rows, chunk_len);
-    IHG_REQUIRE(rowptr && seg_row && seg_begin && seg_part && split_row && split_ptr && counts,
-                "segment_plan: null pointer");
+    IHG_REQUIRE(rowptr && seg && split_row && split_ptr && counts, "segment_plan: null pointer");
+    IHG_REQUIRE((reinterpret_cast<uintptr_t>(seg) & 15) == 0, "segment_plan: seg must be 16-byte aligned");
     IHG_REQUIRE(workspace_bytes >= ihg_segment_plan_workspace_bytes(n_rows),
                 "segment_plan: workspace too small");
     cudaStream_t st = as_stream(stream);
@@ -475,7 +472,7 @@ int ihg_segment_plan_build(const int32_t* rowptr, int64_t n_rows, int32_t chunk_
     if ((rc = exclusive_scan(nsplit, nsplit, n_rows + 1, scratch, st))) return rc;
     if ((rc = exclusive_scan(npart, npart, n_rows + 1, scratch, st))) return rc;
     plan_fill_kernel<<<grid_for(n_rows), 256, 0, st>>>(rowptr, n_rows, chunk_len, nseg, nsplit, npart,
-                                                       seg_row, seg_begin, seg_part, split_row,
+                                                       reinterpret_cast<int4*>(seg), split_row,
                                                        split_ptr, counts);
     IHG_LAUNCH_CHECK();
     return IHG_OK;

@@ -3,137 +3,154 @@
 // (/root/reference/Models/GnnLayers.py:233-234), the index_put_(accumulate=True) backward of
 // the three row gathers (CommonLayers.py:70-72) and EmbeddingBag(mean) (EmbeddingLayers.py:79).
 //
-// Work decomposition: one warp per row chunk (<= chunk_len incidences, from the plan built by
-// ihg_segment_plan_build), LPR lanes x float4 across the feature dimension and 32/LPR rows in
-// flight per step, `kUnroll` steps of independent 128-bit gathers issued before the adds.
-// Rows longer than chunk_len (Zipf head nodes) are split; their partial sums are combined by
-// a second tiny kernel in ascending chunk order.  Summation order is a pure function of the
-// plan => bitwise run-to-run determinism, no float atomics.
+// Work decomposition: the plan (ihg_segment_plan_build) lists row chunks of <= chunk_len
+// incidences as 16-byte records {begin, end, row, partial slot}.  A group of LPR lanes (LPR x
+// float4 spans the feature dimension; 32/LPR groups per warp) owns one chunk at a time and walks
+// a strided sequence of chunks, so Zipf-head chunks spread over all groups.  Per chunk the group
+// keeps kSegUnroll independent 128-bit row gathers in flight; the plan record of the chunk after
+// next and the first column indices of the next chunk are prefetched while the current rows are
+// in flight, so the dependent chain per chunk is one gather latency.  Rows longer than chunk_len
+// are split; their partial sums are combined by a second tiny kernel in ascending chunk order.
+// Summation order is a pure function of the plan => bitwise run-to-run determinism, no float
+// atomics.
 //
-// Roofline: HBM.  Algorithmic bytes per incidence: 4 (col) + 4*dim (source row), per row:
-// 8 (plan) + 4 (scale) + 4*dim (output row).
+// Roofline: HBM.  Algorithmic bytes per incidence: 4 (col) + 4*dim (source row); per row:
+// 16 (plan) + 4 (scale) + 4*dim (output row).
 #include "common.cuh"
 
 namespace ihg {
 
 constexpr int kSegWarpsPerBlock = 8;
-constexpr int kSegUnroll = 4;
-
-template <int LPR, int VPL>
-__device__ __forceinline__ void seg_accumulate(const float* __restrict__ src, int64_t src_ld,
-                                               int32_t src_row_mul, int slot,
-                                               const float* __restrict__ src_scale,
-                                               const int32_t* __restrict__ col, int begin, int end,
-                                               int nvec, int lane, float4 (&acc)[VPL]) {
-    constexpr int G = 32 / LPR;
-    const int g = lane / LPR, c = lane % LPR;
-    for (int j0 = begin; j0 < end; j0 += 32) {
-        const int cnt = min(32, end - j0);
-        const int my_col = (lane < cnt) ? __ldg(col + j0 + lane) : 0;
-        for (int k = 0; k < cnt; k += G * kSegUnroll) {
-            float4 v[kSegUnroll][VPL];
-            float sc[kSegUnroll];
-#pragma unroll
-            for (int u = 0; u < kSegUnroll; ++u) {
-                const int idx = k + u * G + g;
-                const int e = __shfl_sync(0xffffffffu, my_col, idx & 31);
-                const bool ok = idx < cnt;
-                const int64_t s = (int64_t)e * src_row_mul + slot;
-                sc[u] = (ok && src_scale) ? __ldg(src_scale + e) : 1.0f;
-#pragma unroll
-                for (int w = 0; w < VPL; ++w) {
-                    const int cv = c + w * LPR;
-                    v[u][w] = (ok && cv < nvec) ? ldg4(src + s * src_ld + 4 * cv) : f4_zero();
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kSegUnroll; ++u)
-#pragma unroll
-                for (int w = 0; w < VPL; ++w) {
-                    if (src_scale) f4_fma(acc[w], sc[u], v[u][w]);
-                    else f4_add(acc[w], v[u][w]);
-                }
-        }
-    }
-    // combine the 32/LPR row groups (fixed tree)
-#pragma unroll
-    for (int o = 16; o >= LPR; o >>= 1)
-#pragma unroll
-        for (int w = 0; w < VPL; ++w) {
-            acc[w].x += __shfl_xor_sync(0xffffffffu, acc[w].x, o);
-            acc[w].y += __shfl_xor_sync(0xffffffffu, acc[w].y, o);
-            acc[w].z += __shfl_xor_sync(0xffffffffu, acc[w].z, o);
-            acc[w].w += __shfl_xor_sync(0xffffffffu, acc[w].w, o);
-        }
-}
+constexpr int kSegUnroll = 8;
+constexpr int kSegPerGroup = 8;      // chunks a lane group walks through (strided)
 
 template <int LPR, int VPL>
 __global__ void __launch_bounds__(kSegWarpsPerBlock * 32)
 segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src_row_mul,
                       int64_t bound0, int64_t bound1, const float* __restrict__ src_scale,
-                      const float* __restrict__ row_scale, const int32_t* __restrict__ rowptr,
-                      const int32_t* __restrict__ col, int32_t chunk_len, int64_t n_seg,
-                      const int32_t* __restrict__ seg_row, const int32_t* __restrict__ seg_begin,
-                      const int32_t* __restrict__ seg_part, float* __restrict__ partial,
-                      float* __restrict__ out, int64_t out_ld, int dim) {
+                      const float* __restrict__ row_scale, const int32_t* __restrict__ col,
+                      int64_t n_seg, int64_t n_groups, const int4* __restrict__ seg,
+                      float* __restrict__ partial, float* __restrict__ out, int64_t out_ld, int dim) {
+    constexpr int G = 32 / LPR;
+    constexpr unsigned kFull = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int64_t seg = (int64_t)blockIdx.x * kSegWarpsPerBlock + (threadIdx.x >> 5);
-    if (seg >= n_seg) return;
-    const int row = __ldg(seg_row + seg);
-    const int begin = __ldg(seg_begin + seg);
-    const int part = __ldg(seg_part + seg);
-    const int row_end = __ldg(rowptr + row + 1);
-    const int end = min(begin + chunk_len, row_end);
-    const int slot = (row >= bound0) + (row >= bound1);
+    const int gl = lane % LPR;                       // lane within the group == float4 column
+    const int gbase = lane - gl;                     // first lane of the group (shuffle source base)
+    const int64_t group = ((int64_t)blockIdx.x * kSegWarpsPerBlock + (threadIdx.x >> 5)) * G + lane / LPR;
     const int nvec = dim >> 2;
-    float4 acc[VPL];
+
+    // chunk sequence of this group: group, group + n_groups, ...
+    int4 cur = make_int4(0, 0, 0, -1), nxt = make_int4(0, 0, 0, -1);
+    int64_t s = group;
+    if (s < n_seg) cur = __ldg(seg + s);
+    if (s + n_groups < n_seg) nxt = __ldg(seg + s + n_groups);
+    int colv = (s < n_seg && cur.x + gl < cur.y) ? __ldg(col + cur.x + gl) : 0;
+
+    for (int i = 0; i < kSegPerGroup; ++i, s += n_groups) {
+        const bool live = s < n_seg;                 // not warp-uniform: keep shuffles unconditional
+        // prefetch: plan record two chunks ahead, first column batch of the next chunk
+        int4 nxt2 = make_int4(0, 0, 0, -1);
+        if (s + 2 * n_groups < n_seg && i + 2 < kSegPerGroup) nxt2 = __ldg(seg + s + 2 * n_groups);
+        const bool nlive = (s + n_groups < n_seg) && (i + 1 < kSegPerGroup);
+        int ncolv = (nlive && nxt.x + gl < nxt.y) ? __ldg(col + nxt.x + gl) : 0;
+
+        const int begin = cur.x, end = live ? cur.y : cur.x, row = cur.z, part = cur.w;
+        const int slot = (row >= bound0) + (row >= bound1);
+        float4 acc[VPL];
 #pragma unroll
-    for (int w = 0; w < VPL; ++w) acc[w] = f4_zero();
-    seg_accumulate<LPR, VPL>(src, src_ld, src_row_mul, slot, src_scale, col, begin, end, nvec, lane, acc);
-    if (lane < LPR) {
-        if (part < 0) {
-            const float rs = row_scale ? __ldg(row_scale + row) : 1.0f;
+        for (int w = 0; w < VPL; ++w) acc[w] = f4_zero();
+        // longest chunk among the groups of this warp drives the (warp-uniform) trip count
+        int len = end - begin;
 #pragma unroll
-            for (int w = 0; w < VPL; ++w) {
-                const int cv = lane + w * LPR;
-                if (cv < nvec) stg4(out + (int64_t)row * out_ld + 4 * cv, f4_scale(rs, acc[w]));
-            }
-        } else {
+        for (int o = LPR; o < 32; o <<= 1) len = max(len, __shfl_xor_sync(kFull, len, o));
+        for (int j0 = 0; j0 < len; j0 += LPR) {
+            if (j0 > 0) colv = (begin + j0 + gl < end) ? __ldg(col + begin + j0 + gl) : 0;
+            const int cnt = min(LPR, end - begin - j0);          // may be <= 0 for a shorter group
+            for (int k = 0; k < LPR; k += kSegUnroll) {
+                // warp-uniform early exit: every group is past its count
+                if (__all_sync(kFull, k >= cnt)) break;
+                float4 v[kSegUnroll][VPL];
+                float sc[kSegUnroll];
 #pragma unroll
-            for (int w = 0; w < VPL; ++w) {
-                const int cv = lane + w * LPR;
-                if (cv < nvec) stg4(partial + (int64_t)part * dim + 4 * cv, acc[w]);
+                for (int u = 0; u < kSegUnroll; ++u) {
+                    const int idx = k + u;
+                    const int e = __shfl_sync(kFull, colv, gbase + (idx % LPR));
+                    const bool ok = idx < cnt;
+                    const int64_t sr = (int64_t)e * src_row_mul + slot;
+                    sc[u] = (ok && src_scale) ? __ldg(src_scale + e) : 1.0f;
+#pragma unroll
+                    for (int w = 0; w < VPL; ++w) {
+                        const int cv = gl + w * LPR;
+                        v[u][w] = (ok && cv < nvec) ? ldg4(src + sr * src_ld + 4 * cv) : f4_zero();
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kSegUnroll; ++u)
+#pragma unroll
+                    for (int w = 0; w < VPL; ++w) {
+                        if (src_scale) f4_fma(acc[w], sc[u], v[u][w]);
+                        else f4_add(acc[w], v[u][w]);
+                    }
             }
         }
+        if (live) {
+            if (part < 0) {
+                const float rs = row_scale ? __ldg(row_scale + row) : 1.0f;
+#pragma unroll
+                for (int w = 0; w < VPL; ++w) {
+                    const int cv = gl + w * LPR;
+                    if (cv < nvec) stg4(out + (int64_t)row * out_ld + 4 * cv, f4_scale(rs, acc[w]));
+                }
+            } else {
+#pragma unroll
+                for (int w = 0; w < VPL; ++w) {
+                    const int cv = gl + w * LPR;
+                    if (cv < nvec) stg4(partial + (int64_t)part * dim + 4 * cv, acc[w]);
+                }
+            }
+        }
+        cur = nxt;
+        nxt = nxt2;
+        colv = ncolv;
     }
 }
 
-// one warp per split row: out[row] = row_scale * (partial[p0] + partial[p0+1] + ...) in order
+// one lane group per split row: out[row] = row_scale * (partial[p0] + partial[p0+1] + ...) in order
 template <int LPR, int VPL>
 __global__ void __launch_bounds__(kSegWarpsPerBlock * 32)
 segment_fixup_kernel(const float* __restrict__ partial, const int32_t* __restrict__ split_row,
                      const int32_t* __restrict__ split_ptr, int64_t n_split,
                      const float* __restrict__ row_scale, float* __restrict__ out, int64_t out_ld,
                      int dim) {
+    constexpr int G = 32 / LPR;
     const int lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * kSegWarpsPerBlock + (threadIdx.x >> 5);
-    if (i >= n_split || lane >= LPR) return;
+    const int gl = lane % LPR;
+    const int64_t i = ((int64_t)blockIdx.x * kSegWarpsPerBlock + (threadIdx.x >> 5)) * G + lane / LPR;
+    if (i >= n_split) return;
     const int row = split_row[i];
     const int p0 = split_ptr[i], p1 = split_ptr[i + 1];
     const int nvec = dim >> 2;
     float4 acc[VPL];
 #pragma unroll
     for (int w = 0; w < VPL; ++w) acc[w] = f4_zero();
-    for (int p = p0; p < p1; ++p)
+    for (int p = p0; p < p1; p += 4) {
+        float4 v[4][VPL];
 #pragma unroll
-        for (int w = 0; w < VPL; ++w) {
-            const int cv = lane + w * LPR;
-            if (cv < nvec) f4_add(acc[w], ldg4(partial + (int64_t)p * dim + 4 * cv));
-        }
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int w = 0; w < VPL; ++w) {
+                const int cv = gl + w * LPR;
+                v[u][w] = (p + u < p1 && cv < nvec) ? ldg4(partial + (int64_t)(p + u) * dim + 4 * cv) : f4_zero();
+            }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int w = 0; w < VPL; ++w) f4_add(acc[w], v[u][w]);
+    }
     const float rs = row_scale ? row_scale[row] : 1.0f;
 #pragma unroll
     for (int w = 0; w < VPL; ++w) {
-        const int cv = lane + w * LPR;
+        const int cv = gl + w * LPR;
         if (cv < nvec) stg4(out + (int64_t)row * out_ld + 4 * cv, f4_scale(rs, acc[w]));
     }
 }
@@ -143,13 +160,17 @@ static int launch_segment_reduce(const ihg_csr* g, const float* src, int64_t src
                                  int64_t b0, int64_t b1, const float* src_scale,
                                  const float* row_scale, float* partial, float* out, int64_t out_ld,
                                  int dim, cudaStream_t st) {
-    const unsigned blocks = (unsigned)ceil_div(g->n_seg, kSegWarpsPerBlock);
-    segment_reduce_kernel<LPR, VPL><<<blocks, kSegWarpsPerBlock * 32, 0, st>>>(
-        src, src_ld, mul, b0, b1, src_scale, row_scale, g->rowptr, g->col, g->chunk_len, g->n_seg,
-        g->seg_row, g->seg_begin, g->seg_part, partial, out, out_ld, dim);
+    constexpr int G = 32 / LPR;
+    const int64_t groups_per_block = (int64_t)kSegWarpsPerBlock * G;
+    int64_t blocks = ceil_div(ceil_div(g->n_seg, kSegPerGroup), groups_per_block);
+    if (blocks < 1) blocks = 1;
+    const int64_t n_groups = blocks * groups_per_block;        // stride of the chunk sequences
+    segment_reduce_kernel<LPR, VPL><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
+        src, src_ld, mul, b0, b1, src_scale, row_scale, g->col, g->n_seg, n_groups,
+        reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
     IHG_LAUNCH_CHECK();
     if (g->n_split > 0) {
-        const unsigned fb = (unsigned)ceil_div(g->n_split, kSegWarpsPerBlock);
+        const unsigned fb = (unsigned)ceil_div(g->n_split, groups_per_block);
         segment_fixup_kernel<LPR, VPL><<<fb, kSegWarpsPerBlock * 32, 0, st>>>(
             partial, g->split_row, g->split_ptr, g->n_split, row_scale, out, out_ld, dim);
         IHG_LAUNCH_CHECK();
@@ -169,8 +190,7 @@ extern "C" int ihg_segment_reduce(const ihg_csr* g, const float* src, int64_t sr
     IHG_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 256, "segment_reduce: dim=%d must be a multiple of 4, <= 256", dim);
     IHG_REQUIRE(src_ld % 4 == 0 && out_ld % 4 == 0 && src_ld >= dim && out_ld >= dim,
                 "segment_reduce: leading dimensions must be multiples of 4 and >= dim");
-    IHG_REQUIRE(g->n_rows > 0 && g->n_seg >= g->n_rows && g->rowptr && g->seg_row && g->seg_begin && g->seg_part,
-                "segment_reduce: incomplete csr plan");
+    IHG_REQUIRE(g->n_rows > 0 && g->n_seg >= g->n_rows && g->seg, "segment_reduce: incomplete csr plan");
     IHG_REQUIRE(g->nnz == 0 || g->col, "segment_reduce: null col");
     IHG_REQUIRE(g->n_split == 0 || (partial && g->split_row && g->split_ptr),
                 "segment_reduce: split rows need the partial buffer");

@@ -37,31 +37,25 @@ class CsrPlan:
         dev = rowptr.device
         cap_extra = self.nnz // self.chunk_len
         cap_seg = self.n_rows + cap_extra + 1
-        seg_row = torch.empty(cap_seg, dtype=torch.int32, device=dev)
-        seg_begin = torch.empty(cap_seg, dtype=torch.int32, device=dev)
-        seg_part = torch.empty(cap_seg, dtype=torch.int32, device=dev)
+        seg = torch.empty((cap_seg, 4), dtype=torch.int32, device=dev)
         split_row = torch.empty(cap_extra + 1, dtype=torch.int32, device=dev)
         split_ptr = torch.empty(cap_extra + 2, dtype=torch.int32, device=dev)
         counts = torch.zeros(3, dtype=torch.int64, device=dev)
         ws_bytes = _lib.lib().ihg_segment_plan_workspace_bytes(self.n_rows)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _lib.call("ihg_segment_plan_build", _lib.ptr(self.rowptr), self.n_rows, self.chunk_len,
-                  _lib.ptr(seg_row), _lib.ptr(seg_begin), _lib.ptr(seg_part), _lib.ptr(split_row),
-                  _lib.ptr(split_ptr), _lib.ptr(counts), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+                  _lib.ptr(seg), _lib.ptr(split_row), _lib.ptr(split_ptr), _lib.ptr(counts),
+                  _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
         n_seg, n_split, n_part = (int(x) for x in counts.tolist())   # one-time sync at build
         self.n_seg, self.n_split, self.n_part = n_seg, n_split, n_part
-        self.seg_row = seg_row[:n_seg]
-        self.seg_begin = seg_begin[:n_seg]
-        self.seg_part = seg_part[:n_seg]
+        self.seg = seg[:n_seg]                 # [n_seg, 4] = (begin, end, row, partial slot | -1)
         self.split_row = split_row[:max(n_split, 1)]
         self.split_ptr = split_ptr[:n_split + 1]
         self.struct = _lib.IhgCsr(
             n_rows=self.n_rows, nnz=self.nnz, rowptr=self.rowptr.data_ptr(),
             col=self.col.data_ptr() if self.nnz else None, chunk_len=self.chunk_len,
-            n_seg=n_seg, n_split=n_split, n_part=n_part,
-            seg_row=self.seg_row.data_ptr(), seg_begin=self.seg_begin.data_ptr(),
-            seg_part=self.seg_part.data_ptr(), split_row=self.split_row.data_ptr(),
-            split_ptr=self.split_ptr.data_ptr())
+            n_seg=n_seg, n_split=n_split, n_part=n_part, seg=self.seg.data_ptr(),
+            split_row=self.split_row.data_ptr(), split_ptr=self.split_ptr.data_ptr())
         self._partial = {}
 
     def partial(self, dim: int) -> Optional[torch.Tensor]:

@@ -53,9 +53,7 @@ typedef struct ihg_csr {
     int64_t n_seg;             /* work items: one per row chunk (>= n_rows)              */
     int64_t n_split;           /* rows that were split into more than one chunk          */
     int64_t n_part;            /* partial-sum rows needed by split rows                  */
-    const int32_t* seg_row;    /* [n_seg]  row of the chunk                              */
-    const int32_t* seg_begin;  /* [n_seg]  first nnz position of the chunk               */
-    const int32_t* seg_part;   /* [n_seg]  partial slot, or -1 when the row is not split */
+    const int32_t* seg;        /* [n_seg][4] = {begin, end, row, partial slot or -1}     */
     const int32_t* split_row;  /* [n_split]                                              */
     const int32_t* split_ptr;  /* [n_split+1] range of partial slots of each split row   */
 } ihg_csr;
@@ -91,13 +89,12 @@ int ihg_csr_from_keys(const int32_t* keys, const int32_t* values, int64_t n, int
                       void* stream);
 
 /* Load-balancing plan for ihg_segment_reduce.  Capacities the caller must provide:
- *   seg_*      : n_rows + nnz/chunk_len + 1 entries
+ *   seg        : (n_rows + nnz/chunk_len + 1) entries of 4 x int32 (16-byte aligned)
  *   split_row  : nnz/chunk_len + 1,  split_ptr: nnz/chunk_len + 2
  * counts (device int64 [3]) receives n_seg, n_split, n_part. */
 int64_t ihg_segment_plan_workspace_bytes(int64_t n_rows);
 int ihg_segment_plan_build(const int32_t* rowptr, int64_t n_rows, int32_t chunk_len,
-                           int32_t* seg_row, int32_t* seg_begin, int32_t* seg_part,
-                           int32_t* split_row, int32_t* split_ptr, int64_t* counts,
+                           int32_t* seg, int32_t* split_row, int32_t* split_ptr, int64_t* counts,
                            void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------

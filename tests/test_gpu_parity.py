@@ -76,9 +76,11 @@ def test_graph_build_matches_oracle(shape, U, Q, I, E, zipf):
     assert max_rel(g.dv_inv_sqrt.cpu().numpy(), ref.VertexDegrees.pow(-0.5).view(-1).numpy()) < 1e-7
     # plan invariants: every incidence covered exactly once, in order
     p = g.plan
-    seg_row, seg_begin = p.seg_row.cpu().numpy(), p.seg_begin.cpu().numpy()
+    seg = p.seg.cpu().numpy()
+    seg_begin, seg_end, seg_row = seg[:, 0], seg[:, 1], seg[:, 2]
     rowptr = ref.rowptr.numpy()
     ends = np.minimum(seg_begin + p.chunk_len, rowptr[seg_row + 1])
+    assert np.array_equal(ends, seg_end)
     assert (ends - seg_begin).sum() == 3 * E
     assert np.all(np.diff(seg_row) >= 0)
     assert p.n_split == int((np.diff(rowptr) > p.chunk_len).sum())
