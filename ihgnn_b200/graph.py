@@ -18,7 +18,7 @@ import torch
 from . import _lib
 
 INT64_MAX = (1 << 63) - 1
-DEFAULT_CHUNK_LEN = 256
+DEFAULT_CHUNK_LEN = 128
 
 
 class CsrPlan:
