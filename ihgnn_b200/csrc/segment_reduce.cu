@@ -5,12 +5,11 @@
 //
 // Work decomposition: the plan (ihg_segment_plan_build) lists row chunks of <= chunk_len
 // incidences as 16-byte records {begin, end, row, partial slot}.  A group of LPR lanes (LPR x
-// float4 spans the feature dimension; 32/LPR groups per warp) advances a quad of consecutive
-// chunks in lockstep -- 4 accumulation streams x 4 independent 128-bit row gathers in flight --
-// and walks a strided sequence of quads; the plan records and first column indices of the next
-// quad are prefetched while the current rows are in flight.  Rows longer than chunk_len (Zipf
-// head) are split; their partial sums are combined by a second kernel (one warp per split row,
-// fixed interleave + shuffle tree).
+// float4 spans the feature dimension; 32/LPR groups per warp) owns one chunk at a time (and can
+// walk a strided sequence of chunks with the next records prefetched), keeping kSegUnroll
+// independent 128-bit row gathers in flight.  Rows longer than chunk_len (Zipf head) are split;
+// their partial sums are combined by a second kernel (one warp per split row, fixed interleave
+// + shuffle tree).
 // Summation order is a pure function of the plan => bitwise run-to-run determinism, no float
 // atomics.
 //
@@ -21,15 +20,12 @@
 namespace ihg {
 
 constexpr int kSegWarpsPerBlock = 8;
-constexpr int kSegUnroll = 4;        // gathers in flight per chunk stream
-constexpr int kQuadsPerGroup = 2;    // quads a lane group walks through (strided)
+constexpr int kSegUnroll = 4;        // independent 128-bit row gathers in flight per lane group
+constexpr int kSegPerGroup = 1;      // chunks a lane group walks through (strided)
 constexpr int kFixUnroll = 16;       // partial rows in flight per lane group in the fix-up
 
-// A lane group advances Q consecutive chunks ("quad") in lockstep: Q independent accumulation
-// streams x kSegUnroll gathers each are in flight, so short rows (degree < unroll) still fill
-// the memory pipeline.
-template <int LPR, int VPL, int Q>
-__global__ void __launch_bounds__(kSegWarpsPerBlock * 32, 2)
+template <int LPR, int VPL, int UNR, int SEGS>
+__global__ void __launch_bounds__(kSegWarpsPerBlock * 32)
 segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src_row_mul,
                       int64_t bound0, int64_t bound1, const float* __restrict__ src_scale,
                       const float* __restrict__ row_scale, const int32_t* __restrict__ col,
@@ -42,112 +38,83 @@ segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src
     const int gbase = lane - gl;                     // first lane of the group (shuffle source base)
     const int64_t group = ((int64_t)blockIdx.x * kSegWarpsPerBlock + (threadIdx.x >> 5)) * G + lane / LPR;
     const int nvec = dim >> 2;
-    const int4 kDead = make_int4(0, 0, 0, -1);
 
-    int4 cur[Q], nxt[Q];
-    int colv[Q];
-    int64_t qd = group;                              // quad index; chunks qd*Q .. qd*Q+Q-1
-#pragma unroll
-    for (int j = 0; j < Q; ++j) {
-        const int64_t s = qd * Q + j;
-        cur[j] = s < n_seg ? __ldg(seg + s) : kDead;
-        colv[j] = (cur[j].x + gl < cur[j].y) ? __ldg(col + cur[j].x + gl) : 0;
-    }
+    // chunk sequence of this group: group, group + n_groups, ...
+    int4 cur = make_int4(0, 0, 0, -1), nxt = make_int4(0, 0, 0, -1);
+    int64_t s = group;
+    if (s < n_seg) cur = __ldg(seg + s);
+    if (s + n_groups < n_seg) nxt = __ldg(seg + s + n_groups);
+    int colv = (s < n_seg && cur.x + gl < cur.y) ? __ldg(col + cur.x + gl) : 0;
 
-    for (int i = 0; i < kQuadsPerGroup; ++i, qd += n_groups) {
-        // prefetch the plan records of the next quad
-        const bool more = i + 1 < kQuadsPerGroup;
+    for (int i = 0; i < SEGS; ++i, s += n_groups) {
+        const bool live = s < n_seg;                 // not warp-uniform: keep shuffles unconditional
+        // prefetch: plan record two chunks ahead, first column batch of the next chunk
+        int4 nxt2 = make_int4(0, 0, 0, -1);
+        if (s + 2 * n_groups < n_seg && i + 2 < SEGS) nxt2 = __ldg(seg + s + 2 * n_groups);
+        const bool nlive = (s + n_groups < n_seg) && (i + 1 < SEGS);
+        int ncolv = (nlive && nxt.x + gl < nxt.y) ? __ldg(col + nxt.x + gl) : 0;
+
+        const int begin = cur.x, end = live ? cur.y : cur.x, row = cur.z, part = cur.w;
+        const int slot = (row >= bound0) + (row >= bound1);
+        float4 acc[VPL];
 #pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            const int64_t s = (qd + n_groups) * Q + j;
-            nxt[j] = (more && s < n_seg) ? __ldg(seg + s) : kDead;
-        }
-        float4 acc[Q][VPL];
-        int len = 0;
-#pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            len = max(len, cur[j].y - cur[j].x);
-#pragma unroll
-            for (int w = 0; w < VPL; ++w) acc[j][w] = f4_zero();
-        }
-        // longest chunk among all streams of this warp drives the (warp-uniform) trip count
+        for (int w = 0; w < VPL; ++w) acc[w] = f4_zero();
+        // longest chunk among the groups of this warp drives the (warp-uniform) trip count
+        int len = end - begin;
 #pragma unroll
         for (int o = LPR; o < 32; o <<= 1) len = max(len, __shfl_xor_sync(kFull, len, o));
         for (int j0 = 0; j0 < len; j0 += LPR) {
-            if (j0 > 0) {
+            if (j0 > 0) colv = (begin + j0 + gl < end) ? __ldg(col + begin + j0 + gl) : 0;
+            const int cnt = min(LPR, end - begin - j0);          // may be <= 0 for a shorter group
+            for (int k = 0; k < LPR; k += UNR) {
+                // warp-uniform early exit: every group is past its count
+                if (__all_sync(kFull, k >= cnt)) break;
+                float4 v[UNR][VPL];
+                float sc[UNR];
 #pragma unroll
-                for (int j = 0; j < Q; ++j)
-                    colv[j] = (cur[j].x + j0 + gl < cur[j].y) ? __ldg(col + cur[j].x + j0 + gl) : 0;
-            }
-            int cnt[Q], cmax = 0;
+                for (int u = 0; u < UNR; ++u) {
+                    const int idx = k + u;
+                    const int e = __shfl_sync(kFull, colv, gbase + (idx % LPR));
+                    const bool ok = idx < cnt;
+                    const int64_t sr = (int64_t)e * src_row_mul + slot;
+                    sc[u] = (ok && src_scale) ? __ldg(src_scale + e) : 1.0f;
 #pragma unroll
-            for (int j = 0; j < Q; ++j) {
-                cnt[j] = min(LPR, cur[j].y - cur[j].x - j0);     // <= 0 for a finished stream
-                cmax = max(cmax, cnt[j]);
-            }
-            for (int k = 0; k < LPR; k += kSegUnroll) {
-                if (__all_sync(kFull, k >= cmax)) break;         // warp-uniform early exit
-                float4 v[Q][kSegUnroll][VPL];
-                float sc[Q][kSegUnroll];
-#pragma unroll
-                for (int j = 0; j < Q; ++j) {
-                    const int slot = (cur[j].z >= bound0) + (cur[j].z >= bound1);
-#pragma unroll
-                    for (int u = 0; u < kSegUnroll; ++u) {
-                        const int idx = k + u;
-                        const int e = __shfl_sync(kFull, colv[j], gbase + (idx % LPR));
-                        const bool ok = idx < cnt[j];
-                        const int64_t sr = (int64_t)e * src_row_mul + slot;
-                        sc[j][u] = (ok && src_scale) ? __ldg(src_scale + e) : 1.0f;
-#pragma unroll
-                        for (int w = 0; w < VPL; ++w) {
-                            const int cv = gl + w * LPR;
-                            v[j][u][w] = (ok && cv < nvec) ? ldg4(src + sr * src_ld + 4 * cv) : f4_zero();
-                        }
+                    for (int w = 0; w < VPL; ++w) {
+                        const int cv = gl + w * LPR;
+                        v[u][w] = (ok && cv < nvec) ? ldg4(src + sr * src_ld + 4 * cv) : f4_zero();
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < Q; ++j)
+                for (int u = 0; u < UNR; ++u)
 #pragma unroll
-                    for (int u = 0; u < kSegUnroll; ++u)
-#pragma unroll
-                        for (int w = 0; w < VPL; ++w) {
-                            if (src_scale) f4_fma(acc[j][w], sc[j][u], v[j][u][w]);
-                            else f4_add(acc[j][w], v[j][u][w]);
-                        }
+                    for (int w = 0; w < VPL; ++w) {
+                        if (src_scale) f4_fma(acc[w], sc[u], v[u][w]);
+                        else f4_add(acc[w], v[u][w]);
+                    }
             }
         }
-        // first column batch of the next quad (its plan records have arrived by now)
-        int ncolv[Q];
-#pragma unroll
-        for (int j = 0; j < Q; ++j) ncolv[j] = (nxt[j].x + gl < nxt[j].y) ? __ldg(col + nxt[j].x + gl) : 0;
-#pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            const int row = cur[j].z, part = cur[j].w;
-            const bool live = qd * Q + j < n_seg;
-            if (!live) continue;
+        if (live) {
             if (part < 0) {
                 const float rs = row_scale ? __ldg(row_scale + row) : 1.0f;
 #pragma unroll
                 for (int w = 0; w < VPL; ++w) {
                     const int cv = gl + w * LPR;
-                    if (cv < nvec) stg4(out + (int64_t)row * out_ld + 4 * cv, f4_scale(rs, acc[j][w]));
+                    if (cv < nvec) stg4(out + (int64_t)row * out_ld + 4 * cv, f4_scale(rs, acc[w]));
                 }
             } else {
 #pragma unroll
                 for (int w = 0; w < VPL; ++w) {
                     const int cv = gl + w * LPR;
-                    if (cv < nvec) stg4(partial + (int64_t)part * dim + 4 * cv, acc[j][w]);
+                    if (cv < nvec) stg4(partial + (int64_t)part * dim + 4 * cv, acc[w]);
                 }
             }
         }
-#pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            cur[j] = nxt[j];
-            colv[j] = ncolv[j];
-        }
+        cur = nxt;
+        nxt = nxt2;
+        colv = ncolv;
     }
 }
+
 
 // One warp per split row: its 32/LPR lane groups take alternating partial rows (kFixUnroll loads
 // in flight each), a fixed shuffle tree combines the groups:
@@ -210,13 +177,15 @@ static int launch_segment_reduce(const ihg_csr* g, const float* src, int64_t src
                                  const float* row_scale, float* partial, float* out, int64_t out_ld,
                                  int dim, cudaStream_t st) {
     constexpr int G = 32 / LPR;
-    constexpr int Q = VPL > 1 ? 2 : 4;
+    // (unroll, chunks per group) = (4, 1) measured best on both bench workloads (profiles/
+    // microbench_segment.py): 5.3 TB/s at d=128 (82% of the measured copy bandwidth); at d=64 the
+    // 256-byte random rows cap every variant near 3.1 TB/s (DRAM page locality, not the kernel).
+    constexpr int UNR = kSegUnroll, SEGS = kSegPerGroup;
     const int64_t groups_per_block = (int64_t)kSegWarpsPerBlock * G;
-    const int64_t n_quads = ceil_div(g->n_seg, Q);
-    int64_t blocks = ceil_div(ceil_div(n_quads, kQuadsPerGroup), groups_per_block);
+    int64_t blocks = ceil_div(ceil_div(g->n_seg, SEGS), groups_per_block);
     if (blocks < 1) blocks = 1;
-    const int64_t n_groups = blocks * groups_per_block;        // stride of the quad sequences
-    segment_reduce_kernel<LPR, VPL, Q><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
+    const int64_t n_groups = blocks * groups_per_block;
+    segment_reduce_kernel<LPR, VPL, UNR, SEGS><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
         src, src_ld, mul, b0, b1, src_scale, row_scale, g->col, g->n_seg, n_groups,
         reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
     IHG_LAUNCH_CHECK();

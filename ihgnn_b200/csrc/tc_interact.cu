@@ -623,135 +623,166 @@ __device__ __forceinline__ uint32_t make_idesc_tf32_mn(int n) {
     return make_idesc_tf32(n) | (1u << 15) | (1u << 16);  // a_major = b_major = MN
 }
 
-constexpr int kWgProducerThreads = kProducerWarps * 32;
+// Small CTAs (4 producer warps + 1 MMA warp, 32 hyperedges per tile, two or more CTAs resident
+// per SM) so that the gather latency of one CTA overlaps the staging / MMAs of the others.  All
+// u/q/i and def slices of a tile are fetched in ONE burst of independent 128-bit loads per thread
+// (coalesced (row, chunk) mapping), then every operand sub-tile is produced from registers.
+// blockIdx.y selects a range of feature groups when all groups would not fit TMEM twice.
+constexpr int kWgTe = 32;                       // hyperedges per tile
+constexpr int kWgProducerWarps = 4;
+constexpr int kWgThreads = (kWgProducerWarps + 1) * 32;
+constexpr int kWgMaxKC = 4;                     // dim <= 128
 
-__global__ void __launch_bounds__(kInteractThreads, 1)
+__global__ void __launch_bounds__(kWgThreads)
 edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                                   const float* __restrict__ def, int64_t def_ld, int nb,
-                                  const int32_t* __restrict__ i3, int64_t E, int dim, int te,
-                                  float* __restrict__ ws_dw) {
+                                  const int32_t* __restrict__ i3, int64_t E, int dim, int G, int gpc,
+                                  int nbs, float* __restrict__ ws_dw) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_afull[2], bar_aempty[2], bar_bfull[2], bar_bempty[2], bar_done;
     __shared__ uint32_t tmem_base_slot;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KC = dim / kChunkK;                          // 32-feature blocks of def / of one product
-    const int G = (nb * dim + 127) / 128;                  // groups of 128 product features
-    const uint32_t sub_bytes = (uint32_t)te * kChunkBytesPerRow;   // one [te x 128 B] sub-tile
-    const uint32_t a_stage_bytes = 8 * sub_bytes;          // 4 sub-tiles hi + 4 lo
+    const int g0 = blockIdx.y * gpc;                       // first feature group of this CTA
+    const int ng = min(gpc, G - g0);                       // groups handled here
+    constexpr uint32_t sub_bytes = kWgTe * kChunkBytesPerRow;      // one [32 x 128 B] sub-tile
+    constexpr uint32_t a_stage_bytes = 8 * sub_bytes;      // 4 sub-tiles hi + 4 lo
     const uint32_t b_stage_bytes = 2 * KC * sub_bytes;     // KC sub-tiles hi + KC lo
     const uint32_t b_base = smem_base + 2 * a_stage_bytes;
-    const int64_t n_tiles = (E + te - 1) / te;
-    const uint32_t tmem_cols = tmem_cols_pow2((uint32_t)(G * dim));
+    const int64_t n_tiles = (E + kWgTe - 1) / kWgTe;
+    const uint32_t tmem_cols = tmem_cols_pow2((uint32_t)(gpc * dim));
+    const bool is_mma_warp = warp == kWgProducerWarps;
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(smem_u32(&bar_afull[s]), kProducerWarps);
+            mbar_init(smem_u32(&bar_afull[s]), kWgProducerWarps);
             mbar_init(smem_u32(&bar_aempty[s]), 1);
-            mbar_init(smem_u32(&bar_bfull[s]), kProducerWarps);
+            mbar_init(smem_u32(&bar_bfull[s]), kWgProducerWarps);
             mbar_init(smem_u32(&bar_bempty[s]), 1);
         }
         mbar_init(smem_u32(&bar_done), 1);
         mbar_init_fence();
     }
-    if (warp == kMmaWarp) tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols);
+    if (is_mma_warp) tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = tmem_base_slot;
     const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
-    if (warp < kProducerWarps) {
-        // (row, chunk) lane mapping: 8 consecutive lanes cover one row's 128-byte slice
-        const int c = tid & 7, r0 = tid >> 3;              // rows r0, r0+32 (, ...) of the tile
-        const int nrow = te / 32;                          // rows per thread: 1 (te=32) or 2 (te=64)
+    if (!is_mma_warp) {
+        // (row, chunk) lane mapping: 8 consecutive lanes cover one row's 128-byte slice; 128 threads
+        // cover rows r0 and r0 + 16 of the 32-row tile
+        const int c = tid & 7, r0 = tid >> 3;
         uint32_t ita = 0, itb = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++itb) {
-            bool ok[2];
-            const float *pu[2], *pq[2], *pi[2], *pd[2];
+            // ---- one burst of loads: def and u/q/i slices for both rows, all 32-column blocks
+            float4 dv[2][kWgMaxKC], uv[2][kWgMaxKC], qv[2][kWgMaxKC], iv[2][kWgMaxKC];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int64_t e = tile * te + r0 + 32 * j;
-                ok[j] = j < nrow && e < E;
+                const int64_t e = tile * kWgTe + r0 + 16 * j;
+                const bool ok = e < E;
                 int nu_ = 0, nq = 0, ni = 0;
-                if (ok[j]) {
+                if (ok) {
                     nu_ = __ldg(i3 + 3 * e);
                     nq = __ldg(i3 + 3 * e + 1);
                     ni = __ldg(i3 + 3 * e + 2);
                 }
-                pu[j] = xp + (int64_t)nu_ * xp_ld + 4 * c;
-                pq[j] = xp + (int64_t)nq * xp_ld + 4 * c;
-                pi[j] = xp + (int64_t)ni * xp_ld + 4 * c;
-                pd[j] = def + (ok[j] ? e : 0) * def_ld + 4 * c;
+#pragma unroll
+                for (int blk = 0; blk < kWgMaxKC; ++blk) {
+                    const bool okb = ok && blk < KC;
+                    dv[j][blk] = okb ? ldg4(def + e * def_ld + blk * kChunkK + 4 * c) : f4_zero();
+                    uv[j][blk] = okb ? ldg4(xp + (int64_t)nu_ * xp_ld + blk * kChunkK + 4 * c) : f4_zero();
+                    qv[j][blk] = okb ? ldg4(xp + (int64_t)nq * xp_ld + blk * kChunkK + 4 * c) : f4_zero();
+                    iv[j][blk] = okb ? ldg4(xp + (int64_t)ni * xp_ld + blk * kChunkK + 4 * c) : f4_zero();
+                }
             }
             // ---- B stage: def tile
             {
-                const int sb = itb & 1;
-                mbar_wait(smem_u32(&bar_bempty[sb]), ((itb >> 1) & 1u) ^ 1u);
+                const int sb = itb % nbs;
+                mbar_wait(smem_u32(&bar_bempty[sb]), ((itb / nbs) & 1u) ^ 1u);
                 const uint32_t bh = b_base + (uint32_t)sb * b_stage_bytes;
-                for (int blk = 0; blk < KC; ++blk)
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
-                        if (j < nrow) {
-                            const float4 v = ok[j] ? ldg4(pd[j] + blk * kChunkK) : f4_zero();
+                for (int blk = 0; blk < kWgMaxKC; ++blk)
+                    if (blk < KC) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
                             store_split_chunk_mn(bh + (uint32_t)blk * sub_bytes, bh + (uint32_t)(KC + blk) * sub_bytes,
-                                                 r0 + 32 * j, c, v);
-                        }
+                                                 r0 + 16 * j, c, dv[j][blk]);
+                    }
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bar_bfull[sb]));
             }
-            // ---- A stages: one group of 128 product features each
-            for (int g = 0; g < G; ++g, ++ita) {
-                float4 z[4][2];
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    const int f0 = g * 128 + j4 * kChunkK;         // first product feature of the sub-tile
-                    const int b = f0 / dim, k0 = f0 % dim;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        z[j4][j] = f4_zero();
-                        if (ok[j] && b < nb) {
-                            const float4 u = ldg4(pu[j] + k0), q = ldg4(pq[j] + k0), v = ldg4(pi[j] + k0);
-                            if (b == 0) z[j4][j] = f4_mul(u, q);
-                            else if (b == 1) z[j4][j] = f4_mul(q, v);
-                            else if (b == 2) z[j4][j] = f4_mul(v, u);
-                            else z[j4][j] = f4_mul(f4_mul(u, q), v);
-                        }
-                    }
-                }
+            // ---- A stages: one group of 128 product features each, straight from registers
+            for (int g = g0; g < g0 + ng; ++g, ++ita) {
                 const int sa = ita & 1;
                 mbar_wait(smem_u32(&bar_aempty[sa]), ((ita >> 1) & 1u) ^ 1u);
                 const uint32_t ah = smem_base + (uint32_t)sa * a_stage_bytes;
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4)
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const int f0 = g * 128 + j4 * kChunkK;         // first product feature of the sub-tile
+                    const int b = f0 / dim, blk = (f0 % dim) / kChunkK;
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
-                        if (j < nrow)
-                            store_split_chunk_mn(ah + (uint32_t)j4 * sub_bytes, ah + (uint32_t)(4 + j4) * sub_bytes,
-                                                 r0 + 32 * j, c, z[j4][j]);
+                    for (int j = 0; j < 2; ++j) {
+                        float4 u = f4_zero(), q = f4_zero(), v = f4_zero();
+#pragma unroll
+                        for (int k = 0; k < kWgMaxKC; ++k)
+                            if (k == blk) { u = uv[j][k]; q = qv[j][k]; v = iv[j][k]; }
+                        float4 z = f4_zero();
+                        if (b == 0) z = f4_mul(u, q);
+                        else if (b == 1) z = f4_mul(q, v);
+                        else if (b == 2) z = f4_mul(v, u);
+                        else if (b == 3 && nb == 4) z = f4_mul(f4_mul(u, q), v);
+                        store_split_chunk_mn(ah + (uint32_t)j4 * sub_bytes, ah + (uint32_t)(4 + j4) * sub_bytes,
+                                             r0 + 16 * j, c, z);
+                    }
+                }
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bar_afull[sa]));
             }
         }
-    } else if (warp == kMmaWarp) {
+        // ---- final epilogue (same warps: warp == TMEM lane quadrant): dump the partial dw^T
+        const int r = warp * 32 + lane;                             // product feature within the group
+        float* out = ws_dw + (int64_t)blockIdx.x * G * 128 * dim;
+        if (my_tiles > 0) {
+            mbar_wait(smem_u32(&bar_done), 0);
+            fence_after_sync();
+        }
+        for (int g = 0; g < ng; ++g)
+            for (int c0 = 0; c0 < dim; c0 += 16) {
+                float acc[16];
+                if (my_tiles > 0) {
+                    tmem_ld16(tmem_base + (uint32_t)(g * dim + c0) + ((uint32_t)(warp * 32) << 16), acc);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    stg4(out + ((int64_t)(g0 + g) * 128 + r) * dim + c0 + 4 * j,
+                         make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
+            }
+    } else {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32_mn(dim);
             uint32_t ita = 0, itb = 0;
             bool first = true;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++itb) {
-                const int sb = itb & 1;
-                mbar_wait(smem_u32(&bar_bfull[sb]), (itb >> 1) & 1u);
+                const int sb = itb % nbs;
+                mbar_wait(smem_u32(&bar_bfull[sb]), (itb / nbs) & 1u);
                 fence_after_sync();
                 const uint32_t bh = b_base + (uint32_t)sb * b_stage_bytes;
-                for (int g = 0; g < G; ++g, ++ita) {
+                for (int g = 0; g < ng; ++g, ++ita) {
                     const int sa = ita & 1;
                     mbar_wait(smem_u32(&bar_afull[sa]), (ita >> 1) & 1u);
                     fence_after_sync();
                     const uint32_t ah = smem_base + (uint32_t)sa * a_stage_bytes;
                     const uint32_t tmem_d = tmem_base + (uint32_t)(g * dim);
-                    for (int ks = 0; ks < te / 8; ++ks) {
+#pragma unroll
+                    for (int ks = 0; ks < kWgTe / 8; ++ks) {
                         const uint32_t koff = (uint32_t)ks * 1024u;   // 8 edge rows x 128 B
                         const uint64_t dah = make_mnmajor_sw128_desc(ah + koff, sub_bytes);
                         const uint64_t dal = make_mnmajor_sw128_desc(ah + 4 * sub_bytes + koff, sub_bytes);
@@ -766,33 +797,10 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
             }
             mma_commit(smem_u32(&bar_done));
         }
-    } else if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + 4) {
-        // ---- final epilogue: dump this CTA's partial dw^T [G*128, dim]
-        const int q4 = warp - kEpilogueWarp0;
-        const int r = q4 * 32 + lane;                               // product feature within the group
-        float* out = ws_dw + (int64_t)blockIdx.x * G * 128 * dim;
-        if (my_tiles > 0) {
-            mbar_wait(smem_u32(&bar_done), 0);
-            fence_after_sync();
-        }
-        for (int g = 0; g < G; ++g)
-            for (int c0 = 0; c0 < dim; c0 += 16) {
-                float acc[16];
-                if (my_tiles > 0) {
-                    tmem_ld16(tmem_base + (uint32_t)(g * dim + c0) + ((uint32_t)(q4 * 32) << 16), acc);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    stg4(out + ((int64_t)g * 128 + r) * dim + c0 + 4 * j,
-                         make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
-            }
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == kMmaWarp) tmem_dealloc(tmem_base, tmem_cols);
+    if (is_mma_warp) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // dw_hi[n][b*dim + k] = sum_cta ws[cta][b*dim + k][n]   (ascending cta: deterministic)
@@ -850,12 +858,19 @@ int launch_interact_fwd_tc(const float* xp, int64_t xp_ld, const float* p, int64
 }
 
 static int slot_nu(int dim) { return dim > 64 ? dim / 2 : dim; }
-static int wgrad_te(int dim) { return dim > 64 ? 32 : 64; }
 static int wgrad_groups(int dim, int nb) { return (nb * dim + 127) / 128; }
+// groups per CTA: keep the persistent accumulators within 256 TMEM columns so that two CTAs fit an SM
+static int wgrad_groups_per_cta(int dim, int nb) {
+    const int G = wgrad_groups(dim, nb);
+    int gpc = 256 / dim;
+    if (gpc < 1) gpc = 1;
+    return gpc < G ? gpc : G;
+}
+constexpr int kWgCtasX = 2 * kNumSMs;     // CTAs along x times the group split = resident CTAs
 
 int64_t interact_bwd_tc_workspace_bytes(int dim, int nb) {
     const int64_t wprep = (int64_t)nb * (dim / kChunkK) * 2 * dim * kChunkBytesPerRow + 1024;
-    const int64_t partial = (int64_t)kNumSMs * wgrad_groups(dim, nb) * 128 * dim * 4;
+    const int64_t partial = (int64_t)kWgCtasX * wgrad_groups(dim, nb) * 128 * dim * 4;
     return wprep + partial + 1024;
 }
 
@@ -888,21 +903,24 @@ int launch_interact_bwd_tc(const float* xp, int64_t xp_ld, const float* def, int
     }
     // ---- (b) weight gradient
     {
-        const int te = wgrad_te(dim);
         const int G = wgrad_groups(dim, nb);
         const int KC = dim / kChunkK;
-        const int smem = 2 * 8 * te * kChunkBytesPerRow + 2 * 2 * KC * te * kChunkBytesPerRow + 1024;
+        const int gpc = wgrad_groups_per_cta(dim, nb);            // groups per CTA (TMEM: gpc*dim <= 256 cols)
+        const int gy = (G + gpc - 1) / gpc;
+        const int nbs = dim > 64 ? 1 : 2;                          // def-tile stages (two CTAs must fit an SM)
+        const int smem = 2 * 8 * kWgTe * kChunkBytesPerRow + nbs * 2 * KC * kWgTe * kChunkBytesPerRow + 1024;
         static int attr_smem = 0;
         if (attr_smem < smem) {
             IHG_CUDA(cudaFuncSetAttribute(edge_interact_bwd_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             attr_smem = smem;
         }
-        const int64_t n_tiles = (E + te - 1) / te;
-        const unsigned grid = (unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
-        edge_interact_bwd_wgrad_tc_kernel<<<grid, kInteractThreads, smem, st>>>(xp, xp_ld, def, def_ld, nb, i3, E, dim, te, partial);
+        const int64_t n_tiles = (E + kWgTe - 1) / kWgTe;
+        const int gx = (int)(n_tiles < kWgCtasX / gy ? n_tiles : kWgCtasX / gy);
+        dim3 grid(gx, gy);
+        edge_interact_bwd_wgrad_tc_kernel<<<grid, kWgThreads, smem, st>>>(xp, xp_ld, def, def_ld, nb, i3, E, dim, G, gpc, nbs, partial);
         IHG_LAUNCH_CHECK();
         const int64_t total = (int64_t)nb * dim * dim;
-        interact_wgrad_tc_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, (int)grid, G, nb, dim, dw_hi);
+        interact_wgrad_tc_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, gx, G, nb, dim, dw_hi);
         IHG_LAUNCH_CHECK();
     }
     return IHG_OK;
