@@ -22,7 +22,6 @@ namespace ihg {
 constexpr int kSegWarpsPerBlock = 8;
 constexpr int kSegUnroll = 4;        // independent 128-bit row gathers in flight per lane group
 constexpr int kSegPerGroup = 1;      // chunks a lane group walks through (strided)
-constexpr int kFixUnroll = 16;       // partial rows in flight per lane group in the fix-up
 
 template <int LPR, int VPL, int UNR, int SEGS>
 __global__ void __launch_bounds__(kSegWarpsPerBlock * 32)
@@ -116,8 +115,9 @@ segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src
 }
 
 
-// One warp per split row: its 32/LPR lane groups take alternating partial rows (kFixUnroll loads
-// in flight each), a fixed shuffle tree combines the groups:
+// One block per split row: its 8 x 32/LPR lane groups take interleaved partial rows (the
+// compiler keeps ~4 loads in flight per lane, so parallelism comes from the groups), a fixed
+// shuffle tree combines the groups of a warp and warp 0 adds the 8 warp sums in order:
 //   out[row] = row_scale * sum of partial[p0 .. p1)        (fixed order => deterministic)
 template <int LPR, int VPL>
 __global__ void __launch_bounds__(kSegWarpsPerBlock * 32)
@@ -126,32 +126,22 @@ segment_fixup_kernel(const float* __restrict__ partial, const int32_t* __restric
                      const float* __restrict__ row_scale, float* __restrict__ out, int64_t out_ld,
                      int dim) {
     constexpr int G = 32 / LPR;
-    constexpr int U = VPL > 1 ? kFixUnroll / 2 : kFixUnroll;
-    const int lane = threadIdx.x & 31;
+    __shared__ float4 warp_sum[kSegWarpsPerBlock][LPR * VPL];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane % LPR, g = lane / LPR;
-    const int64_t i = (int64_t)blockIdx.x * kSegWarpsPerBlock + (threadIdx.x >> 5);
-    if (i >= n_split) return;                        // warp-uniform
+    const int64_t i = blockIdx.x;
     const int row = split_row[i];
     const int p0 = split_ptr[i], p1 = split_ptr[i + 1];
     const int nvec = dim >> 2;
     float4 acc[VPL];
 #pragma unroll
     for (int w = 0; w < VPL; ++w) acc[w] = f4_zero();
-    for (int p = p0 + g; p < p1; p += G * U) {
-        float4 v[U][VPL];
+    for (int p = p0 + warp * G + g; p < p1; p += kSegWarpsPerBlock * G)
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int w = 0; w < VPL; ++w) {
-                const int cv = gl + w * LPR;
-                const int pp = p + u * G;
-                v[u][w] = (pp < p1 && cv < nvec) ? ldg4(partial + (int64_t)pp * dim + 4 * cv) : f4_zero();
-            }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int w = 0; w < VPL; ++w) f4_add(acc[w], v[u][w]);
-    }
+        for (int w = 0; w < VPL; ++w) {
+            const int cv = gl + w * LPR;
+            if (cv < nvec) f4_add(acc[w], ldg4(partial + (int64_t)p * dim + 4 * cv));
+        }
 #pragma unroll
     for (int o = 16; o >= LPR; o >>= 1)
 #pragma unroll
@@ -162,11 +152,19 @@ segment_fixup_kernel(const float* __restrict__ partial, const int32_t* __restric
             acc[w].w += __shfl_xor_sync(0xffffffffu, acc[w].w, o);
         }
     if (g == 0) {
+#pragma unroll
+        for (int w = 0; w < VPL; ++w) warp_sum[warp][gl + w * LPR] = acc[w];
+    }
+    __syncthreads();
+    if (warp == 0 && g == 0) {
         const float rs = row_scale ? row_scale[row] : 1.0f;
 #pragma unroll
         for (int w = 0; w < VPL; ++w) {
             const int cv = gl + w * LPR;
-            if (cv < nvec) stg4(out + (int64_t)row * out_ld + 4 * cv, f4_scale(rs, acc[w]));
+            float4 t = warp_sum[0][cv];
+#pragma unroll
+            for (int k = 1; k < kSegWarpsPerBlock; ++k) f4_add(t, warp_sum[k][cv]);
+            if (cv < nvec) stg4(out + (int64_t)row * out_ld + 4 * cv, f4_scale(rs, t));
         }
     }
 }
@@ -190,8 +188,7 @@ static int launch_segment_reduce(const ihg_csr* g, const float* src, int64_t src
         reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
     IHG_LAUNCH_CHECK();
     if (g->n_split > 0) {
-        const unsigned fb = (unsigned)ceil_div(g->n_split, kSegWarpsPerBlock);
-        segment_fixup_kernel<LPR, VPL><<<fb, kSegWarpsPerBlock * 32, 0, st>>>(
+        segment_fixup_kernel<LPR, VPL><<<(unsigned)g->n_split, kSegWarpsPerBlock * 32, 0, st>>>(
             partial, g->split_row, g->split_ptr, g->n_split, row_scale, out, out_ld, dim);
         IHG_LAUNCH_CHECK();
     }

@@ -55,6 +55,10 @@ __device__ __forceinline__ float4 lds4(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // 32 lanes x 32 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -478,18 +482,21 @@ edge_interact_bwd_slot_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                 // load phase: coalesced gathers into the staging tiles
 #pragma unroll
                 for (int itr = 0; itr < 8; ++itr) {
+                    // asynchronous 16-byte copies straight into the staging tiles: all 24 gathers of
+                    // this lane are in flight at once and cost no registers
                     const int r = itr * 4 + rs;
-                    float4 a = f4_zero(), b = f4_zero(), d = f4_zero();
                     const int n0 = slot_ids[q4][0][r];
                     if (n0 >= 0 && 4 * c < ncol) {
-                        a = ldg4(xp + (int64_t)n0 * xp_ld + col + 4 * c);
-                        b = ldg4(xp + (int64_t)slot_ids[q4][1][r] * xp_ld + col + 4 * c);
-                        d = ldg4(xp + (int64_t)slot_ids[q4][2][r] * xp_ld + col + 4 * c);
+                        cp_async16(su + epi_off(r, c), xp + (int64_t)n0 * xp_ld + col + 4 * c);
+                        cp_async16(sq + epi_off(r, c), xp + (int64_t)slot_ids[q4][1][r] * xp_ld + col + 4 * c);
+                        cp_async16(si + epi_off(r, c), xp + (int64_t)slot_ids[q4][2][r] * xp_ld + col + 4 * c);
+                    } else {
+                        sts4(su + epi_off(r, c), f4_zero());
+                        sts4(sq + epi_off(r, c), f4_zero());
+                        sts4(si + epi_off(r, c), f4_zero());
                     }
-                    sts4(su + epi_off(r, c), a);
-                    sts4(sq + epi_off(r, c), b);
-                    sts4(si + epi_off(r, c), d);
                 }
+                cp_async_wait_all();
                 __syncwarp();
                 if (!waited) {
                     mbar_wait(smem_u32(&bar_tfull[buf]), (t >> 1) & 1u);
