@@ -200,7 +200,9 @@ int ihg_node_linear(const float* x, int64_t x_ld, const float* w, int32_t n_type
 
 int64_t ihg_node_linear_wgrad_workspace_bytes(int32_t n_types, int32_t n_out, int32_t n_in) {
     const int64_t G = wgrad_grid_g(n_types);
-    return ws_slice(G * n_types * (int64_t)n_out * n_in, 4) + ws_slice(G * n_types * (int64_t)n_out, 4) + 1024;
+    const int64_t simt = ws_slice(G * n_types * (int64_t)n_out * n_in, 4) + ws_slice(G * n_types * (int64_t)n_out, 4) + 1024;
+    const int64_t tcb = node_wgrad_tc_eligible(n_types, n_out, n_in) ? node_wgrad_tc_workspace_bytes(n_types, n_out, n_in) : 0;
+    return simt > tcb ? simt : tcb;
 }
 
 int ihg_node_linear_wgrad(const float* dy, int64_t dy_ld, const float* x, int64_t x_ld,
@@ -216,9 +218,12 @@ int ihg_node_linear_wgrad(const float* dy, int64_t dy_ld, const float* x, int64_
                 "node_linear_wgrad: workspace too small");
     if (n_types == 1) bound0 = bound1 = n_rows;
     IHG_REQUIRE(n_rows > 0 && 0 <= bound0 && bound0 <= bound1 && bound1 <= n_rows, "node_linear_wgrad: bad bounds");
+    cudaStream_t st = as_stream(stream);
+    if (node_wgrad_tc_eligible(n_types, n_out, n_in) && x_ld % 4 == 0)
+        return launch_node_wgrad_tc(dy, dy_ld, x, x_ld, n_rows, bound0, bound1, n_types, n_out, n_in, dw, db,
+                                    workspace, st);
     TypeTiles tt{bound0, bound1, n_rows};
     const int G = wgrad_grid_g(n_types);
-    cudaStream_t st = as_stream(stream);
     Workspace ws(workspace, workspace_bytes);
     float* ws_dw = ws.take<float>((int64_t)G * n_types * n_out * n_in);
     float* ws_db = ws.take<float>((int64_t)G * n_types * n_out);

@@ -40,42 +40,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
-// Per-warp staging tile for the epilogues: 32 rows x 128 B, 16-byte chunks XOR-swizzled by
-// row & 7.  Written thread-per-row (TMEM order), read with 8 lanes per row (coalesced global
-// access: one full 128-byte line per row instead of 32 partial lines per request).
-constexpr int kEpiStageBytes = 32 * 128;
-__device__ __forceinline__ uint32_t epi_off(int row, int chunk) {
-    return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
-}
-__device__ __forceinline__ void sts4(uint32_t addr, const float4& v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ float4 lds4(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-// 32 lanes x 32 consecutive fp32 columns
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 // wprep[(b*KC + kc)] = { hi tile [dim rows x 128 B, SW128], lo tile } of
 //   W_b[n][kc*32 .. kc*32+32) = w_hi[n*w_ld + b*dim + kc*32 + k]           (transposed == 0)
 //   W_b^T[k][nc*32 .. +32)    = w_hi[(nc*32 + n)*w_ld + b*dim + k]         (transposed == 1)
@@ -600,36 +564,6 @@ interact_prep_weights_t_kernel(const float* __restrict__ w_hi, int64_t w_ld, int
 // The accumulators (G groups x dim columns) stay in TMEM across all tiles of the CTA; one
 // partial [G*128, dim] per CTA goes to the workspace and a second kernel sums them in order.
 // =========================================================================================
-// MN-major tf32 operands must use the SWIZZLE_128B_BASE32B canonical layout (the only MN-major
-// layout the tensor core accepts for 32-bit types): rows of 128 B (32 consecutive MN elements)
-// per K index, K atoms of 4 rows (512 B), the 32-byte chunk index XORed with row % 4.
-__device__ __forceinline__ uint32_t sw128b32_offset(int row, int chunk16) {
-    return (uint32_t)(row * 128 + ((((chunk16 >> 1) ^ (row & 3)) << 5) | ((chunk16 & 1) << 4)));
-}
-__device__ __forceinline__ void store_split_chunk_mn(uint32_t hi_tile, uint32_t lo_tile, int row,
-                                                     int chunk16, const float4& v) {
-    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-    split_tf32(v.x, h0, l0);
-    split_tf32(v.y, h1, l1);
-    split_tf32(v.z, h2, l2);
-    split_tf32(v.w, h3, l3);
-    const uint32_t off = sw128b32_offset(row, chunk16);
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(hi_tile + off), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(lo_tile + off), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
-}
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;   // stride between 32-feature MN blocks
-    d |= (uint64_t)(512 >> 4) << 32;                     // stride between 4-edge K atoms
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)1 << 61;                              // SWIZZLE_128B_BASE32B
-    return d;
-}
-__device__ __forceinline__ uint32_t make_idesc_tf32_mn(int n) {
-    return make_idesc_tf32(n) | (1u << 15) | (1u << 16);  // a_major = b_major = MN
-}
-
 // Small CTAs (4 producer warps + 1 MMA warp, 32 hyperedges per tile, two or more CTAs resident
 // per SM) so that the gather latency of one CTA overlaps the staging / MMAs of the others.  All
 // u/q/i and def slices of a tile are fetched in ONE burst of independent 128-bit loads per thread

@@ -128,6 +128,235 @@ node_linear_tc_kernel(const float* __restrict__ x, int64_t x_ld, const float* __
     if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
 }
 
+// =========================================================================================
+// Weight gradient of the typed node Linear on tensor cores:
+//   dw[t][n][k] = sum_{r in type t} dy[r][n] * x[r][k]
+// A = dy tile, B = x tile, both [32 rows x 32 features] sub-tiles in the MN-major
+// SWIZZLE_128B_BASE32B layout (the row index is the MMA K dimension); M is padded to 128 with
+// zero sub-tiles.  One accumulator [128 x n_in] per node type stays in TMEM across all tiles of
+// the CTA; partials go to the workspace and are summed in CTA order (deterministic).
+// Small CTAs (4 producer warps + 1 MMA warp), several resident per SM.
+// =========================================================================================
+constexpr int kNwTe = 32;
+constexpr int kNwThreads = 5 * 32;
+constexpr int kNwMaxBlk = 4;
+
+__global__ void __launch_bounds__(kNwThreads)
+node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* __restrict__ x,
+                     int64_t x_ld, int64_t b0, int64_t b1, int64_t n_rows, int n_types, int n_out,
+                     int n_in, float* __restrict__ ws_dw) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_done;
+    __shared__ uint32_t tmem_base_slot;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KA = n_out / kChunkK, KB = n_in / kChunkK;
+    constexpr uint32_t sub_bytes = kNwTe * kChunkBytesPerRow;             // 4 KB
+    const uint32_t a_bytes = 8 * sub_bytes;                               // 4 hi + 4 lo sub-tiles (M = 128)
+    const uint32_t stage_bytes = a_bytes + 2 * (uint32_t)KB * sub_bytes;
+    const bool is_mma_warp = warp == 4;
+    const uint32_t tmem_cols = tmem_cols_pow2((uint32_t)(n_types * n_in));
+
+    // tiles never straddle a node-type boundary
+    const int64_t lo[3] = {0, b0, b1}, hi[3] = {b0, b1, n_rows};
+    int64_t tiles_t[3], tile_base[4];
+    tile_base[0] = 0;
+    for (int t = 0; t < 3; ++t) {
+        tiles_t[t] = (hi[t] - lo[t] + kNwTe - 1) / kNwTe;
+        tile_base[t + 1] = tile_base[t] + tiles_t[t];
+    }
+    const int64_t n_tiles = tile_base[3];
+
+    // zero the M-padding sub-tiles once (A blocks >= KA of both stages, hi and lo)
+    for (uint32_t off = tid * 16; off < 2 * stage_bytes; off += kNwThreads * 16) {
+        const uint32_t in_stage = off % stage_bytes;
+        if (in_stage < a_bytes) sts4(smem_base + off, f4_zero());
+    }
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&bar_full[s]), 4);
+            mbar_init(smem_u32(&bar_empty[s]), 1);
+        }
+        mbar_init(smem_u32(&bar_done), 1);
+        mbar_init_fence();
+    }
+    if (is_mma_warp) tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (!is_mma_warp) {
+        const int c = tid & 7, r0 = tid >> 3;            // rows r0, r0 + 16; chunk c of every block
+        uint32_t it = 0;
+        uint32_t started = 0;                            // bit t set once type t's accumulator is live
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            int t = 0;
+            while (t < 2 && tile >= tile_base[t + 1]) ++t;
+            started |= 1u << (n_types > 1 ? t : 0);
+            const int64_t row0 = lo[t] + (tile - tile_base[t]) * kNwTe;
+            float4 av[2][kNwMaxBlk], bv[2][kNwMaxBlk];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int64_t r = row0 + r0 + 16 * j;
+                const bool ok = r < hi[t];
+#pragma unroll
+                for (int blk = 0; blk < kNwMaxBlk; ++blk) {
+                    av[j][blk] = (ok && blk < KA) ? ldg4(dy + r * dy_ld + blk * kChunkK + 4 * c) : f4_zero();
+                    bv[j][blk] = (ok && blk < KB) ? ldg4(x + r * x_ld + blk * kChunkK + 4 * c) : f4_zero();
+                }
+            }
+            const int s = it & 1;
+            mbar_wait(smem_u32(&bar_empty[s]), ((it >> 1) & 1u) ^ 1u);
+            const uint32_t ah = smem_base + (uint32_t)s * stage_bytes;
+            const uint32_t bh = ah + a_bytes;
+#pragma unroll
+            for (int blk = 0; blk < kNwMaxBlk; ++blk)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (blk < KA)
+                        store_split_chunk_mn(ah + (uint32_t)blk * sub_bytes, ah + (uint32_t)(4 + blk) * sub_bytes,
+                                             r0 + 16 * j, c, av[j][blk]);
+                    if (blk < KB)
+                        store_split_chunk_mn(bh + (uint32_t)blk * sub_bytes, bh + (uint32_t)(KB + blk) * sub_bytes,
+                                             r0 + 16 * j, c, bv[j][blk]);
+                }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
+        }
+        // final epilogue: warp == TMEM lane quadrant; rows n < n_out of every type's accumulator
+        const int n = warp * 32 + lane;
+        float* out = ws_dw + (int64_t)blockIdx.x * n_types * n_out * n_in;
+        const bool any = blockIdx.x < n_tiles;
+        if (any) {
+            mbar_wait(smem_u32(&bar_done), 0);
+            fence_after_sync();
+        }
+        for (int t = 0; t < n_types; ++t)
+            for (int c0 = 0; c0 < n_in; c0 += 16) {
+                float acc[16];
+                if (any && ((started >> t) & 1u)) {      // block-uniform: untouched accumulators are undefined
+                    tmem_ld16(tmem_base + (uint32_t)(t * n_in + c0) + ((uint32_t)(warp * 32) << 16), acc);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+                }
+                if (n < n_out) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        stg4(out + ((int64_t)t * n_out + n) * n_in + c0 + 4 * j,
+                             make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
+                }
+            }
+    } else if (lane == 0) {
+        const uint32_t idesc = make_idesc_tf32_mn(n_in);
+        uint32_t it = 0;
+        uint32_t started = 0;                            // bit t set once type t's accumulator is live
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            int t = 0;
+            while (t < 2 && tile >= tile_base[t + 1]) ++t;
+            const int tt = n_types > 1 ? t : 0;
+            const int s = it & 1;
+            mbar_wait(smem_u32(&bar_full[s]), (it >> 1) & 1u);
+            fence_after_sync();
+            const uint32_t ah = smem_base + (uint32_t)s * stage_bytes;
+            const uint32_t bh = ah + a_bytes;
+            const uint32_t tmem_d = tmem_base + (uint32_t)(tt * n_in);
+#pragma unroll
+            for (int ks = 0; ks < kNwTe / 8; ++ks) {
+                const uint32_t koff = (uint32_t)ks * 1024u;
+                mma_3xtf32(tmem_d, make_mnmajor_sw128_desc(ah + koff, sub_bytes),
+                           make_mnmajor_sw128_desc(ah + 4 * sub_bytes + koff, sub_bytes),
+                           make_mnmajor_sw128_desc(bh + koff, sub_bytes),
+                           make_mnmajor_sw128_desc(bh + (uint32_t)KB * sub_bytes + koff, sub_bytes), idesc,
+                           ((started >> tt) & 1u) ? 1u : (ks > 0 ? 1u : 0u));
+            }
+            started |= 1u << tt;
+            mma_commit(smem_u32(&bar_empty[s]));
+        }
+        mma_commit(smem_u32(&bar_done));
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (is_mma_warp) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// column sums of dy per node type (bias gradient), two-pass deterministic
+__global__ void __launch_bounds__(256)
+typed_colsum_kernel(const float* __restrict__ dy, int64_t dy_ld, int64_t lo, int64_t hi, int n_out,
+                    float* __restrict__ ws_db) {
+    // block b sums rows lo + b, lo + b + gridDim.x, ... ; thread = column
+    const int c = threadIdx.x;
+    float s = 0.f;
+    if (c < n_out)
+        for (int64_t r = lo + blockIdx.x; r < hi; r += gridDim.x) s += __ldg(dy + r * dy_ld + c);
+    if (c < n_out) ws_db[(int64_t)blockIdx.x * n_out + c] = s;
+}
+__global__ void __launch_bounds__(256)
+colsum_reduce_kernel(const float* __restrict__ ws_db, int G, int n_out, float* __restrict__ db) {
+    const int c = threadIdx.x;
+    if (c >= n_out) return;
+    float s = 0.f;
+    for (int g = 0; g < G; ++g) s += ws_db[(int64_t)g * n_out + c];
+    db[c] = s;
+}
+
+bool node_wgrad_tc_eligible(int n_types, int n_out, int n_in) {
+    static const bool disabled = getenv("IHG_DISABLE_TC") != nullptr;
+    if (disabled) return false;
+    return n_out % 32 == 0 && n_in % 32 == 0 && n_out <= 128 && n_in <= 128 && n_types * n_in <= 512;
+}
+constexpr int kNwCtas = 2 * kNumSMs;
+constexpr int kColsumBlocks = 256;
+
+int64_t node_wgrad_tc_workspace_bytes(int n_types, int n_out, int n_in) {
+    return (int64_t)kNwCtas * n_types * n_out * n_in * 4 + (int64_t)kColsumBlocks * n_types * n_out * 4 + 1024;
+}
+
+__global__ void __launch_bounds__(256)
+wgrad_partials_sum_kernel(const float* __restrict__ ws, int G, int64_t n, float* __restrict__ dst) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int g = 0; g < G; ++g) s += ws[(int64_t)g * n + i];
+        dst[i] = s;
+    }
+}
+
+int launch_node_wgrad_tc(const float* dy, int64_t dy_ld, const float* x, int64_t x_ld, int64_t n_rows,
+                         int64_t b0, int64_t b1, int n_types, int n_out, int n_in, float* dw, float* db,
+                         void* workspace, cudaStream_t st) {
+    float* ws_dw = static_cast<float*>(workspace);
+    float* ws_db = ws_dw + (int64_t)kNwCtas * n_types * n_out * n_in;
+    const int KB = n_in / kChunkK;
+    const int smem = 2 * (8 + 2 * KB) * kNwTe * kChunkBytesPerRow + 1024;
+    static int attr_smem = 0;
+    if (attr_smem < smem) {
+        IHG_CUDA(cudaFuncSetAttribute(node_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    int64_t n_tiles = 0;
+    const int64_t lo[3] = {0, b0, b1}, hi[3] = {b0, b1, n_rows};
+    for (int t = 0; t < 3; ++t) n_tiles += (hi[t] - lo[t] + kNwTe - 1) / kNwTe;
+    const int grid = (int)(n_tiles < kNwCtas ? n_tiles : kNwCtas);
+    node_wgrad_tc_kernel<<<grid, kNwThreads, smem, st>>>(dy, dy_ld, x, x_ld, b0, b1, n_rows, n_types, n_out, n_in, ws_dw);
+    IHG_LAUNCH_CHECK();
+    const int64_t nw = (int64_t)n_types * n_out * n_in;
+    wgrad_partials_sum_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(ws_dw, grid, nw, dw);
+    IHG_LAUNCH_CHECK();
+    if (db) {
+        for (int t = 0; t < n_types; ++t) {
+            const int64_t l = n_types > 1 ? lo[t] : 0, h = n_types > 1 ? hi[t] : n_rows;
+            typed_colsum_kernel<<<kColsumBlocks, 256, 0, st>>>(dy, dy_ld, l, h, n_out, ws_db + (int64_t)t * kColsumBlocks * n_out);
+            IHG_LAUNCH_CHECK();
+            colsum_reduce_kernel<<<1, 256, 0, st>>>(ws_db + (int64_t)t * kColsumBlocks * n_out, kColsumBlocks, n_out, db + (int64_t)t * n_out);
+            IHG_LAUNCH_CHECK();
+        }
+    }
+    return IHG_OK;
+}
+
 bool node_linear_tc_eligible(int n_out, int n_in, int64_t x_ld, int64_t y_ld, const float* addend,
                              int64_t addend_ld) {
     static const bool disabled = getenv("IHG_DISABLE_TC") != nullptr;

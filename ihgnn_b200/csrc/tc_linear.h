@@ -13,6 +13,11 @@ int launch_node_linear_tc(const float* x, int64_t x_ld, const float* w, int n_ty
                           int64_t addend_ld, int64_t n_rows, int64_t bound0, int64_t bound1,
                           float* y, int64_t y_ld, cudaStream_t st);
 
+bool node_wgrad_tc_eligible(int n_types, int n_out, int n_in);
+int64_t node_wgrad_tc_workspace_bytes(int n_types, int n_out, int n_in);
+int launch_node_wgrad_tc(const float* dy, int64_t dy_ld, const float* x, int64_t x_ld, int64_t n_rows,
+                         int64_t b0, int64_t b1, int n_types, int n_out, int n_in, float* dw, float* db,
+                         void* workspace, cudaStream_t st);
 bool interact_tc_eligible(int dim);
 int64_t interact_fwd_tc_workspace_bytes(int dim, int nb);
 int launch_interact_prep(const float* w_hi, int64_t w_ld, int nb, int dim, int transposed,

@@ -263,3 +263,24 @@ def test_node_linear_tensor_core_path(n_in, n_out, typed):
     want_t = torch.einsum("rn,rnk->rk", dy.double(), w.double()[tid])
     got_t = F_.node_linear(dy.to(DEV), w.to(DEV), transpose_w=True, bounds=(b0, b1) if typed else None).cpu()
     assert max_rel(got_t.numpy(), want_t.numpy()) < 3e-6
+
+
+@pytest.mark.parametrize("n_in,n_out", [(32, 32), (64, 64), (128, 128), (64, 96), (128, 32), (48, 24)])
+@pytest.mark.parametrize("typed", [False, True])
+def test_node_linear_wgrad(n_in, n_out, typed):
+    """dw[t] = sum_{r in t} dy[r]^T x[r], db[t] = sum dy[r] (tensor-core MN-major path when the
+    dimensions are multiples of 32, FFMA otherwise) against fp64."""
+    from ihgnn_b200 import functional as F_
+    gen = torch.Generator().manual_seed(n_in * 77 + n_out)
+    rows, b0, b1 = 5000, 1777, 1800          # a 23-row type in the middle, ragged 32-row tiles
+    x = torch.randn(rows, n_in, generator=gen)
+    dy = torch.randn(rows, n_out, generator=gen)
+    T = 3 if typed else 1
+    dw, db = F_.node_linear_wgrad(dy.to(DEV), x.to(DEV), T, (b0, b1) if typed else None, True)
+    segs = [(0, b0), (b0, b1), (b1, rows)] if typed else [(0, rows)]
+    for t, (lo, hi) in enumerate(segs):
+        want = dy[lo:hi].double().t() @ x[lo:hi].double()
+        assert max_rel(dw[t].cpu().numpy(), want.numpy()) < 3e-6, t
+        assert max_rel(db[t].cpu().numpy(), dy[lo:hi].double().sum(0).numpy()) < 3e-6, t
+    dw2, _ = F_.node_linear_wgrad(dy.to(DEV), x.to(DEV), T, (b0, b1) if typed else None, True)
+    assert torch.equal(dw, dw2)
