@@ -153,9 +153,11 @@ node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* _
     const int KA = n_out / kChunkK, KB = n_in / kChunkK;
     constexpr uint32_t sub_bytes = kNwTe * kChunkBytesPerRow;             // 4 KB
     const uint32_t a_bytes = 8 * sub_bytes;                               // 4 hi + 4 lo sub-tiles (M = 128)
-    const uint32_t stage_bytes = a_bytes + 2 * (uint32_t)KB * sub_bytes;
+    const int NB = KB + 1;                                                // + the constant "ones" block (bias gradient)
+    const uint32_t stage_bytes = a_bytes + 2 * (uint32_t)NB * sub_bytes;
     const bool is_mma_warp = warp == 4;
-    const uint32_t tmem_cols = tmem_cols_pow2((uint32_t)(n_types * n_in));
+    const int acc_cols = n_in + 16;                                       // column n_in accumulates sum_r dy[r][n]
+    const uint32_t tmem_cols = tmem_cols_pow2((uint32_t)(n_types * acc_cols));
 
     // tiles never straddle a node-type boundary
     const int64_t lo[3] = {0, b0, b1}, hi[3] = {b0, b1, n_rows};
@@ -167,10 +169,14 @@ node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* _
     }
     const int64_t n_tiles = tile_base[3];
 
-    // zero the M-padding sub-tiles once (A blocks >= KA of both stages, hi and lo)
-    for (uint32_t off = tid * 16; off < 2 * stage_bytes; off += kNwThreads * 16) {
-        const uint32_t in_stage = off % stage_bytes;
-        if (in_stage < a_bytes) sts4(smem_base + off, f4_zero());
+    // once: zero the whole operand area (M-padding sub-tiles of A stay zero), then set column 0 of
+    // the extra B block to 1.0 so that accumulator column n_in collects the bias gradient
+    for (uint32_t off = tid * 16; off < 2 * stage_bytes; off += kNwThreads * 16) sts4(smem_base + off, f4_zero());
+    __syncthreads();
+    if (tid < 2 * kNwTe) {
+        const int s = tid / kNwTe, r = tid % kNwTe;
+        sts4(smem_base + (uint32_t)s * stage_bytes + a_bytes + (uint32_t)KB * sub_bytes + sw128b32_offset(r, 0),
+             make_float4(1.f, 0.f, 0.f, 0.f));
     }
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -219,7 +225,7 @@ node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* _
                         store_split_chunk_mn(ah + (uint32_t)blk * sub_bytes, ah + (uint32_t)(4 + blk) * sub_bytes,
                                              r0 + 16 * j, c, av[j][blk]);
                     if (blk < KB)
-                        store_split_chunk_mn(bh + (uint32_t)blk * sub_bytes, bh + (uint32_t)(KB + blk) * sub_bytes,
+                        store_split_chunk_mn(bh + (uint32_t)blk * sub_bytes, bh + (uint32_t)(NB + blk) * sub_bytes,
                                              r0 + 16 * j, c, bv[j][blk]);
                 }
             fence_async_smem();
@@ -228,17 +234,17 @@ node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* _
         }
         // final epilogue: warp == TMEM lane quadrant; rows n < n_out of every type's accumulator
         const int n = warp * 32 + lane;
-        float* out = ws_dw + (int64_t)blockIdx.x * n_types * n_out * n_in;
+        float* out = ws_dw + (int64_t)blockIdx.x * n_types * n_out * acc_cols;
         const bool any = blockIdx.x < n_tiles;
         if (any) {
             mbar_wait(smem_u32(&bar_done), 0);
             fence_after_sync();
         }
         for (int t = 0; t < n_types; ++t)
-            for (int c0 = 0; c0 < n_in; c0 += 16) {
+            for (int c0 = 0; c0 < acc_cols; c0 += 16) {
                 float acc[16];
                 if (any && ((started >> t) & 1u)) {      // block-uniform: untouched accumulators are undefined
-                    tmem_ld16(tmem_base + (uint32_t)(t * n_in + c0) + ((uint32_t)(warp * 32) << 16), acc);
+                    tmem_ld16(tmem_base + (uint32_t)(t * acc_cols + c0) + ((uint32_t)(warp * 32) << 16), acc);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[j] = 0.f;
@@ -246,12 +252,12 @@ node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* _
                 if (n < n_out) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        stg4(out + ((int64_t)t * n_out + n) * n_in + c0 + 4 * j,
+                        stg4(out + ((int64_t)t * n_out + n) * acc_cols + c0 + 4 * j,
                              make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
                 }
             }
     } else if (lane == 0) {
-        const uint32_t idesc = make_idesc_tf32_mn(n_in);
+        const uint32_t idesc = make_idesc_tf32_mn(acc_cols);
         uint32_t it = 0;
         uint32_t started = 0;                            // bit t set once type t's accumulator is live
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -263,14 +269,14 @@ node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* _
             fence_after_sync();
             const uint32_t ah = smem_base + (uint32_t)s * stage_bytes;
             const uint32_t bh = ah + a_bytes;
-            const uint32_t tmem_d = tmem_base + (uint32_t)(tt * n_in);
+            const uint32_t tmem_d = tmem_base + (uint32_t)(tt * acc_cols);
 #pragma unroll
             for (int ks = 0; ks < kNwTe / 8; ++ks) {
                 const uint32_t koff = (uint32_t)ks * 1024u;
                 mma_3xtf32(tmem_d, make_mnmajor_sw128_desc(ah + koff, sub_bytes),
                            make_mnmajor_sw128_desc(ah + 4 * sub_bytes + koff, sub_bytes),
                            make_mnmajor_sw128_desc(bh + koff, sub_bytes),
-                           make_mnmajor_sw128_desc(bh + (uint32_t)KB * sub_bytes + koff, sub_bytes), idesc,
+                           make_mnmajor_sw128_desc(bh + (uint32_t)NB * sub_bytes + koff, sub_bytes), idesc,
                            ((started >> tt) & 1u) ? 1u : (ks > 0 ? 1u : 0u));
             }
             started |= 1u << tt;
@@ -283,44 +289,31 @@ node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* _
     if (is_mma_warp) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// column sums of dy per node type (bias gradient), two-pass deterministic
-__global__ void __launch_bounds__(256)
-typed_colsum_kernel(const float* __restrict__ dy, int64_t dy_ld, int64_t lo, int64_t hi, int n_out,
-                    float* __restrict__ ws_db) {
-    // block b sums rows lo + b, lo + b + gridDim.x, ... ; thread = column
-    const int c = threadIdx.x;
-    float s = 0.f;
-    if (c < n_out)
-        for (int64_t r = lo + blockIdx.x; r < hi; r += gridDim.x) s += __ldg(dy + r * dy_ld + c);
-    if (c < n_out) ws_db[(int64_t)blockIdx.x * n_out + c] = s;
-}
-__global__ void __launch_bounds__(256)
-colsum_reduce_kernel(const float* __restrict__ ws_db, int G, int n_out, float* __restrict__ db) {
-    const int c = threadIdx.x;
-    if (c >= n_out) return;
-    float s = 0.f;
-    for (int g = 0; g < G; ++g) s += ws_db[(int64_t)g * n_out + c];
-    db[c] = s;
-}
-
 bool node_wgrad_tc_eligible(int n_types, int n_out, int n_in) {
     static const bool disabled = getenv("IHG_DISABLE_TC") != nullptr;
     if (disabled) return false;
-    return n_out % 32 == 0 && n_in % 32 == 0 && n_out <= 128 && n_in <= 128 && n_types * n_in <= 512;
+    return n_out % 32 == 0 && n_in % 32 == 0 && n_out <= 128 && n_in <= 128 && n_types * (n_in + 16) <= 512;
 }
 constexpr int kNwCtas = 2 * kNumSMs;
-constexpr int kColsumBlocks = 256;
 
 int64_t node_wgrad_tc_workspace_bytes(int n_types, int n_out, int n_in) {
-    return (int64_t)kNwCtas * n_types * n_out * n_in * 4 + (int64_t)kColsumBlocks * n_types * n_out * 4 + 1024;
+    return (int64_t)kNwCtas * n_types * n_out * (n_in + 16) * 4 + 1024;
 }
 
+// dw[t][n][k] = sum_g ws[g][t][n][k],  db[t][n] = sum_g ws[g][t][n][n_in]   (ascending g)
 __global__ void __launch_bounds__(256)
-wgrad_partials_sum_kernel(const float* __restrict__ ws, int G, int64_t n, float* __restrict__ dst) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+wgrad_partials_sum_kernel(const float* __restrict__ ws, int G, int n_types, int n_out, int n_in,
+                          float* __restrict__ dw, float* __restrict__ db) {
+    const int acc_cols = n_in + 16;
+    const int64_t rows = (int64_t)n_types * n_out;
+    const int64_t total = rows * (n_in + 1);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / (n_in + 1);
+        const int k = (int)(i % (n_in + 1));
         float s = 0.f;
-        for (int g = 0; g < G; ++g) s += ws[(int64_t)g * n + i];
-        dst[i] = s;
+        for (int g = 0; g < G; ++g) s += ws[((int64_t)g * rows + r) * acc_cols + k];
+        if (k < n_in) dw[r * n_in + k] = s;
+        else if (db) db[r] = s;
     }
 }
 
@@ -328,9 +321,8 @@ int launch_node_wgrad_tc(const float* dy, int64_t dy_ld, const float* x, int64_t
                          int64_t b0, int64_t b1, int n_types, int n_out, int n_in, float* dw, float* db,
                          void* workspace, cudaStream_t st) {
     float* ws_dw = static_cast<float*>(workspace);
-    float* ws_db = ws_dw + (int64_t)kNwCtas * n_types * n_out * n_in;
     const int KB = n_in / kChunkK;
-    const int smem = 2 * (8 + 2 * KB) * kNwTe * kChunkBytesPerRow + 1024;
+    const int smem = 2 * (8 + 2 * (KB + 1)) * kNwTe * kChunkBytesPerRow + 1024;
     static int attr_smem = 0;
     if (attr_smem < smem) {
         IHG_CUDA(cudaFuncSetAttribute(node_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -342,18 +334,9 @@ int launch_node_wgrad_tc(const float* dy, int64_t dy_ld, const float* x, int64_t
     const int grid = (int)(n_tiles < kNwCtas ? n_tiles : kNwCtas);
     node_wgrad_tc_kernel<<<grid, kNwThreads, smem, st>>>(dy, dy_ld, x, x_ld, b0, b1, n_rows, n_types, n_out, n_in, ws_dw);
     IHG_LAUNCH_CHECK();
-    const int64_t nw = (int64_t)n_types * n_out * n_in;
-    wgrad_partials_sum_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(ws_dw, grid, nw, dw);
+    const int64_t total = (int64_t)n_types * n_out * (n_in + 1);
+    wgrad_partials_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws_dw, grid, n_types, n_out, n_in, dw, db);
     IHG_LAUNCH_CHECK();
-    if (db) {
-        for (int t = 0; t < n_types; ++t) {
-            const int64_t l = n_types > 1 ? lo[t] : 0, h = n_types > 1 ? hi[t] : n_rows;
-            typed_colsum_kernel<<<kColsumBlocks, 256, 0, st>>>(dy, dy_ld, l, h, n_out, ws_db + (int64_t)t * kColsumBlocks * n_out);
-            IHG_LAUNCH_CHECK();
-            colsum_reduce_kernel<<<1, 256, 0, st>>>(ws_db + (int64_t)t * kColsumBlocks * n_out, kColsumBlocks, n_out, db + (int64_t)t * n_out);
-            IHG_LAUNCH_CHECK();
-        }
-    }
     return IHG_OK;
 }
 
