@@ -1,0 +1,315 @@
+"""Multi-GPU hypergraph convolution: hyperedge partition + row-sharded node tables (SURVEY.md
+section 8e; the reference itself is single-device).
+
+Partition (host side, numpy -- `PartitionPlan`):
+  * nodes are row-sharded in contiguous equal ranges *within each node type*, so every rank owns
+    U/G users, Q/G queries and I/G items and the slot -> node-type hoisting stays valid;
+  * a hyperedge lives on the rank that owns its user, so the user row is always local and at
+    most two of the three gathers are remote;
+  * remote query / item rows referenced by local hyperedges form the rank's halo; local node
+    numbering is [own users | own queries, halo queries | own items, halo items].
+The graph is static across steps (Dataset.py:91-96 caches it), so send / receive row lists are
+planned once.
+
+Per layer and direction there are two exchange steps, adjoint to each other:
+  halo_exchange   owners send the boundary rows other ranks reference      (all-to-all)
+  halo_reduce     ranks send their partial sums of halo rows back; the owner adds its own
+                  partial and the received ones in ascending source rank order and applies Dv^-1
+                  (all-to-all + one deterministic segmented reduction = reduce-scatter)
+Pack / unpack are the library's row-gather kernels; the ordered sum is ihg_segment_reduce over a
+small CSR built at plan time.  Dense weight gradients are all-reduced.
+
+CUDA only (NCCL).  The planner is pure numpy and is exercised on CPU by tests/test_dist_gloo.py.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+
+def _splits(n: int, world: int) -> np.ndarray:
+    return np.array([(n * r) // world for r in range(world + 1)], dtype=np.int64)
+
+
+class PartitionPlan:
+    """Index plan of one rank.  All arrays are numpy int64 unless noted.
+
+    Node id spaces:
+      global   u, U+q, U+Q+i                                   (Helpers/Graph.py:110-111)
+      own      [own users | own queries | own items]           rows this rank owns (n_own)
+      local    [own users | own queries, halo queries | own items, halo items]   (n_local)
+    """
+
+    def __init__(self, user, query, item, user_count: int, query_count: int, item_count: int,
+                 world: int, rank: int):
+        user = np.asarray(user, dtype=np.int64)
+        query = np.asarray(query, dtype=np.int64)
+        item = np.asarray(item, dtype=np.int64)
+        self.world, self.rank = world, rank
+        self.U, self.Q, self.I = user_count, query_count, item_count
+        self.ub, self.qb, self.ib = _splits(user_count, world), _splits(query_count, world), _splits(item_count, world)
+        r = rank
+        self.Uo = int(self.ub[r + 1] - self.ub[r])
+        self.Qo = int(self.qb[r + 1] - self.qb[r])
+        self.Io = int(self.ib[r + 1] - self.ib[r])
+        self.n_own = self.Uo + self.Qo + self.Io
+        self.own_bounds = (self.Uo, self.Uo + self.Qo)
+
+        edge_owner = np.searchsorted(self.ub, user, side="right") - 1
+        self.edge_ids = np.nonzero(edge_owner == r)[0]            # ascending global hyperedge ids
+        eu, eq, ei = user[self.edge_ids], query[self.edge_ids], item[self.edge_ids]
+        self.edge_count = int(self.edge_ids.shape[0])
+
+        # halo = remote queries / items referenced by local hyperedges, sorted by (owner, id)
+        q_need = np.unique(eq[(eq < self.qb[r]) | (eq >= self.qb[r + 1])])
+        i_need = np.unique(ei[(ei < self.ib[r]) | (ei >= self.ib[r + 1])])
+        self.Qh, self.Ih = int(q_need.shape[0]), int(i_need.shape[0])
+        self.n_local = self.n_own + self.Qh + self.Ih
+        self.local_bounds = (self.Uo, self.Uo + self.Qo + self.Qh)
+        q_owner = np.searchsorted(self.qb, q_need, side="right") - 1
+        i_owner = np.searchsorted(self.ib, i_need, side="right") - 1
+
+        # ---- local ids of the hyperedges' nodes
+        lu = eu - self.ub[r]
+        q_own = (eq >= self.qb[r]) & (eq < self.qb[r + 1])
+        lq = np.where(q_own, self.Uo + (eq - self.qb[r]), self.Uo + self.Qo + np.searchsorted(q_need, eq))
+        i_own = (ei >= self.ib[r]) & (ei < self.ib[r + 1])
+        i_base = self.Uo + self.Qo + self.Qh
+        li = np.where(i_own, i_base + (ei - self.ib[r]), i_base + self.Io + np.searchsorted(i_need, ei))
+        self.i3_local = np.stack([lu, lq, li], axis=1) if self.edge_count else np.zeros((0, 3), np.int64)
+
+        # ---- what I receive: per source rank s, [queries from s | items from s], ids ascending
+        recv_local_rows: List[np.ndarray] = []       # local row index of every received row
+        self.recv_counts = np.zeros(world, dtype=np.int64)
+        for s in range(world):
+            qs = np.nonzero(q_owner == s)[0]
+            is_ = np.nonzero(i_owner == s)[0]
+            recv_local_rows.append(np.concatenate([self.Uo + self.Qo + qs, i_base + self.Io + is_]))
+            self.recv_counts[s] = qs.shape[0] + is_.shape[0]
+        self.recv_rows = np.concatenate(recv_local_rows) if world else np.zeros(0, np.int64)
+        self.R = int(self.recv_counts.sum())
+        assert self.R == self.Qh + self.Ih
+
+        # ---- what I send: rank d's request list for rows I own (same rule, evaluated for d)
+        send_rows: List[np.ndarray] = []             # own-layout row index of every sent row
+        self.send_counts = np.zeros(world, dtype=np.int64)
+        for d in range(world):
+            if d == r:
+                send_rows.append(np.zeros(0, np.int64))
+                continue
+            dm = edge_owner == d
+            dq = np.unique(query[dm])
+            dq = dq[(dq >= self.qb[r]) & (dq < self.qb[r + 1])]
+            di = np.unique(item[dm])
+            di = di[(di >= self.ib[r]) & (di < self.ib[r + 1])]
+            send_rows.append(np.concatenate([self.Uo + (dq - self.qb[r]), self.Uo + self.Qo + (di - self.ib[r])]))
+            self.send_counts[d] = dq.shape[0] + di.shape[0]
+        self.send_rows = np.concatenate(send_rows)
+        self.S = int(self.send_counts.sum())
+
+        # ---- own layout -> local layout
+        self.own_to_local = np.concatenate([
+            np.arange(self.Uo), self.Uo + np.arange(self.Qo), i_base + np.arange(self.Io)]).astype(np.int64)
+        # unpack permutation of halo_exchange: local row <- concat([own rows (n_own); received rows (R)])
+        self.unpack_perm = np.empty(self.n_local, dtype=np.int64)
+        self.unpack_perm[self.own_to_local] = np.arange(self.n_own)
+        self.unpack_perm[self.recv_rows] = self.n_own + np.arange(self.R)
+
+        # ---- ordered sum of halo_reduce: own row v <- [its own partial (local row), then the rows
+        # received for it in ascending source rank]; entries index concat([s_local (n_local); recv (S)])
+        keys = np.concatenate([np.arange(self.n_own), self.send_rows])
+        vals = np.concatenate([self.own_to_local, self.n_local + np.arange(self.S)])
+        order = np.argsort(keys, kind="stable")
+        self.reduce_col = vals[order]
+        counts = np.bincount(keys, minlength=self.n_own)
+        self.reduce_rowptr = np.zeros(self.n_own + 1, dtype=np.int64)
+        np.cumsum(counts, out=self.reduce_rowptr[1:])
+
+        # ---- global degrees of the rows I own (Graph.py:112,120 on the whole hypergraph)
+        deg = np.concatenate([
+            np.bincount(user, minlength=user_count)[self.ub[r]:self.ub[r + 1]],
+            np.bincount(query, minlength=query_count)[self.qb[r]:self.qb[r + 1]],
+            np.bincount(item, minlength=item_count)[self.ib[r]:self.ib[r + 1]]]).astype(np.float32)
+        deg[deg == 0] = np.float32(1e-8)
+        self.vertex_degrees_own = deg
+        self.dv_inv_own = (np.float32(1.0) / deg).astype(np.float32)
+
+    def own_global_ids(self) -> np.ndarray:
+        """Global node ids of the own rows, in own-layout order."""
+        r = self.rank
+        return np.concatenate([np.arange(self.ub[r], self.ub[r + 1]),
+                               self.U + np.arange(self.qb[r], self.qb[r + 1]),
+                               self.U + self.Q + np.arange(self.ib[r], self.ib[r + 1])])
+
+
+# ----------------------------------------------------------------------------------------
+# device side (CUDA + NCCL)
+# ----------------------------------------------------------------------------------------
+class ShardedHyperGraph:
+    """The device-resident local piece of a partitioned hypergraph plus its exchange plan."""
+
+    def __init__(self, plan: PartitionPlan, device, group=None):
+        from . import _lib
+        from .graph import CsrPlan, csr_from_keys
+        self.plan, self.group = plan, group
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("ihgnn_b200.dist runs on CUDA (NCCL) only; the planner (PartitionPlan) is the host part")
+        self.device = dev
+        t = lambda a, dt=torch.int64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+        self.EdgeCount = plan.edge_count
+        self.node_count = plan.n_local
+        self.i3 = t(plan.i3_local, torch.int32).contiguous()
+        edge_of = torch.arange(plan.edge_count, device=dev, dtype=torch.int32).repeat_interleave(3)
+        rowptr, _perm, col = csr_from_keys(self.i3.reshape(-1), plan.n_local, values=edge_of)
+        self.rowptr, self.col = rowptr, col
+        self.plan_csr = CsrPlan(rowptr, col)
+        self.type_bounds = plan.local_bounds           # slot(row) for the per-slot gradient reduce
+        self.own_bounds = plan.own_bounds              # node types of the own rows (typed Linear)
+        self.dv_inv_own = t(plan.dv_inv_own, torch.float32)
+        self.send_rows = t(plan.send_rows)
+        self.unpack_perm = t(plan.unpack_perm)
+        self.recv_rows = t(plan.recv_rows)
+        self.send_counts = [int(x) for x in plan.send_counts]
+        self.recv_counts = [int(x) for x in plan.recv_counts]
+        self.reduce_csr = CsrPlan(t(plan.reduce_rowptr, torch.int32), t(plan.reduce_col, torch.int32))
+        self.n_own, self.n_local, self.S, self.R = plan.n_own, plan.n_local, plan.S, plan.R
+        # Dv^-1 of every local row (own + halo): exchanged once, the graph is static
+        self.dv_inv_local = HaloExchangeFn.apply(self.dv_inv_own.view(-1, 1).expand(-1, 4).contiguous(), self)[:, 0].contiguous()
+
+    # compatibility with the single-GPU graph object the kernels' wrappers expect
+    @property
+    def plan_(self):
+        return self.plan_csr
+
+
+def _all_to_all(out: torch.Tensor, inp: torch.Tensor, out_counts, in_counts, group) -> None:
+    import torch.distributed as dist
+    dist.all_to_all_single(out, inp, output_split_sizes=out_counts, input_split_sizes=in_counts, group=group)
+
+
+class HaloExchangeFn(torch.autograd.Function):
+    """x_own [n_own, d] -> x_local [n_local, d]: pack the rows other ranks reference, all-to-all,
+    unpack into the local layout.  Backward = halo_reduce without scaling."""
+
+    @staticmethod
+    def forward(ctx, x_own, g: ShardedHyperGraph):
+        from . import functional as F_
+        ctx.g = g
+        d = int(x_own.shape[1])
+        send = F_.gather_rows_raw(x_own, g.send_rows, 0)
+        buf = torch.empty((g.n_own + g.R, d), dtype=torch.float32, device=x_own.device)
+        _all_to_all(buf[g.n_own:], send, g.recv_counts, g.send_counts, g.group)
+        F_.copy_rows_raw(x_own, buf[:g.n_own])
+        return F_.gather_rows_raw(buf, g.unpack_perm, 0)
+
+    @staticmethod
+    def backward(ctx, dx_local):
+        return _halo_reduce(dx_local.contiguous(), ctx.g, None), None
+
+
+class ShardedScatterMeanFn(torch.autograd.Function):
+    """ef [E_local, d] -> Dv^-1 * (sum over ALL hyperedges containing the row) for the own rows:
+    local segmented sum over own + halo rows, then halo_reduce.  Backward: halo_exchange of the
+    gradient, then the node -> hyperedge gather-sum with the (exchanged-once) Dv^-1 of the local rows."""
+
+    @staticmethod
+    def forward(ctx, ef, g: "ShardedHyperGraph"):
+        from . import _lib
+        from . import functional as F_
+        ctx.g = g
+        ef = _lib.rows_f32(ef)
+        s_local = F_.segment_reduce(g.plan_csr, ef, int(ef.shape[1]))
+        return _halo_reduce(s_local, g, g.dv_inv_own)
+
+    @staticmethod
+    def backward(ctx, dout_own):
+        from . import functional as F_
+        g = ctx.g
+        g_local = HaloExchangeFn.apply(dout_own.contiguous(), g)
+        return F_.edge_gather_sum(g_local, g.i3, node_scale=g.dv_inv_local), None
+
+
+def _halo_reduce(s_local: torch.Tensor, g: ShardedHyperGraph, row_scale: Optional[torch.Tensor]) -> torch.Tensor:
+    from . import functional as F_
+    d = int(s_local.shape[1])
+    send = F_.gather_rows_raw(s_local, g.recv_rows, 0)            # my partial sums of halo rows
+    buf = torch.empty((g.n_local + g.S, d), dtype=torch.float32, device=s_local.device)
+    _all_to_all(buf[g.n_local:], send, g.send_counts, g.recv_counts, g.group)
+    F_.copy_rows_raw(s_local, buf[:g.n_local])
+    return F_.segment_reduce(g.reduce_csr, buf, d, row_scale=row_scale)
+
+
+def halo_exchange(x_own, g):
+    return HaloExchangeFn.apply(x_own, g)
+
+
+class _LocalGraphView:
+    """What the edge / segment kernels' autograd Functions read from a graph object."""
+
+    def __init__(self, g: ShardedHyperGraph):
+        self.i3, self.plan, self.EdgeCount = g.i3, g.plan_csr, g.EdgeCount
+        self.type_bounds = g.type_bounds
+        self.dv_inv = None
+
+
+class ShardedIHGNNLayer(torch.nn.Module):
+    """IHGNNLayer (Models/GnnLayers.py:156-236) over a partitioned hypergraph.  Holds the same
+    parameters (`feature_interactor.aggregation`, `feature_transform`) as the single-GPU layer;
+    input / output are the rank's own rows [n_own, d].  Dense weight gradients must be
+    all-reduced by the caller (`allreduce_dense_grads`)."""
+
+    def __init__(self, graph: ShardedHyperGraph, dim: int, feature_interaction_order: int):
+        super().__init__()
+        from .layers import FeatureInteractor
+
+        class _DS:           # the attribute FeatureInteractor reads
+            pass
+        ds = _DS()
+        ds.graph = _LocalGraphView(graph)
+        ds.graph.type_bounds = graph.own_bounds        # FeatureInteractor's typed Linear runs on own rows
+        self.g = graph
+        self.view = _LocalGraphView(graph)
+        self.order = feature_interaction_order
+        self.feature_interactor = FeatureInteractor(ds, feature_interaction_order, dim, dim)
+        self.feature_transform = torch.nn.Linear(dim, dim)
+
+    def forward(self, x_own: torch.Tensor) -> torch.Tensor:
+        from . import functional as F_
+        from .layers import _EdgeGatherSumFn, _EdgeInteractFn, _split_first_order
+        g, fi = self.g, self.feature_interactor
+        wt, bt = self.feature_transform.weight, self.feature_transform.bias
+        d = fi.node_feature_dimension
+        w_lo = _split_first_order(fi.aggregation.weight, d)
+        zeros = torch.zeros_like(bt)
+        if self.order == 1:
+            w_f = torch.matmul(w_lo, wt)
+            b_f = torch.matmul(w_lo, bt) + torch.stack([fi.aggregation.bias, zeros, zeros])
+            p_own = F_.typed_linear(x_own, w_f, b_f, g.own_bounds)
+            p = halo_exchange(p_own, g)
+            ef = _EdgeGatherSumFn.apply(p, self.view, None, 1.0, None)
+        else:
+            xp_own = F_.typed_linear(x_own, wt.unsqueeze(0), bt.unsqueeze(0), None)
+            b_lo = torch.stack([fi.aggregation.bias, zeros, zeros])
+            p_own = F_.typed_linear(xp_own, w_lo, b_lo, g.own_bounds)
+            both = halo_exchange(torch.cat([xp_own, p_own], 1), g)     # one exchange for both row sets
+            xp, p = both[:, :d], both[:, d:]
+            ef = _EdgeInteractFn.apply(xp, p, fi.aggregation.weight[:, 3 * d:], self.view, self.order)
+        return ShardedScatterMeanFn.apply(ef, g)
+
+
+def allreduce_dense_grads(module: torch.nn.Module, group=None) -> None:
+    """Sum the (small, dense) weight gradients over ranks: every rank saw only its hyperedges."""
+    import torch.distributed as dist
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n

@@ -111,6 +111,28 @@ def node_linear_wgrad(dy: torch.Tensor, x: torch.Tensor, n_types: int,
     return dw, db
 
 
+def gather_rows_raw(table: torch.Tensor, idx: torch.Tensor, offset: int = 0) -> torch.Tensor:
+    """out[b] = table[idx[b] + offset] (no autograd); idx int64 on the device."""
+    _lib.require_cuda(table, idx)
+    table = _lib.rows_f32(table)
+    B, d = int(idx.numel()), int(table.shape[1])
+    out = _empty((B, d), table)
+    if B:
+        _lib.call("ihg_gather_rows", _lib.ptr(table), _lib.ld(table), _lib.ptr(idx), offset, B,
+                  _lib.ptr(out), d, d, _lib.stream_ptr(), tag="gather_rows", algo_bytes=B * (8 + 8 * d))
+    return out
+
+
+def copy_rows_raw(src: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst[r] = src[r] for 2-D row-major tensors with equal shapes (128-bit vectorised)."""
+    _lib.require_cuda(src, dst)
+    src = _lib.rows_f32(src)
+    n, d = int(src.shape[0]), int(src.shape[1])
+    if n:
+        _lib.call("ihg_copy_rows", _lib.ptr(src), _lib.ld(src), _lib.ptr(dst), _lib.ld(dst), n, d,
+                  _lib.stream_ptr(), tag="copy_rows", algo_bytes=n * 8 * d)
+
+
 # --------------------------------------------------------------------------------------
 # autograd Functions
 # --------------------------------------------------------------------------------------
