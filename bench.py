@@ -207,15 +207,38 @@ def run_gpu_arm(args, log, layers, d):
 
     # --- build: graph indices on the device, model with the reference's own initialisers
     t_build0 = time.perf_counter()
-    ds = GraphDataset.from_search_log(log, dev)
-    graph = ds.hypergraph
+    torch.manual_seed(0)
+    B, NEG = 100, 10                                                      # GlobalSettings.py:26,39
+    if world == 1:
+        ds = GraphDataset.from_search_log(log, dev)
+        graph = ds.hypergraph
+        model = RawGnn(device=dev, dataset=ds, embedding_size=d, gnn_layer_type=IHGNNLayer,
+                       gnn_layer_count=layers, feature_interaction_order=3, phase2_attention=False,
+                       predictions=HemPredictionLayer, lambda_muq=0.5).to(dev)
+        E, N = graph.EdgeCount, graph.node_count
+        x = model.embeddings.embed_all().detach().clone().requires_grad_(True)
+        conv_layers = list(model.gnns)
+        sync_conv = lambda: None
+        sync_all = lambda: None
+        parallelism = "single"
+    else:
+        # weak scaling: the global log is `world` x the workload; hyperedges live with their user's
+        # owner, node rows are sharded per type, boundary rows travel by all-to-all (ihgnn_b200/dist.py)
+        from ihgnn_b200.dist import PartitionPlan, ShardedHyperGraph, ShardedRawGnn, allreduce_dense_grads
+        plan = PartitionPlan(log.pos_user, log.pos_query, log.pos_item, log.user_count, log.query_count,
+                             log.item_count, world, rank)
+        sg = ShardedHyperGraph(plan, dev)
+        words, offsets = log.bag_inputs()
+        model = ShardedRawGnn(sg, words, offsets, log.vocab_size, d, layers, 3).to(dev)
+        E, N = log.edge_count, log.node_count                             # global counts
+        x = model.input_features().detach().clone().requires_grad_(True)
+        conv_layers = list(model.gnns)
+        sync_conv = lambda: [allreduce_dense_grads(g) for g in conv_layers]
+        sync_all = model.sync_grads
+        parallelism = (f"hyperedges partitioned by user owner x{world}, node rows sharded per type, "
+                       f"halo all-to-all (rank0: {plan.n_own} own + {plan.R} halo rows, {plan.edge_count} hyperedges)")
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build0
-    torch.manual_seed(0)
-    model = RawGnn(device=dev, dataset=ds, embedding_size=d, gnn_layer_type=IHGNNLayer,
-                   gnn_layer_count=layers, feature_interaction_order=3, phase2_attention=False,
-                   predictions=HemPredictionLayer, lambda_muq=0.5).to(dev)
-    E, N = graph.EdgeCount, graph.node_count
 
     def barrier():
         if dist is not None:
@@ -223,14 +246,17 @@ def run_gpu_arm(args, log, layers, d):
         torch.cuda.synchronize()
 
     # --- M1: conv stack fwd+bwd, inputs resident in HBM -------------------------------
-    x = model.embeddings.embed_all().detach().clone().requires_grad_(True)
-
     def conv_step():
         x.grad = None
         for p in model.parameters():
             p.grad = None
-        outs = model.conv_stack(x)
+        outs = [x]
+        h = x
+        for gnn in conv_layers:
+            h = gnn(h)
+            outs.append(h)
         torch.cat(outs, 1).sum().backward()
+        sync_conv()
 
     for _ in range(args.warmup):
         conv_step()
@@ -254,12 +280,11 @@ def run_gpu_arm(args, log, layers, d):
 
     # --- e2e: a full training step through the public API, host batch in, loss out -----
     opt = torch.optim.Adam(model.parameters(), 1e-3)                      # Main.py:192
-    rng = np.random.default_rng(123)
-    B, NEG = 100, 10                                                      # GlobalSettings.py:26,39
+    rng = np.random.default_rng(123)                                     # same batches on every rank
     n_batches = 8
     host_batches = []
     for _ in range(n_batches):
-        pick = rng.integers(0, E, size=B)
+        pick = rng.integers(0, log.edge_count, size=B)
         pu, pq, pi = log.pos_user[pick], log.pos_query[pick], log.pos_item[pick]
         users = np.concatenate([pu, np.repeat(pu, NEG)])
         queries = np.concatenate([pq, np.repeat(pq, NEG)])
@@ -275,6 +300,7 @@ def run_gpu_arm(args, log, layers, d):
         loss = torch.nn.functional.binary_cross_entropy_with_logits(scores, flags)
         opt.zero_grad(set_to_none=True)
         loss.backward()
+        sync_all()
         opt.step()
         loss_host.copy_(loss.detach().view(1), non_blocking=False)        # loss.item() of the reference
         return loss_host
@@ -296,7 +322,7 @@ def run_gpu_arm(args, log, layers, d):
         tt = torch.tensor([t_conv, t_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_conv, t_e2e = float(tt[0]), float(tt[1])
-    total_units = E * layers * world          # replicas: every rank convolves its own copy of the workload
+    total_units = E * layers                  # E is the GLOBAL hyperedge count (world x the workload at N > 1)
     value = total_units / t_conv
     e2e_value = total_units / t_e2e
 
@@ -308,7 +334,7 @@ def run_gpu_arm(args, log, layers, d):
     peak, peak_src = measured_peaks()
     dom_tag = max(kern, key=lambda k: kern[k]["ms"])
     dom = kern[dom_tag]
-    conv_bytes = layers * conv_algorithmic_bytes(E, N, d)
+    conv_bytes = layers * conv_algorithmic_bytes(E, N, d)       # global E, N: aggregate over all ranks
     roofline = {
         "bound": "hbm", "kernel": dom_tag, "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
         "frac": dom["gbs"] / peak, "traffic": None, "peak_source": peak_src,
@@ -316,7 +342,8 @@ def run_gpu_arm(args, log, layers, d):
         "algorithmic_bytes_per_launch": dom["bytes"] / dom["calls"],
         # whole conv step against SURVEY 8(d)'s E(60+76d)+N(28d+12) bytes per layer
         "conv_step": {"algorithmic_bytes": conv_bytes, "achieved": conv_bytes / t_conv / 1e9,
-                      "frac": conv_bytes / t_conv / 1e9 / peak},
+                      "frac": conv_bytes / t_conv / 1e9 / (peak * world),
+                      "note": "aggregate over all ranks against n_gpus x the measured single-GPU peak"},
     }
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -329,14 +356,14 @@ def run_gpu_arm(args, log, layers, d):
         "warmup": args.warmup, "ms_per_step": t_conv * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "layers": layers, "dim": d, "hyperedges": E, "nodes": N,
-                   "interaction_order": 3, "parallelism": f"replicas x{world}" if world > 1 else "single",
+                   "interaction_order": 3, "parallelism": parallelism,
                    "l2_policy": "inputs larger than L2 (no flush): per step the kernels stream "
                                 f"{conv_bytes / 1e9:.1f} GB algorithmic vs 126 MB L2",
                    "graph_build_s": t_build},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
-                "train_samples_per_s": B * (1 + NEG) * world / t_e2e,
+                "train_samples_per_s": B * (1 + NEG) / t_e2e,
                 "what": "RawGnn.forward(batch) -> BCEWithLogits -> backward -> Adam.step, batch indices "
                         "from pinned host memory, loss copied back every step"},
         "gpu_launches": int(launches),
@@ -365,7 +392,8 @@ def main():
 
     w = synth.WORKLOADS[args.workload]
     layers, d = w["layers"], w["dim"]
-    log = synth.make_workload(args.workload, scale=args.scale)
+    world = int(os.environ.get("WORLD_SIZE", "1")) if args.impl == "ours" else 1
+    log = synth.make_workload(args.workload, scale=args.scale * world)   # weak scaling: world x the workload
     if args.impl == "reference":
         run_reference_arm(args, log, layers, d)
     else:

@@ -313,3 +313,136 @@ def allreduce_dense_grads(module: torch.nn.Module, group=None) -> None:
         n = g.numel()
         g.copy_(flat[off:off + n].view_as(g))
         off += n
+
+
+# ----------------------------------------------------------------------------------------
+# sharded model: row-sharded embedding tables + sharded conv stack + replicated scorer
+# ----------------------------------------------------------------------------------------
+class _FetchRowsFn(torch.autograd.Function):
+    """Rows of a row-sharded matrix by GLOBAL id, available on every rank:
+    out[j] = F[global_ids[j]].  Each rank fills the rows it owns into a zero buffer, one
+    all-reduce(sum) completes it (the batch head needs only B x 3 rows, SURVEY 8e "tiny").
+    Backward: every rank already holds the full gradient; it scatter-adds the rows it owns
+    (duplicates summed in ascending j: deterministic)."""
+
+    @staticmethod
+    def forward(ctx, f_own, local_rows, positions, total: int, group):
+        import torch.distributed as dist
+        from . import functional as F_
+        from . import _lib
+        d = int(f_own.shape[1])
+        out = torch.zeros((total, d), dtype=torch.float32, device=f_own.device)
+        if positions.numel():
+            mine = F_.gather_rows_raw(f_own, local_rows, 0)
+            _lib.call("ihg_scatter_add_rows", _lib.ptr(mine), d, _lib.ptr(positions), 0, int(positions.numel()),
+                      _lib.ptr(out), d, d, _lib.stream_ptr())
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+        ctx.save_for_backward(local_rows, positions)
+        ctx.shape = tuple(f_own.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import functional as F_
+        from . import _lib
+        local_rows, positions = ctx.saved_tensors
+        d = int(dout.shape[1])
+        df = torch.zeros(ctx.shape, dtype=torch.float32, device=dout.device)
+        if positions.numel():
+            mine = F_.gather_rows_raw(dout.contiguous(), positions, 0)
+            _lib.call("ihg_scatter_add_rows", _lib.ptr(mine), d, _lib.ptr(local_rows), 0, int(local_rows.numel()),
+                      _lib.ptr(df), d, d, _lib.stream_ptr())
+        return df, None, None, None, None
+
+
+class ShardedRawGnn(torch.nn.Module):
+    """RawGnn (Models/RawGnn.py:14-144) over a partitioned hypergraph: user / item embedding rows
+    are sharded like the nodes, the vocabulary table, conv weights and item biases are replicated
+    (their gradients are all-reduced by `sync_grads`).  `forward` takes the GLOBAL batch indices
+    (identical on every rank) and returns the scores of the whole batch on every rank."""
+
+    def __init__(self, graph: ShardedHyperGraph, bag_words: np.ndarray, bag_offsets: np.ndarray,
+                 vocab_size: int, embedding_size: int, layer_count: int, feature_interaction_order: int,
+                 lambda_muq: float = 0.5):
+        super().__init__()
+        from .graph import CsrPlan, csr_from_keys
+        from .layers import HemPredictionLayer
+        p, dev = graph.plan, graph.device
+        self.g, self.lambda_muq = graph, lambda_muq
+        d = embedding_size
+        self.embedding_user = torch.nn.Parameter(torch.empty(p.Uo, d))
+        self.embedding_item = torch.nn.Parameter(torch.empty(p.Io, d))
+        self.embedding_bag_vocabulary = torch.nn.Parameter(torch.empty(vocab_size + 1, d))
+        for w, rows in ((self.embedding_user, p.U + 1), (self.embedding_item, p.I + 1), (self.embedding_bag_vocabulary, vocab_size + 1)):
+            bound = (6.0 / (rows + d)) ** 0.5               # xavier_uniform_ of the full table (fan_out = rows)
+            torch.nn.init.uniform_(w, -bound, bound)
+        self.gnns = torch.nn.ModuleList()
+        for k in range(layer_count):
+            order = feature_interaction_order if (k == 0 or feature_interaction_order == 1) else 1
+            self.gnns.append(ShardedIHGNNLayer(graph, d, order))
+        self.prediction_layer = HemPredictionLayer(d * (1 + layer_count), lambda_muq, p.I)
+        # bag CSR of the own queries (+ its transpose) for EmbeddingBag(mean)
+        words = np.asarray(bag_words, dtype=np.int64)
+        ptr = np.concatenate([np.asarray(bag_offsets, dtype=np.int64), [words.shape[0]]])
+        q0, q1 = int(p.qb[p.rank]), int(p.qb[p.rank + 1])
+        own_words = torch.as_tensor(words[ptr[q0]:ptr[q1]], dtype=torch.int32, device=dev)
+        own_ptr = torch.as_tensor(ptr[q0:q1 + 1] - ptr[q0], dtype=torch.int32, device=dev)
+        lens = (own_ptr[1:] - own_ptr[:-1]).to(torch.float32)
+        self.bag_inv_len = torch.where(lens > 0, 1.0 / lens.clamp(min=1.0), torch.zeros_like(lens))
+        self.bag_plan = CsrPlan(own_ptr, own_words)
+        bag_of = torch.repeat_interleave(torch.arange(p.Qo, device=dev, dtype=torch.int32), (own_ptr[1:] - own_ptr[:-1]).to(torch.int64))
+        wptr, _perm, bags = csr_from_keys(own_words, vocab_size + 1, values=bag_of)
+        self.word_plan = CsrPlan(wptr, bags)
+
+    def input_features(self) -> torch.Tensor:
+        from .layers import _BagMeanFn
+
+        class _T:
+            pass
+        t = _T()
+        t.bag_plan, t.word_plan, t.bag_inv_len = self.bag_plan, self.word_plan, self.bag_inv_len
+        q = _BagMeanFn.apply(self.embedding_bag_vocabulary, t)
+        return torch.cat([self.embedding_user, q, self.embedding_item])
+
+    def output_features(self) -> torch.Tensor:
+        h = self.input_features()
+        outs = [h]
+        for gnn in self.gnns:
+            h = gnn(h)
+            outs.append(h)
+        return torch.cat(outs, 1)
+
+    def forward(self, users: torch.Tensor, queries: torch.Tensor, items: torch.Tensor) -> torch.Tensor:
+        p = self.g.plan
+        f_own = self.output_features()
+        B = int(users.numel())
+        r = p.rank
+        ids = torch.cat([users, queries, items])                       # per-type global ids, [3B]
+        cache = getattr(self, "_range_cache", None)
+        if cache is None or cache[0] != B:
+            mk = lambda a, b_, c: torch.tensor([a] * B + [b_] * B + [c] * B, device=ids.device)
+            cache = (B, mk(p.ub[r], p.qb[r], p.ib[r]), mk(p.ub[r + 1], p.qb[r + 1], p.ib[r + 1]),
+                     mk(0, p.Uo, p.Uo + p.Qo))
+            self._range_cache = cache
+        _, lo, hi, base = cache
+        mine = (ids >= lo) & (ids < hi)
+        positions = torch.nonzero(mine).view(-1)
+        local_rows = (ids - lo + base)[positions]
+        rows = _FetchRowsFn.apply(f_own, local_rows, positions, 3 * B, self.g.group)
+        return self.prediction_layer(rows[:B], rows[B:2 * B], rows[2 * B:], items)
+
+    def sync_grads(self) -> None:
+        """All-reduce the gradients of the replicated parameters whose per-rank gradients are
+        partial sums (conv weights, vocabulary table).  items_bias sees identical gradients on
+        every rank (the scores are computed redundantly), so it needs no reduction."""
+        import torch.distributed as dist
+        grads = [q.grad for q in list(self.gnns.parameters()) + [self.embedding_bag_vocabulary] if q.grad is not None]
+        if not grads:
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.g.group)
+        off = 0
+        for g in grads:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n
