@@ -26,7 +26,9 @@ constexpr int kSegPerGroup = 1;      // chunks a lane group walks through (strid
 template <int LPR, int VPL, int UNR, int SEGS>
 __global__ void __launch_bounds__(kSegWarpsPerBlock * 32)
 segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src_row_mul,
-                      int64_t bound0, int64_t bound1, const float* __restrict__ src_scale,
+                      int64_t bound0, int64_t bound1, const int32_t* __restrict__ row_slot,
+                      const float* __restrict__ init, int64_t init_ld,
+                      const float* __restrict__ src_scale,
                       const float* __restrict__ row_scale, const int32_t* __restrict__ col,
                       int64_t n_seg, int64_t n_groups, const int4* __restrict__ seg,
                       float* __restrict__ partial, float* __restrict__ out, int64_t out_ld, int dim) {
@@ -54,10 +56,14 @@ segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src
         int ncolv = (nlive && nxt.x + gl < nxt.y) ? __ldg(col + nxt.x + gl) : 0;
 
         const int begin = cur.x, end = live ? cur.y : cur.x, row = cur.z, part = cur.w;
-        const int slot = (row >= bound0) + (row >= bound1);
+        const int slot = row_slot ? (live ? __ldg(row_slot + row) : 0) : (row >= bound0) + (row >= bound1);
         float4 acc[VPL];
 #pragma unroll
-        for (int w = 0; w < VPL; ++w) acc[w] = f4_zero();
+        for (int w = 0; w < VPL; ++w) {
+            const int cv = gl + w * LPR;
+            // an optional initial row (e.g. the rank's own partial sum) opens the ordered sum
+            acc[w] = (init && live && part < 0 && cv < nvec) ? ldg4(init + (int64_t)row * init_ld + 4 * cv) : f4_zero();
+        }
         // longest chunk among the groups of this warp drives the (warp-uniform) trip count
         int len = end - begin;
 #pragma unroll
@@ -123,6 +129,7 @@ template <int LPR, int VPL>
 __global__ void __launch_bounds__(kSegWarpsPerBlock * 32)
 segment_fixup_kernel(const float* __restrict__ partial, const int32_t* __restrict__ split_row,
                      const int32_t* __restrict__ split_ptr, int64_t n_split,
+                     const float* __restrict__ init, int64_t init_ld,
                      const float* __restrict__ row_scale, float* __restrict__ out, int64_t out_ld,
                      int dim) {
     constexpr int G = 32 / LPR;
@@ -161,9 +168,9 @@ segment_fixup_kernel(const float* __restrict__ partial, const int32_t* __restric
 #pragma unroll
         for (int w = 0; w < VPL; ++w) {
             const int cv = gl + w * LPR;
-            float4 t = warp_sum[0][cv];
+            float4 t = (init && cv < nvec) ? ldg4(init + (int64_t)row * init_ld + 4 * cv) : f4_zero();
 #pragma unroll
-            for (int k = 1; k < kSegWarpsPerBlock; ++k) f4_add(t, warp_sum[k][cv]);
+            for (int k = 0; k < kSegWarpsPerBlock; ++k) f4_add(t, warp_sum[k][cv]);
             if (cv < nvec) stg4(out + (int64_t)row * out_ld + 4 * cv, f4_scale(rs, t));
         }
     }
@@ -171,7 +178,8 @@ segment_fixup_kernel(const float* __restrict__ partial, const int32_t* __restric
 
 template <int LPR, int VPL>
 static int launch_segment_reduce(const ihg_csr* g, const float* src, int64_t src_ld, int32_t mul,
-                                 int64_t b0, int64_t b1, const float* src_scale,
+                                 int64_t b0, int64_t b1, const int32_t* row_slot, const float* init,
+                                 int64_t init_ld, const float* src_scale,
                                  const float* row_scale, float* partial, float* out, int64_t out_ld,
                                  int dim, cudaStream_t st) {
     constexpr int G = 32 / LPR;
@@ -184,12 +192,12 @@ static int launch_segment_reduce(const ihg_csr* g, const float* src, int64_t src
     if (blocks < 1) blocks = 1;
     const int64_t n_groups = blocks * groups_per_block;
     segment_reduce_kernel<LPR, VPL, UNR, SEGS><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
-        src, src_ld, mul, b0, b1, src_scale, row_scale, g->col, g->n_seg, n_groups,
+        src, src_ld, mul, b0, b1, row_slot, init, init_ld, src_scale, row_scale, g->col, g->n_seg, n_groups,
         reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
     IHG_LAUNCH_CHECK();
     if (g->n_split > 0) {
         segment_fixup_kernel<LPR, VPL><<<(unsigned)g->n_split, kSegWarpsPerBlock * 32, 0, st>>>(
-            partial, g->split_row, g->split_ptr, g->n_split, row_scale, out, out_ld, dim);
+            partial, g->split_row, g->split_ptr, g->n_split, init, init_ld, row_scale, out, out_ld, dim);
         IHG_LAUNCH_CHECK();
     }
     return IHG_OK;
@@ -201,6 +209,7 @@ using namespace ihg;
 
 extern "C" int ihg_segment_reduce(const ihg_csr* g, const float* src, int64_t src_ld,
                                   int32_t src_row_mul, int64_t bound0, int64_t bound1,
+                                  const int32_t* row_slot, const float* init, int64_t init_ld,
                                   const float* src_scale, const float* row_scale, float* partial,
                                   float* out, int64_t out_ld, int32_t dim, void* stream) {
     IHG_REQUIRE(g && src && out, "segment_reduce: null pointer");
@@ -212,10 +221,11 @@ extern "C" int ihg_segment_reduce(const ihg_csr* g, const float* src, int64_t sr
     IHG_REQUIRE(g->n_split == 0 || (partial && g->split_row && g->split_ptr),
                 "segment_reduce: split rows need the partial buffer");
     IHG_REQUIRE(src_row_mul >= 1, "segment_reduce: src_row_mul must be >= 1");
+    IHG_REQUIRE(!init || (init_ld % 4 == 0 && init_ld >= dim), "segment_reduce: bad init leading dimension");
     cudaStream_t st = as_stream(stream);
     const int nvec = dim / 4;
 #define IHG_SEG_CASE(L, V) \
-    return launch_segment_reduce<L, V>(g, src, src_ld, src_row_mul, bound0, bound1, src_scale, row_scale, partial, out, out_ld, dim, st)
+    return launch_segment_reduce<L, V>(g, src, src_ld, src_row_mul, bound0, bound1, row_slot, init, init_ld, src_scale, row_scale, partial, out, out_ld, dim, st)
     if (nvec <= 1) IHG_SEG_CASE(1, 1);
     if (nvec <= 2) IHG_SEG_CASE(2, 1);
     if (nvec <= 4) IHG_SEG_CASE(4, 1);

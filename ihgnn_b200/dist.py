@@ -39,7 +39,10 @@ class PartitionPlan:
     Node id spaces:
       global   u, U+q, U+Q+i                                   (Helpers/Graph.py:110-111)
       own      [own users | own queries | own items]           rows this rank owns (n_own)
-      local    [own users | own queries, halo queries | own items, halo items]   (n_local)
+      local    [own rows | halo rows from rank 0 | halo rows from rank 1 | ...]   (n_local);
+               the chunk received from a rank holds its queries (ascending id) then its items,
+               i.e. the local table IS the all-to-all receive layout: no unpack pass, and the
+               halo partial sums travelling back are a contiguous slice.
     """
 
     def __init__(self, user, query, item, user_count: int, query_count: int, item_count: int,
@@ -62,38 +65,40 @@ class PartitionPlan:
         eu, eq, ei = user[self.edge_ids], query[self.edge_ids], item[self.edge_ids]
         self.edge_count = int(self.edge_ids.shape[0])
 
-        # halo = remote queries / items referenced by local hyperedges, sorted by (owner, id)
+        # halo = remote queries / items referenced by local hyperedges
         q_need = np.unique(eq[(eq < self.qb[r]) | (eq >= self.qb[r + 1])])
         i_need = np.unique(ei[(ei < self.ib[r]) | (ei >= self.ib[r + 1])])
-        self.Qh, self.Ih = int(q_need.shape[0]), int(i_need.shape[0])
-        self.n_local = self.n_own + self.Qh + self.Ih
-        self.local_bounds = (self.Uo, self.Uo + self.Qo + self.Qh)
         q_owner = np.searchsorted(self.qb, q_need, side="right") - 1
         i_owner = np.searchsorted(self.ib, i_need, side="right") - 1
+        self.recv_counts = np.zeros(world, dtype=np.int64)
+        q_local = np.zeros(q_need.shape[0], dtype=np.int64)      # local row of every needed query
+        i_local = np.zeros(i_need.shape[0], dtype=np.int64)
+        slot = [np.zeros(self.Uo, np.int32), np.ones(self.Qo, np.int32), np.full(self.Io, 2, np.int32)]
+        off = self.n_own
+        for s in range(world):
+            qs = np.nonzero(q_owner == s)[0]
+            is_ = np.nonzero(i_owner == s)[0]
+            q_local[qs] = off + np.arange(qs.shape[0])
+            i_local[is_] = off + qs.shape[0] + np.arange(is_.shape[0])
+            slot += [np.ones(qs.shape[0], np.int32), np.full(is_.shape[0], 2, np.int32)]
+            self.recv_counts[s] = qs.shape[0] + is_.shape[0]
+            off += int(self.recv_counts[s])
+        self.R = int(self.recv_counts.sum())
+        self.n_local = self.n_own + self.R
+        self.row_slot = np.concatenate(slot).astype(np.int32)    # node type (= hyperedge slot) of every local row
 
         # ---- local ids of the hyperedges' nodes
         lu = eu - self.ub[r]
         q_own = (eq >= self.qb[r]) & (eq < self.qb[r + 1])
-        lq = np.where(q_own, self.Uo + (eq - self.qb[r]), self.Uo + self.Qo + np.searchsorted(q_need, eq))
+        lq = np.where(q_own, self.Uo + (eq - self.qb[r]),
+                      q_local[np.minimum(np.searchsorted(q_need, eq), max(q_need.shape[0] - 1, 0))] if q_need.shape[0] else 0)
         i_own = (ei >= self.ib[r]) & (ei < self.ib[r + 1])
-        i_base = self.Uo + self.Qo + self.Qh
-        li = np.where(i_own, i_base + (ei - self.ib[r]), i_base + self.Io + np.searchsorted(i_need, ei))
+        li = np.where(i_own, self.Uo + self.Qo + (ei - self.ib[r]),
+                      i_local[np.minimum(np.searchsorted(i_need, ei), max(i_need.shape[0] - 1, 0))] if i_need.shape[0] else 0)
         self.i3_local = np.stack([lu, lq, li], axis=1) if self.edge_count else np.zeros((0, 3), np.int64)
 
-        # ---- what I receive: per source rank s, [queries from s | items from s], ids ascending
-        recv_local_rows: List[np.ndarray] = []       # local row index of every received row
-        self.recv_counts = np.zeros(world, dtype=np.int64)
-        for s in range(world):
-            qs = np.nonzero(q_owner == s)[0]
-            is_ = np.nonzero(i_owner == s)[0]
-            recv_local_rows.append(np.concatenate([self.Uo + self.Qo + qs, i_base + self.Io + is_]))
-            self.recv_counts[s] = qs.shape[0] + is_.shape[0]
-        self.recv_rows = np.concatenate(recv_local_rows) if world else np.zeros(0, np.int64)
-        self.R = int(self.recv_counts.sum())
-        assert self.R == self.Qh + self.Ih
-
         # ---- what I send: rank d's request list for rows I own (same rule, evaluated for d)
-        send_rows: List[np.ndarray] = []             # own-layout row index of every sent row
+        send_rows: List[np.ndarray] = []             # own (= local) row index of every sent row
         self.send_counts = np.zeros(world, dtype=np.int64)
         for d in range(world):
             if d == r:
@@ -109,21 +114,11 @@ class PartitionPlan:
         self.send_rows = np.concatenate(send_rows)
         self.S = int(self.send_counts.sum())
 
-        # ---- own layout -> local layout
-        self.own_to_local = np.concatenate([
-            np.arange(self.Uo), self.Uo + np.arange(self.Qo), i_base + np.arange(self.Io)]).astype(np.int64)
-        # unpack permutation of halo_exchange: local row <- concat([own rows (n_own); received rows (R)])
-        self.unpack_perm = np.empty(self.n_local, dtype=np.int64)
-        self.unpack_perm[self.own_to_local] = np.arange(self.n_own)
-        self.unpack_perm[self.recv_rows] = self.n_own + np.arange(self.R)
-
-        # ---- ordered sum of halo_reduce: own row v <- [its own partial (local row), then the rows
-        # received for it in ascending source rank]; entries index concat([s_local (n_local); recv (S)])
-        keys = np.concatenate([np.arange(self.n_own), self.send_rows])
-        vals = np.concatenate([self.own_to_local, self.n_local + np.arange(self.S)])
-        order = np.argsort(keys, kind="stable")
-        self.reduce_col = vals[order]
-        counts = np.bincount(keys, minlength=self.n_own)
+        # ---- ordered sum of halo_reduce: own row v <- its own partial (the `init` row), then the
+        # rows received for it in ascending source rank; CSR over the receive buffer [S rows]
+        order = np.argsort(self.send_rows, kind="stable")
+        self.reduce_col = order.astype(np.int64)
+        counts = np.bincount(self.send_rows, minlength=self.n_own)
         self.reduce_rowptr = np.zeros(self.n_own + 1, dtype=np.int64)
         np.cumsum(counts, out=self.reduce_rowptr[1:])
 
@@ -151,7 +146,6 @@ class ShardedHyperGraph:
     """The device-resident local piece of a partitioned hypergraph plus its exchange plan."""
 
     def __init__(self, plan: PartitionPlan, device, group=None):
-        from . import _lib
         from .graph import CsrPlan, csr_from_keys
         self.plan, self.group = plan, group
         dev = torch.device(device)
@@ -161,28 +155,21 @@ class ShardedHyperGraph:
         t = lambda a, dt=torch.int64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
         self.EdgeCount = plan.edge_count
         self.node_count = plan.n_local
+        self.n_own, self.n_local, self.S, self.R = plan.n_own, plan.n_local, plan.S, plan.R
         self.i3 = t(plan.i3_local, torch.int32).contiguous()
         edge_of = torch.arange(plan.edge_count, device=dev, dtype=torch.int32).repeat_interleave(3)
         rowptr, _perm, col = csr_from_keys(self.i3.reshape(-1), plan.n_local, values=edge_of)
         self.rowptr, self.col = rowptr, col
         self.plan_csr = CsrPlan(rowptr, col)
-        self.type_bounds = plan.local_bounds           # slot(row) for the per-slot gradient reduce
+        self.row_slot = t(plan.row_slot, torch.int32)  # slot(row) for the per-slot gradient reduce
         self.own_bounds = plan.own_bounds              # node types of the own rows (typed Linear)
         self.dv_inv_own = t(plan.dv_inv_own, torch.float32)
         self.send_rows = t(plan.send_rows)
-        self.unpack_perm = t(plan.unpack_perm)
-        self.recv_rows = t(plan.recv_rows)
         self.send_counts = [int(x) for x in plan.send_counts]
         self.recv_counts = [int(x) for x in plan.recv_counts]
         self.reduce_csr = CsrPlan(t(plan.reduce_rowptr, torch.int32), t(plan.reduce_col, torch.int32))
-        self.n_own, self.n_local, self.S, self.R = plan.n_own, plan.n_local, plan.S, plan.R
         # Dv^-1 of every local row (own + halo): exchanged once, the graph is static
         self.dv_inv_local = HaloExchangeFn.apply(self.dv_inv_own.view(-1, 1).expand(-1, 4).contiguous(), self)[:, 0].contiguous()
-
-    # compatibility with the single-GPU graph object the kernels' wrappers expect
-    @property
-    def plan_(self):
-        return self.plan_csr
 
 
 def _all_to_all(out: torch.Tensor, inp: torch.Tensor, out_counts, in_counts, group) -> None:
@@ -191,19 +178,20 @@ def _all_to_all(out: torch.Tensor, inp: torch.Tensor, out_counts, in_counts, gro
 
 
 class HaloExchangeFn(torch.autograd.Function):
-    """x_own [n_own, d] -> x_local [n_local, d]: pack the rows other ranks reference, all-to-all,
-    unpack into the local layout.  Backward = halo_reduce without scaling."""
+    """x_own [n_own, d] -> x_local [n_local, d] = [x_own ; rows received from the owners]: pack the
+    rows other ranks reference, all-to-all straight into the tail of the local table.
+    Backward = halo_reduce without scaling."""
 
     @staticmethod
-    def forward(ctx, x_own, g: ShardedHyperGraph):
+    def forward(ctx, x_own, g: "ShardedHyperGraph"):
         from . import functional as F_
         ctx.g = g
         d = int(x_own.shape[1])
         send = F_.gather_rows_raw(x_own, g.send_rows, 0)
-        buf = torch.empty((g.n_own + g.R, d), dtype=torch.float32, device=x_own.device)
-        _all_to_all(buf[g.n_own:], send, g.recv_counts, g.send_counts, g.group)
-        F_.copy_rows_raw(x_own, buf[:g.n_own])
-        return F_.gather_rows_raw(buf, g.unpack_perm, 0)
+        x_local = torch.empty((g.n_local, d), dtype=torch.float32, device=x_own.device)
+        _all_to_all(x_local[g.n_own:], send, g.recv_counts, g.send_counts, g.group)
+        F_.copy_rows_raw(x_own, x_local[:g.n_own])
+        return x_local
 
     @staticmethod
     def backward(ctx, dx_local):
@@ -233,13 +221,13 @@ class ShardedScatterMeanFn(torch.autograd.Function):
 
 
 def _halo_reduce(s_local: torch.Tensor, g: ShardedHyperGraph, row_scale: Optional[torch.Tensor]) -> torch.Tensor:
+    """own rows <- row_scale * (own partial + partials received from the ranks holding them as halo
+    rows, ascending source rank).  The halo partials are the contiguous tail of s_local."""
     from . import functional as F_
     d = int(s_local.shape[1])
-    send = F_.gather_rows_raw(s_local, g.recv_rows, 0)            # my partial sums of halo rows
-    buf = torch.empty((g.n_local + g.S, d), dtype=torch.float32, device=s_local.device)
-    _all_to_all(buf[g.n_local:], send, g.send_counts, g.recv_counts, g.group)
-    F_.copy_rows_raw(s_local, buf[:g.n_local])
-    return F_.segment_reduce(g.reduce_csr, buf, d, row_scale=row_scale)
+    recv = torch.empty((g.S, d), dtype=torch.float32, device=s_local.device)
+    _all_to_all(recv, s_local[g.n_own:], g.send_counts, g.recv_counts, g.group)
+    return F_.segment_reduce(g.reduce_csr, recv, d, row_scale=row_scale, init=s_local[:g.n_own])
 
 
 def halo_exchange(x_own, g):
@@ -251,7 +239,8 @@ class _LocalGraphView:
 
     def __init__(self, g: ShardedHyperGraph):
         self.i3, self.plan, self.EdgeCount = g.i3, g.plan_csr, g.EdgeCount
-        self.type_bounds = g.type_bounds
+        self.type_bounds = (1 << 62, 1 << 62)          # unused: row_slot gives the slot of a local row
+        self.row_slot = g.row_slot
         self.dv_inv = None
 
 

@@ -31,9 +31,13 @@ def segment_reduce(plan: CsrPlan, src: torch.Tensor, dim: int, *, src_row_mul: i
                    bounds: Tuple[int, int] = (INT64_MAX, INT64_MAX),
                    src_scale: Optional[torch.Tensor] = None,
                    row_scale: Optional[torch.Tensor] = None,
-                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[r] = row_scale[r] * sum_{j in row r} src_scale[col j] * src[col[j]*mul + slot(r)]."""
-    _lib.require_cuda(src, src_scale, row_scale, out)
+                   out: Optional[torch.Tensor] = None,
+                   row_slot: Optional[torch.Tensor] = None,
+                   init: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r] = row_scale[r] * (init[r] + sum_{j in row r} src_scale[col j] * src[col[j]*mul + slot(r)])."""
+    _lib.require_cuda(src, src_scale, row_scale, out, row_slot, init)
+    if init is not None:
+        init = _lib.rows_f32(init)
     if src_row_mul == 1:
         src = _lib.rows_f32(src)
         src_ld = _lib.ld(src)
@@ -43,7 +47,8 @@ def segment_reduce(plan: CsrPlan, src: torch.Tensor, dim: int, *, src_row_mul: i
     if out is None:
         out = _empty((plan.n_rows, dim), src)
     _lib.call("ihg_segment_reduce", plan.ref(), _lib.ptr(src), src_ld, src_row_mul, bounds[0],
-              bounds[1], _lib.ptr(src_scale), _lib.ptr(row_scale), _lib.ptr(plan.partial(dim)),
+              bounds[1], _lib.ptr(row_slot), _lib.ptr(init), _lib.ld(init) if init is not None else 0,
+              _lib.ptr(src_scale), _lib.ptr(row_scale), _lib.ptr(plan.partial(dim)),
               _lib.ptr(out), _lib.ld(out), dim, _lib.stream_ptr(),
               tag=f"segment_reduce[mul={src_row_mul}]",
               algo_bytes=plan.nnz * (4 + 4 * dim) + plan.n_rows * (4 * dim + 16))

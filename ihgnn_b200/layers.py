@@ -203,7 +203,8 @@ class _EdgeInteractFn(torch.autograd.Function):
                   _lib.ptr(w_hi), _lib.ld(w_hi), order, _lib.ptr(g.i3), E, _lib.ptr(slot_grad),
                   _lib.ptr(dw_hi), dim, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(),
                   tag="edge_interact_bwd", algo_bytes=E * (12 + 28 * dim))
-        dxp = F_.segment_reduce(g.plan, slot_grad, dim, src_row_mul=3, bounds=g.type_bounds)
+        dxp = F_.segment_reduce(g.plan, slot_grad, dim, src_row_mul=3, bounds=g.type_bounds,
+                                row_slot=getattr(g, "row_slot", None))
         return dxp, dp, dw_hi, None, None
 
 

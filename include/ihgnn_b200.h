@@ -103,13 +103,17 @@ int ihg_segment_plan_build(const int32_t* rowptr, int64_t n_rows, int32_t chunk_
  * Deterministic segmented reduction over CSR rows:
  *   out[r, 0:dim] = row_scale[r] * sum_{j in row r, ascending}
  *                       src_scale[s(j)] * src[s(j), 0:dim],
- *   s(j) = col[j] * src_row_mul + slot(r),  slot(r) = (r >= bound0) + (r >= bound1)
+ *   s(j) = col[j] * src_row_mul + slot(r),  slot(r) = row_slot[r] if row_slot is given, else
+ *   (r >= bound0) + (r >= bound1)
  * (src_row_mul = 3 with the node-type bounds reads the per-slot gradient rows [E,3,dim];
- * src_row_mul = 1 with bounds = INT64_MAX is the plain SpMM).  row_scale / src_scale may be
+ * src_row_mul = 1 with bounds = INT64_MAX is the plain SpMM).  `init` (nullable, [n_rows, dim],
+ * row stride init_ld) is added first: out = row_scale * (init[r] + sum ...) -- the multi-GPU
+ * reduce adds the rank's own partial before the received ones.  row_scale / src_scale may be
  * null (= 1).  `partial` is scratch of csr->n_part * dim floats.  dim % 4 == 0, dim <= 256.
  * ------------------------------------------------------------------------------------ */
 int ihg_segment_reduce(const ihg_csr* csr_host, const float* src, int64_t src_ld,
                        int32_t src_row_mul, int64_t bound0, int64_t bound1,
+                       const int32_t* row_slot, const float* init, int64_t init_ld,
                        const float* src_scale, const float* row_scale, float* partial,
                        float* out, int64_t out_ld, int32_t dim, void* stream);
 

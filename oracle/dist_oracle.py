@@ -44,8 +44,7 @@ class _HaloExchange(torch.autograd.Function):
         ctx.plan = plan
         send = x_own[torch.from_numpy(plan.send_rows)]
         recv = _a2a_rows(send, [int(c) for c in plan.send_counts], [int(c) for c in plan.recv_counts])
-        buf = torch.cat([x_own, recv])
-        return buf[torch.from_numpy(plan.unpack_perm)]
+        return torch.cat([x_own, recv])              # local layout == [own rows ; receive layout]
 
     @staticmethod
     def backward(ctx, dx_local):
@@ -55,13 +54,12 @@ class _HaloExchange(torch.autograd.Function):
 def _halo_reduce(s_local: torch.Tensor, plan) -> torch.Tensor:
     """own rows <- own partial + partials received from the ranks that hold them as halo rows,
     summed in the plan's fixed order (own first, then ascending source rank)."""
-    send = s_local[torch.from_numpy(plan.recv_rows)]
+    send = s_local[plan.n_own:]
     recv = _a2a_rows(send, [int(c) for c in plan.recv_counts], [int(c) for c in plan.send_counts])
-    buf = torch.cat([s_local, recv])
-    out = torch.zeros((plan.n_own, s_local.shape[1]), dtype=s_local.dtype)
+    out = s_local[:plan.n_own].clone()
     rowptr, col = plan.reduce_rowptr, plan.reduce_col
     rows = torch.repeat_interleave(torch.arange(plan.n_own), torch.from_numpy(rowptr[1:] - rowptr[:-1]))
-    out.index_add_(0, rows, buf[torch.from_numpy(col)])
+    out.index_add_(0, rows, recv[torch.from_numpy(col)])
     return out
 
 
