@@ -292,6 +292,16 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
 // columns per unit, so that nb accumulators of NU columns fit TMEM twice (double buffering).
 // =========================================================================================
 constexpr int kSlotAStages = 2;
+// Roles of the slot-gradient kernel: the def-tile producers are light, the product-rule epilogue
+// (three gathered rows in, three gradient rows out per hyperedge) is the heavy part, so it gets
+// 8 warps: two per TMEM lane quadrant, alternating 16-column slabs.
+constexpr int kSlotProducerWarps = 4;
+constexpr int kSlotEpiWarp0 = 4;          // warps 4..11; quadrant = warp % 4
+constexpr int kSlotEpiWarps = 8;
+constexpr int kSlotStageBytes = 32 * 64;  // per-warp staging tile: 32 rows x 16 fp32
+__device__ __forceinline__ uint32_t epi_off16(int row, int chunk) {      // chunk in [0,4)
+    return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
 
 __global__ void __launch_bounds__(kInteractThreads, 1)
 edge_interact_bwd_slot_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
@@ -303,7 +313,7 @@ edge_interact_bwd_slot_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
     __shared__ __align__(8) uint64_t bar_afull[kSlotAStages], bar_aempty[kSlotAStages];
     __shared__ __align__(8) uint64_t bar_bfull[8], bar_bempty[8], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ int32_t slot_ids[4][3][32];
+    __shared__ int32_t slot_ids[kSlotEpiWarps][3][32];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KC = dim / kChunkK;                 // chunks along the contraction (n)
@@ -312,7 +322,7 @@ edge_interact_bwd_slot_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
     const uint32_t a_stage_bytes = 2 * kATileBytes;
     const uint32_t b_base = smem_base + kSlotAStages * a_stage_bytes;
     const uint32_t b_stage_bytes = 2 * b_tile_bytes;
-    const uint32_t epi_base = b_base + (uint32_t)b_stages * b_stage_bytes;   // 12 x 4 KB staging tiles
+    const uint32_t epi_base = b_base + (uint32_t)b_stages * b_stage_bytes;   // 24 x 2 KB staging tiles
     const int64_t n_tiles = (E + kTileM - 1) / kTileM;
     const int64_t n_units = n_tiles * UH;
     const uint32_t acc_cols = (uint32_t)(nb * nu);
@@ -320,7 +330,7 @@ edge_interact_bwd_slot_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
 
     if (tid == 0) {
         for (int s = 0; s < kSlotAStages; ++s) {
-            mbar_init(smem_u32(&bar_afull[s]), kProducerWarps);
+            mbar_init(smem_u32(&bar_afull[s]), kSlotProducerWarps);
             mbar_init(smem_u32(&bar_aempty[s]), 1);
         }
         for (int s = 0; s < b_stages; ++s) {
@@ -329,7 +339,7 @@ edge_interact_bwd_slot_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&bar_tfull[s]), 1);
-            mbar_init(smem_u32(&bar_tempty[s]), 4);
+            mbar_init(smem_u32(&bar_tempty[s]), kSlotEpiWarps);
         }
         mbar_init_fence();
     }
@@ -339,24 +349,24 @@ edge_interact_bwd_slot_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
     fence_after_sync();
     const uint32_t tmem_base = tmem_base_slot;
 
-    if (warp < kProducerWarps) {
+    if (warp < kSlotProducerWarps) {
         // ---- A producer: def tile rows, split to tf32 hi/lo; (row, chunk) lane mapping
-        const int c = tid & 7, r0 = tid >> 3;
+        const int c = tid & 7, r0 = tid >> 3;                 // rows r0 + 16 j
         uint32_t it = 0;
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
             const int64_t e0 = (u / UH) * kTileM;
             for (int nc = 0; nc < KC; ++nc, ++it) {
-                float4 v[4];
+                float4 v[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int64_t e = e0 + r0 + 32 * j;
+                for (int j = 0; j < 8; ++j) {
+                    const int64_t e = e0 + r0 + 16 * j;
                     v[j] = e < E ? ldg4(def + e * def_ld + nc * kChunkK + 4 * c) : f4_zero();
                 }
                 const int s = it % kSlotAStages;
                 mbar_wait(smem_u32(&bar_aempty[s]), ((it / kSlotAStages) & 1u) ^ 1u);
                 const uint32_t a_hi = smem_base + (uint32_t)s * a_stage_bytes;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) store_split_chunk(a_hi, a_hi + kATileBytes, r0 + 32 * j, c, v[j]);
+                for (int j = 0; j < 8; ++j) store_split_chunk(a_hi, a_hi + kATileBytes, r0 + 16 * j, c, v[j]);
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bar_afull[s]));
@@ -413,51 +423,49 @@ edge_interact_bwd_slot_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                 mma_commit(smem_u32(&bar_tfull[buf]));
             }
         }
-    } else {
-        // ---- epilogue: product rule.  Global traffic (u,q,i gathers, slot_grad stores) uses the
+    } else if (warp >= kSlotEpiWarp0 && warp < kSlotEpiWarp0 + kSlotEpiWarps) {
+        // ---- epilogue: product rule.  Global traffic (u,q,i gathers, slot_grad stores) uses a
         // coalesced (row, chunk) mapping; the math runs thread-per-row (TMEM order); three per-warp
-        // staging tiles transpose between the two.
-        const int q4 = warp - kEpilogueWarp0;
-        const uint32_t su = epi_base + (uint32_t)(q4 * 3) * kEpiStageBytes;
-        const uint32_t sq = su + kEpiStageBytes, si = sq + kEpiStageBytes;
-        const int c = lane & 7, rs = lane >> 3;
+        // staging tiles transpose between the two.  Slabs of 16 columns alternate between the two
+        // warps of a quadrant.
+        const int ew = warp - kSlotEpiWarp0;
+        const int q4 = warp & 3, half = ew >> 2;
+        const uint32_t su = epi_base + (uint32_t)(ew * 3) * kSlotStageBytes;
+        const uint32_t sq = su + kSlotStageBytes, si = sq + kSlotStageBytes;
+        const int c = lane & 3, rs = lane >> 2;              // 8 rows x 4 chunks per request
         uint32_t t = 0;
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++t) {
             const uint32_t buf = t & 1u;
             const int h = (int)(u % UH);
             const int64_t e0 = (u / UH) * kTileM + q4 * 32;
-            // node ids of this warp's 32 rows, kept in shared memory (registers are needed by the
-            // product-rule math): ids[s][row], -1 marks rows beyond E
             __syncwarp();
             {
                 const int64_t e = e0 + lane;
                 const bool ok = e < E;
-                slot_ids[q4][0][lane] = ok ? __ldg(i3 + 3 * e) : -1;
-                slot_ids[q4][1][lane] = ok ? __ldg(i3 + 3 * e + 1) : 0;
-                slot_ids[q4][2][lane] = ok ? __ldg(i3 + 3 * e + 2) : 0;
+                slot_ids[ew][0][lane] = ok ? __ldg(i3 + 3 * e) : -1;
+                slot_ids[ew][1][lane] = ok ? __ldg(i3 + 3 * e + 1) : 0;
+                slot_ids[ew][2][lane] = ok ? __ldg(i3 + 3 * e + 2) : 0;
             }
             __syncwarp();
             const uint32_t taddr = tmem_base + buf * acc_cols + ((uint32_t)(q4 * 32) << 16);
             bool waited = false;
-            for (int c0 = 0; c0 < nu; c0 += 32) {
+            for (int c0 = 16 * half; c0 < nu; c0 += 32) {
                 const int col = h * nu + c0;
-                const int ncol = min(32, nu - c0);           // 32, or 16 for nu = 48
                 __syncwarp();
-                // load phase: coalesced gathers into the staging tiles
+                // load phase: asynchronous 16-byte copies straight into the staging tiles -- all 12
+                // gathers of this lane are in flight at once and cost no registers
 #pragma unroll
-                for (int itr = 0; itr < 8; ++itr) {
-                    // asynchronous 16-byte copies straight into the staging tiles: all 24 gathers of
-                    // this lane are in flight at once and cost no registers
-                    const int r = itr * 4 + rs;
-                    const int n0 = slot_ids[q4][0][r];
-                    if (n0 >= 0 && 4 * c < ncol) {
-                        cp_async16(su + epi_off(r, c), xp + (int64_t)n0 * xp_ld + col + 4 * c);
-                        cp_async16(sq + epi_off(r, c), xp + (int64_t)slot_ids[q4][1][r] * xp_ld + col + 4 * c);
-                        cp_async16(si + epi_off(r, c), xp + (int64_t)slot_ids[q4][2][r] * xp_ld + col + 4 * c);
+                for (int itr = 0; itr < 4; ++itr) {
+                    const int r = itr * 8 + rs;
+                    const int n0 = slot_ids[ew][0][r];
+                    if (n0 >= 0) {
+                        cp_async16(su + epi_off16(r, c), xp + (int64_t)n0 * xp_ld + col + 4 * c);
+                        cp_async16(sq + epi_off16(r, c), xp + (int64_t)slot_ids[ew][1][r] * xp_ld + col + 4 * c);
+                        cp_async16(si + epi_off16(r, c), xp + (int64_t)slot_ids[ew][2][r] * xp_ld + col + 4 * c);
                     } else {
-                        sts4(su + epi_off(r, c), f4_zero());
-                        sts4(sq + epi_off(r, c), f4_zero());
-                        sts4(si + epi_off(r, c), f4_zero());
+                        sts4(su + epi_off16(r, c), f4_zero());
+                        sts4(sq + epi_off16(r, c), f4_zero());
+                        sts4(si + epi_off16(r, c), f4_zero());
                     }
                 }
                 cp_async_wait_all();
@@ -467,30 +475,30 @@ edge_interact_bwd_slot_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                     fence_after_sync();
                     waited = true;
                 }
-                // compute phase: thread = row `lane`, 16 columns at a time, results overwrite inputs
-                for (int hc = 0; hc < ncol; hc += 16) {
+                // compute phase: thread = row `lane`, results overwrite the inputs
+                {
                     float uu[16], qq[16], ii[16];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 a = lds4(su + epi_off(lane, hc / 4 + j));
-                        const float4 b = lds4(sq + epi_off(lane, hc / 4 + j));
-                        const float4 d = lds4(si + epi_off(lane, hc / 4 + j));
+                        const float4 a = lds4(su + epi_off16(lane, j));
+                        const float4 b = lds4(sq + epi_off16(lane, j));
+                        const float4 d = lds4(si + epi_off16(lane, j));
                         uu[4 * j] = a.x; uu[4 * j + 1] = a.y; uu[4 * j + 2] = a.z; uu[4 * j + 3] = a.w;
                         qq[4 * j] = b.x; qq[4 * j + 1] = b.y; qq[4 * j + 2] = b.z; qq[4 * j + 3] = b.w;
                         ii[4 * j] = d.x; ii[4 * j + 1] = d.y; ii[4 * j + 2] = d.z; ii[4 * j + 3] = d.w;
                     }
                     float du[16], dq[16], di[16], dz[16];
-                    tmem_ld16(taddr + (uint32_t)(c0 + hc), dz);                       // b = 0: u*q
+                    tmem_ld16(taddr + (uint32_t)c0, dz);                              // b = 0: u*q
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { du[j] = dz[j] * qq[j]; dq[j] = dz[j] * uu[j]; }
-                    tmem_ld16(taddr + (uint32_t)(nu + c0 + hc), dz);                  // b = 1: q*i
+                    tmem_ld16(taddr + (uint32_t)(nu + c0), dz);                       // b = 1: q*i
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { dq[j] = fmaf(dz[j], ii[j], dq[j]); di[j] = dz[j] * qq[j]; }
-                    tmem_ld16(taddr + (uint32_t)(2 * nu + c0 + hc), dz);              // b = 2: i*u
+                    tmem_ld16(taddr + (uint32_t)(2 * nu + c0), dz);                   // b = 2: i*u
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { di[j] = fmaf(dz[j], uu[j], di[j]); du[j] = fmaf(dz[j], ii[j], du[j]); }
                     if (nb == 4) {
-                        tmem_ld16(taddr + (uint32_t)(3 * nu + c0 + hc), dz);          // b = 3: u*q*i
+                        tmem_ld16(taddr + (uint32_t)(3 * nu + c0), dz);               // b = 3: u*q*i
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             du[j] = fmaf(dz[j], qq[j] * ii[j], du[j]);
@@ -500,23 +508,27 @@ edge_interact_bwd_slot_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        sts4(su + epi_off(lane, hc / 4 + j), make_float4(du[4 * j], du[4 * j + 1], du[4 * j + 2], du[4 * j + 3]));
-                        sts4(sq + epi_off(lane, hc / 4 + j), make_float4(dq[4 * j], dq[4 * j + 1], dq[4 * j + 2], dq[4 * j + 3]));
-                        sts4(si + epi_off(lane, hc / 4 + j), make_float4(di[4 * j], di[4 * j + 1], di[4 * j + 2], di[4 * j + 3]));
+                        sts4(su + epi_off16(lane, j), make_float4(du[4 * j], du[4 * j + 1], du[4 * j + 2], du[4 * j + 3]));
+                        sts4(sq + epi_off16(lane, j), make_float4(dq[4 * j], dq[4 * j + 1], dq[4 * j + 2], dq[4 * j + 3]));
+                        sts4(si + epi_off16(lane, j), make_float4(di[4 * j], di[4 * j + 1], di[4 * j + 2], di[4 * j + 3]));
                     }
                 }
                 __syncwarp();
                 // store phase: coalesced slot_grad rows
 #pragma unroll
-                for (int itr = 0; itr < 8; ++itr) {
-                    const int r = itr * 4 + rs;
-                    if (slot_ids[q4][0][r] >= 0 && 4 * c < ncol) {
+                for (int itr = 0; itr < 4; ++itr) {
+                    const int r = itr * 8 + rs;
+                    if (slot_ids[ew][0][r] >= 0) {
                         float* out = slot_grad + (e0 + r) * 3 * (int64_t)dim + col + 4 * c;
-                        stg4(out, lds4(su + epi_off(r, c)));
-                        stg4(out + dim, lds4(sq + epi_off(r, c)));
-                        stg4(out + 2 * dim, lds4(si + epi_off(r, c)));
+                        stg4(out, lds4(su + epi_off16(r, c)));
+                        stg4(out + dim, lds4(sq + epi_off16(r, c)));
+                        stg4(out + 2 * dim, lds4(si + epi_off16(r, c)));
                     }
                 }
+            }
+            if (!waited) {                       // a warp without a slab still has to hand the buffer back
+                mbar_wait(smem_u32(&bar_tfull[buf]), (t >> 1) & 1u);
+                fence_after_sync();
             }
             fence_before_sync();
             __syncwarp();
@@ -828,9 +840,10 @@ int launch_interact_bwd_tc(const float* xp, int64_t xp_ld, const float* def, int
         interact_prep_weights_t_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w_hi, w_ld, nb, dim, nu, wprep);
         IHG_LAUNCH_CHECK();
         const uint32_t b_stage = 2u * (uint32_t)nu * kChunkBytesPerRow;
-        int b_stages = (int)((172 * 1024 - kSlotAStages * 2 * kATileBytes) / b_stage);
+        const int epi_bytes = kSlotEpiWarps * 3 * kSlotStageBytes;                 // 48 KB
+        int b_stages = (int)((220 * 1024 - epi_bytes - kSlotAStages * 2 * kATileBytes) / b_stage);
         if (b_stages > 8) b_stages = 8;
-        const int smem = kSlotAStages * 2 * kATileBytes + b_stages * (int)b_stage + 12 * kEpiStageBytes + 1024;
+        const int smem = kSlotAStages * 2 * kATileBytes + b_stages * (int)b_stage + epi_bytes + 1024;
         static int attr_smem = 0;
         if (attr_smem < smem) {
             IHG_CUDA(cudaFuncSetAttribute(edge_interact_bwd_slot_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
