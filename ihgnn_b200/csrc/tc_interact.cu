@@ -586,6 +586,10 @@ constexpr int kWgProducerWarps = 4;
 constexpr int kWgThreads = (kWgProducerWarps + 1) * 32;
 constexpr int kWgMaxKC = 4;                     // dim <= 128
 
+// TKC = dim / 32 as a compile-time constant (1, 2, 4) lets the register-resident row slices be
+// indexed statically (the kernel is bound by the producers' instruction issue); TKC = 0 is the
+// generic path (dim = 96).
+template <int TKC>
 __global__ void __launch_bounds__(kWgThreads)
 edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                                   const float* __restrict__ def, int64_t def_ld, int nb,
@@ -596,7 +600,8 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
     __shared__ uint32_t tmem_base_slot;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int KC = dim / kChunkK;                          // 32-feature blocks of def / of one product
+    const int KC = TKC > 0 ? TKC : dim / kChunkK;          // 32-feature blocks of def / of one product
+    constexpr int NBLK = TKC > 0 ? TKC : kWgMaxKC;         // register-resident blocks per row
     const int g0 = blockIdx.y * gpc;                       // first feature group of this CTA
     const int ng = min(gpc, G - g0);                       // groups handled here
     constexpr uint32_t sub_bytes = kWgTe * kChunkBytesPerRow;      // one [32 x 128 B] sub-tile
@@ -631,7 +636,7 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
         uint32_t ita = 0, itb = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++itb) {
             // ---- one burst of loads: def and u/q/i slices for both rows, all 32-column blocks
-            float4 dv[2][kWgMaxKC], uv[2][kWgMaxKC], qv[2][kWgMaxKC], iv[2][kWgMaxKC];
+            float4 dv[2][NBLK], uv[2][NBLK], qv[2][NBLK], iv[2][NBLK];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int64_t e = tile * kWgTe + r0 + 16 * j;
@@ -643,7 +648,7 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                     ni = __ldg(i3 + 3 * e + 2);
                 }
 #pragma unroll
-                for (int blk = 0; blk < kWgMaxKC; ++blk) {
+                for (int blk = 0; blk < NBLK; ++blk) {
                     const bool okb = ok && blk < KC;
                     dv[j][blk] = okb ? ldg4(def + e * def_ld + blk * kChunkK + 4 * c) : f4_zero();
                     uv[j][blk] = okb ? ldg4(xp + (int64_t)nu_ * xp_ld + blk * kChunkK + 4 * c) : f4_zero();
@@ -657,7 +662,7 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                 mbar_wait(smem_u32(&bar_bempty[sb]), ((itb / nbs) & 1u) ^ 1u);
                 const uint32_t bh = b_base + (uint32_t)sb * b_stage_bytes;
 #pragma unroll
-                for (int blk = 0; blk < kWgMaxKC; ++blk)
+                for (int blk = 0; blk < NBLK; ++blk)
                     if (blk < KC) {
 #pragma unroll
                         for (int j = 0; j < 2; ++j)
@@ -675,14 +680,25 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                 const uint32_t ah = smem_base + (uint32_t)sa * a_stage_bytes;
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
-                    const int f0 = g * 128 + j4 * kChunkK;         // first product feature of the sub-tile
-                    const int b = f0 / dim, blk = (f0 % dim) / kChunkK;
+                    // sub-tile st = 4 g + j4 of the product features: block b = st / KC, columns blk = st % KC
+                    int b, blk;
+                    if (TKC == 4) { b = g; blk = j4; }
+                    else if (TKC == 2) { b = 2 * g + (j4 >> 1); blk = j4 & 1; }
+                    else if (TKC == 1) { b = 4 * g + j4; blk = 0; }
+                    else { const int st = 4 * g + j4; b = st / KC; blk = st % KC; }
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         float4 u = f4_zero(), q = f4_zero(), v = f4_zero();
+                        if (TKC > 0) {
+                            // blk is a compile-time constant after unrolling: plain register reads
+                            u = uv[j][TKC == 4 ? j4 : (TKC == 2 ? (j4 & 1) : 0)];
+                            q = qv[j][TKC == 4 ? j4 : (TKC == 2 ? (j4 & 1) : 0)];
+                            v = iv[j][TKC == 4 ? j4 : (TKC == 2 ? (j4 & 1) : 0)];
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < kWgMaxKC; ++k)
-                            if (k == blk) { u = uv[j][k]; q = qv[j][k]; v = iv[j][k]; }
+                            for (int k = 0; k < NBLK; ++k)
+                                if (k == blk) { u = uv[j][k]; q = qv[j][k]; v = iv[j][k]; }
+                        }
                         float4 z = f4_zero();
                         if (b == 0) z = f4_mul(u, q);
                         else if (b == 1) z = f4_mul(q, v);
@@ -863,15 +879,19 @@ int launch_interact_bwd_tc(const float* xp, int64_t xp_ld, const float* def, int
         const int gy = (G + gpc - 1) / gpc;
         const int nbs = dim > 64 ? 1 : 2;                          // def-tile stages (two CTAs must fit an SM)
         const int smem = 2 * 8 * kWgTe * kChunkBytesPerRow + nbs * 2 * KC * kWgTe * kChunkBytesPerRow + 1024;
-        static int attr_smem = 0;
-        if (attr_smem < smem) {
-            IHG_CUDA(cudaFuncSetAttribute(edge_interact_bwd_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_smem = smem;
-        }
         const int64_t n_tiles = (E + kWgTe - 1) / kWgTe;
         const int gx = (int)(n_tiles < kWgCtasX / gy ? n_tiles : kWgCtasX / gy);
         dim3 grid(gx, gy);
-        edge_interact_bwd_wgrad_tc_kernel<<<grid, kWgThreads, smem, st>>>(xp, xp_ld, def, def_ld, nb, i3, E, dim, G, gpc, nbs, partial);
+#define IHG_WG_LAUNCH(T)                                                                                            \
+        do {                                                                                                        \
+            IHG_CUDA(cudaFuncSetAttribute(edge_interact_bwd_wgrad_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            edge_interact_bwd_wgrad_tc_kernel<T><<<grid, kWgThreads, smem, st>>>(xp, xp_ld, def, def_ld, nb, i3, E, dim, G, gpc, nbs, partial); \
+        } while (0)
+        if (KC == 4) IHG_WG_LAUNCH(4);
+        else if (KC == 2) IHG_WG_LAUNCH(2);
+        else if (KC == 1) IHG_WG_LAUNCH(1);
+        else IHG_WG_LAUNCH(0);
+#undef IHG_WG_LAUNCH
         IHG_LAUNCH_CHECK();
         const int64_t total = (int64_t)nb * dim * dim;
         interact_wgrad_tc_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, gx, G, nb, dim, dw_hi);
