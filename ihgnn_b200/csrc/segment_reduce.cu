@@ -23,8 +23,8 @@ constexpr int kSegWarpsPerBlock = 8;
 constexpr int kSegUnroll = 4;        // independent 128-bit row gathers in flight per lane group
 constexpr int kSegPerGroup = 1;      // chunks a lane group walks through (strided)
 
-template <int LPR, int VPL, int UNR, int SEGS>
-__global__ void __launch_bounds__(kSegWarpsPerBlock * 32)
+template <int LPR, int VPL, int UNR, int SEGS, int MINB>
+__global__ void __launch_bounds__(kSegWarpsPerBlock * 32, MINB)
 segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src_row_mul,
                       int64_t bound0, int64_t bound1, const int32_t* __restrict__ row_slot,
                       const float* __restrict__ init, int64_t init_ld,
@@ -186,12 +186,13 @@ static int launch_segment_reduce(const ihg_csr* g, const float* src, int64_t src
     // (unroll, chunks per group) = (4, 1) measured best on both bench workloads (profiles/
     // microbench_segment.py): 5.3 TB/s at d=128 (82% of the measured copy bandwidth); at d=64 the
     // 256-byte random rows cap every variant near 3.1 TB/s (DRAM page locality, not the kernel).
-    constexpr int UNR = kSegUnroll, SEGS = kSegPerGroup;
+    constexpr int SEGS = kSegPerGroup;
     const int64_t groups_per_block = (int64_t)kSegWarpsPerBlock * G;
     int64_t blocks = ceil_div(ceil_div(g->n_seg, SEGS), groups_per_block);
     if (blocks < 1) blocks = 1;
     const int64_t n_groups = blocks * groups_per_block;
-    segment_reduce_kernel<LPR, VPL, UNR, SEGS><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
+    // unroll 4 with >= 4 resident blocks per SM measured best (profiles/microbench_segment.py)
+    segment_reduce_kernel<LPR, VPL, kSegUnroll, SEGS, 4><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
         src, src_ld, mul, b0, b1, row_slot, init, init_ld, src_scale, row_scale, g->col, g->n_seg, n_groups,
         reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
     IHG_LAUNCH_CHECK();

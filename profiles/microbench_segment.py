@@ -34,6 +34,12 @@ nbytes = 3 * E * (4 + 4 * d) + N * (4 * d + 16)
 t = timeit(lambda: F_.segment_reduce(g.plan, ef, d, row_scale=g.dv_inv))
 print(f"{name} d={d} chunk={chunk} variant={os.environ.get('IHG_SEG_VARIANT','0')}: segment_reduce {t*1e3:.1f} us  "
       f"{nbytes/t/1e6:.0f} GB/s  (n_seg={g.plan.n_seg} n_split={g.plan.n_split} n_part={g.plan.n_part})")
+if os.environ.get("IHG_GS_ONLY"):
+    t = timeit(lambda: F_.edge_gather_sum(x, g.i3))
+    print(f"{name} d={d} gs_variant={os.environ.get('IHG_GS_VARIANT','0')}: edge_gather_sum {t*1e3:.1f} us  {E*(12+16*d)/t/1e6:.0f} GB/s algorithmic")
+    t = timeit(lambda: F_.edge_gather_sum(x, g.i3, node_scale=g.dv_inv))
+    print(f"    with node_scale: {t*1e3:.1f} us")
+    sys.exit(0)
 if os.environ.get("IHG_SEG_REF"):
     col = g.col.to(torch.int64)
     t = timeit(lambda: torch.index_select(ef, 0, col))
