@@ -191,8 +191,9 @@ static int launch_segment_reduce(const ihg_csr* g, const float* src, int64_t src
     int64_t blocks = ceil_div(ceil_div(g->n_seg, SEGS), groups_per_block);
     if (blocks < 1) blocks = 1;
     const int64_t n_groups = blocks * groups_per_block;
-    // unroll 4 with >= 4 resident blocks per SM measured best (profiles/microbench_segment.py)
-    segment_reduce_kernel<LPR, VPL, kSegUnroll, SEGS, 4><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
+    // unroll 4, no forced occupancy: forcing >= 4 blocks/SM wins in the isolated microbenchmark
+    // but loses in the real step (1.14 vs 1.07 ms at amazon-full), so the in-situ winner stays
+    segment_reduce_kernel<LPR, VPL, kSegUnroll, SEGS, 1><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
         src, src_ld, mul, b0, b1, row_slot, init, init_ld, src_scale, row_scale, g->col, g->n_seg, n_groups,
         reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
     IHG_LAUNCH_CHECK();
