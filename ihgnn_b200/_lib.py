@@ -50,6 +50,8 @@ SIGNATURES = {
     "ihg_edge_gather_sum": (c_int32, [P, I64, P, F32, P, P, I64, P, I64, I32, P]),
     "ihg_edge_interact_fwd_workspace_bytes": (I64, [I32, I32]),
     "ihg_edge_interact_fwd": (c_int32, [P, I64, P, I64, P, I64, I32, P, I64, P, I64, I32, P, I64, P]),
+    "ihg_feature_interact_fwd": (c_int32, [P, I64, P, I64, P, I32, P, I64, P, I64, I32, P, I64, P]),
+    "ihg_feature_interact_supported": (c_int32, [I32]),
     "ihg_edge_interact_bwd_workspace_bytes": (I64, [I32, I32]),
     "ihg_edge_interact_bwd": (c_int32, [P, I64, P, I64, P, I64, I32, P, I64, P, P, I32, P, I64, P]),
     "ihg_node_linear": (c_int32, [P, I64, P, I32, I32, I32, I32, P, P, I64, I64, I64, I64, P, I64, P]),

@@ -406,6 +406,23 @@ int ihg_edge_interact_fwd(const float* xp, int64_t xp_ld, const float* p, int64_
     return IHG_OK;
 }
 
+int ihg_feature_interact_supported(int32_t dim) { return interact_tc_eligible(dim) ? 1 : 0; }
+
+int ihg_feature_interact_fwd(const float* xp, int64_t xp_ld, const float* w_agg, int64_t w_ld,
+                             const float* bias, int32_t order, const int32_t* i3, int64_t E,
+                             float* ef, int64_t ef_ld, int32_t dim, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
+    IHG_REQUIRE(xp && w_agg && i3 && ef, "feature_interact_fwd: null pointer");
+    if (int rc = check_interact("feature_interact_fwd", order, dim)) return rc;
+    IHG_REQUIRE(interact_tc_eligible(dim) && xp_ld % 4 == 0 && ef_ld % 4 == 0,
+                "feature_interact_fwd: dim=%d is not supported by the tensor-core path", dim);
+    IHG_REQUIRE(workspace && workspace_bytes >= ihg_edge_interact_fwd_workspace_bytes(dim, order),
+                "feature_interact_fwd: workspace too small");
+    if (E == 0) return IHG_OK;
+    return launch_interact_fwd_full_tc(xp, xp_ld, w_agg, w_ld, bias, order == 3 ? 4 : 3, i3, E, ef, ef_ld, dim,
+                                       workspace, as_stream(stream));
+}
+
 int64_t ihg_edge_interact_bwd_workspace_bytes(int32_t dim, int32_t order) {
     const int nb = order == 3 ? 4 : 3;
     const int64_t simt = ws_slice((int64_t)kInteractWgradG * nb * dim * dim, 4) + 1024;

@@ -86,6 +86,14 @@ static inline InteractSmem interact_smem(int dim) {
     return s;
 }
 
+// kFull = false: hoisted form -- only the nb product blocks are contracted, the epilogue adds the
+//                 gathered first-order rows p[u]+p[q]+p[i] (used by the multi-GPU layer, where p
+//                 travels with the halo exchange).
+// kFull = true:  the whole FeatureInteractor.forward -- the raw u, q, i slices (already in the
+//                 producers' registers) are three more A blocks contracted with
+//                 aggregation.weight[:, :3d], so there is no p table, no p gather and the epilogue
+//                 only adds the bias and stores.  nb counts ALL blocks (6 or 7) in this mode.
+template <bool kFull>
 __global__ void __launch_bounds__(kInteractThreads, 1)
 edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const float* __restrict__ p,
                             int64_t p_ld, const uint8_t* __restrict__ wprep, int nb,
@@ -157,12 +165,16 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
                     mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
                     const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes;
                     const uint32_t a_lo = a_hi + kATileBytes;
+                    const int pb = kFull ? b - 3 : b;             // product block; < 0: raw row block b
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float4 z;
-                        if (b == 0) z = f4_mul(u[j], q[j]);
-                        else if (b == 1) z = f4_mul(q[j], v[j]);
-                        else if (b == 2) z = f4_mul(v[j], u[j]);
+                        if (kFull && b == 0) z = u[j];
+                        else if (kFull && b == 1) z = q[j];
+                        else if (kFull && b == 2) z = v[j];
+                        else if (pb == 0) z = f4_mul(u[j], q[j]);
+                        else if (pb == 1) z = f4_mul(q[j], v[j]);
+                        else if (pb == 2) z = f4_mul(v[j], u[j]);
                         else z = f4_mul(f4_mul(u[j], q[j]), v[j]);
                         store_split_chunk(a_hi, a_lo, r0 + 32 * j, c, z);
                     }
@@ -234,9 +246,9 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
             for (int itr = 0; itr < 8; ++itr) {
                 const int64_t e = e0 + itr * 4 + rs;
                 const bool ok = e < E;
-                nu[itr] = ok ? __ldg(i3 + 3 * e) : -1;
-                nq[itr] = ok ? __ldg(i3 + 3 * e + 1) : 0;
-                ni[itr] = ok ? __ldg(i3 + 3 * e + 2) : 0;
+                nu[itr] = ok ? (kFull ? 0 : __ldg(i3 + 3 * e)) : -1;
+                nq[itr] = (ok && !kFull) ? __ldg(i3 + 3 * e + 1) : 0;
+                ni[itr] = (ok && !kFull) ? __ldg(i3 + 3 * e + 2) : 0;
             }
             mbar_wait(smem_u32(&bar_tfull[buf]), (t >> 1) & 1u);
             fence_after_sync();
@@ -255,7 +267,9 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int itr = hb * 4 + k;
-                        if (nu[itr] >= 0) {
+                        if (kFull) {
+                            base[k] = p ? ldg4(p + c0 + 4 * c) : f4_zero();      // p = aggregation bias [dim]
+                        } else if (nu[itr] >= 0) {
                             base[k] = ldg4(p + (int64_t)nu[itr] * p_ld + c0 + 4 * c);
                             f4_add(base[k], ldg4(p + (int64_t)nq[itr] * p_ld + c0 + 4 * c));
                             f4_add(base[k], ldg4(p + (int64_t)ni[itr] * p_ld + c0 + 4 * c));
@@ -793,7 +807,7 @@ bool interact_tc_eligible(int dim) {
 }
 
 int64_t interact_fwd_tc_workspace_bytes(int dim, int nb) {
-    return (int64_t)nb * (dim / kChunkK) * 2 * dim * kChunkBytesPerRow + 1024;
+    return (int64_t)(3 + nb) * (dim / kChunkK) * 2 * dim * kChunkBytesPerRow + 1024;   // sized for the full form
 }
 
 int launch_interact_prep(const float* w_hi, int64_t w_ld, int nb, int dim, int transposed,
@@ -805,25 +819,35 @@ int launch_interact_prep(const float* w_hi, int64_t w_ld, int nb, int dim, int t
     return IHG_OK;
 }
 
+template <bool kFull>
+static int launch_interact_fwd_tc_impl(const float* xp, int64_t xp_ld, const float* p, int64_t p_ld,
+                                       const float* w, int64_t w_ld, int nblk, const int32_t* i3, int64_t E,
+                                       float* ef, int64_t ef_ld, int dim, void* workspace, cudaStream_t st) {
+    // 1024-byte aligned weight staging area inside the caller's workspace
+    uint8_t* wprep = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    if (int rc = launch_interact_prep(w, w_ld, nblk, dim, 0, wprep, st)) return rc;
+    const InteractSmem cfg = interact_smem(dim);
+    const int smem = cfg.stages * (int)cfg.stage_bytes + 4 * kEpiStageBytes + 1024;
+    IHG_CUDA(cudaFuncSetAttribute(edge_interact_fwd_tc_kernel<kFull>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t n_tiles = (E + kTileM - 1) / kTileM;
+    const unsigned grid = (unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+    edge_interact_fwd_tc_kernel<kFull><<<grid, kInteractThreads, smem, st>>>(xp, xp_ld, p, p_ld, wprep, nblk, i3, E, ef,
+                                                                             ef_ld, dim, cfg.stages, cfg.stage_bytes);
+    IHG_LAUNCH_CHECK();
+    return IHG_OK;
+}
+
+// hoisted form: w = aggregation.weight[:, 3d:] (nb product blocks), p = first-order rows [N, dim]
 int launch_interact_fwd_tc(const float* xp, int64_t xp_ld, const float* p, int64_t p_ld,
                            const float* w_hi, int64_t w_ld, int nb, const int32_t* i3, int64_t E,
                            float* ef, int64_t ef_ld, int dim, void* workspace, cudaStream_t st) {
-    // 1024-byte aligned weight staging area inside the caller's workspace
-    uint8_t* wprep = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
-    if (int rc = launch_interact_prep(w_hi, w_ld, nb, dim, 0, wprep, st)) return rc;
-    const InteractSmem cfg = interact_smem(dim);
-    const int smem = cfg.stages * (int)cfg.stage_bytes + 4 * kEpiStageBytes + 1024;
-    static int attr_smem = 0;
-    if (attr_smem < smem) {
-        IHG_CUDA(cudaFuncSetAttribute(edge_interact_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
-    }
-    const int64_t n_tiles = (E + kTileM - 1) / kTileM;
-    const unsigned grid = (unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
-    edge_interact_fwd_tc_kernel<<<grid, kInteractThreads, smem, st>>>(xp, xp_ld, p, p_ld, wprep, nb, i3, E, ef,
-                                                                      ef_ld, dim, cfg.stages, cfg.stage_bytes);
-    IHG_LAUNCH_CHECK();
-    return IHG_OK;
+    return launch_interact_fwd_tc_impl<false>(xp, xp_ld, p, p_ld, w_hi, w_ld, nb, i3, E, ef, ef_ld, dim, workspace, st);
+}
+// full form: w = aggregation.weight (3 + nb blocks), bias [dim] or null
+int launch_interact_fwd_full_tc(const float* xp, int64_t xp_ld, const float* w_agg, int64_t w_ld,
+                                const float* bias, int nb, const int32_t* i3, int64_t E, float* ef,
+                                int64_t ef_ld, int dim, void* workspace, cudaStream_t st) {
+    return launch_interact_fwd_tc_impl<true>(xp, xp_ld, bias, 0, w_agg, w_ld, 3 + nb, i3, E, ef, ef_ld, dim, workspace, st);
 }
 
 static int slot_nu(int dim) { return dim > 64 ? dim / 2 : dim; }

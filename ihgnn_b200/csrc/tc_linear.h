@@ -26,6 +26,9 @@ int launch_interact_fwd_tc(const float* xp, int64_t xp_ld, const float* p, int64
                            const float* w_hi, int64_t w_ld, int nb, const int32_t* i3, int64_t E,
                            float* ef, int64_t ef_ld, int dim, void* workspace, cudaStream_t st);
 
+int launch_interact_fwd_full_tc(const float* xp, int64_t xp_ld, const float* w_agg, int64_t w_ld,
+                                const float* bias, int nb, const int32_t* i3, int64_t E, float* ef,
+                                int64_t ef_ld, int dim, void* workspace, cudaStream_t st);
 int64_t interact_bwd_tc_workspace_bytes(int dim, int nb);
 int launch_interact_bwd_tc(const float* xp, int64_t xp_ld, const float* def, int64_t def_ld,
                            const float* w_hi, int64_t w_ld, int nb, const int32_t* i3, int64_t E,

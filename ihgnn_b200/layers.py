@@ -208,6 +208,55 @@ class _EdgeInteractFn(torch.autograd.Function):
         return dxp, dp, dw_hi, None, None
 
 
+class _FeatureInteractFn(torch.autograd.Function):
+    """The whole order-2/3 FeatureInteractor.forward (CommonLayers.py:68-85) in one tensor-core
+    kernel: ef = aggregation.weight . cat(u, q, i, u*q, q*i, i*u [, u*q*i]) + bias, the raw rows
+    being three more operand blocks (no first-order table, no gather in the epilogue).
+    Backward uses the hoisted algebra: dP = H^T-reduce(def) per node, then the typed node Linear
+    backward for the first-order blocks, plus the product-rule kernels for the rest."""
+
+    @staticmethod
+    def forward(ctx, xp, w_agg, bias, graph: PpsHyperGraph, order: int):
+        xp, w_agg = _lib.rows_f32(xp), _lib.rows_f32(w_agg)
+        bias = bias.contiguous()
+        dim, E = int(xp.shape[1]), graph.EdgeCount
+        ef = torch.empty((E, dim), dtype=torch.float32, device=xp.device)
+        ws_bytes = _lib.lib().ihg_edge_interact_fwd_workspace_bytes(dim, order)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=xp.device)
+        _lib.call("ihg_feature_interact_fwd", _lib.ptr(xp), _lib.ld(xp), _lib.ptr(w_agg), _lib.ld(w_agg),
+                  _lib.ptr(bias), order, _lib.ptr(graph.i3), E, _lib.ptr(ef), dim, dim, _lib.ptr(ws),
+                  ws_bytes, _lib.stream_ptr(), tag="edge_interact_fwd", algo_bytes=E * (12 + 16 * dim))
+        ctx.graph, ctx.order = graph, order
+        ctx.save_for_backward(xp, w_agg)
+        return ef
+
+    @staticmethod
+    def backward(ctx, def_):
+        xp, w_agg = ctx.saved_tensors
+        g, order = ctx.graph, ctx.order
+        def_ = _lib.rows_f32(def_)
+        dim, E = int(xp.shape[1]), g.EdgeCount
+        nb = 4 if order == 3 else 3
+        w_hi = w_agg[:, 3 * dim:]
+        w_lo = _split_first_order(w_agg, dim).contiguous()              # [3, dim, dim]
+        dp = F_.segment_reduce(g.plan, def_, dim)
+        slot_grad = torch.empty((E, 3, dim), dtype=torch.float32, device=xp.device)
+        dw_hi = torch.empty((dim, nb * dim), dtype=torch.float32, device=xp.device)
+        ws_bytes = _lib.lib().ihg_edge_interact_bwd_workspace_bytes(dim, order)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xp.device)
+        _lib.call("ihg_edge_interact_bwd", _lib.ptr(xp), _lib.ld(xp), _lib.ptr(def_), _lib.ld(def_),
+                  _lib.ptr(w_hi), _lib.ld(w_hi), order, _lib.ptr(g.i3), E, _lib.ptr(slot_grad),
+                  _lib.ptr(dw_hi), dim, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(),
+                  tag="edge_interact_bwd", algo_bytes=E * (12 + 28 * dim))
+        dxp_hi = F_.segment_reduce(g.plan, slot_grad, dim, src_row_mul=3, bounds=g.type_bounds)
+        # first-order blocks: dX' = dP . W_a[:, slot] (typed by node type) + the product-rule part
+        dxp = F_.node_linear(dp, w_lo, transpose_w=True, addend=dxp_hi, bounds=g.type_bounds)
+        dw_lo, db_lo = F_.node_linear_wgrad(dp, xp, 3, g.type_bounds, True)
+        dw = torch.cat([dw_lo[0], dw_lo[1], dw_lo[2], dw_hi], 1)
+        # every hyperedge has exactly one user: sum_e def[e] == sum over user rows of dP
+        return dxp, dw, db_lo[0], None, None
+
+
 class _ScatterMeanFn(torch.autograd.Function):
     """out[v] = row_scale[v] * sum_{e contains v} ef[e]   (thsp.matmul(incidence, ef) * Dv^-1,
     GnnLayers.py:233-234); backward is the node -> hyperedge gather-sum."""
@@ -259,12 +308,19 @@ class FeatureInteractor(nn.Module):
     def forward(self, node_features: Tensor) -> Tensor:
         _lib.require_cuda(node_features)
         g, d = self.graph, self.node_feature_dimension
+        if self._full_supported():
+            return _FeatureInteractFn.apply(node_features, self.aggregation.weight, self.aggregation.bias,
+                                            g, self.max_order)
         p = self._first_order(node_features)
         if self.max_order == 1:
             return _EdgeGatherSumFn.apply(p, g, None, 1.0, None)
         if self.output_dimension != d:
             raise NotImplementedError("order 2/3 FeatureInteractor requires output_dimension == node_feature_dimension")
         return _EdgeInteractFn.apply(node_features, p, self.aggregation.weight[:, 3 * d:], g, self.max_order)
+
+    def _full_supported(self) -> bool:
+        return (self.max_order in (2, 3) and self.output_dimension == self.node_feature_dimension
+                and bool(_lib.lib().ihg_feature_interact_supported(self.node_feature_dimension)))
 
 
 class IHGNNLayer(nn.Module):

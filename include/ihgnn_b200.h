@@ -144,6 +144,19 @@ int ihg_edge_interact_fwd(const float* xp, int64_t xp_ld, const float* p, int64_
                           const float* w_hi, int64_t w_ld, int32_t order, const int32_t* i3,
                           int64_t edge_count, float* ef, int64_t ef_ld, int32_t dim,
                           void* workspace, int64_t workspace_bytes, void* stream);
+/* The whole FeatureInteractor.forward of order 2/3 in one call (CommonLayers.py:68-85):
+ *   ef[e,:] = aggregation.weight . cat(u, q, i, u*q, q*i, i*u [, u*q*i]) + bias
+ * w_agg = aggregation.weight [dim, K*dim] (K = 6 or 7, row stride w_ld), bias [dim] or null.
+ * Tensor-core path only (dim % 32 == 0, dim <= 128): the raw rows are three more operand blocks
+ * next to the products, so no first-order table is gathered.  Same workspace size as
+ * ihg_edge_interact_fwd.  Returns IHG_ERR_INVALID_ARGUMENT for other dims (use the hoisted
+ * ihg_edge_interact_fwd there). */
+int ihg_feature_interact_fwd(const float* xp, int64_t xp_ld, const float* w_agg, int64_t w_ld,
+                             const float* bias, int32_t order, const int32_t* i3,
+                             int64_t edge_count, float* ef, int64_t ef_ld, int32_t dim,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+/* 1 if ihg_feature_interact_fwd supports this dim on this build, else 0. */
+int ihg_feature_interact_supported(int32_t dim);
 int64_t ihg_edge_interact_bwd_workspace_bytes(int32_t dim, int32_t order);
 int ihg_edge_interact_bwd(const float* xp, int64_t xp_ld, const float* def, int64_t def_ld,
                           const float* w_hi, int64_t w_ld, int32_t order, const int32_t* i3,
