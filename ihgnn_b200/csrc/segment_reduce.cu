@@ -23,8 +23,8 @@ constexpr int kSegWarpsPerBlock = 8;
 constexpr int kSegUnroll = 4;        // independent 128-bit row gathers in flight per lane group
 constexpr int kSegPerGroup = 1;      // chunks a lane group walks through (strided)
 
-template <int LPR, int VPL, int UNR, int SEGS, int MINB>
-__global__ void __launch_bounds__(kSegWarpsPerBlock * 32, MINB)
+template <int LPR, int VPL, int UNR, int SEGS>
+__global__ void __launch_bounds__(kSegWarpsPerBlock * 32)
 segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src_row_mul,
                       int64_t bound0, int64_t bound1, const int32_t* __restrict__ row_slot,
                       const float* __restrict__ init, int64_t init_ld,
@@ -193,7 +193,7 @@ static int launch_segment_reduce(const ihg_csr* g, const float* src, int64_t src
     const int64_t n_groups = blocks * groups_per_block;
     // unroll 4, no forced occupancy: forcing >= 4 blocks/SM wins in the isolated microbenchmark
     // but loses in the real step (1.14 vs 1.07 ms at amazon-full), so the in-situ winner stays
-    segment_reduce_kernel<LPR, VPL, kSegUnroll, SEGS, 1><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
+    segment_reduce_kernel<LPR, VPL, kSegUnroll, SEGS><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
         src, src_ld, mul, b0, b1, row_slot, init, init_ld, src_scale, row_scale, g->col, g->n_seg, n_groups,
         reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
     IHG_LAUNCH_CHECK();
