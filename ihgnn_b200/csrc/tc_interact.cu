@@ -132,63 +132,56 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
         // ======================= producers =======================
         // lane mapping (row, chunk): 8 consecutive lanes read one row's 128-byte slice, so a warp
         // request touches 4 full lines; thread owns chunk c of rows r0, r0+32, r0+64, r0+96.
-        // Work units (tile, kc) are software-pipelined: the 12 gathers of unit n+1 are issued into a
-        // second register set before the stages of unit n are produced, so the gather latency
-        // overlaps the split / store work and the MMA back-pressure waits.
         const int c = tid & 7, r0 = tid >> 3;
-        const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        const int64_t n_units = my_tiles * KC;
         uint32_t it = 0;                    // global chunk counter (stage ring position)
-        float4 ua[4], qa[4], va[4], ub[4], qb[4], vb[4];
-
-        auto prefetch = [&](int64_t unit, float4 (&u)[4], float4 (&q)[4], float4 (&v)[4]) {
-            const int64_t tile = blockIdx.x + (unit / KC) * gridDim.x;
-            const int kc = (int)(unit % KC);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const float *pu[4], *pq[4], *pi[4];
+            bool ok[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int64_t e = tile * kTileM + r0 + 32 * j;
-                if (e < E) {
-                    const int nu = __ldg(i3 + 3 * e), nq = __ldg(i3 + 3 * e + 1), ni = __ldg(i3 + 3 * e + 2);
-                    u[j] = ldg4(xp + (int64_t)nu * xp_ld + kc * kChunkK + 4 * c);
-                    q[j] = ldg4(xp + (int64_t)nq * xp_ld + kc * kChunkK + 4 * c);
-                    v[j] = ldg4(xp + (int64_t)ni * xp_ld + kc * kChunkK + 4 * c);
-                } else {
-                    u[j] = q[j] = v[j] = f4_zero();
+                ok[j] = e < E;
+                int nu = 0, nq = 0, ni = 0;
+                if (ok[j]) {
+                    nu = __ldg(i3 + 3 * e);
+                    nq = __ldg(i3 + 3 * e + 1);
+                    ni = __ldg(i3 + 3 * e + 2);
                 }
+                pu[j] = xp + (int64_t)nu * xp_ld + 4 * c;
+                pq[j] = xp + (int64_t)nq * xp_ld + 4 * c;
+                pi[j] = xp + (int64_t)ni * xp_ld + 4 * c;
             }
-        };
-        auto produce = [&](const float4 (&u)[4], const float4 (&q)[4], const float4 (&v)[4]) {
-            for (int b = 0; b < nb; ++b, ++it) {
-                const int s = it % stages;
-                const uint32_t ph = (it / stages) & 1u;
-                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
-                const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes;
-                const uint32_t a_lo = a_hi + kATileBytes;
-                const int pb = kFull ? b - 3 : b;             // product block; < 0: raw row block b
+            for (int kc = 0; kc < KC; ++kc) {
+                float4 u[4], q[4], v[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float4 z;
-                    if (kFull && b == 0) z = u[j];
-                    else if (kFull && b == 1) z = q[j];
-                    else if (kFull && b == 2) z = v[j];
-                    else if (pb == 0) z = f4_mul(u[j], q[j]);
-                    else if (pb == 1) z = f4_mul(q[j], v[j]);
-                    else if (pb == 2) z = f4_mul(v[j], u[j]);
-                    else z = f4_mul(f4_mul(u[j], q[j]), v[j]);
-                    store_split_chunk(a_hi, a_lo, r0 + 32 * j, c, z);
+                    u[j] = ok[j] ? ldg4(pu[j] + kc * kChunkK) : f4_zero();
+                    q[j] = ok[j] ? ldg4(pq[j] + kc * kChunkK) : f4_zero();
+                    v[j] = ok[j] ? ldg4(pi[j] + kc * kChunkK) : f4_zero();
                 }
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
-            }
-        };
-        if (n_units > 0) prefetch(0, ua, qa, va);
-        for (int64_t unit = 0; unit < n_units; unit += 2) {
-            if (unit + 1 < n_units) prefetch(unit + 1, ub, qb, vb);
-            produce(ua, qa, va);
-            if (unit + 1 < n_units) {
-                if (unit + 2 < n_units) prefetch(unit + 2, ua, qa, va);
-                produce(ub, qb, vb);
+                for (int b = 0; b < nb; ++b, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1u;
+                    mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+                    const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes;
+                    const uint32_t a_lo = a_hi + kATileBytes;
+                    const int pb = kFull ? b - 3 : b;             // product block; < 0: raw row block b
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4 z;
+                        if (kFull && b == 0) z = u[j];
+                        else if (kFull && b == 1) z = q[j];
+                        else if (kFull && b == 2) z = v[j];
+                        else if (pb == 0) z = f4_mul(u[j], q[j]);
+                        else if (pb == 1) z = f4_mul(q[j], v[j]);
+                        else if (pb == 2) z = f4_mul(v[j], u[j]);
+                        else z = f4_mul(f4_mul(u[j], q[j]), v[j]);
+                        store_split_chunk(a_hi, a_lo, r0 + 32 * j, c, z);
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
+                }
             }
         }
     } else if (warp == kLoadWarp) {
