@@ -22,10 +22,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ---- operand split ---------------------------------------------------------------------
+// Round-to-nearest (ties away from zero, == cvt.rna.tf32.f32) to the 10 explicit mantissa bits of
+// tf32, done with integer add + mask on the full-rate ALU pipe: the cvt instruction runs on the
+// 16-lane conversion pipe and was measured to dominate the operand producers (an in-kernel
+// clock64 trace showed ~900 cycles per 128x32 stage, ~60 % of it in cvt).
 __device__ __forceinline__ uint32_t rna_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
+    return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
 }
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
     hi = rna_tf32(x);
