@@ -93,8 +93,20 @@ static inline InteractSmem interact_smem(int dim) {
 //                 producers' registers) are three more A blocks contracted with
 //                 aggregation.weight[:, :3d], so there is no p table, no p gather and the epilogue
 //                 only adds the bias and stores.  nb counts ALL blocks (6 or 7) in this mode.
+// Forward-kernel roles: 16 producer warps (an in-kernel clock64 trace showed the operand
+// producers, not the gathers or the MMAs, bound the tile time; with 2 warps per scheduler their
+// dependent ALU chains and proxy fences left the issue slots mostly idle), 4 epilogue warps,
+// 1 MMA warp, 1 weight-loader warp.
+constexpr int kFwdProducerWarps = 16;
+constexpr int kFwdEpiWarp0 = kFwdProducerWarps;          // multiple of 4: warp % 4 == TMEM quadrant
+constexpr int kFwdMmaWarp = kFwdProducerWarps + 4;
+constexpr int kFwdLoadWarp = kFwdProducerWarps + 5;
+constexpr int kFwdThreads = (kFwdProducerWarps + 6) * 32;
+constexpr int kFwdItems = kTileM * 8 / (kFwdProducerWarps * 32);   // (row, chunk) items per producer thread
+constexpr int kFwdRowStep = kFwdProducerWarps * 4;                 // rows covered by one pass of the producers
+
 template <bool kFull>
-__global__ void __launch_bounds__(kInteractThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const float* __restrict__ p,
                             int64_t p_ld, const uint8_t* __restrict__ wprep, int nb,
                             const int32_t* __restrict__ i3, int64_t E, float* __restrict__ ef,
@@ -113,7 +125,7 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(smem_u32(&bar_full[s]), kProducerWarps + 1);
+            mbar_init(smem_u32(&bar_full[s]), kFwdProducerWarps + 1);
             mbar_init(smem_u32(&bar_empty[s]), 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -122,24 +134,24 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
         }
         mbar_init_fence();
     }
-    if (warp == kMmaWarp) tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols);
+    if (warp == kFwdMmaWarp) tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = tmem_base_slot;
 
-    if (warp < kProducerWarps) {
+    if (warp < kFwdProducerWarps) {
         // ======================= producers =======================
         // lane mapping (row, chunk): 8 consecutive lanes read one row's 128-byte slice, so a warp
-        // request touches 4 full lines; thread owns chunk c of rows r0, r0+32, r0+64, r0+96.
+        // request touches 4 full lines; thread owns chunk c of rows r0 + kFwdRowStep * j.
         const int c = tid & 7, r0 = tid >> 3;
         uint32_t it = 0;                    // global chunk counter (stage ring position)
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const float *pu[4], *pq[4], *pi[4];
-            bool ok[4];
+            const float *pu[kFwdItems], *pq[kFwdItems], *pi[kFwdItems];
+            bool ok[kFwdItems];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int64_t e = tile * kTileM + r0 + 32 * j;
+            for (int j = 0; j < kFwdItems; ++j) {
+                const int64_t e = tile * kTileM + r0 + kFwdRowStep * j;
                 ok[j] = e < E;
                 int nu = 0, nq = 0, ni = 0;
                 if (ok[j]) {
@@ -152,9 +164,9 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
                 pi[j] = xp + (int64_t)ni * xp_ld + 4 * c;
             }
             for (int kc = 0; kc < KC; ++kc) {
-                float4 u[4], q[4], v[4];
+                float4 u[kFwdItems], q[kFwdItems], v[kFwdItems];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < kFwdItems; ++j) {
                     u[j] = ok[j] ? ldg4(pu[j] + kc * kChunkK) : f4_zero();
                     q[j] = ok[j] ? ldg4(pq[j] + kc * kChunkK) : f4_zero();
                     v[j] = ok[j] ? ldg4(pi[j] + kc * kChunkK) : f4_zero();
@@ -167,7 +179,7 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
                     const uint32_t a_lo = a_hi + kATileBytes;
                     const int pb = kFull ? b - 3 : b;             // product block; < 0: raw row block b
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < kFwdItems; ++j) {
                         float4 z;
                         if (kFull && b == 0) z = u[j];
                         else if (kFull && b == 1) z = q[j];
@@ -176,7 +188,7 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
                         else if (pb == 1) z = f4_mul(q[j], v[j]);
                         else if (pb == 2) z = f4_mul(v[j], u[j]);
                         else z = f4_mul(f4_mul(u[j], q[j]), v[j]);
-                        store_split_chunk(a_hi, a_lo, r0 + 32 * j, c, z);
+                        store_split_chunk(a_hi, a_lo, r0 + kFwdRowStep * j, c, z);
                     }
                     fence_async_smem();
                     __syncwarp();
@@ -184,7 +196,7 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
                 }
             }
         }
-    } else if (warp == kLoadWarp) {
+    } else if (warp == kFwdLoadWarp) {
         // ======================= weight loader =======================
         if (lane == 0) {
             uint32_t it = 0;
@@ -201,7 +213,7 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
                     }
             }
         }
-    } else if (warp == kMmaWarp) {
+    } else if (warp == kFwdMmaWarp) {
         // ======================= MMA issuer =======================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(dim);
@@ -233,7 +245,7 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
         }
     } else {
         // ======================= epilogue =======================
-        const int q4 = warp - kEpilogueWarp0;           // TMEM lane quadrant == warp % 4
+        const int q4 = warp - kFwdEpiWarp0;             // TMEM lane quadrant == warp % 4
         const uint32_t stg = epi_base + (uint32_t)q4 * kEpiStageBytes;
         const int c = lane & 7, rs = lane >> 3;         // (row-in-group, chunk) mapping for global access
         uint32_t t = 0;
@@ -294,7 +306,7 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == kMmaWarp) tmem_dealloc(tmem_base, tmem_cols);
+    if (warp == kFwdMmaWarp) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 
@@ -831,7 +843,7 @@ static int launch_interact_fwd_tc_impl(const float* xp, int64_t xp_ld, const flo
     IHG_CUDA(cudaFuncSetAttribute(edge_interact_fwd_tc_kernel<kFull>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t n_tiles = (E + kTileM - 1) / kTileM;
     const unsigned grid = (unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
-    edge_interact_fwd_tc_kernel<kFull><<<grid, kInteractThreads, smem, st>>>(xp, xp_ld, p, p_ld, wprep, nblk, i3, E, ef,
+    edge_interact_fwd_tc_kernel<kFull><<<grid, kFwdThreads, smem, st>>>(xp, xp_ld, p, p_ld, wprep, nblk, i3, E, ef,
                                                                              ef_ld, dim, cfg.stages, cfg.stage_bytes);
     IHG_LAUNCH_CHECK();
     return IHG_OK;
