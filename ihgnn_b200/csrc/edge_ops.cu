@@ -406,7 +406,10 @@ int ihg_edge_interact_fwd(const float* xp, int64_t xp_ld, const float* p, int64_
     return IHG_OK;
 }
 
-int ihg_feature_interact_supported(int32_t dim) { return interact_tc_eligible(dim) ? 1 : 0; }
+int ihg_feature_interact_supported(int32_t dim) {
+    static const bool hoisted_only = getenv("IHG_HOISTED_FWD") != nullptr;     // A/B switch for measurements
+    return (!hoisted_only && interact_tc_eligible(dim)) ? 1 : 0;
+}
 
 int ihg_feature_interact_fwd(const float* xp, int64_t xp_ld, const float* w_agg, int64_t w_ld,
                              const float* bias, int32_t order, const int32_t* i3, int64_t E,

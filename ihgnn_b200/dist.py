@@ -184,14 +184,8 @@ class HaloExchangeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_own, g: "ShardedHyperGraph"):
-        from . import functional as F_
         ctx.g = g
-        d = int(x_own.shape[1])
-        send = F_.gather_rows_raw(x_own, g.send_rows, 0)
-        x_local = torch.empty((g.n_local, d), dtype=torch.float32, device=x_own.device)
-        _all_to_all(x_local[g.n_own:], send, g.recv_counts, g.send_counts, g.group)
-        F_.copy_rows_raw(x_own, x_local[:g.n_own])
-        return x_local
+        return _halo_exchange(x_own, g)
 
     @staticmethod
     def backward(ctx, dx_local):
@@ -218,6 +212,73 @@ class ShardedScatterMeanFn(torch.autograd.Function):
         g = ctx.g
         g_local = HaloExchangeFn.apply(dout_own.contiguous(), g)
         return F_.edge_gather_sum(g_local, g.i3, node_scale=g.dv_inv_local), None
+
+
+def _halo_exchange(x_own: torch.Tensor, g: "ShardedHyperGraph") -> torch.Tensor:
+    """[n_own, d] -> [n_local, d] = [own rows ; rows received from their owners] (no autograd)."""
+    from . import functional as F_
+    d = int(x_own.shape[1])
+    send = F_.gather_rows_raw(x_own, g.send_rows, 0)
+    x_local = torch.empty((g.n_local, d), dtype=torch.float32, device=x_own.device)
+    _all_to_all(x_local[g.n_own:], send, g.recv_counts, g.send_counts, g.group)
+    F_.copy_rows_raw(x_own, x_local[:g.n_own])
+    return x_local
+
+
+class ShardedFeatureInteractFn(torch.autograd.Function):
+    """Order 2/3 FeatureInteractor over a partitioned hypergraph, un-hoisted tensor-core forward:
+    only the projected rows xp travel (d floats per boundary row); backward reduces the
+    per-row gradients [dxp_hi | dP] of own + halo rows to their owners in ONE exchange and then
+    applies the typed first-order Linear backward on the own rows."""
+
+    @staticmethod
+    def forward(ctx, xp_own, w_agg, bias, g: "ShardedHyperGraph", order: int):
+        from . import _lib
+        xp_own = _lib.rows_f32(xp_own)
+        w_agg = _lib.rows_f32(w_agg)
+        bias = bias.contiguous()
+        dim, E = int(xp_own.shape[1]), g.EdgeCount
+        xp_local = _halo_exchange(xp_own, g)
+        ef = torch.empty((E, dim), dtype=torch.float32, device=xp_own.device)
+        ws_bytes = _lib.lib().ihg_edge_interact_fwd_workspace_bytes(dim, order)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=xp_own.device)
+        _lib.call("ihg_feature_interact_fwd", _lib.ptr(xp_local), dim, _lib.ptr(w_agg), _lib.ld(w_agg),
+                  _lib.ptr(bias), order, _lib.ptr(g.i3), E, _lib.ptr(ef), dim, dim, _lib.ptr(ws), ws_bytes,
+                  _lib.stream_ptr(), tag="edge_interact_fwd", algo_bytes=E * (12 + 16 * dim))
+        ctx.g, ctx.order = g, order
+        ctx.save_for_backward(xp_own, xp_local, w_agg)
+        return ef
+
+    @staticmethod
+    def backward(ctx, def_):
+        from . import _lib
+        from . import functional as F_
+        from .layers import _split_first_order
+        xp_own, xp_local, w_agg = ctx.saved_tensors
+        g, order = ctx.g, ctx.order
+        def_ = _lib.rows_f32(def_)
+        dim, E = int(xp_own.shape[1]), g.EdgeCount
+        nb = 4 if order == 3 else 3
+        w_hi = w_agg[:, 3 * dim:]
+        w_lo = _split_first_order(w_agg, dim).contiguous()
+        slot_grad = torch.empty((E, 3, dim), dtype=torch.float32, device=def_.device)
+        dw_hi = torch.empty((dim, nb * dim), dtype=torch.float32, device=def_.device)
+        ws_bytes = _lib.lib().ihg_edge_interact_bwd_workspace_bytes(dim, order)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=def_.device)
+        _lib.call("ihg_edge_interact_bwd", _lib.ptr(xp_local), dim, _lib.ptr(def_), _lib.ld(def_),
+                  _lib.ptr(w_hi), _lib.ld(w_hi), order, _lib.ptr(g.i3), E, _lib.ptr(slot_grad),
+                  _lib.ptr(dw_hi), dim, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(),
+                  tag="edge_interact_bwd", algo_bytes=E * (12 + 28 * dim))
+        # per-row gradients of the local rows, side by side: [ product-rule part | dP ]
+        both = torch.empty((g.n_local, 2 * dim), dtype=torch.float32, device=def_.device)
+        F_.segment_reduce(g.plan_csr, slot_grad, dim, src_row_mul=3, row_slot=g.row_slot, out=both[:, :dim])
+        F_.segment_reduce(g.plan_csr, def_, dim, out=both[:, dim:])
+        own = _halo_reduce(both, g, None)                                  # [n_own, 2 dim]
+        dxp_hi, dp = own[:, :dim], own[:, dim:]
+        dxp = F_.node_linear(dp, w_lo, transpose_w=True, addend=dxp_hi, bounds=g.own_bounds)
+        dw_lo, db_lo = F_.node_linear_wgrad(dp, xp_own, 3, g.own_bounds, True)
+        dw = torch.cat([dw_lo[0], dw_lo[1], dw_lo[2], dw_hi], 1)
+        return dxp, dw, db_lo[0], None, None
 
 
 def _halo_reduce(s_local: torch.Tensor, g: ShardedHyperGraph, row_scale: Optional[torch.Tensor]) -> torch.Tensor:
@@ -280,12 +341,16 @@ class ShardedIHGNNLayer(torch.nn.Module):
             p = halo_exchange(p_own, g)
             ef = _EdgeGatherSumFn.apply(p, self.view, None, 1.0, None)
         else:
+            from . import _lib
             xp_own = F_.typed_linear(x_own, wt.unsqueeze(0), bt.unsqueeze(0), None)
-            b_lo = torch.stack([fi.aggregation.bias, zeros, zeros])
-            p_own = F_.typed_linear(xp_own, w_lo, b_lo, g.own_bounds)
-            both = halo_exchange(torch.cat([xp_own, p_own], 1), g)     # one exchange for both row sets
-            xp, p = both[:, :d], both[:, d:]
-            ef = _EdgeInteractFn.apply(xp, p, fi.aggregation.weight[:, 3 * d:], self.view, self.order)
+            if _lib.lib().ihg_feature_interact_supported(d):
+                ef = ShardedFeatureInteractFn.apply(xp_own, fi.aggregation.weight, fi.aggregation.bias, g, self.order)
+            else:
+                b_lo = torch.stack([fi.aggregation.bias, zeros, zeros])
+                p_own = F_.typed_linear(xp_own, w_lo, b_lo, g.own_bounds)
+                both = halo_exchange(torch.cat([xp_own, p_own], 1), g)     # one exchange for both row sets
+                xp, p = both[:, :d], both[:, d:]
+                ef = _EdgeInteractFn.apply(xp, p, fi.aggregation.weight[:, 3 * d:], self.view, self.order)
         return ShardedScatterMeanFn.apply(ef, g)
 
 
