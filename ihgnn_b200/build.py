@@ -53,9 +53,9 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def _compile(nvcc: str, src: str) -> str:
-    obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
-    cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(REPO, "include"), "-c", src, "-o", obj]
+def _compile(nvcc: str, src: str, obj_dir: str = OBJ_DIR, extra=()) -> str:
+    obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", os.path.join(REPO, "include"), "-c", src, "-o", obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc failed on {src}:\n{res.stdout}\n{res.stderr}")
@@ -86,8 +86,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def build_trace() -> str:
+    """Dev-only instrumented copy (clock64 probes, -DIHG_TRACE) -> build/libihgnn_trace.so."""
+    nvcc = _nvcc()
+    obj_dir = os.path.join(REPO, "build", "obj_trace")
+    os.makedirs(obj_dir, exist_ok=True)
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(lambda s: _compile(nvcc, s, obj_dir, ("-DIHG_TRACE",)), sources()))
+    out = os.path.join(REPO, "build", "libihgnn_trace.so")
+    res = subprocess.run([nvcc, "-shared", "-o", out, *objs], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
+    ap.add_argument("--trace", action="store_true", help="also build the instrumented dev library")
     args = ap.parse_args()
     print(build(force=args.force, verbose=True))
+    if args.trace:
+        print(build_trace())

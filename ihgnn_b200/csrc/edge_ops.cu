@@ -422,7 +422,11 @@ int ihg_feature_interact_fwd(const float* xp, int64_t xp_ld, const float* w_agg,
     IHG_REQUIRE(workspace && workspace_bytes >= ihg_edge_interact_fwd_workspace_bytes(dim, order),
                 "feature_interact_fwd: workspace too small");
     if (E == 0) return IHG_OK;
-    return launch_interact_fwd_full_tc(xp, xp_ld, w_agg, w_ld, bias, order == 3 ? 4 : 3, i3, E, ef, ef_ld, dim,
+    static const bool smem_operand = getenv("IHG_FWD_SS") != nullptr;          // A/B switch: A operand in shared memory
+    if (smem_operand)
+        return launch_interact_fwd_full_tc(xp, xp_ld, w_agg, w_ld, bias, order == 3 ? 4 : 3, i3, E, ef, ef_ld, dim,
+                                           workspace, as_stream(stream));
+    return launch_interact_fwd_full_ts(xp, xp_ld, w_agg, w_ld, bias, order == 3 ? 4 : 3, i3, E, ef, ef_ld, dim,
                                        workspace, as_stream(stream));
 }
 

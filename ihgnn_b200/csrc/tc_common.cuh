@@ -127,6 +127,30 @@ __device__ __forceinline__ void mma_3xtf32(uint32_t tmem_d, uint64_t a_hi, uint6
     mma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
     mma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
 }
+// ---- MMA issue discipline -----------------------------------------------------------------
+// The issuing warp must run its loop in warp-uniform control flow and guard only the asm with
+// elect_one(): under `if (lane == 0)` ptxas cannot prove the operands uniform and wraps EVERY
+// tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall, which measured 57-186 cycles
+// per MMA against a 32-cycle tensor floor (profiles/microbench_mma2.cu: 32.0 cycles with this
+// shape).  Values loaded from shared memory (the TMEM base) are made provably uniform with
+// warp_uniform() so they live in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
+
+// D[tmem] (+)= A[tmem] . B[smem descriptor]: A operand read from tensor memory (lane = row,
+// one 32-bit column per K element), one K step of 8
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint32_t mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }

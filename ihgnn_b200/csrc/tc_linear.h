@@ -26,6 +26,10 @@ int launch_interact_fwd_tc(const float* xp, int64_t xp_ld, const float* p, int64
                            const float* w_hi, int64_t w_ld, int nb, const int32_t* i3, int64_t E,
                            float* ef, int64_t ef_ld, int dim, void* workspace, cudaStream_t st);
 
+// same contract, A operand in tensor memory (tc_interact_ts.cu)
+int launch_interact_fwd_full_ts(const float* xp, int64_t xp_ld, const float* w_agg, int64_t w_ld,
+                                const float* bias, int nb, const int32_t* i3, int64_t E, float* ef,
+                                int64_t ef_ld, int dim, void* workspace, cudaStream_t st);
 int launch_interact_fwd_full_tc(const float* xp, int64_t xp_ld, const float* w_agg, int64_t w_ld,
                                 const float* bias, int nb, const int32_t* i3, int64_t E, float* ef,
                                 int64_t ef_ld, int dim, void* workspace, cudaStream_t st);
