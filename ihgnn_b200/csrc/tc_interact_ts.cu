@@ -3,21 +3,20 @@
 //   ef[e,:] = aggregation.weight . cat(u, q, i, u*q, q*i, i*u [, u*q*i]) + bias
 //   (/root/reference/Models/CommonLayers.py:68-85; u,q,i = projected rows of the hyperedge's nodes)
 //
-// Why: with both operands in shared memory the 3xTF32 contraction is shared-memory-bandwidth
-// bound -- per 32-wide K chunk the tensor core reads A_hi twice, A_lo once (48 KB) and the
-// producers write 32 KB of split operand, ~100 KB of traffic for 384 cycles of MMA at d = 64
-// (measured: 13 K cycles per 128-hyperedge tile against a 5.4 K-cycle tensor floor).  Here the
-// split A operand never touches shared memory: the producers build it in registers and write it
-// to TMEM with tcgen05.st (thread = one hyperedge row = one TMEM lane, no swizzle, no proxy
-// fence), and the MMA reads A from TMEM and only the weight chunk from shared memory.
+// The split (3xTF32) A operand never touches shared memory: the producers build it in registers
+// and write it to TMEM with tcgen05.st (thread = one hyperedge row = one TMEM lane: no swizzle,
+// no proxy fence), the MMA reads A from TMEM and only the weight chunk from shared memory.
 //
-// Persistent, warp-specialised, one CTA per SM, 128 hyperedges per tile:
-//   warps 0-15  producers.  A "granule" is (tile, 32-column slice): the 128-byte slices of the
-//               u/q/i rows are gathered with cp.async (8 lanes per row: coalesced, no
-//               registers) into a double-buffered staging area one granule ahead; then thread
-//               (row = 32*(warp%4)+lane, column group = warp/4) reads its 8 columns of u, q, i
-//               once and produces the 6-7 operand blocks hi/lo into the TMEM A ring;
-//   warp 20     MMA issuer: 4 K-steps x 3 tcgen05.mma (A in TMEM, B descriptor) per chunk;
+// Persistent, warp-specialised, one CTA per SM, 128 hyperedges per tile.  A "granule" is
+// (tile, 32-column slice kc); a "chunk" is (granule, operand block b) = 12 MMAs (4 K steps x 3).
+//   warps 22-25 gather: cp.async the 128-byte slices of the u/q/i rows of a granule into a ring
+//               of staging buffers (8 lanes per row: coalesced, no registers), completion on an
+//               mbarrier (cp.async.mbarrier.arrive.noinc);
+//   warps 0-15  producers, four groups of four warps; group g owns chunks c = g (mod 4), so four
+//               chunks are in flight and the per-chunk barrier traffic is paid once per 32
+//               columns: thread = row 32*(warp%4)+lane reads its slices, forms the block's
+//               products, splits hi/lo and tcgen05.st's them into the TMEM A ring;
+//   warp 20     MMA issuer (warp-uniform loop + elect.sync, see tc_common.cuh);
 //   warp 21     weight loader: cp.async.bulk of the pre-split, pre-swizzled weight chunks;
 //   warps 16-19 epilogue: tcgen05.ld the accumulator, add bias, staged coalesced store of ef.
 // TMEM map (512 columns): [0, 2*dim) two accumulator buffers; then A stages of 64 columns
@@ -32,6 +31,12 @@ using namespace tc;
 #ifdef IHG_TRACE
 // dev-only clock64 probes of block 0 (python -m ihgnn_b200.build --trace; profiles/trace_fwd_kernel.py)
 __device__ long long g_ts_trace[8][8192];
+__device__ long long g_ts_cta[160][2];             // per-CTA start / end (globaltimer ns)
+__device__ __forceinline__ long long ts_gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 #define TS_PROBE(cond, rowi, idx)                                                     \
     do {                                                                              \
         if (blockIdx.x == 0 && (cond) && (idx) < 8192) g_ts_trace[rowi][idx] = clock64(); \
@@ -45,15 +50,19 @@ __device__ long long g_ts_trace[8][8192];
 namespace {
 
 constexpr int kTsProducerWarps = 16;
-constexpr int kTsProducerThreads = kTsProducerWarps * 32;
+constexpr int kTsGroups = kTsProducerWarps / 4;
 constexpr int kTsEpiWarp0 = kTsProducerWarps;
 constexpr int kTsMmaWarp = kTsProducerWarps + 4;
 constexpr int kTsLoadWarp = kTsProducerWarps + 5;
-constexpr int kTsThreads = (kTsProducerWarps + 6) * 32;
+constexpr int kTsGatherWarp0 = kTsProducerWarps + 6;
+constexpr int kTsGatherWarps = 4;
+constexpr int kTsGatherThreads = kTsGatherWarps * 32;
+constexpr int kTsThreads = (kTsProducerWarps + 6 + kTsGatherWarps) * 32;
 constexpr int kTsGranuleBytes = 3 * kTileM * kChunkBytesPerRow;           // 48 KB: u, q, i slices
-constexpr int kTsCopies = 3 * kTileM * 8 / kTsProducerThreads;            // 16-byte cp.async per thread per granule
+constexpr int kTsCopies = 3 * kTileM * 8 / kTsGatherThreads;              // 16-byte cp.async per gather thread per granule
 constexpr int kTsMaxAStages = 6;
 constexpr int kTsMaxWStages = 6;
+constexpr int kTsMaxGranules = 3;
 
 __device__ __forceinline__ void mbar_expect_tx_(uint32_t mbar, uint32_t bytes) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(mbar), "r"(bytes) : "memory");
@@ -66,8 +75,9 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, 
     const uint32_t n = valid ? 16u : 0u;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
 }
-__device__ __forceinline__ void producer_barrier() {
-    asm volatile("bar.sync 1, %0;" ::"n"(kTsProducerThreads) : "memory");
+// arrive on `mbar` once all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive(uint32_t mbar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(mbar) : "memory");
 }
 // this warp's TMEM lane quadrant x 8 consecutive 32-bit columns <- 8 registers per thread
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
@@ -81,15 +91,56 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ uint32_t stage_off(int table, int row, int chunk) {
     return (uint32_t)((table * kTileM + row) * kChunkBytesPerRow + ((chunk ^ (row & 7)) << 4));
 }
+// hi = tf32(x) rounded to nearest; lo = x - hi is passed as is: the tensor core reads its top
+// 19 bits, |lo - tf32(lo)| <= 2^-10 |lo| <= 2^-21 |x|
+__device__ __forceinline__ void split_fast(float x, uint32_t& hi, uint32_t& lo) {
+    hi = rna_tf32(x);
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// One chunk of operand block B for this thread's row: 32 columns in four passes of 8.
+//   B: 0,1,2 = u, q, i;  3,4,5 = u*q, q*i, i*u;  6 = u*q*i
+template <int B>
+__device__ __forceinline__ void produce_chunk(uint32_t gbuf, int row, uint32_t ta) {
+    constexpr bool need_u = B == 0 || B == 3 || B == 5 || B == 6;
+    constexpr bool need_q = B == 1 || B == 3 || B == 4 || B == 6;
+    constexpr bool need_v = B == 2 || B == 4 || B == 5 || B == 6;
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+        float z[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float4 a = f4_zero(), b = f4_zero(), c = f4_zero();
+            if (need_u) a = lds4(gbuf + stage_off(0, row, 2 * pass + h));
+            if (need_q) b = lds4(gbuf + stage_off(1, row, 2 * pass + h));
+            if (need_v) c = lds4(gbuf + stage_off(2, row, 2 * pass + h));
+            float4 r;
+            if (B == 0) r = a;
+            else if (B == 1) r = b;
+            else if (B == 2) r = c;
+            else if (B == 3) r = f4_mul(a, b);
+            else if (B == 4) r = f4_mul(b, c);
+            else if (B == 5) r = f4_mul(c, a);
+            else r = f4_mul(f4_mul(a, b), c);
+            z[4 * h] = r.x, z[4 * h + 1] = r.y, z[4 * h + 2] = r.z, z[4 * h + 3] = r.w;
+        }
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) split_fast(z[k], hi[k], lo[k]);
+        tmem_st8(ta + 8u * pass, hi);
+        tmem_st8(ta + 32u + 8u * pass, lo);
+    }
+}
 
 __global__ void __launch_bounds__(kTsThreads, 1)
 feature_interact_fwd_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, const float* __restrict__ bias,
                                const uint8_t* __restrict__ wprep, int nb, const int32_t* __restrict__ i3,
                                int64_t E, float* __restrict__ ef, int64_t ef_ld, int dim, int a_stages,
-                               int w_stages) {
+                               int w_stages, int n_gran) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_afull[kTsMaxAStages], bar_aempty[kTsMaxAStages];
     __shared__ __align__(8) uint64_t bar_wfull[kTsMaxWStages], bar_wempty[kTsMaxWStages];
+    __shared__ __align__(8) uint64_t bar_gfull[kTsMaxGranules], bar_gempty[kTsMaxGranules];
     __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_slot;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -99,18 +150,22 @@ feature_interact_fwd_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, cons
     const uint32_t w_stage_bytes = 2u * (uint32_t)dim * kChunkBytesPerRow;     // hi + lo weight chunk
     const int64_t n_tiles = (E + kTileM - 1) / kTileM;
     const int64_t my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    // shared memory map: [W ring][2 granules][4 epilogue staging tiles]
+    // shared memory map: [W ring][granule ring][4 epilogue staging tiles]
     const uint32_t gran_base = smem_base + (uint32_t)w_stages * w_stage_bytes;
-    const uint32_t epi_base = gran_base + 2u * kTsGranuleBytes;
+    const uint32_t epi_base = gran_base + (uint32_t)n_gran * kTsGranuleBytes;
 
     if (tid == 0) {
         for (int s = 0; s < a_stages; ++s) {
-            mbar_init(smem_u32(&bar_afull[s]), kTsProducerWarps);
+            mbar_init(smem_u32(&bar_afull[s]), 4);                       // the four warps of one group
             mbar_init(smem_u32(&bar_aempty[s]), 1);
         }
         for (int s = 0; s < w_stages; ++s) {
             mbar_init(smem_u32(&bar_wfull[s]), 1);
             mbar_init(smem_u32(&bar_wempty[s]), 1);
+        }
+        for (int s = 0; s < n_gran; ++s) {
+            mbar_init(smem_u32(&bar_gfull[s]), kTsGatherThreads);
+            mbar_init(smem_u32(&bar_gempty[s]), 4 * nb);                 // one arrival per warp per chunk
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&bar_tfull[s]), 1);
@@ -124,135 +179,89 @@ feature_interact_fwd_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, cons
     fence_after_sync();
     const uint32_t tmem_base = tmem_base_slot;
     const uint32_t tmem_a0 = tmem_base + 2u * (uint32_t)dim;
+#ifdef IHG_TRACE
+    if (tid == 0 && blockIdx.x < 160) g_ts_cta[blockIdx.x][0] = ts_gtime();
+#endif
 
     if (warp < kTsProducerWarps) {
         // ======================= producers =======================
-        const int64_t G = my_tiles * KC;                    // granules of this CTA
-        const int quad = warp & 3, cg = warp >> 2;
+        const int group = warp >> 2, quad = warp & 3;
         const int row = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        // cp.async mapping: copy j of this thread = (row, table, 16-byte chunk)
-        int crow[kTsCopies], ctab[kTsCopies], cchk[kTsCopies];
-#pragma unroll
-        for (int j = 0; j < kTsCopies; ++j) {
-            const int idx = tid + kTsProducerThreads * j;
-            crow[j] = idx / 24;
-            ctab[j] = (idx % 24) >> 3;
-            cchk[j] = idx & 7;
-        }
-        int ids_cur[kTsCopies], ids_nxt[kTsCopies];
-        auto load_ids = [&](int64_t tile_local, int (&ids)[kTsCopies]) {
-#pragma unroll
-            for (int j = 0; j < kTsCopies; ++j) {
-                const int64_t e = (blockIdx.x + tile_local * gridDim.x) * kTileM + crow[j];
-                ids[j] = (tile_local < my_tiles && e < E) ? __ldg(i3 + 3 * e + ctab[j]) : -1;
+        const int64_t total_chunks = my_tiles * chunks_per_tile;
+        // chunk c = granule * nb + b; this group takes c = group, group + 4, ...
+        int b = group, gb = 0, s = group;            // block, granule ring slot, A ring slot
+        uint32_t gph = 0, ph = 0;
+        // (kTsGroups <= nb and kTsGroups <= a_stages: no wrap in the initial position)
+        for (int64_t c = group; c < total_chunks; c += kTsGroups) {
+            TS_PROBE(tid == 0, 1, c >> 2);
+            mbar_wait(smem_u32(&bar_gfull[gb]), gph);
+            mbar_wait(smem_u32(&bar_aempty[s]), ph ^ 1u);
+            TS_PROBE(tid == 0, 2, c >> 2);
+            fence_after_sync();
+            const uint32_t gbuf = gran_base + (uint32_t)gb * kTsGranuleBytes;
+            const uint32_t ta = tmem_a0 + (uint32_t)s * 64u + lane_addr;
+            switch (b) {
+                case 0: produce_chunk<0>(gbuf, row, ta); break;
+                case 1: produce_chunk<1>(gbuf, row, ta); break;
+                case 2: produce_chunk<2>(gbuf, row, ta); break;
+                case 3: produce_chunk<3>(gbuf, row, ta); break;
+                case 4: produce_chunk<4>(gbuf, row, ta); break;
+                case 5: produce_chunk<5>(gbuf, row, ta); break;
+                default: produce_chunk<6>(gbuf, row, ta); break;
             }
-        };
-        auto issue = [&](int64_t g) {
-            const int kc = (int)(g % KC);
-            const uint32_t buf = gran_base + (uint32_t)(g & 1) * kTsGranuleBytes;
-#pragma unroll
-            for (int j = 0; j < kTsCopies; ++j) {
-                const bool ok = ids_cur[j] >= 0;
-                const float* src = xp + (int64_t)(ok ? ids_cur[j] : 0) * xp_ld + kc * kChunkK + 4 * cchk[j];
-                cp_async16_zfill(buf + stage_off(ctab[j], crow[j], cchk[j]), src, ok);
-            }
-        };
-        load_ids(0, ids_cur);
-        if (G > 0) issue(0);
-        load_ids(1, ids_nxt);
-        uint32_t it = 0;                                    // A-ring position
-        int pending = -1;                                   // A stage written but not yet published
-        for (int64_t g = 0; g < G; ++g) {
-            TS_PROBE(tid == 0, 0, g);
-            cp_async_wait_all();
-            TS_PROBE(tid == 0, 6, g);
-            producer_barrier();                             // granule g landed; everyone is done reading g-1
-            TS_PROBE(tid == 0, 7, g);
-            if (g + 1 < G) {
-                const bool new_tile = (g + 1) % KC == 0;
-                if (new_tile) {
-#pragma unroll
-                    for (int j = 0; j < kTsCopies; ++j) ids_cur[j] = ids_nxt[j];
-                }
-                issue(g + 1);
-                if (new_tile) load_ids((g + 1) / KC + 1, ids_nxt);
-            }
-            TS_PROBE(tid == 0, 4, 7000 + g);
-            const uint32_t buf = gran_base + (uint32_t)(g & 1) * kTsGranuleBytes;
-            float u[8], q[8], v[8];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float4 a = lds4(buf + stage_off(0, row, 2 * cg + h));
-                const float4 b = lds4(buf + stage_off(1, row, 2 * cg + h));
-                const float4 c = lds4(buf + stage_off(2, row, 2 * cg + h));
-                u[4 * h] = a.x, u[4 * h + 1] = a.y, u[4 * h + 2] = a.z, u[4 * h + 3] = a.w;
-                q[4 * h] = b.x, q[4 * h + 1] = b.y, q[4 * h + 2] = b.z, q[4 * h + 3] = b.w;
-                v[4 * h] = c.x, v[4 * h + 1] = c.y, v[4 * h + 2] = c.z, v[4 * h + 3] = c.w;
-            }
-            TS_PROBE(tid == 0, 5, 7000 + g);
-            for (int b = 0; b < nb; ++b, ++it) {
-                const int s = it % a_stages;
-                const uint32_t ph = (it / a_stages) & 1u;
-                float z[8];
-                switch (b) {
-                    case 0:
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) z[k] = u[k];
-                        break;
-                    case 1:
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) z[k] = q[k];
-                        break;
-                    case 2:
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) z[k] = v[k];
-                        break;
-                    case 3:
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) z[k] = u[k] * q[k];
-                        break;
-                    case 4:
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) z[k] = q[k] * v[k];
-                        break;
-                    case 5:
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) z[k] = v[k] * u[k];
-                        break;
-                    default:
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) z[k] = u[k] * q[k] * v[k];
-                        break;
-                }
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) split_tf32(z[k], hi[k], lo[k]);
-                TS_PROBE(tid == 0, 6, 1000 + it);
-                // publish the previous chunk only now: its tcgen05.st latency overlapped the split above
-                if (pending >= 0) {
-                    tmem_st_wait();
-                    fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&bar_afull[pending]));
-                }
-                TS_PROBE(tid == 0, 1, it);
-                mbar_wait(smem_u32(&bar_aempty[s]), ph ^ 1u);
-                TS_PROBE(tid == 0, 2, it);
-                fence_after_sync();
-                const uint32_t ta = tmem_a0 + (uint32_t)s * 64u + (uint32_t)(8 * cg) + lane_addr;
-                tmem_st8(ta, hi);
-                tmem_st8(ta + 32u, lo);
-                pending = s;
-                TS_PROBE(tid == 0, 3, it);
-            }
-        }
-        if (pending >= 0) {
+            TS_PROBE(tid == 0, 3, c >> 2);
             tmem_st_wait();
             fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bar_afull[pending]));
+            if (lane == 0) {
+                mbar_arrive(smem_u32(&bar_afull[s]));
+                mbar_arrive(smem_u32(&bar_gempty[gb]));
+            }
+            TS_PROBE(tid == 0, 6, c >> 2);
+            b += kTsGroups;
+            while (b >= nb) {
+                b -= nb;
+                if (++gb == n_gran) gb = 0, gph ^= 1u;
+            }
+            s += kTsGroups;
+            if (s >= a_stages) s -= a_stages, ph ^= 1u;
         }
+    } else if (warp >= kTsGatherWarp0) {
+        // ======================= gather =======================
+        const int gt = tid - kTsGatherWarp0 * 32;
+        const int chk = gt & 7, row0 = gt >> 3;       // copy j: 16-byte chunk chk of row row0 + 16 (j / 3), table j % 3
+        const uint32_t off0 = stage_off(0, row0, chk);    // (row0 + 16 m) % 8 == row0 % 8: same swizzle for all j
+        int gb = 0;
+        uint32_t gph = 0;
+        for (int64_t t = 0; t < my_tiles; ++t) {
+            const int64_t k0 = 3 * ((blockIdx.x + t * gridDim.x) * kTileM + row0);     // offset of i3[e0 + row0][0]
+            for (int kc = 0; kc < KC; ++kc) {
+                mbar_wait(smem_u32(&bar_gempty[gb]), gph ^ 1u);
+                const uint32_t gbuf = gran_base + (uint32_t)gb * kTsGranuleBytes + off0;
+                const float* col = xp + kc * kChunkK + 4 * chk;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    int ids[kTsCopies / 2];
+#pragma unroll
+                    for (int j = 0; j < kTsCopies / 2; ++j) {
+                        const int jj = j + half * (kTsCopies / 2);
+                        const int64_t k = k0 + 48 * (jj / 3) + (jj % 3);
+                        ids[j] = k < 3 * E ? __ldg(i3 + k) : -1;
+                    }
+#pragma unroll
+                    for (int j = 0; j < kTsCopies / 2; ++j) {
+                        const int jj = j + half * (kTsCopies / 2);
+                        const bool ok = ids[j] >= 0;
+                        cp_async16_zfill(gbuf + (uint32_t)(((jj % 3) * kTileM + 16 * (jj / 3)) * kChunkBytesPerRow),
+                                         col + (int64_t)(ok ? ids[j] : 0) * xp_ld, ok);
+                    }
+                }
+                cp_async_arrive(smem_u32(&bar_gfull[gb]));
+                if (++gb == n_gran) gb = 0, gph ^= 1u;
+            }
+        }
+        cp_async_wait_all();
     } else if (warp == kTsLoadWarp) {
         // ======================= weight loader =======================
         if (lane == 0) {
@@ -280,12 +289,10 @@ feature_interact_fwd_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, cons
         for (int64_t t = 0; t < my_tiles; ++t) {
             const uint32_t buf = (uint32_t)t & 1u;
             mbar_wait(smem_u32(&bar_tempty[buf]), (((uint32_t)t >> 1) & 1u) ^ 1u);
-            fence_after_sync();
             const uint32_t tmem_d = tmu + buf * (uint32_t)dim;
             for (int ci = 0; ci < chunks_per_tile; ++ci) {
                 TS_PROBE(lane == 0, 4, t * chunks_per_tile + ci);
                 mbar_wait(smem_u32(&bar_wfull[sw]), pw);
-                TS_PROBE(lane == 0, 0, 4096 + t * chunks_per_tile + ci);
                 mbar_wait(smem_u32(&bar_afull[sa]), pa);
                 TS_PROBE(lane == 0, 5, t * chunks_per_tile + ci);
                 fence_after_sync();
@@ -303,13 +310,12 @@ feature_interact_fwd_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, cons
                     }
                     mma_commit(smem_u32(&bar_aempty[sa]));
                     mma_commit(smem_u32(&bar_wempty[sw]));
+                    if (ci == chunks_per_tile - 1) mma_commit(smem_u32(&bar_tfull[buf]));
                 }
                 __syncwarp();
                 if (++sa == a_stages) sa = 0, pa ^= 1u;
                 if (++sw == w_stages) sw = 0, pw ^= 1u;
             }
-            if (elect_one()) mma_commit(smem_u32(&bar_tfull[buf]));
-            __syncwarp();
         }
     } else {
         // ======================= epilogue =======================
@@ -351,6 +357,9 @@ feature_interact_fwd_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, cons
     }
     fence_before_sync();
     __syncthreads();
+#ifdef IHG_TRACE
+    if (tid == 0 && blockIdx.x < 160) g_ts_cta[blockIdx.x][1] = ts_gtime();
+#endif
     if (warp == kTsMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
@@ -365,14 +374,15 @@ int launch_interact_fwd_full_ts(const float* xp, int64_t xp_ld, const float* w_a
     int a_stages = (512 - 2 * dim) / 64;
     if (a_stages > kTsMaxAStages) a_stages = kTsMaxAStages;
     const int w_stage_bytes = 2 * dim * kChunkBytesPerRow;
-    int w_stages = (226 * 1024 - 2 * kTsGranuleBytes - 4 * kEpiStageBytes - 1024) / w_stage_bytes;
+    const int n_gran = dim <= 64 ? 3 : 2;            // d = 128 needs the room for a third weight stage
+    int w_stages = (226 * 1024 - n_gran * kTsGranuleBytes - 4 * kEpiStageBytes - 1024) / w_stage_bytes;
     if (w_stages > kTsMaxWStages) w_stages = kTsMaxWStages;
-    const int smem = w_stages * w_stage_bytes + 2 * kTsGranuleBytes + 4 * kEpiStageBytes + 1024;
+    const int smem = w_stages * w_stage_bytes + n_gran * kTsGranuleBytes + 4 * kEpiStageBytes + 1024;
     IHG_CUDA(cudaFuncSetAttribute(feature_interact_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t n_tiles = (E + kTileM - 1) / kTileM;
     const unsigned grid = (unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
     feature_interact_fwd_ts_kernel<<<grid, kTsThreads, smem, st>>>(xp, xp_ld, bias, wprep, 3 + nb, i3, E, ef, ef_ld,
-                                                                   dim, a_stages, w_stages);
+                                                                   dim, a_stages, w_stages, n_gran);
     IHG_LAUNCH_CHECK();
     return IHG_OK;
 }
@@ -384,5 +394,9 @@ extern "C" int ihg_debug_read_trace(long long* dst, int n) {
     if (n > 8 * 8192) n = 8 * 8192;
     cudaDeviceSynchronize();
     return (int)cudaMemcpyFromSymbol(dst, ihg::g_ts_trace, (size_t)n * sizeof(long long));
+}
+extern "C" int ihg_debug_read_cta_times(long long* dst) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(dst, ihg::g_ts_cta, sizeof(long long) * 320);
 }
 #endif
