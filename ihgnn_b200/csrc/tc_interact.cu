@@ -215,32 +215,34 @@ edge_interact_fwd_tc_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
         }
     } else if (warp == kFwdMmaWarp) {
         // ======================= MMA issuer =======================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(dim);
-            uint32_t it = 0, t = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
-                const uint32_t buf = t & 1u;
-                mbar_wait(smem_u32(&bar_tempty[buf]), ((t >> 1) & 1u) ^ 1u);
+        // warp-uniform loop, one elected lane issues (tc_common.cuh: MMA issue discipline)
+        const uint32_t tmu = warp_uniform(tmem_base);
+        const uint32_t idesc = make_idesc_tf32(dim);
+        uint32_t it = 0, t = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+            const uint32_t buf = t & 1u;
+            mbar_wait(smem_u32(&bar_tempty[buf]), ((t >> 1) & 1u) ^ 1u);
+            const uint32_t tmem_d = tmu + buf * (uint32_t)dim;
+            for (int ci = 0; ci < chunks_per_tile; ++ci, ++it) {
+                const int s = it % stages;
+                const uint32_t ph = (it / stages) & 1u;
+                mbar_wait(smem_u32(&bar_full[s]), ph);
                 fence_after_sync();
-                const uint32_t tmem_d = tmem_base + buf * (uint32_t)dim;
-                for (int ci = 0; ci < chunks_per_tile; ++ci, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1u;
-                    mbar_wait(smem_u32(&bar_full[s]), ph);
-                    fence_after_sync();
-                    const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes;
-                    const uint64_t dah = make_kmajor_sw128_desc(a_hi);
-                    const uint64_t dal = make_kmajor_sw128_desc(a_hi + kATileBytes);
-                    const uint64_t dbh = make_kmajor_sw128_desc(a_hi + 2 * kATileBytes);
-                    const uint64_t dbl = make_kmajor_sw128_desc(a_hi + 2 * kATileBytes + b_tile_bytes);
+                const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes;
+                const uint64_t dah = make_kmajor_sw128_desc(a_hi);
+                const uint64_t dal = make_kmajor_sw128_desc(a_hi + kATileBytes);
+                const uint64_t dbh = make_kmajor_sw128_desc(a_hi + 2 * kATileBytes);
+                const uint64_t dbl = make_kmajor_sw128_desc(a_hi + 2 * kATileBytes + b_tile_bytes);
+                if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < kChunkK / 8; ++ks)
                         mma_3xtf32(tmem_d, advance_desc_k(dah, 8 * ks), advance_desc_k(dal, 8 * ks),
                                    advance_desc_k(dbh, 8 * ks), advance_desc_k(dbl, 8 * ks), idesc,
                                    (ci > 0 || ks > 0) ? 1u : 0u);
                     mma_commit(smem_u32(&bar_empty[s]));          // stage may be refilled
+                    if (ci == chunks_per_tile - 1) mma_commit(smem_u32(&bar_tfull[buf]));   // accumulator complete
                 }
-                mma_commit(smem_u32(&bar_tfull[buf]));            // accumulator complete
+                __syncwarp();
             }
         }
     } else {
@@ -415,38 +417,41 @@ edge_interact_bwd_slot_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
             }
         }
     } else if (warp == kMmaWarp) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(nu);
-            uint32_t ita = 0, itb = 0, t = 0;
-            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++t) {
-                const uint32_t buf = t & 1u;
-                mbar_wait(smem_u32(&bar_tempty[buf]), ((t >> 1) & 1u) ^ 1u);
-                fence_after_sync();
-                for (int nc = 0; nc < KC; ++nc, ++ita) {
-                    const int sa = ita % kSlotAStages;
-                    mbar_wait(smem_u32(&bar_afull[sa]), (ita / kSlotAStages) & 1u);
+        // warp-uniform loop, one elected lane issues (tc_common.cuh: MMA issue discipline)
+        const uint32_t tmu = warp_uniform(tmem_base);
+        const uint32_t idesc = make_idesc_tf32(nu);
+        uint32_t ita = 0, itb = 0, t = 0;
+        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++t) {
+            const uint32_t buf = t & 1u;
+            mbar_wait(smem_u32(&bar_tempty[buf]), ((t >> 1) & 1u) ^ 1u);
+            for (int nc = 0; nc < KC; ++nc, ++ita) {
+                const int sa = ita % kSlotAStages;
+                mbar_wait(smem_u32(&bar_afull[sa]), (ita / kSlotAStages) & 1u);
+                const uint32_t a_hi = smem_base + (uint32_t)sa * a_stage_bytes;
+                const uint64_t dah = make_kmajor_sw128_desc(a_hi);
+                const uint64_t dal = make_kmajor_sw128_desc(a_hi + kATileBytes);
+                for (int b = 0; b < nb; ++b, ++itb) {
+                    const int sb = itb % b_stages;
+                    mbar_wait(smem_u32(&bar_bfull[sb]), (itb / b_stages) & 1u);
                     fence_after_sync();
-                    const uint32_t a_hi = smem_base + (uint32_t)sa * a_stage_bytes;
-                    const uint64_t dah = make_kmajor_sw128_desc(a_hi);
-                    const uint64_t dal = make_kmajor_sw128_desc(a_hi + kATileBytes);
-                    for (int b = 0; b < nb; ++b, ++itb) {
-                        const int sb = itb % b_stages;
-                        mbar_wait(smem_u32(&bar_bfull[sb]), (itb / b_stages) & 1u);
-                        fence_after_sync();
-                        const uint32_t bh = b_base + (uint32_t)sb * b_stage_bytes;
-                        const uint64_t dbh = make_kmajor_sw128_desc(bh);
-                        const uint64_t dbl = make_kmajor_sw128_desc(bh + b_tile_bytes);
-                        const uint32_t tmem_d = tmem_base + buf * acc_cols + (uint32_t)(b * nu);
+                    const uint32_t bh = b_base + (uint32_t)sb * b_stage_bytes;
+                    const uint64_t dbh = make_kmajor_sw128_desc(bh);
+                    const uint64_t dbl = make_kmajor_sw128_desc(bh + b_tile_bytes);
+                    const uint32_t tmem_d = tmu + buf * acc_cols + (uint32_t)(b * nu);
+                    if (elect_one()) {
 #pragma unroll
                         for (int ks = 0; ks < kChunkK / 8; ++ks)
                             mma_3xtf32(tmem_d, advance_desc_k(dah, 8 * ks), advance_desc_k(dal, 8 * ks),
                                        advance_desc_k(dbh, 8 * ks), advance_desc_k(dbl, 8 * ks), idesc,
                                        (nc > 0 || ks > 0) ? 1u : 0u);
                         mma_commit(smem_u32(&bar_bempty[sb]));
+                        if (b == nb - 1) {
+                            mma_commit(smem_u32(&bar_aempty[sa]));
+                            if (nc == KC - 1) mma_commit(smem_u32(&bar_tfull[buf]));
+                        }
                     }
-                    mma_commit(smem_u32(&bar_aempty[sa]));
+                    __syncwarp();
                 }
-                mma_commit(smem_u32(&bar_tfull[buf]));
             }
         }
     } else if (warp >= kSlotEpiWarp0 && warp < kSlotEpiWarp0 + kSlotEpiWarps) {
@@ -761,21 +766,22 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                          make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
             }
     } else {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32_mn(dim);
-            uint32_t ita = 0, itb = 0;
-            bool first = true;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++itb) {
-                const int sb = itb % nbs;
-                mbar_wait(smem_u32(&bar_bfull[sb]), (itb / nbs) & 1u);
+        // warp-uniform loop, one elected lane issues (tc_common.cuh: MMA issue discipline)
+        const uint32_t tmu = warp_uniform(tmem_base);
+        const uint32_t idesc = make_idesc_tf32_mn(dim);
+        uint32_t ita = 0, itb = 0;
+        bool first = true;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++itb) {
+            const int sb = itb % nbs;
+            mbar_wait(smem_u32(&bar_bfull[sb]), (itb / nbs) & 1u);
+            const uint32_t bh = b_base + (uint32_t)sb * b_stage_bytes;
+            for (int g = 0; g < ng; ++g, ++ita) {
+                const int sa = ita & 1;
+                mbar_wait(smem_u32(&bar_afull[sa]), (ita >> 1) & 1u);
                 fence_after_sync();
-                const uint32_t bh = b_base + (uint32_t)sb * b_stage_bytes;
-                for (int g = 0; g < ng; ++g, ++ita) {
-                    const int sa = ita & 1;
-                    mbar_wait(smem_u32(&bar_afull[sa]), (ita >> 1) & 1u);
-                    fence_after_sync();
-                    const uint32_t ah = smem_base + (uint32_t)sa * a_stage_bytes;
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(g * dim);
+                const uint32_t ah = smem_base + (uint32_t)sa * a_stage_bytes;
+                const uint32_t tmem_d = tmu + (uint32_t)(g * dim);
+                if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < kWgTe / 8; ++ks) {
                         const uint32_t koff = (uint32_t)ks * 1024u;   // 8 edge rows x 128 B
@@ -786,12 +792,14 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                         mma_3xtf32(tmem_d, dah, dal, dbh, dbl, idesc, (first && ks == 0) ? 0u : 1u);
                     }
                     mma_commit(smem_u32(&bar_aempty[sa]));
+                    if (g == ng - 1) mma_commit(smem_u32(&bar_bempty[sb]));
                 }
-                mma_commit(smem_u32(&bar_bempty[sb]));
-                first = false;
+                __syncwarp();
             }
-            mma_commit(smem_u32(&bar_done));
+            first = false;
         }
+        if (elect_one()) mma_commit(smem_u32(&bar_done));
+        __syncwarp();
     }
     fence_before_sync();
     __syncthreads();

@@ -109,20 +109,25 @@ node_linear_tc_kernel(const float* __restrict__ x, int64_t x_ld, const float* __
             }
         fence_async_smem();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
+            // warp-uniform issue, one elected lane (tc_common.cuh: MMA issue discipline)
             fence_after_sync();
+            const uint32_t tmu = warp_uniform(tmem_d);
             for (int ch = 0; ch < nch; ++ch) {
                 const uint32_t a_hi = a_base + (uint32_t)ch * 32768;
                 const uint32_t b_hi = b_base + (uint32_t)ch * 2 * b_tile;
                 const uint64_t dah = make_kmajor_sw128_desc(a_hi), dal = make_kmajor_sw128_desc(a_hi + 16384);
                 const uint64_t dbh = make_kmajor_sw128_desc(b_hi), dbl = make_kmajor_sw128_desc(b_hi + b_tile);
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < kChunkK / 8; ++ks)
-                    mma_3xtf32(tmem_d, advance_desc_k(dah, 8 * ks), advance_desc_k(dal, 8 * ks),
-                               advance_desc_k(dbh, 8 * ks), advance_desc_k(dbl, 8 * ks), idesc,
-                               (kc0 + ch > 0 || ks > 0) ? 1u : 0u);
+                    for (int ks = 0; ks < kChunkK / 8; ++ks)
+                        mma_3xtf32(tmu, advance_desc_k(dah, 8 * ks), advance_desc_k(dal, 8 * ks),
+                                   advance_desc_k(dbh, 8 * ks), advance_desc_k(dbl, 8 * ks), idesc,
+                                   (kc0 + ch > 0 || ks > 0) ? 1u : 0u);
+                    if (ch == nch - 1) mma_commit(mbar);
+                }
+                __syncwarp();
             }
-            mma_commit(mbar);
         }
         // the operand tiles are reused by the next phase / the epilogue: wait for the MMAs
         mbar_wait(mbar, phase);
@@ -293,7 +298,9 @@ node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* _
                              make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
                 }
             }
-    } else if (lane == 0) {
+    } else {
+        // warp-uniform loop, one elected lane issues (tc_common.cuh: MMA issue discipline)
+        const uint32_t tmu = warp_uniform(tmem_base);
         const uint32_t idesc = make_idesc_tf32_mn(acc_cols);
         uint32_t it = 0;
         uint32_t started = 0;                            // bit t set once type t's accumulator is live
@@ -306,20 +313,24 @@ node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* _
             fence_after_sync();
             const uint32_t ah = smem_base + (uint32_t)s * stage_bytes;
             const uint32_t bh = ah + a_bytes;
-            const uint32_t tmem_d = tmem_base + (uint32_t)(tt * acc_cols);
+            const uint32_t tmem_d = tmu + (uint32_t)(tt * acc_cols);
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < kNwTe / 8; ++ks) {
-                const uint32_t koff = (uint32_t)ks * 1024u;
-                mma_3xtf32(tmem_d, make_mnmajor_sw128_desc(ah + koff, sub_bytes),
-                           make_mnmajor_sw128_desc(ah + 4 * sub_bytes + koff, sub_bytes),
-                           make_mnmajor_sw128_desc(bh + koff, sub_bytes),
-                           make_mnmajor_sw128_desc(bh + (uint32_t)NB * sub_bytes + koff, sub_bytes), idesc,
-                           ((started >> tt) & 1u) ? 1u : (ks > 0 ? 1u : 0u));
+                for (int ks = 0; ks < kNwTe / 8; ++ks) {
+                    const uint32_t koff = (uint32_t)ks * 1024u;
+                    mma_3xtf32(tmem_d, make_mnmajor_sw128_desc(ah + koff, sub_bytes),
+                               make_mnmajor_sw128_desc(ah + 4 * sub_bytes + koff, sub_bytes),
+                               make_mnmajor_sw128_desc(bh + koff, sub_bytes),
+                               make_mnmajor_sw128_desc(bh + (uint32_t)NB * sub_bytes + koff, sub_bytes), idesc,
+                               ((started >> tt) & 1u) ? 1u : (ks > 0 ? 1u : 0u));
+                }
+                mma_commit(smem_u32(&bar_empty[s]));
             }
+            __syncwarp();
             started |= 1u << tt;
-            mma_commit(smem_u32(&bar_empty[s]));
         }
-        mma_commit(smem_u32(&bar_done));
+        if (elect_one()) mma_commit(smem_u32(&bar_done));
+        __syncwarp();
     }
     fence_before_sync();
     __syncthreads();
