@@ -895,7 +895,11 @@ int launch_interact_bwd_tc(const float* xp, int64_t xp_ld, const float* def, int
     float* partial = reinterpret_cast<float*>(wprep + ((wprep_bytes + 1023) & ~(int64_t)1023));
     // ---- (a) slot gradients
     const int nu = slot_nu(dim);
-    {
+    static const bool slot_ss = getenv("IHG_SLOT_SS") != nullptr;      // A/B switch: both operands in shared memory
+    if (!slot_ss) {
+        if (int rc = launch_interact_bwd_slot_ts(xp, xp_ld, def, def_ld, w_hi, w_ld, nb, i3, E, slot_grad, dim, wprep, st))
+            return rc;
+    } else {
         const int64_t total = (int64_t)nb * (dim / kChunkK) * dim * 8;
         interact_prep_weights_t_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w_hi, w_ld, nb, dim, nu, wprep);
         IHG_LAUNCH_CHECK();

@@ -49,13 +49,13 @@ __device__ __forceinline__ long long ts_gtime() {
 
 namespace {
 
-constexpr int kTsProducerWarps = 16;
+constexpr int kTsProducerWarps = 12;
 constexpr int kTsGroups = kTsProducerWarps / 4;
 constexpr int kTsEpiWarp0 = kTsProducerWarps;
 constexpr int kTsMmaWarp = kTsProducerWarps + 4;
 constexpr int kTsLoadWarp = kTsProducerWarps + 5;
 constexpr int kTsGatherWarp0 = kTsProducerWarps + 6;
-constexpr int kTsGatherWarps = 4;
+constexpr int kTsGatherWarps = 8;
 constexpr int kTsGatherThreads = kTsGatherWarps * 32;
 constexpr int kTsThreads = (kTsProducerWarps + 6 + kTsGatherWarps) * 32;
 constexpr int kTsGranuleBytes = 3 * kTileM * kChunkBytesPerRow;           // 48 KB: u, q, i slices
@@ -149,7 +149,11 @@ feature_interact_fwd_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, cons
     const int chunks_per_tile = KC * nb;
     const uint32_t w_stage_bytes = 2u * (uint32_t)dim * kChunkBytesPerRow;     // hi + lo weight chunk
     const int64_t n_tiles = (E + kTileM - 1) / kTileM;
-    const int64_t my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // every CTA runs the same number of tiles (the CTAs of a cluster share weight stages in lock
+    // step); tiles past the end are all-invalid rows: zero-filled gathers, no stores
+    const int64_t my_tiles = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t cl_rank = cluster_ctarank(), cl_size = cluster_nctarank();
+    const uint16_t cl_mask = (uint16_t)((1u << cl_size) - 1u);
     // shared memory map: [W ring][granule ring][4 epilogue staging tiles]
     const uint32_t gran_base = smem_base + (uint32_t)w_stages * w_stage_bytes;
     const uint32_t epi_base = gran_base + (uint32_t)n_gran * kTsGranuleBytes;
@@ -161,7 +165,7 @@ feature_interact_fwd_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, cons
         }
         for (int s = 0; s < w_stages; ++s) {
             mbar_init(smem_u32(&bar_wfull[s]), 1);
-            mbar_init(smem_u32(&bar_wempty[s]), 1);
+            mbar_init(smem_u32(&bar_wempty[s]), cl_size);                // one commit from every CTA of the cluster
         }
         for (int s = 0; s < n_gran; ++s) {
             mbar_init(smem_u32(&bar_gfull[s]), kTsGatherThreads);
@@ -177,6 +181,7 @@ feature_interact_fwd_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, cons
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    if (cl_size > 1) cluster_sync();            // peers' barriers are initialised before anyone signals them
     const uint32_t tmem_base = tmem_base_slot;
     const uint32_t tmem_a0 = tmem_base + 2u * (uint32_t)dim;
 #ifdef IHG_TRACE
@@ -230,8 +235,9 @@ feature_interact_fwd_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, cons
     } else if (warp >= kTsGatherWarp0) {
         // ======================= gather =======================
         const int gt = tid - kTsGatherWarp0 * 32;
-        const int chk = gt & 7, row0 = gt >> 3;       // copy j: 16-byte chunk chk of row row0 + 16 (j / 3), table j % 3
-        const uint32_t off0 = stage_off(0, row0, chk);    // (row0 + 16 m) % 8 == row0 % 8: same swizzle for all j
+        constexpr int kRowStep = kTsGatherThreads / 8;      // rows covered by one pass of the gather threads
+        const int chk = gt & 7, row0 = gt >> 3;       // copy j: 16-byte chunk chk of row row0 + kRowStep (j / 3), table j % 3
+        const uint32_t off0 = stage_off(0, row0, chk);    // (row0 + kRowStep m) % 8 == row0 % 8: same swizzle for all j
         int gb = 0;
         uint32_t gph = 0;
         for (int64_t t = 0; t < my_tiles; ++t) {
@@ -246,14 +252,14 @@ feature_interact_fwd_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, cons
 #pragma unroll
                     for (int j = 0; j < kTsCopies / 2; ++j) {
                         const int jj = j + half * (kTsCopies / 2);
-                        const int64_t k = k0 + 48 * (jj / 3) + (jj % 3);
+                        const int64_t k = k0 + 3 * kRowStep * (jj / 3) + (jj % 3);
                         ids[j] = k < 3 * E ? __ldg(i3 + k) : -1;
                     }
 #pragma unroll
                     for (int j = 0; j < kTsCopies / 2; ++j) {
                         const int jj = j + half * (kTsCopies / 2);
                         const bool ok = ids[j] >= 0;
-                        cp_async16_zfill(gbuf + (uint32_t)(((jj % 3) * kTileM + 16 * (jj / 3)) * kChunkBytesPerRow),
+                        cp_async16_zfill(gbuf + (uint32_t)(((jj % 3) * kTileM + kRowStep * (jj / 3)) * kChunkBytesPerRow),
                                          col + (int64_t)(ok ? ids[j] : 0) * xp_ld, ok);
                     }
                 }
@@ -264,18 +270,25 @@ feature_interact_fwd_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, cons
         cp_async_wait_all();
     } else if (warp == kTsLoadWarp) {
         // ======================= weight loader =======================
+        // Each CTA of the cluster fetches 1 / cl_size of every weight chunk and multicasts it to
+        // all of them: the chunk crosses the L2 -> SM fabric once per cluster, not once per CTA
+        // (weight streaming was 2/3 of this kernel's L2 traffic and the fabric, ~33 B/clk/SM with
+        // every SM pulling, was the bound).
         if (lane == 0) {
+            const uint32_t piece = w_stage_bytes / cl_size;
             uint32_t it = 0;
             for (int64_t t = 0; t < my_tiles; ++t)
                 for (int kc = 0; kc < KC; ++kc)
                     for (int b = 0; b < nb; ++b, ++it) {
                         const int s = it % w_stages;
                         const uint32_t ph = (it / w_stages) & 1u;
-                        mbar_wait(smem_u32(&bar_wempty[s]), ph ^ 1u);
+                        mbar_wait(smem_u32(&bar_wempty[s]), ph ^ 1u);      // every CTA of the cluster released the stage
                         const uint32_t full = smem_u32(&bar_wfull[s]);
                         mbar_expect_tx_(full, w_stage_bytes);
-                        bulk_g2s_(smem_base + (uint32_t)s * w_stage_bytes,
-                                  wprep + (int64_t)(b * KC + kc) * w_stage_bytes, w_stage_bytes, full);
+                        const uint32_t dst = smem_base + (uint32_t)s * w_stage_bytes + cl_rank * piece;
+                        const uint8_t* src = wprep + (int64_t)(b * KC + kc) * w_stage_bytes + cl_rank * piece;
+                        if (cl_size > 1) bulk_g2s_multicast(dst, src, piece, full, cl_mask);
+                        else bulk_g2s_(dst, src, piece, full);
                     }
         }
     } else if (warp == kTsMmaWarp) {
@@ -309,7 +322,8 @@ feature_interact_fwd_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, cons
                         mma_tf32_ts(tmem_d, a_hi + 8u * ks, bh, idesc, 1u);
                     }
                     mma_commit(smem_u32(&bar_aempty[sa]));
-                    mma_commit(smem_u32(&bar_wempty[sw]));
+                    if (cl_size > 1) mma_commit_multicast(smem_u32(&bar_wempty[sw]), cl_mask);
+                    else mma_commit(smem_u32(&bar_wempty[sw]));
                     if (ci == chunks_per_tile - 1) mma_commit(smem_u32(&bar_tfull[buf]));
                 }
                 __syncwarp();
@@ -360,6 +374,7 @@ feature_interact_fwd_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, cons
 #ifdef IHG_TRACE
     if (tid == 0 && blockIdx.x < 160) g_ts_cta[blockIdx.x][1] = ts_gtime();
 #endif
+    if (cl_size > 1) cluster_sync();            // no peer may still multicast into / signal this CTA
     if (warp == kTsMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
@@ -380,9 +395,25 @@ int launch_interact_fwd_full_ts(const float* xp, int64_t xp_ld, const float* w_a
     const int smem = w_stages * w_stage_bytes + n_gran * kTsGranuleBytes + 4 * kEpiStageBytes + 1024;
     IHG_CUDA(cudaFuncSetAttribute(feature_interact_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t n_tiles = (E + kTileM - 1) / kTileM;
-    const unsigned grid = (unsigned)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
-    feature_interact_fwd_ts_kernel<<<grid, kTsThreads, smem, st>>>(xp, xp_ld, bias, wprep, 3 + nb, i3, E, ef, ef_ld,
-                                                                   dim, a_stages, w_stages, n_gran);
+    // clusters of CTAs share the weight stream; the grid is what the device can keep resident
+    static int cluster = -1, max_ctas = 0;
+    if (cluster < 0) {
+        IHG_CUDA(cudaFuncSetAttribute(feature_interact_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        cluster = pick_cluster(feature_interact_fwd_ts_kernel, kTsThreads, 226 * 1024, 4, &max_ctas);
+    }
+    int64_t ctas = n_tiles < max_ctas ? n_tiles : max_ctas;
+    ctas = (ctas + cluster - 1) / cluster * cluster;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(kTsThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    IHG_CUDA(cudaLaunchKernelEx(&cfg, feature_interact_fwd_ts_kernel, xp, xp_ld, bias, (const uint8_t*)wprep, 3 + nb, i3, E,
+                                ef, ef_ld, dim, a_stages, w_stages, n_gran));
     IHG_LAUNCH_CHECK();
     return IHG_OK;
 }

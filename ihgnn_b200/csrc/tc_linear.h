@@ -26,6 +26,10 @@ int launch_interact_fwd_tc(const float* xp, int64_t xp_ld, const float* p, int64
                            const float* w_hi, int64_t w_ld, int nb, const int32_t* i3, int64_t E,
                            float* ef, int64_t ef_ld, int dim, void* workspace, cudaStream_t st);
 
+// slot gradients with the def tile in tensor memory (tc_interact_slot_ts.cu)
+int launch_interact_bwd_slot_ts(const float* xp, int64_t xp_ld, const float* def, int64_t def_ld,
+                                const float* w_hi, int64_t w_ld, int nb, const int32_t* i3, int64_t E,
+                                float* slot_grad, int dim, uint8_t* wprep, cudaStream_t st);
 // same contract, A operand in tensor memory (tc_interact_ts.cu)
 int launch_interact_fwd_full_ts(const float* xp, int64_t xp_ld, const float* w_agg, int64_t w_ld,
                                 const float* bias, int nb, const int32_t* i3, int64_t E, float* ef,
@@ -37,5 +41,31 @@ int64_t interact_bwd_tc_workspace_bytes(int dim, int nb);
 int launch_interact_bwd_tc(const float* xp, int64_t xp_ld, const float* def, int64_t def_ld,
                            const float* w_hi, int64_t w_ld, int nb, const int32_t* i3, int64_t E,
                            float* slot_grad, float* dw_hi, int dim, void* workspace, cudaStream_t st);
+
+// Largest cluster size <= `want` (a power of two) for which the device keeps (almost) one CTA
+// per SM resident; *max_ctas = resident CTAs at that size.  A persistent kernel must not need a
+// second wave, so a size that strands more than 8 SMs is rejected.  IHG_CLUSTER overrides `want`.
+template <class Kernel>
+inline int pick_cluster(Kernel kernel, int threads, int smem_bytes, int want, int* max_ctas) {
+    if (const char* e = getenv("IHG_CLUSTER")) want = atoi(e);
+    for (; want > 1; want >>= 1) {
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3(kNumSMs / want * want);
+        q.blockDim = dim3(threads);
+        q.dynamicSmemBytes = smem_bytes;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = want, qa[0].val.clusterDim.y = 1, qa[0].val.clusterDim.z = 1;
+        q.attrs = qa, q.numAttrs = 1;
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, kernel, &q) == cudaSuccess && n_clusters * want >= kNumSMs - 8) {
+            *max_ctas = n_clusters * want > kNumSMs ? kNumSMs / want * want : n_clusters * want;
+            return want;
+        }
+        (void)cudaGetLastError();
+    }
+    *max_ctas = kNumSMs;
+    return 1;
+}
 
 }  // namespace ihg
