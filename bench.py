@@ -36,6 +36,28 @@ METRIC = "hypergraph_conv_hyperedge_layers_per_sec_fwd_bwd"
 UNIT = "hyperedge-layers/s"
 
 
+# C-ABI call tag -> kernel name in the committed ncu --set full extract
+_TAG_KERNEL = {"segment_reduce[mul=1]": "segment_reduce_kernel", "segment_reduce[mul=3]": "segment_reduce_kernel",
+               "edge_gather_sum": "edge_gather_sum_kernel", "edge_interact_fwd": "feature_interact_fwd_ts_kernel",
+               "node_linear": "node_linear_tc_kernel"}
+
+
+def ncu_traffic(workload, tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed ncu capture of this workload (profiles/r01_ncu_traffic.json); None if not captured."""
+    try:
+        with open(os.path.join(REPO, "profiles", "r01_ncu_traffic.json")) as f:
+            t = json.load(f)
+        if t.get("workload") != workload or tag not in _TAG_KERNEL:
+            return None, None
+        for name, b in t["dram_bytes_per_launch"].items():
+            if _TAG_KERNEL[tag] in name:
+                return float(b), t.get("source")
+    except (OSError, ValueError, KeyError):
+        pass
+    return None, None
+
+
 def measured_peaks():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -334,10 +356,11 @@ def run_gpu_arm(args, log, layers, d):
     peak, peak_src = measured_peaks()
     dom_tag = max(kern, key=lambda k: kern[k]["ms"])
     dom = kern[dom_tag]
+    traffic, traffic_src = ncu_traffic(args.workload, dom_tag)
     conv_bytes = layers * conv_algorithmic_bytes(E, N, d)       # global E, N: aggregate over all ranks
     roofline = {
         "bound": "hbm", "kernel": dom_tag, "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
-        "frac": dom["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+        "frac": dom["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "kernel_avg_ms": dom["avg_ms"], "kernel_share_of_step": dom["ms_per_step"] / (t_conv * 1e3),
         "algorithmic_bytes_per_launch": dom["bytes"] / dom["calls"],
         # whole conv step against SURVEY 8(d)'s E(60+76d)+N(28d+12) bytes per layer

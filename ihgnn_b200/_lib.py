@@ -61,7 +61,8 @@ SIGNATURES = {
     "ihg_gather_rows": (c_int32, [P, I64, P, I64, I64, P, I64, I32, P]),
     "ihg_scatter_add_rows": (c_int32, [P, I64, P, I64, I64, P, I64, I32, P]),
     "ihg_hem_score_fwd": (c_int32, [P, I64, P, I64, P, I64, P, P, F32, I64, I32, P, P]),
-    "ihg_hem_score_bwd": (c_int32, [P, P, I64, P, I64, P, I64, P, F32, I64, I32, P, P, P, P, I64, P]),
+    "ihg_hem_score_bwd": (c_int32, [P, P, I64, P, I64, P, I64, P, F32, I64, I32, P, P, P, P, I64, P, I64, P]),
+    "ihg_hem_score_bwd_workspace_bytes": (I64, [I64]),
 }
 
 # Optional per-call profiler (bench.py installs one): an object with

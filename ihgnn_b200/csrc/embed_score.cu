@@ -134,22 +134,37 @@ hem_score_bwd_kernel(const float* __restrict__ dscore, const float* __restrict__
     }
 }
 
-// d_bias[i] = sum of dscore[b] over b with item_idx[b] == i, ascending b (leader scheme)
+// d_bias[i] = sum of dscore[b] over b with item_idx[b] == i.  Order-independent (hence
+// bit-reproducible) without an O(B^2) scan: the addends are converted to 64-bit fixed point
+// relative to max|dscore| (2^-38 of the largest addend, 14 bits finer than fp32) and summed with
+// integer atomics, which are associative.
+//   ws[0] = max |dscore| bits, ws[1 ..] = per-item accumulators
 __global__ void __launch_bounds__(256)
-hem_bias_grad_kernel(const float* __restrict__ dscore, const int64_t* __restrict__ item_idx,
-                     int64_t count, float* __restrict__ d_bias) {
-    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < count;
-         b += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t my = __ldg(item_idx + b);
-        bool leader = true;
-        for (int64_t j = 0; j < b; ++j)
-            if (__ldg(item_idx + j) == my) { leader = false; break; }
-        if (!leader) continue;
-        float s = __ldg(dscore + b);
-        for (int64_t j = b + 1; j < count; ++j)
-            if (__ldg(item_idx + j) == my) s += __ldg(dscore + j);
-        d_bias[my] = s;
+hem_bias_max_kernel(const float* __restrict__ dscore, int64_t count, unsigned long long* __restrict__ ws) {
+    unsigned m = 0;
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < count; b += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, __float_as_uint(fabsf(__ldg(dscore + b))));
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(ws, (unsigned long long)m);
+}
+__device__ __forceinline__ int hem_bias_shift(const unsigned long long* ws) {
+    const int e = (int)((unsigned)ws[0] >> 23) - 127;          // floor(log2(max |g|)) (max is finite, >= 0)
+    return 38 - e;
+}
+__global__ void __launch_bounds__(256)
+hem_bias_accum_kernel(const float* __restrict__ dscore, const int64_t* __restrict__ item_idx, int64_t count,
+                      unsigned long long* __restrict__ ws) {
+    const int sh = hem_bias_shift(ws);
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < count; b += (int64_t)gridDim.x * blockDim.x) {
+        const long long q = __double2ll_rn(scalbn((double)__ldg(dscore + b), sh));
+        atomicAdd(ws + 1 + __ldg(item_idx + b), (unsigned long long)q);
     }
+}
+__global__ void __launch_bounds__(256)
+hem_bias_finish_kernel(const unsigned long long* __restrict__ ws, int64_t item_count, float* __restrict__ d_bias) {
+    const int sh = hem_bias_shift(ws);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < item_count; i += (int64_t)gridDim.x * blockDim.x)
+        d_bias[i] = (float)scalbn((double)(long long)ws[1 + i], -sh);
 }
 
 static unsigned blocks_for(int64_t n, int threads) {
@@ -216,11 +231,15 @@ int ihg_hem_score_fwd(const float* user_f, int64_t user_ld, const float* query_f
     return IHG_OK;
 }
 
+int64_t ihg_hem_score_bwd_workspace_bytes(int64_t item_count) {
+    return item_count > 0 ? (item_count + 1) * 8 : 0;
+}
+
 int ihg_hem_score_bwd(const float* dscore, const float* user_f, int64_t user_ld,
                       const float* query_f, int64_t query_ld, const float* item_f, int64_t item_ld,
                       const int64_t* item_idx, float lambda_muq, int64_t count, int32_t dim,
                       float* d_user, float* d_query, float* d_item, float* d_bias,
-                      int64_t item_count, void* stream) {
+                      int64_t item_count, void* workspace, int64_t workspace_bytes, void* stream) {
     IHG_REQUIRE(dscore && query_f && item_f, "hem_score_bwd: null pointer");
     IHG_REQUIRE(dim > 0 && dim % 4 == 0 && query_ld % 4 == 0 && item_ld % 4 == 0 && (!user_f || user_ld % 4 == 0),
                 "hem_score_bwd: dim and leading dimensions must be multiples of 4");
@@ -229,11 +248,18 @@ int ihg_hem_score_bwd(const float* dscore, const float* user_f, int64_t user_ld,
         IHG_REQUIRE(item_count > 0, "hem_score_bwd: item_count must be given with d_bias");
         if (item_idx) {
             IHG_REQUIRE(count <= 65536, "hem_score_bwd: count=%lld exceeds the 65536-row batch limit", (long long)count);
-            IHG_CUDA(cudaMemsetAsync(d_bias, 0, (size_t)item_count * 4, st));
+            IHG_REQUIRE(workspace && workspace_bytes >= ihg_hem_score_bwd_workspace_bytes(item_count),
+                        "hem_score_bwd: workspace too small");
+            unsigned long long* ws = static_cast<unsigned long long*>(workspace);
+            IHG_CUDA(cudaMemsetAsync(ws, 0, (size_t)(item_count + 1) * 8, st));
             if (count > 0) {
-                hem_bias_grad_kernel<<<blocks_for(count, 256), 256, 0, st>>>(dscore, item_idx, count, d_bias);
+                hem_bias_max_kernel<<<blocks_for(count, 256), 256, 0, st>>>(dscore, count, ws);
+                IHG_LAUNCH_CHECK();
+                hem_bias_accum_kernel<<<blocks_for(count, 256), 256, 0, st>>>(dscore, item_idx, count, ws);
                 IHG_LAUNCH_CHECK();
             }
+            hem_bias_finish_kernel<<<blocks_for(item_count, 256), 256, 0, st>>>(ws, item_count, d_bias);
+            IHG_LAUNCH_CHECK();
         } else {
             IHG_REQUIRE(count == item_count, "hem_score_bwd: all-items form needs count == item_count");
             IHG_CUDA(cudaMemcpyAsync(d_bias, dscore, (size_t)count * 4, cudaMemcpyDeviceToDevice, st));

@@ -287,11 +287,13 @@ class HemScoreFn(torch.autograd.Function):
         d_query = _empty((B, D), item_f) if need[1] else None
         d_item = _empty((B, D), item_f) if need[2] else None
         d_bias = torch.empty(ctx.n_items, dtype=_F32, device=item_f.device) if need[3] else None
+        ws_bytes = _lib.lib().ihg_hem_score_bwd_workspace_bytes(ctx.n_items) if (need[3] and item_idx is not None) else 0
+        ws = torch.empty(ws_bytes // 8, dtype=torch.int64, device=item_f.device) if ws_bytes else None
         _lib.call("ihg_hem_score_bwd", _lib.ptr(dscore), _lib.ptr(user_f),
                   _lib.ld(user_f) if user_f is not None else 0, _lib.ptr(query_f), _lib.ld(query_f),
                   _lib.ptr(item_f), _lib.ld(item_f), _lib.ptr(item_idx), ctx.lam, B, D,
                   _lib.ptr(d_user), _lib.ptr(d_query), _lib.ptr(d_item), _lib.ptr(d_bias),
-                  ctx.n_items, _lib.stream_ptr())
+                  ctx.n_items, _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
         return d_user, d_query, d_item, d_bias, None, None
 
 

@@ -203,7 +203,9 @@ int ihg_scatter_add_rows(const float* g, int64_t g_ld, const int64_t* idx, int64
  *   m = lambda*q + (1-lambda)*u   (u null: m = q);  score[b] = sum_D item[b]*m[b] + bias[b']
  *   b' = item_idx[b] (item_idx null: b' = b, "all items").  Dot-product branch only.
  * bwd: d_item = g*m, d_query = g*lambda*item, d_user = g*(1-lambda)*item (null = skip),
- *      d_bias[i] = sum_{b: idx[b]==i} g[b] in ascending b (d_bias pre-zeroed by the callee).
+ *      d_bias[i] = sum_{b: idx[b]==i} g[b], summed in 64-bit fixed point (order-independent,
+ *      bit-reproducible; resolution 2^-38 of max|g|).  workspace: 8-byte aligned device scratch of
+ *      ihg_hem_score_bwd_workspace_bytes(item_count) bytes (only read when d_bias && item_idx).
  * ------------------------------------------------------------------------------------ */
 int ihg_hem_score_fwd(const float* user_f, int64_t user_ld, const float* query_f,
                       int64_t query_ld, const float* item_f, int64_t item_ld,
@@ -213,7 +215,8 @@ int ihg_hem_score_bwd(const float* dscore, const float* user_f, int64_t user_ld,
                       const float* query_f, int64_t query_ld, const float* item_f,
                       int64_t item_ld, const int64_t* item_idx, float lambda_muq, int64_t count,
                       int32_t dim, float* d_user, float* d_query, float* d_item, float* d_bias,
-                      int64_t item_count, void* stream);
+                      int64_t item_count, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t ihg_hem_score_bwd_workspace_bytes(int64_t item_count);
 
 #ifdef __cplusplus
 }
