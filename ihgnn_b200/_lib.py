@@ -63,6 +63,7 @@ SIGNATURES = {
     "ihg_hem_score_fwd": (c_int32, [P, I64, P, I64, P, I64, P, P, F32, I64, I32, P, P]),
     "ihg_hem_score_bwd": (c_int32, [P, P, I64, P, I64, P, I64, P, F32, I64, I32, P, P, P, P, I64, P, I64, P]),
     "ihg_hem_score_bwd_workspace_bytes": (I64, [I64]),
+    "ihg_halo_copy": (c_int32, [P, P, P, I32, P, I64, I64, I32, P]),
 }
 
 # Optional per-call profiler (bench.py installs one): an object with

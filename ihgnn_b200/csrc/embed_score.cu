@@ -40,6 +40,33 @@ gather_rows_kernel(const float* __restrict__ table, int64_t table_ld,
     }
 }
 
+// Segmented row copy with one (source base, destination base) pair per segment: the halo
+// exchange over NVLink peer memory.  Flat row r belongs to segment s with seg_off[s] <= r <
+// seg_off[s+1]; it is read from seg_src[s] at row (src_rows ? src_rows[r] : r - seg_off[s]) and
+// written to seg_dst[s] at row r - seg_off[s].  Either side may be a peer-mapped pointer.
+struct HaloSegs {
+    const float* src[16];
+    float* dst[16];
+    int64_t off[17];
+    int n;
+};
+__global__ void __launch_bounds__(256)
+halo_copy_kernel(HaloSegs segs, const int64_t* __restrict__ src_rows, int64_t src_ld, int64_t dst_ld, int nvec) {
+    const int64_t total = segs.off[segs.n] * nvec;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / nvec;
+        const int c = (int)(t % nvec);
+        int sg = 0;
+        while (sg + 1 < segs.n && r >= segs.off[sg + 1]) ++sg;
+        const int64_t k = r - segs.off[sg];
+        const int64_t srow = src_rows ? __ldg(src_rows + r) : k;
+        // peer memory is not read-only cached: plain loads
+        const float4 v = *reinterpret_cast<const float4*>(segs.src[sg] + srow * src_ld + 4 * c);
+        *reinterpret_cast<float4*>(segs.dst[sg] + k * dst_ld + 4 * c) = v;
+    }
+}
+
 // One block per source row b.  The first occurrence of an index ("leader") sums every later
 // duplicate in ascending b and adds the total to the destination row once => deterministic.
 __global__ void __launch_bounds__(128)
@@ -199,6 +226,30 @@ int ihg_gather_rows(const float* table, int64_t table_ld, const int64_t* idx, in
     if (count <= 0) return IHG_OK;
     gather_rows_kernel<<<blocks_for(count * (dim / 4), 256), 256, 0, as_stream(stream)>>>(
         table, table_ld, idx, idx_offset, count, out, out_ld, dim / 4);
+    IHG_LAUNCH_CHECK();
+    return IHG_OK;
+}
+
+int ihg_halo_copy(const void* const* seg_src, void* const* seg_dst, const int64_t* seg_off, int32_t n_seg,
+                  const int64_t* src_rows, int64_t src_ld, int64_t dst_ld, int32_t dim, void* stream) {
+    IHG_REQUIRE(seg_src && seg_dst && seg_off, "halo_copy: null pointer");
+    IHG_REQUIRE(n_seg >= 1 && n_seg <= 16, "halo_copy: n_seg=%d outside [1, 16]", n_seg);
+    IHG_REQUIRE(dim > 0 && dim % 4 == 0 && src_ld % 4 == 0 && dst_ld % 4 == 0,
+                "halo_copy: dim and leading dimensions must be multiples of 4");
+    HaloSegs segs;
+    segs.n = n_seg;
+    for (int i = 0; i < n_seg; ++i) {
+        segs.src[i] = static_cast<const float*>(seg_src[i]);
+        segs.dst[i] = static_cast<float*>(seg_dst[i]);
+        segs.off[i] = seg_off[i];
+        IHG_REQUIRE(seg_off[i + 1] >= seg_off[i], "halo_copy: seg_off must be non-decreasing");
+    }
+    segs.off[n_seg] = seg_off[n_seg];
+    const int64_t rows = seg_off[n_seg] - seg_off[0];
+    IHG_REQUIRE(seg_off[0] == 0, "halo_copy: seg_off[0] must be 0");
+    if (rows <= 0) return IHG_OK;
+    halo_copy_kernel<<<blocks_for(rows * (dim / 4), 256), 256, 0, as_stream(stream)>>>(segs, src_rows, src_ld,
+                                                                                       dst_ld, dim / 4);
     IHG_LAUNCH_CHECK();
     return IHG_OK;
 }

@@ -23,6 +23,7 @@ CUDA only (NCCL).  The planner is pure numpy and is exercised on CPU by tests/te
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -168,8 +169,60 @@ class ShardedHyperGraph:
         self.send_counts = [int(x) for x in plan.send_counts]
         self.recv_counts = [int(x) for x in plan.recv_counts]
         self.reduce_csr = CsrPlan(t(plan.reduce_rowptr, torch.int32), t(plan.reduce_col, torch.int32))
+        self.p2p = None                                # set by enable_peer_memory()
         # Dv^-1 of every local row (own + halo): exchanged once, the graph is static
         self.dv_inv_local = HaloExchangeFn.apply(self.dv_inv_own.view(-1, 1).expand(-1, 4).contiguous(), self)[:, 0].contiguous()
+        if os.environ.get("IHG_P2P", "1") != "0":
+            self.enable_peer_memory()
+
+    # ---- NVLink peer memory (torch symmetric memory: VMM allocations mapped into every rank) ----
+    def enable_peer_memory(self) -> bool:
+        """Switch halo_exchange / halo_reduce from NCCL all-to-all to direct peer-memory copies:
+        owners write boundary rows straight into the halo tail of the readers' local tables, and
+        pull the halo partial sums straight out of the holders' buffers (one kernel per exchange,
+        `ihg_halo_copy`, plus a symmetric-memory barrier).  Returns False (and keeps NCCL) when
+        symmetric memory is not available."""
+        import torch.distributed as dist
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+        except ImportError:
+            return False
+        world, rank = self.plan.world, self.plan.rank
+        if world < 2 or world > 16:
+            return False
+        meta = torch.zeros((world, world + 2), dtype=torch.int64, device=self.device)
+        mine = torch.tensor([self.n_own, self.n_local] + self.send_counts, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(meta, mine, group=self.group)
+        meta = meta.cpu().numpy()
+        n_own_of = meta[:, 0]
+        send_of = meta[:, 2:]                                   # send_of[s][d] = rows s sends to d = rows d receives from s
+        # row where MY chunk starts in peer d's local table (its halo chunks are ordered by source rank)
+        self._peer_row = [int(n_own_of[d] + send_of[:rank, d].sum()) for d in range(world)]
+        self._max_local = int(meta[:, 1].max())
+        self._send_off = np.concatenate([[0], np.cumsum(self.send_counts)]).astype(np.int64)
+        self._symm = symm_mem
+        self._bufs = {}
+        self.p2p = True
+        return True
+
+    def peer_buffer(self, key, cols: int):
+        """Persistent symmetric [max n_local, cols] fp32 buffer for call site `key` (allocated and
+        rendezvoused on first use -- a collective, so every rank must reach it in the same order)."""
+        k = (key, cols)
+        if k not in self._bufs:
+            buf = self._symm.empty((self._max_local, cols), dtype=torch.float32, device=self.device)
+            hdl = self._symm.rendezvous(buf, group=self.group if self.group is not None else torch.distributed.group.WORLD)
+            world, rank = self.plan.world, self.plan.rank
+            base = [int(p) for p in hdl.buffer_ptrs]
+            row_bytes = cols * 4
+            import ctypes
+            peers = [d for d in range(world) if d != rank]
+            n = len(peers)
+            chunk = (ctypes.c_void_p * n)(*[base[d] + self._peer_row[d] * row_bytes for d in peers])   # my chunk in d's table
+            own = (ctypes.c_void_p * n)(*[buf.data_ptr()] * n)
+            off = (ctypes.c_int64 * (n + 1))(*([0] + list(np.cumsum([self.send_counts[d] for d in peers]))))
+            self._bufs[k] = (buf, hdl, chunk, own, off, n)
+        return self._bufs[k]
 
 
 def _all_to_all(out: torch.Tensor, inp: torch.Tensor, out_counts, in_counts, group) -> None:
@@ -183,13 +236,19 @@ class HaloExchangeFn(torch.autograd.Function):
     Backward = halo_reduce without scaling."""
 
     @staticmethod
-    def forward(ctx, x_own, g: "ShardedHyperGraph"):
-        ctx.g = g
-        return _halo_exchange(x_own, g)
+    def forward(ctx, x_own, g: "ShardedHyperGraph", key=None):
+        ctx.g, ctx.key = g, key
+        return _halo_exchange(x_own, g, key)
 
     @staticmethod
     def backward(ctx, dx_local):
-        return _halo_reduce(dx_local.contiguous(), ctx.g, None), None
+        g, key = ctx.g, ctx.key
+        dx_local = dx_local.contiguous()
+        if g.p2p and key is not None:              # the incoming gradient is an ordinary tensor: stage it
+            buf = reduce_buffer(g, ("xb", key), int(dx_local.shape[1]), dx_local)
+            buf.copy_(dx_local)
+            return _halo_reduce(buf, g, None, ("xb", key)), None, None
+        return _halo_reduce(dx_local, g, None), None, None
 
 
 class ShardedScatterMeanFn(torch.autograd.Function):
@@ -198,26 +257,41 @@ class ShardedScatterMeanFn(torch.autograd.Function):
     gradient, then the node -> hyperedge gather-sum with the (exchanged-once) Dv^-1 of the local rows."""
 
     @staticmethod
-    def forward(ctx, ef, g: "ShardedHyperGraph"):
+    def forward(ctx, ef, g: "ShardedHyperGraph", key=None):
         from . import _lib
         from . import functional as F_
-        ctx.g = g
+        ctx.g, ctx.key = g, key
         ef = _lib.rows_f32(ef)
-        s_local = F_.segment_reduce(g.plan_csr, ef, int(ef.shape[1]))
-        return _halo_reduce(s_local, g, g.dv_inv_own)
+        d = int(ef.shape[1])
+        s_local = F_.segment_reduce(g.plan_csr, ef, d, out=reduce_buffer(g, ("sm", key), d, ef))
+        return _halo_reduce(s_local, g, g.dv_inv_own, ("sm", key) if key is not None else None)
 
     @staticmethod
     def backward(ctx, dout_own):
         from . import functional as F_
-        g = ctx.g
-        g_local = HaloExchangeFn.apply(dout_own.contiguous(), g)
-        return F_.edge_gather_sum(g_local, g.i3, node_scale=g.dv_inv_local), None
+        g, key = ctx.g, ctx.key
+        g_local = _halo_exchange(dout_own.contiguous(), g, ("smb", key) if key is not None else None)
+        return F_.edge_gather_sum(g_local, g.i3, node_scale=g.dv_inv_local), None, None
 
 
-def _halo_exchange(x_own: torch.Tensor, g: "ShardedHyperGraph") -> torch.Tensor:
-    """[n_own, d] -> [n_local, d] = [own rows ; rows received from their owners] (no autograd)."""
+def _halo_exchange(x_own: torch.Tensor, g: "ShardedHyperGraph", key=None) -> torch.Tensor:
+    """[n_own, d] -> [n_local, d] = [own rows ; rows received from their owners] (no autograd).
+    `key` names the call site: with peer memory the result lives in that site's persistent buffer."""
     from . import functional as F_
+    from . import _lib
     d = int(x_own.shape[1])
+    if g.p2p and key is not None:
+        buf, hdl, chunk, own, off, n = g.peer_buffer(("x", key), d)
+        x_own = _lib.rows_f32(x_own)
+        # push: row send_rows[r] of my table -> my chunk in the reader's local table.  send_rows is
+        # ordered by destination rank and holds nothing for myself, so the flat order matches `off`.
+        src = (type(own))(*[x_own.data_ptr()] * n)
+        _lib.call("ihg_halo_copy", src, chunk, off, n, _lib.ptr(g.send_rows), _lib.ld(x_own), d, d,
+                  _lib.stream_ptr(), tag="halo_push", algo_bytes=g.S * (8 + 8 * d))
+        x_local = buf[:g.n_local]
+        F_.copy_rows_raw(x_own, x_local[:g.n_own])
+        hdl.barrier(channel=0)                      # every rank's pushes have landed
+        return x_local
     send = F_.gather_rows_raw(x_own, g.send_rows, 0)
     x_local = torch.empty((g.n_local, d), dtype=torch.float32, device=x_own.device)
     _all_to_all(x_local[g.n_own:], send, g.recv_counts, g.send_counts, g.group)
@@ -232,13 +306,14 @@ class ShardedFeatureInteractFn(torch.autograd.Function):
     applies the typed first-order Linear backward on the own rows."""
 
     @staticmethod
-    def forward(ctx, xp_own, w_agg, bias, g: "ShardedHyperGraph", order: int):
+    def forward(ctx, xp_own, w_agg, bias, g: "ShardedHyperGraph", order: int, key=None):
         from . import _lib
         xp_own = _lib.rows_f32(xp_own)
         w_agg = _lib.rows_f32(w_agg)
         bias = bias.contiguous()
         dim, E = int(xp_own.shape[1]), g.EdgeCount
-        xp_local = _halo_exchange(xp_own, g)
+        ctx.key = key
+        xp_local = _halo_exchange(xp_own, g, ("fi", key) if key is not None else None)
         ef = torch.empty((E, dim), dtype=torch.float32, device=xp_own.device)
         ws_bytes = _lib.lib().ihg_edge_interact_fwd_workspace_bytes(dim, order)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=xp_own.device)
@@ -270,29 +345,53 @@ class ShardedFeatureInteractFn(torch.autograd.Function):
                   _lib.ptr(dw_hi), dim, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(),
                   tag="edge_interact_bwd", algo_bytes=E * (12 + 28 * dim))
         # per-row gradients of the local rows, side by side: [ product-rule part | dP ]
-        both = torch.empty((g.n_local, 2 * dim), dtype=torch.float32, device=def_.device)
+        rkey = ("fib", ctx.key) if ctx.key is not None else None
+        both = reduce_buffer(g, rkey, 2 * dim, def_)
         F_.segment_reduce(g.plan_csr, slot_grad, dim, src_row_mul=3, row_slot=g.row_slot, out=both[:, :dim])
         F_.segment_reduce(g.plan_csr, def_, dim, out=both[:, dim:])
-        own = _halo_reduce(both, g, None)                                  # [n_own, 2 dim]
+        own = _halo_reduce(both, g, None, rkey)                            # [n_own, 2 dim]
         dxp_hi, dp = own[:, :dim], own[:, dim:]
         dxp = F_.node_linear(dp, w_lo, transpose_w=True, addend=dxp_hi, bounds=g.own_bounds)
         dw_lo, db_lo = F_.node_linear_wgrad(dp, xp_own, 3, g.own_bounds, True)
         dw = torch.cat([dw_lo[0], dw_lo[1], dw_lo[2], dw_hi], 1)
-        return dxp, dw, db_lo[0], None, None
+        return dxp, dw, db_lo[0], None, None, None
 
 
-def _halo_reduce(s_local: torch.Tensor, g: ShardedHyperGraph, row_scale: Optional[torch.Tensor]) -> torch.Tensor:
+def _halo_reduce(s_local: torch.Tensor, g: ShardedHyperGraph, row_scale: Optional[torch.Tensor], key=None) -> torch.Tensor:
     """own rows <- row_scale * (own partial + partials received from the ranks holding them as halo
-    rows, ascending source rank).  The halo partials are the contiguous tail of s_local."""
+    rows, ascending source rank).  The halo partials are the contiguous tail of s_local.
+    With peer memory (`key` names the call site and s_local must be that site's peer buffer, see
+    `reduce_buffer`) the owner pulls the partials straight out of the holders' buffers."""
     from . import functional as F_
+    from . import _lib
     d = int(s_local.shape[1])
     recv = torch.empty((g.S, d), dtype=torch.float32, device=s_local.device)
+    if g.p2p and key is not None:
+        buf, hdl, chunk, own, off, n = g.peer_buffer(("s", key), d)
+        assert s_local.data_ptr() == buf.data_ptr(), "halo_reduce: s_local must be the call site's peer buffer"
+        import ctypes
+        peers = [r for r in range(g.plan.world) if r != g.plan.rank]
+        dst = (ctypes.c_void_p * n)(*[recv.data_ptr() + int(g._send_off[r]) * d * 4 for r in peers])
+        hdl.barrier(channel=0)                      # every rank's partial sums are complete
+        _lib.call("ihg_halo_copy", chunk, dst, off, n, None, d, d, d, _lib.stream_ptr(),
+                  tag="halo_pull", algo_bytes=g.S * 8 * d)
+        out = F_.segment_reduce(g.reduce_csr, recv, d, row_scale=row_scale, init=s_local[:g.n_own])
+        hdl.barrier(channel=0)                      # holders may overwrite their buffers again
+        return out
     _all_to_all(recv, s_local[g.n_own:], g.send_counts, g.recv_counts, g.group)
     return F_.segment_reduce(g.reduce_csr, recv, d, row_scale=row_scale, init=s_local[:g.n_own])
 
 
-def halo_exchange(x_own, g):
-    return HaloExchangeFn.apply(x_own, g)
+def halo_exchange(x_own, g, key=None):
+    return HaloExchangeFn.apply(x_own, g, key)
+
+
+def reduce_buffer(g: ShardedHyperGraph, key, cols: int, like: torch.Tensor) -> torch.Tensor:
+    """[n_local, cols] buffer for partial sums that will go through `_halo_reduce(.., key=key)`:
+    the call site's peer buffer when peer memory is on, a fresh tensor otherwise."""
+    if g.p2p and key is not None:
+        return g.peer_buffer(("s", key), cols)[0][:g.n_local]
+    return torch.empty((g.n_local, cols), dtype=torch.float32, device=like.device)
 
 
 class _LocalGraphView:
@@ -311,6 +410,8 @@ class ShardedIHGNNLayer(torch.nn.Module):
     input / output are the rank's own rows [n_own, d].  Dense weight gradients must be
     all-reduced by the caller (`allreduce_dense_grads`)."""
 
+    _count = 0
+
     def __init__(self, graph: ShardedHyperGraph, dim: int, feature_interaction_order: int):
         super().__init__()
         from .layers import FeatureInteractor
@@ -323,6 +424,8 @@ class ShardedIHGNNLayer(torch.nn.Module):
         self.g = graph
         self.view = _LocalGraphView(graph)
         self.order = feature_interaction_order
+        ShardedIHGNNLayer._count += 1
+        self.uid = ShardedIHGNNLayer._count           # names this layer's persistent peer-memory buffers
         self.feature_interactor = FeatureInteractor(ds, feature_interaction_order, dim, dim)
         self.feature_transform = torch.nn.Linear(dim, dim)
 
@@ -338,20 +441,20 @@ class ShardedIHGNNLayer(torch.nn.Module):
             w_f = torch.matmul(w_lo, wt)
             b_f = torch.matmul(w_lo, bt) + torch.stack([fi.aggregation.bias, zeros, zeros])
             p_own = F_.typed_linear(x_own, w_f, b_f, g.own_bounds)
-            p = halo_exchange(p_own, g)
+            p = halo_exchange(p_own, g, (self.uid, "p"))
             ef = _EdgeGatherSumFn.apply(p, self.view, None, 1.0, None)
         else:
             from . import _lib
             xp_own = F_.typed_linear(x_own, wt.unsqueeze(0), bt.unsqueeze(0), None)
             if _lib.lib().ihg_feature_interact_supported(d):
-                ef = ShardedFeatureInteractFn.apply(xp_own, fi.aggregation.weight, fi.aggregation.bias, g, self.order)
+                ef = ShardedFeatureInteractFn.apply(xp_own, fi.aggregation.weight, fi.aggregation.bias, g, self.order, self.uid)
             else:
                 b_lo = torch.stack([fi.aggregation.bias, zeros, zeros])
                 p_own = F_.typed_linear(xp_own, w_lo, b_lo, g.own_bounds)
-                both = halo_exchange(torch.cat([xp_own, p_own], 1), g)     # one exchange for both row sets
+                both = halo_exchange(torch.cat([xp_own, p_own], 1), g, (self.uid, "xpp"))     # one exchange for both row sets
                 xp, p = both[:, :d], both[:, d:]
                 ef = _EdgeInteractFn.apply(xp, p, fi.aggregation.weight[:, 3 * d:], self.view, self.order)
-        return ShardedScatterMeanFn.apply(ef, g)
+        return ShardedScatterMeanFn.apply(ef, g, self.uid)
 
 
 def allreduce_dense_grads(module: torch.nn.Module, group=None) -> None:

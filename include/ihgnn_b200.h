@@ -199,6 +199,18 @@ int ihg_scatter_add_rows(const float* g, int64_t g_ld, const int64_t* idx, int64
                          int64_t count, float* out, int64_t out_ld, int32_t dim, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Multi-GPU halo exchange over NVLink peer memory (no reference counterpart: the reference is
+ * single-device).  Segmented row copy, one (source base, destination base) pair per
+ * peer; the pointer and offset tables are HOST arrays (n_seg <= 16), either side may be a
+ * peer-mapped device pointer.  Flat row r of segment s (seg_off[s] <= r < seg_off[s+1]) is read
+ * from seg_src[s] at row (src_rows ? src_rows[r] : r - seg_off[s]) and written to seg_dst[s] at
+ * row r - seg_off[s].  src_rows: device int64 or null.
+ * ------------------------------------------------------------------------------------ */
+int ihg_halo_copy(const void* const* seg_src, void* const* seg_dst, const int64_t* seg_off,
+                  int32_t n_seg, const int64_t* src_rows, int64_t src_ld, int64_t dst_ld,
+                  int32_t dim, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * a10 HemPredictionLayer.forward                   Models/PredictionLayers.py:21-44
  *   m = lambda*q + (1-lambda)*u   (u null: m = q);  score[b] = sum_D item[b]*m[b] + bias[b']
  *   b' = item_idx[b] (item_idx null: b' = b, "all items").  Dot-product branch only.
