@@ -53,17 +53,30 @@ struct HaloSegs {
 __global__ void __launch_bounds__(256)
 halo_copy_kernel(HaloSegs segs, const int64_t* __restrict__ src_rows, int64_t src_ld, int64_t dst_ld, int nvec) {
     const int64_t total = segs.off[segs.n] * nvec;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = t / nvec;
-        const int c = (int)(t % nvec);
-        int sg = 0;
-        while (sg + 1 < segs.n && r >= segs.off[sg + 1]) ++sg;
-        const int64_t k = r - segs.off[sg];
-        const int64_t srow = src_rows ? __ldg(src_rows + r) : k;
-        // peer memory is not read-only cached: plain loads
-        const float4 v = *reinterpret_cast<const float4*>(segs.src[sg] + srow * src_ld + 4 * c);
-        *reinterpret_cast<float4*>(segs.dst[sg] + k * dst_ld + 4 * c) = v;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    constexpr int kU = 4;                           // independent 16-byte copies in flight per thread
+    for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += kU * stride) {
+        float4 v[kU];
+        float* dst[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int64_t t = t0 + u * stride;
+            dst[u] = nullptr;
+            if (t < total) {
+                const int64_t r = t / nvec;
+                const int c = (int)(t - r * nvec);
+                int sg = 0;
+                while (sg + 1 < segs.n && r >= segs.off[sg + 1]) ++sg;
+                const int64_t k = r - segs.off[sg];
+                const int64_t srow = src_rows ? __ldg(src_rows + r) : k;
+                // peer memory is not read-only cached: plain loads
+                v[u] = *reinterpret_cast<const float4*>(segs.src[sg] + srow * src_ld + 4 * c);
+                dst[u] = segs.dst[sg] + k * dst_ld + 4 * c;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+            if (dst[u]) *reinterpret_cast<float4*>(dst[u]) = v[u];
     }
 }
 

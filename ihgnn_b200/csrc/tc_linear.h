@@ -8,6 +8,11 @@ namespace ihg {
 
 bool node_linear_tc_eligible(int n_out, int n_in, int64_t x_ld, int64_t y_ld, const float* addend,
                              int64_t addend_ld);
+// persistent variant: A operand in tensor memory, weights resident in shared memory (tc_linear_ts.cu)
+bool node_linear_ts_eligible(int n_out, int n_in);
+int launch_node_linear_ts(const float* x, int64_t x_ld, const float* w, int n_types, int n_out, int n_in,
+                          int transpose_w, const float* bias, const float* addend, int64_t addend_ld,
+                          int64_t n_rows, int64_t bound0, int64_t bound1, float* y, int64_t y_ld, cudaStream_t st);
 int launch_node_linear_tc(const float* x, int64_t x_ld, const float* w, int n_types, int n_out,
                           int n_in, int transpose_w, const float* bias, const float* addend,
                           int64_t addend_ld, int64_t n_rows, int64_t bound0, int64_t bound1,

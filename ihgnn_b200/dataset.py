@@ -47,6 +47,7 @@ class GraphDataset:
         self.pos_query = np.asarray(pos_query, dtype=np.int64)
         self.pos_item = np.asarray(pos_item, dtype=np.int64)
         self._hgraph: Optional[PpsHyperGraph] = None
+        self._cgraph: Optional[PpsHyperGraph] = None
 
     def __len__(self) -> int:
         return int(self.pos_user.shape[0])
@@ -61,7 +62,21 @@ class GraphDataset:
 
     @property
     def graph(self) -> PpsHyperGraph:                       # Dataset.py:79-82
-        return self.hypergraph
+        """The graph the layers convolve over.  Hyperedge ids never leave the layers (their outputs
+        are node features), so this copy numbers the hyperedges by ascending user (stable): the
+        user third of every edge -> node reduction then reads hyperedge rows sequentially and the
+        u-row gathers of consecutive hyperedges hit the same row.  Same hypergraph, same results up
+        to fp32 summation order inside query / item rows.  `hypergraph` keeps the reference's
+        interaction order (bit-exact I3 / Adjacency); IHG_EDGE_ORDER=file uses it here too."""
+        if self._cgraph is None:
+            if os.environ.get("IHG_EDGE_ORDER", "user") == "file":
+                self._cgraph = self.hypergraph
+            else:
+                order = np.argsort(self.pos_user, kind="stable")
+                self._cgraph = PpsHyperGraph.from_tensors(
+                    self.pos_user[order], self.pos_query[order], self.pos_item[order],
+                    self.user_count, self.query_count, self.item_count, GraphDataset.device)
+        return self._cgraph
 
     @classmethod
     def from_search_log(cls, log: SearchLogSet, device) -> "GraphDataset":

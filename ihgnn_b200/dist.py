@@ -202,8 +202,18 @@ class ShardedHyperGraph:
         self._send_off = np.concatenate([[0], np.cumsum(self.send_counts)]).astype(np.int64)
         self._symm = symm_mem
         self._bufs = {}
-        self.p2p = True
-        return True
+        # probe once (allocation + rendezvous + barrier); every rank must agree on the outcome
+        ok = 1
+        try:
+            probe = symm_mem.empty((1024,), dtype=torch.float32, device=self.device)
+            hdl = symm_mem.rendezvous(probe, group=self.group if self.group is not None else dist.group.WORLD)
+            hdl.barrier(channel=0)
+        except Exception:                                   # noqa: BLE001 - any failure means "keep NCCL"
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        self.p2p = True if int(flag.item()) == 1 else None
+        return self.p2p is True
 
     def peer_buffer(self, key, cols: int):
         """Persistent symmetric [max n_local, cols] fp32 buffer for call site `key` (allocated and

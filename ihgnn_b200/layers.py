@@ -337,7 +337,7 @@ class IHGNNLayer(nn.Module):
         if phase2_attention:
             # dead and broken in the reference (Main.py:57; GnnLayers.py:161-164 vs :62,90)
             raise NotImplementedError("phase2_attention is not supported (dead code path in the reference)")
-        graph: PpsHyperGraph = dataset.hypergraph
+        graph: PpsHyperGraph = dataset.graph          # reference: dataset.hypergraph (the same object there; GnnLayers.py:185)
         self.graph = graph
         self.Dv_neg_1 = graph.dv_inv.view(-1, 1)            # GnnLayers.py:187
         # aggregation Linear first, then the projection Linear: same RNG order as :193,:218
