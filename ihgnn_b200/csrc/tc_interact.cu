@@ -807,17 +807,28 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
 }
 
 // dw_hi[n][b*dim + k] = sum_cta ws[cta][b*dim + k][n]   (ascending cta: deterministic)
+// 256 threads = 32 outputs x 8 slices of the CTA range, combined in ascending slice order.
 __global__ void __launch_bounds__(256)
 interact_wgrad_tc_reduce_kernel(const float* __restrict__ ws, int n_cta, int G, int nb, int dim,
                                 float* __restrict__ dw_hi) {
+    __shared__ float part[8][32];
     const int64_t total = (int64_t)nb * dim * dim;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int n = idx % dim;                 // fastest: coalesced reads of ws rows
-        const int f = idx / dim;                 // product feature b*dim + k
-        float s = 0.f;
-        for (int c = 0; c < n_cta; ++c) s += ws[((int64_t)c * G * 128 + f) * dim + n];
-        dw_hi[(int64_t)n * nb * dim + f] = s;
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int64_t idx = (int64_t)blockIdx.x * 32 + lane;
+    const int n = (int)(idx % dim);              // fastest: coalesced reads of ws rows
+    const int64_t f = idx / dim;                 // product feature b*dim + k
+    float s = 0.f;
+    if (idx < total) {
+        const int c0 = (int)((int64_t)slice * n_cta / 8), c1 = (int)((int64_t)(slice + 1) * n_cta / 8);
+        for (int c = c0; c < c1; ++c) s += ws[((int64_t)c * G * 128 + f) * dim + n];
+    }
+    part[slice][lane] = s;
+    __syncthreads();
+    if (slice == 0 && idx < total) {
+        float t = part[0][lane];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) t += part[q][lane];
+        dw_hi[(int64_t)n * nb * dim + f] = t;
     }
 }
 
@@ -942,7 +953,7 @@ int launch_interact_bwd_tc(const float* xp, int64_t xp_ld, const float* def, int
 #undef IHG_WG_LAUNCH
         IHG_LAUNCH_CHECK();
         const int64_t total = (int64_t)nb * dim * dim;
-        interact_wgrad_tc_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, gx, G, nb, dim, dw_hi);
+        interact_wgrad_tc_reduce_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(partial, gx, G, nb, dim, dw_hi);
         IHG_LAUNCH_CHECK();
     }
     return IHG_OK;

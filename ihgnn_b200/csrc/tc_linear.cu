@@ -349,19 +349,33 @@ int64_t node_wgrad_tc_workspace_bytes(int n_types, int n_out, int n_in) {
 }
 
 // dw[t][n][k] = sum_g ws[g][t][n][k],  db[t][n] = sum_g ws[g][t][n][n_in]   (ascending g)
+// 256 threads = 32 outputs x 8 slices: slice s sums the contiguous range of partials
+// [s*G/8, (s+1)*G/8) in ascending g, the slice sums are combined in ascending s (fixed order,
+// deterministic; 8x the loads in flight of a one-thread-per-output loop).
 __global__ void __launch_bounds__(256)
 wgrad_partials_sum_kernel(const float* __restrict__ ws, int G, int n_types, int n_out, int n_in,
                           float* __restrict__ dw, float* __restrict__ db) {
+    __shared__ float part[8][32];
     const int acc_cols = n_in + 16;
     const int64_t rows = (int64_t)n_types * n_out;
     const int64_t total = rows * (n_in + 1);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / (n_in + 1);
-        const int k = (int)(i % (n_in + 1));
-        float s = 0.f;
-        for (int g = 0; g < G; ++g) s += ws[((int64_t)g * rows + r) * acc_cols + k];
-        if (k < n_in) dw[r * n_in + k] = s;
-        else if (db) db[r] = s;
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+    const int64_t r = i / (n_in + 1);
+    const int k = (int)(i % (n_in + 1));
+    float s = 0.f;
+    if (i < total) {
+        const int g0 = (int)((int64_t)slice * G / 8), g1 = (int)((int64_t)(slice + 1) * G / 8);
+        for (int g = g0; g < g1; ++g) s += ws[((int64_t)g * rows + r) * acc_cols + k];
+    }
+    part[slice][lane] = s;
+    __syncthreads();
+    if (slice == 0 && i < total) {
+        float t = part[0][lane];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) t += part[q][lane];
+        if (k < n_in) dw[r * n_in + k] = t;
+        else if (db) db[r] = t;
     }
 }
 
@@ -383,7 +397,7 @@ int launch_node_wgrad_tc(const float* dy, int64_t dy_ld, const float* x, int64_t
     node_wgrad_tc_kernel<<<grid, kNwThreads, smem, st>>>(dy, dy_ld, x, x_ld, b0, b1, n_rows, n_types, n_out, n_in, ws_dw);
     IHG_LAUNCH_CHECK();
     const int64_t total = (int64_t)n_types * n_out * (n_in + 1);
-    wgrad_partials_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws_dw, grid, n_types, n_out, n_in, dw, db);
+    wgrad_partials_sum_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(ws_dw, grid, n_types, n_out, n_in, dw, db);
     IHG_LAUNCH_CHECK();
     return IHG_OK;
 }
