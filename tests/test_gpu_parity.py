@@ -197,7 +197,8 @@ def test_indexed_embedding_lookups(golden):
         assert np.array_equal(i.cpu().numpy(), golden["state.embeddings.embedding_item.weight"][1:])
 
 
-@pytest.mark.parametrize("order,dim,layers", [(3, 64, 2), (3, 128, 2), (2, 32, 1), (1, 128, 3), (3, 48, 1)])
+@pytest.mark.parametrize("order,dim,layers", [(3, 64, 2), (3, 128, 2), (2, 32, 1), (1, 128, 3), (3, 48, 1),
+                                              (3, 96, 1), (2, 128, 1), (3, 32, 2)])
 def test_medium_graph_vs_oracle(order, dim, layers):
     """Seeded medium-size case (heavy Zipf head, split rows, ragged tiles) against the oracle
     in fp64, through the whole RawGnn stack: forward scores, loss and every gradient."""
@@ -284,3 +285,71 @@ def test_node_linear_wgrad(n_in, n_out, typed):
         assert max_rel(db[t].cpu().numpy(), dy[lo:hi].double().sum(0).numpy()) < 3e-6, t
     dw2, _ = F_.node_linear_wgrad(dy.to(DEV), x.to(DEV), T, (b0, b1) if typed else None, True)
     assert torch.equal(dw, dw2)
+
+
+def test_node_linear_many_tiles_per_cta():
+    """The persistent typed Linear streams several 128-row tiles per CTA (ring wrap-around, TMEM
+    accumulator double buffering, a tiny middle type served by a single CTA)."""
+    from ihgnn_b200 import functional as F_
+    gen = torch.Generator().manual_seed(5)
+    rows, b0, b1, d = 60_013, 41_000, 41_050, 64
+    x = torch.randn(rows, d, generator=gen)
+    w = torch.randn(3, d, d, generator=gen) / d ** 0.5
+    b = torch.randn(3, d, generator=gen)
+    tid = torch.zeros(rows, dtype=torch.long)
+    tid[b0:] = 1
+    tid[b1:] = 2
+    want = torch.einsum("rk,rnk->rn", x.double(), w.double()[tid]) + b.double()[tid]
+    got = F_.node_linear(x.to(DEV), w.to(DEV), bias=b.to(DEV), bounds=(b0, b1)).cpu()
+    assert max_rel(got.numpy(), want.numpy()) < 3e-6
+    got2 = F_.node_linear(x.to(DEV), w.to(DEV), bias=b.to(DEV), bounds=(b0, b1)).cpu()
+    assert torch.equal(got, got2)
+
+
+def test_halo_copy_segments():
+    """ihg_halo_copy (the peer-memory exchange kernel) with local pointers: indexed push and
+    contiguous pull over three segments, one of them empty."""
+    import ctypes
+    from ihgnn_b200 import _lib
+    gen = torch.Generator().manual_seed(11)
+    d = 48
+    table = torch.randn(500, d, generator=gen).to(DEV)
+    counts = [70, 0, 133]
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    rows = torch.randint(0, 500, (int(off[-1]),), generator=gen).to(DEV)
+    outs = [torch.zeros(max(c, 1), d, device=DEV) for c in counts]
+    n = len(counts)
+    src = (ctypes.c_void_p * n)(*[table.data_ptr()] * n)
+    dst = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
+    offs = (ctypes.c_int64 * (n + 1))(*off.tolist())
+    _lib.call("ihg_halo_copy", src, dst, offs, n, _lib.ptr(rows), d, d, d, _lib.stream_ptr())
+    for s_, c in enumerate(counts):
+        assert torch.equal(outs[s_][:c], table[rows[off[s_]:off[s_ + 1]]])
+    # pull: contiguous source segments -> one flat destination
+    flat = torch.zeros(int(off[-1]), d, device=DEV)
+    src2 = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
+    dst2 = (ctypes.c_void_p * n)(*[flat.data_ptr() + int(off[s_]) * d * 4 for s_ in range(n)])
+    _lib.call("ihg_halo_copy", src2, dst2, offs, n, None, d, d, d, _lib.stream_ptr())
+    assert torch.equal(flat, table[rows])
+
+
+def test_hem_bias_gradient_fixed_point():
+    """d_bias = index_add of dscore by item: 64-bit fixed-point atomics must match fp64 to fp32
+    rounding for duplicate-heavy batches and tiny gradients, and be bit-reproducible."""
+    from ihgnn_b200 import functional as F_
+    gen = torch.Generator().manual_seed(3)
+    B, D, n_items = 4096, 32, 97
+    for scale in (1.0, 1e-9):
+        q = torch.randn(B, D, generator=gen).to(DEV).requires_grad_(True)
+        it = torch.randn(B, D, generator=gen).to(DEV).requires_grad_(True)
+        bias = torch.zeros(n_items, device=DEV, requires_grad=True)
+        idx = torch.randint(0, n_items, (B,), generator=gen).to(DEV)
+        g = (torch.randn(B, generator=gen) * scale).to(DEV)
+        out = []
+        for _ in range(2):
+            bias.grad = None
+            F_.hem_score(None, q, it, bias, idx, 1.0).backward(g)
+            out.append(bias.grad.clone())
+        want = torch.zeros(n_items, dtype=torch.float64).index_add_(0, idx.cpu(), g.cpu().double())
+        assert max_rel(out[0].cpu().numpy(), want.numpy()) < 1e-6
+        assert torch.equal(out[0], out[1])
