@@ -280,12 +280,26 @@ def run_gpu_arm(args, log, layers, d):
         torch.cat(outs, 1).sum().backward()
         sync_conv()
 
+    # nvidia-smi needs a moment to start: launch it before the warm-up, keep warming up (untimed)
+    # until its first sample has arrived, and let it run through both timed regions so that the
+    # reported clocks are the clocks under this load even when the timed region is ~100 ms
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         conv_step()
+    t_wait = time.time()
+    while True:                                   # every rank must run the same number of steps
+        done = 1 if (sampler.proc is None or sampler.rows or time.time() - t_wait > 5.0) else 0
+        if dist is not None:
+            flag = torch.tensor([done], device=dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            done = int(flag.item())
+        if done:
+            break
+        conv_step()
+    n_before = len(sampler.rows)
     prof = KernelProfiler()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     _lib.profiler = prof
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -297,7 +311,6 @@ def run_gpu_arm(args, log, layers, d):
     launches = _lib.launch_count() - launches0
     _lib.profiler = None
     t_conv = ev0.elapsed_time(ev1) * 1e-3 / args.steps
-    clocks = sampler.stop()
     kern = prof.summary(args.steps)
 
     # --- e2e: a full training step through the public API, host batch in, loss out -----
@@ -338,6 +351,8 @@ def run_gpu_arm(args, log, layers, d):
     ev1.record()
     barrier()
     t_e2e = ev0.elapsed_time(ev1) * 1e-3 / e2e_steps
+    sampler.rows = sampler.rows[max(n_before - 1, 0):]       # samples from the timed regions (conv + e2e) on
+    clocks = sampler.stop()
 
     # --- max over ranks ---------------------------------------------------------------
     if dist is not None:
