@@ -192,7 +192,11 @@ static int launch_segment_reduce(const ihg_csr* g, const float* src, int64_t src
     if (blocks < 1) blocks = 1;
     const int64_t n_groups = blocks * groups_per_block;
     // unroll 4, no forced occupancy: forcing >= 4 blocks/SM wins in the isolated microbenchmark
-    // but loses in the real step (1.14 vs 1.07 ms at amazon-full), so the in-situ winner stays
+    // but loses in the real step (1.14 vs 1.07 ms at amazon-full), so the in-situ winner stays.
+    // Also tried and rejected (r01): staging a whole column batch (16 rows) per lane group with
+    // cp.async into a per-thread shared-memory ring -- 4x the bytes in flight per group but 64 KB of
+    // shared memory per block (3 blocks/SM) and a drain per batch: 1.29 vs 1.07 ms.  Numbering the
+    // hyperedges by user (sequential reads for a third of the incidences) moved it by < 1 %.
     segment_reduce_kernel<LPR, VPL, kSegUnroll, SEGS><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
         src, src_ld, mul, b0, b1, row_slot, init, init_ld, src_scale, row_scale, g->col, g->n_seg, n_groups,
         reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
