@@ -319,7 +319,8 @@ def run_gpu_arm(args, log, layers, d):
     kern = prof.summary(args.steps)
 
     # --- e2e: a full training step through the public API, host batch in, loss out -----
-    opt = torch.optim.Adam(model.parameters(), 1e-3)                      # Main.py:192
+    # Main.py:192 builds torch.optim.Adam(params, lr); fused=True is the same update in one kernel
+    opt = torch.optim.Adam(model.parameters(), 1e-3, fused=os.environ.get("IHG_ADAM", "fused") == "fused")
     rng = np.random.default_rng(123)                                     # same batches on every rank
     n_batches = 8
     host_batches = []
@@ -407,7 +408,7 @@ def run_gpu_arm(args, log, layers, d):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
                 "train_samples_per_s": B * (1 + NEG) / t_e2e,
-                "what": "RawGnn.forward(batch) -> BCEWithLogits -> backward -> Adam.step, batch indices "
+                "what": "RawGnn.forward(batch) -> BCEWithLogits -> backward -> Adam(fused).step, batch indices "
                         "from pinned host memory, loss copied back every step"},
         "gpu_launches": int(launches),
         "roofline": roofline,

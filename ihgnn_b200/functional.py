@@ -250,6 +250,48 @@ def gather_rows(table, idx, offset: int = 0):
     return GatherRowsFn.apply(table, idx, offset)
 
 
+class GatherRowsMultiFn(torch.autograd.Function):
+    """Several row selections out of ONE table (the user / query / item rows of a batch,
+    RawGnn.py:128-133): outs[j][b] = table[idx_j[b] + offset_j].  Backward builds the dense table
+    gradient once and scatter-adds every selection into it in order (deterministic), instead of one
+    dense gradient per selection plus autograd's accumulation adds."""
+
+    @staticmethod
+    def forward(ctx, table, offsets, *idxs):
+        _lib.require_cuda(table, *idxs)
+        table = _lib.rows_f32(table)
+        idxs = tuple(i.to(torch.int64).contiguous() for i in idxs)
+        d = int(table.shape[1])
+        outs = []
+        for idx, off in zip(idxs, offsets):
+            B = int(idx.numel())
+            out = _empty((B, d), table)
+            if B:
+                _lib.call("ihg_gather_rows", _lib.ptr(table), _lib.ld(table), _lib.ptr(idx), int(off), B,
+                          _lib.ptr(out), d, d, _lib.stream_ptr())
+            outs.append(out)
+        ctx.save_for_backward(*idxs)
+        ctx.offsets, ctx.shape = tuple(int(o) for o in offsets), tuple(table.shape)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        idxs = ctx.saved_tensors
+        dt = torch.zeros(ctx.shape, dtype=_F32, device=idxs[0].device)
+        d = ctx.shape[1]
+        for g, idx, off in zip(gs, idxs, ctx.offsets):
+            if g is None or idx.numel() == 0:
+                continue
+            g = _lib.rows_f32(g)
+            _lib.call("ihg_scatter_add_rows", _lib.ptr(g), _lib.ld(g), _lib.ptr(idx), off,
+                      int(idx.numel()), _lib.ptr(dt), d, d, _lib.stream_ptr())
+        return (dt, None) + (None,) * len(idxs)
+
+
+def gather_rows_multi(table, idxs, offsets):
+    return GatherRowsMultiFn.apply(table, tuple(offsets), *idxs)
+
+
 class HemScoreFn(torch.autograd.Function):
     """HemPredictionLayer.forward, dot-product branch
     (/root/reference/Models/PredictionLayers.py:21-44)."""

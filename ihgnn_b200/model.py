@@ -77,17 +77,29 @@ class RawGnn(nn.Module):
         return torch.cat(self.conv_stack(self.embeddings.embed_all()), 1)
 
     def forward(self, user_indices: Tensor, query_indices: Tensor, item_indices: Optional[Tensor] = None):
-        if self._saved_output_feature is None:
-            output_feature = self.output_features()
-        else:
-            output_feature = self._saved_output_feature
         ds = self.dataset
-        fu = F_.gather_rows(output_feature, user_indices, 0)                              # :128
-        fq = F_.gather_rows(output_feature, query_indices, ds.query_start_index_in_graph)  # :129
+        if self._saved_output_feature is None:
+            # training: cat(gnn_outputs, 1)[rows] == cat([o[rows] for o in gnn_outputs], 1)  (RawGnn.py:121-133):
+            # gather the batch rows out of every layer's table and concatenate the small results -- the
+            # [N, d(1+L)] table and its dense gradient are never materialised
+            outs = self.conv_stack(self.embeddings.embed_all())
+            idxs = [user_indices, query_indices] + ([item_indices] if item_indices is not None else [])
+            offs = [0, ds.query_start_index_in_graph, ds.item_start_index_in_graph][:len(idxs)]
+            picked = [F_.gather_rows_multi(o, idxs, offs) for o in outs]           # one dense gradient per table
+            fu = torch.cat([p[0] for p in picked], 1)                                      # :128
+            fq = torch.cat([p[1] for p in picked], 1)                                      # :129
+            if item_indices is not None:
+                fi = torch.cat([p[2] for p in picked], 1)                                  # :131
+            else:
+                fi = torch.cat([o[ds.item_start_index_in_graph:] for o in outs], 1)        # :133
+            return self.prediction_layer(fu, fq, fi, item_indices)
+        output_feature = self._saved_output_feature
+        fu = F_.gather_rows(output_feature, user_indices, 0)
+        fq = F_.gather_rows(output_feature, query_indices, ds.query_start_index_in_graph)
         if item_indices is not None:
-            fi = F_.gather_rows(output_feature, item_indices, ds.item_start_index_in_graph)  # :131
+            fi = F_.gather_rows(output_feature, item_indices, ds.item_start_index_in_graph)
         else:
-            fi = output_feature[ds.item_start_index_in_graph:]                              # :133
+            fi = output_feature[ds.item_start_index_in_graph:]
         return self.prediction_layer(fu, fq, fi, item_indices)
 
     def save_features_for_test(self) -> None:
