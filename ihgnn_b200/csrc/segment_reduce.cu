@@ -209,6 +209,146 @@ static int launch_segment_reduce(const ihg_csr* g, const float* src, int64_t src
     return IHG_OK;
 }
 
+
+// =========================================================================================
+// Two-hop reduce: the order-1 node -> hyperedge -> node round trip without the hyperedge
+// intermediate.
+//   out[r] = row_scale[r] * alpha * sum_{e contains r} sum_{n in e} node_scale[n] * src[n]
+// which is  _ScatterMean(edge_gather_sum(src))  of an order-1 IHGNN layer
+// (/root/reference/Models/CommonLayers.py:58-66 + GnnLayers.py:233-234 after hoisting the
+// aggregation Linear to node level), HGCN's H De^-1 H^T product (GnnLayers.py:148-151) and both of
+// their backward passes (H H^T is symmetric).  A row's own contribution is deg(r) * ns[r] * src[r];
+// the two OTHER nodes of every incident hyperedge come from the precomputed neighbour list
+// nbr[j] = (i3[col[j], slot+1 mod 3], i3[col[j], slot+2 mod 3]).  Instead of writing [E,dim] and
+// reading it back three times, the kernel gathers 2 node rows per incidence -- a win whenever the
+// node table ([N,dim]) is L2-resident while the hyperedge table ([E,dim]) is not.
+// Same chunk plan / fixed summation order / fix-up kernel as segment_reduce.
+// =========================================================================================
+__global__ void two_hop_index_kernel(const int4* __restrict__ seg, int64_t n_seg,
+                                     const int32_t* __restrict__ col, const int32_t* __restrict__ i3,
+                                     int64_t bound0, int64_t bound1,
+                                     const int32_t* __restrict__ row_slot, int2* __restrict__ nbr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= n_seg) return;
+    const int4 c = __ldg(seg + s);
+    const int row = c.z;
+    const int slot = row_slot ? __ldg(row_slot + row) : (row >= bound0) + (row >= bound1);
+    const int a = slot == 2 ? 0 : slot + 1, b = slot == 0 ? 2 : slot - 1;      // (slot+1)%3, (slot+2)%3
+    for (int j = c.x + lane; j < c.y; j += 32) {
+        const int64_t e = __ldg(col + j);
+        nbr[j] = make_int2(__ldg(i3 + 3 * e + a), __ldg(i3 + 3 * e + b));
+    }
+}
+
+template <int LPR, int VPL, int UNR>
+__global__ void __launch_bounds__(kSegWarpsPerBlock * 32)
+two_hop_reduce_kernel(const float* __restrict__ src, int64_t src_ld,
+                      const float* __restrict__ node_scale, float alpha,
+                      const float* __restrict__ row_scale, const int2* __restrict__ nbr,
+                      int64_t n_seg, const int4* __restrict__ seg, float* __restrict__ partial,
+                      float* __restrict__ out, int64_t out_ld, int dim) {
+    constexpr int G = 32 / LPR;
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % LPR;
+    const int gbase = lane - gl;
+    const int64_t group = ((int64_t)blockIdx.x * kSegWarpsPerBlock + (threadIdx.x >> 5)) * G + lane / LPR;
+    const int nvec = dim >> 2;
+    const bool live = group < n_seg;                 // not warp-uniform: keep shuffles unconditional
+    const int4 cur = live ? __ldg(seg + group) : make_int4(0, 0, 0, -1);
+    const int begin = cur.x, end = cur.y, row = cur.z, part = cur.w;
+    int2 nv = (begin + gl < end) ? __ldg(nbr + begin + gl) : make_int2(0, 0);
+
+    // the row's own term, issued early so that its latency hides behind the gathers
+    float4 own[VPL];
+    float own_w = 0.0f;
+    if (live && end > begin) own_w = (float)(end - begin) * (node_scale ? __ldg(node_scale + row) : 1.0f);
+#pragma unroll
+    for (int w = 0; w < VPL; ++w) {
+        const int cv = gl + w * LPR;
+        own[w] = (live && end > begin && cv < nvec) ? ldg4(src + (int64_t)row * src_ld + 4 * cv) : f4_zero();
+    }
+
+    float4 acc[VPL];
+#pragma unroll
+    for (int w = 0; w < VPL; ++w) acc[w] = f4_zero();
+    int len = end - begin;
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) len = max(len, __shfl_xor_sync(kFull, len, o));
+    for (int j0 = 0; j0 < len; j0 += LPR) {
+        // prefetch the next neighbour batch while this one is being gathered
+        const int jn = begin + j0 + LPR + gl;
+        const int2 nn = (jn < end) ? __ldg(nbr + jn) : make_int2(0, 0);
+        const int cnt = min(LPR, end - begin - j0);              // may be <= 0 for a shorter group
+        for (int k = 0; k < LPR; k += UNR) {
+            if (__all_sync(kFull, k >= cnt)) break;
+            float4 v[UNR][2][VPL];
+            float sc[UNR][2];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int idx = k + u;
+                const int na = __shfl_sync(kFull, nv.x, gbase + (idx % LPR));
+                const int nb = __shfl_sync(kFull, nv.y, gbase + (idx % LPR));
+                const bool ok = idx < cnt;
+                sc[u][0] = (ok && node_scale) ? __ldg(node_scale + na) : 1.0f;
+                sc[u][1] = (ok && node_scale) ? __ldg(node_scale + nb) : 1.0f;
+#pragma unroll
+                for (int w = 0; w < VPL; ++w) {
+                    const int cv = gl + w * LPR;
+                    const bool okc = ok && cv < nvec;
+                    v[u][0][w] = okc ? ldg4(src + (int64_t)na * src_ld + 4 * cv) : f4_zero();
+                    v[u][1][w] = okc ? ldg4(src + (int64_t)nb * src_ld + 4 * cv) : f4_zero();
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+#pragma unroll
+                for (int w = 0; w < VPL; ++w) {
+                    if (node_scale) {
+                        f4_fma(acc[w], sc[u][0], v[u][0][w]);
+                        f4_fma(acc[w], sc[u][1], v[u][1][w]);
+                    } else {
+                        f4_add(acc[w], v[u][0][w]);
+                        f4_add(acc[w], v[u][1][w]);
+                    }
+                }
+        }
+        nv = nn;
+    }
+    if (live) {
+        const float rs = (part < 0 && row_scale) ? alpha * __ldg(row_scale + row) : alpha;
+#pragma unroll
+        for (int w = 0; w < VPL; ++w) {
+            const int cv = gl + w * LPR;
+            if (cv >= nvec) continue;
+            f4_fma(acc[w], own_w, own[w]);
+            float* dst = part < 0 ? out + (int64_t)row * out_ld + 4 * cv : partial + (int64_t)part * dim + 4 * cv;
+            stg4(dst, f4_scale(rs, acc[w]));
+        }
+    }
+}
+
+template <int LPR, int VPL>
+static int launch_two_hop(const ihg_csr* g, const int32_t* nbr, const float* src, int64_t src_ld,
+                          const float* node_scale, float alpha, const float* row_scale,
+                          float* partial, float* out, int64_t out_ld, int dim, cudaStream_t st) {
+    constexpr int G = 32 / LPR;
+    const int64_t groups_per_block = (int64_t)kSegWarpsPerBlock * G;
+    int64_t blocks = ceil_div(g->n_seg, groups_per_block);
+    if (blocks < 1) blocks = 1;
+    two_hop_reduce_kernel<LPR, VPL, 4><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
+        src, src_ld, node_scale, alpha, row_scale, reinterpret_cast<const int2*>(nbr), g->n_seg,
+        reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
+    IHG_LAUNCH_CHECK();
+    if (g->n_split > 0) {
+        segment_fixup_kernel<LPR, VPL><<<(unsigned)g->n_split, kSegWarpsPerBlock * 32, 0, st>>>(
+            partial, g->split_row, g->split_ptr, g->n_split, nullptr, 0, row_scale, out, out_ld, dim);
+        IHG_LAUNCH_CHECK();
+    }
+    return IHG_OK;
+}
+
 }  // namespace ihg
 
 using namespace ihg;
@@ -240,4 +380,45 @@ extern "C" int ihg_segment_reduce(const ihg_csr* g, const float* src, int64_t sr
     if (nvec <= 32) IHG_SEG_CASE(32, 1);
     IHG_SEG_CASE(32, 2);
 #undef IHG_SEG_CASE
+}
+
+extern "C" int ihg_two_hop_index_build(const ihg_csr* g, const int32_t* i3, int64_t bound0,
+                                       int64_t bound1, const int32_t* row_slot, int32_t* nbr,
+                                       void* stream) {
+    IHG_REQUIRE(g && i3 && nbr, "two_hop_index_build: null pointer");
+    IHG_REQUIRE(g->n_rows > 0 && g->n_seg >= g->n_rows && g->seg, "two_hop_index_build: incomplete csr plan");
+    if (g->nnz == 0) return IHG_OK;
+    IHG_REQUIRE(g->col, "two_hop_index_build: null col");
+    const int warps = 8;
+    two_hop_index_kernel<<<(unsigned)ceil_div(g->n_seg, warps), warps * 32, 0, as_stream(stream)>>>(
+        reinterpret_cast<const int4*>(g->seg), g->n_seg, g->col, i3, bound0, bound1, row_slot,
+        reinterpret_cast<int2*>(nbr));
+    IHG_LAUNCH_CHECK();
+    return IHG_OK;
+}
+
+extern "C" int ihg_two_hop_reduce(const ihg_csr* g, const int32_t* nbr, const float* src,
+                                  int64_t src_ld, const float* node_scale, float alpha,
+                                  const float* row_scale, float* partial, float* out,
+                                  int64_t out_ld, int32_t dim, void* stream) {
+    IHG_REQUIRE(g && src && out, "two_hop_reduce: null pointer");
+    IHG_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 256, "two_hop_reduce: dim=%d must be a multiple of 4, <= 256", dim);
+    IHG_REQUIRE(src_ld % 4 == 0 && out_ld % 4 == 0 && src_ld >= dim && out_ld >= dim,
+                "two_hop_reduce: leading dimensions must be multiples of 4 and >= dim");
+    IHG_REQUIRE(g->n_rows > 0 && g->n_seg >= g->n_rows && g->seg, "two_hop_reduce: incomplete csr plan");
+    IHG_REQUIRE(g->nnz == 0 || nbr, "two_hop_reduce: null neighbour list");
+    IHG_REQUIRE(g->n_split == 0 || (partial && g->split_row && g->split_ptr),
+                "two_hop_reduce: split rows need the partial buffer");
+    cudaStream_t st = as_stream(stream);
+    const int nvec = dim / 4;
+#define IHG_TH_CASE(L, V) \
+    return launch_two_hop<L, V>(g, nbr, src, src_ld, node_scale, alpha, row_scale, partial, out, out_ld, dim, st)
+    if (nvec <= 1) IHG_TH_CASE(1, 1);
+    if (nvec <= 2) IHG_TH_CASE(2, 1);
+    if (nvec <= 4) IHG_TH_CASE(4, 1);
+    if (nvec <= 8) IHG_TH_CASE(8, 1);
+    if (nvec <= 16) IHG_TH_CASE(16, 1);
+    if (nvec <= 32) IHG_TH_CASE(32, 1);
+    IHG_TH_CASE(32, 2);
+#undef IHG_TH_CASE
 }

@@ -239,22 +239,34 @@ node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* _
         const int c = tid & 7, r0 = tid >> 3;            // rows r0, r0 + 16; chunk c of every block
         uint32_t it = 0;
         uint32_t started = 0;                            // bit t set once type t's accumulator is live
+        // Software pipeline: the loads of tile i+1 are issued BEFORE tile i is split and stored, so
+        // every thread keeps 8-16 independent 128-bit loads in flight across the wait / store phase
+        // (the 112 KB of operand stages allow only two CTAs per SM; without this the kernel was
+        // load-latency bound at ~1.3 TB/s).
+        float4 av[2][kNwMaxBlk], bv[2][kNwMaxBlk];
+        auto load_tile = [&](int64_t tile, float4 (&a)[2][kNwMaxBlk], float4 (&b)[2][kNwMaxBlk]) {
+            int t = 0;
+            while (t < 2 && tile >= tile_base[t + 1]) ++t;
+            const int64_t row0 = lo[t] + (tile - tile_base[t]) * kNwTe;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int64_t r = row0 + r0 + 16 * j;
+                const bool ok = tile < n_tiles && r < hi[t];
+#pragma unroll
+                for (int blk = 0; blk < kNwMaxBlk; ++blk) {
+                    a[j][blk] = (ok && blk < KA) ? ldg4(dy + r * dy_ld + blk * kChunkK + 4 * c) : f4_zero();
+                    b[j][blk] = (ok && blk < KB) ? ldg4(x + r * x_ld + blk * kChunkK + 4 * c) : f4_zero();
+                }
+            }
+            return t;
+        };
+        if ((int64_t)blockIdx.x < n_tiles) load_tile(blockIdx.x, av, bv);
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             int t = 0;
             while (t < 2 && tile >= tile_base[t + 1]) ++t;
             started |= 1u << (n_types > 1 ? t : 0);
-            const int64_t row0 = lo[t] + (tile - tile_base[t]) * kNwTe;
-            float4 av[2][kNwMaxBlk], bv[2][kNwMaxBlk];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int64_t r = row0 + r0 + 16 * j;
-                const bool ok = r < hi[t];
-#pragma unroll
-                for (int blk = 0; blk < kNwMaxBlk; ++blk) {
-                    av[j][blk] = (ok && blk < KA) ? ldg4(dy + r * dy_ld + blk * kChunkK + 4 * c) : f4_zero();
-                    bv[j][blk] = (ok && blk < KB) ? ldg4(x + r * x_ld + blk * kChunkK + 4 * c) : f4_zero();
-                }
-            }
+            float4 an[2][kNwMaxBlk], bn[2][kNwMaxBlk];
+            load_tile(tile + gridDim.x, an, bn);
             const int s = it & 1;
             mbar_wait(smem_u32(&bar_empty[s]), ((it >> 1) & 1u) ^ 1u);
             const uint32_t ah = smem_base + (uint32_t)s * stage_bytes;
@@ -273,6 +285,13 @@ node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* _
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int blk = 0; blk < kNwMaxBlk; ++blk) {
+                    av[j][blk] = an[j][blk];
+                    bv[j][blk] = bn[j][blk];
+                }
         }
         // final epilogue: warp == TMEM lane quadrant; rows n < n_out of every type's accumulator
         const int n = warp * 32 + lane;

@@ -194,6 +194,11 @@ class ShardedHyperGraph:
         if os.environ.get("IHG_P2P", "1") != "0":
             self.enable_peer_memory()
 
+    @property
+    def two_hop_nbr(self) -> torch.Tensor:
+        """Neighbour list of the local CSR for `ihg_two_hop_reduce` (built on first use)."""
+        return self.plan_csr.two_hop_nbr(self.i3, row_slot=self.row_slot)
+
     # ---- NVLink peer memory (torch symmetric memory: VMM allocations mapped into every rank) ----
     def enable_peer_memory(self) -> bool:
         """Switch halo_exchange / halo_reduce from NCCL all-to-all to direct peer-memory copies:
@@ -301,6 +306,31 @@ class ShardedScatterMeanFn(torch.autograd.Function):
         g, key = ctx.g, ctx.key
         g_local = _halo_exchange(dout_own.contiguous(), g, ("smb", key) if key is not None else None)
         return F_.edge_gather_sum(g_local, g.i3, node_scale=g.dv_inv_local), None, None
+
+
+class ShardedTwoHopFn(torch.autograd.Function):
+    """Order-1 round trip over a partitioned hypergraph without the [E_local, d] intermediate:
+    p_local [n_local, d] -> Dv^-1 * H H^T p for the own rows.  One two-hop pass over the local table
+    (`ihg_two_hop_reduce`) replaces gather-sum + segmented sum; then halo_reduce.  Backward: halo_exchange
+    of the gradient, the same two-hop pass with Dv^-1 as the node scale; the result is the gradient of
+    the LOCAL table (its halo part travels back through HaloExchangeFn.backward)."""
+
+    @staticmethod
+    def forward(ctx, p_local, g: "ShardedHyperGraph", key=None):
+        from . import _lib
+        from . import functional as F_
+        ctx.g, ctx.key = g, key
+        p_local = _lib.rows_f32(p_local)
+        d = int(p_local.shape[1])
+        s_local = F_.two_hop_reduce(g.plan_csr, g.two_hop_nbr, p_local, out=reduce_buffer(g, ("sm", key), d, p_local))
+        return _halo_reduce(s_local, g, g.dv_inv_own, ("sm", key) if key is not None else None)
+
+    @staticmethod
+    def backward(ctx, dout_own):
+        from . import functional as F_
+        g, key = ctx.g, ctx.key
+        g_local = _halo_exchange(dout_own.contiguous(), g, ("smb", key) if key is not None else None)
+        return F_.two_hop_reduce(g.plan_csr, g.two_hop_nbr, g_local, node_scale=g.dv_inv_local), None, None
 
 
 def _halo_exchange(x_own: torch.Tensor, g: "ShardedHyperGraph", key=None) -> torch.Tensor:
@@ -471,6 +501,8 @@ class ShardedIHGNNLayer(torch.nn.Module):
             b_f = torch.matmul(w_lo, bt) + torch.stack([fi.aggregation.bias, zeros, zeros])
             p_own = F_.typed_linear(x_own, w_f, b_f, g.own_bounds)
             p = halo_exchange(p_own, g, (self.uid, "p"))
+            if F_.two_hop_enabled(g.n_local, d):
+                return ShardedTwoHopFn.apply(p, g, self.uid)
             ef = _EdgeGatherSumFn.apply(p, self.view, None, 1.0, None)
         else:
             from . import _lib

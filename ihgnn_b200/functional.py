@@ -6,6 +6,7 @@ allocator), the current stream and the autograd tape.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -52,6 +53,35 @@ def segment_reduce(plan: CsrPlan, src: torch.Tensor, dim: int, *, src_row_mul: i
               _lib.ptr(out), _lib.ld(out), dim, _lib.stream_ptr(),
               tag=f"segment_reduce[mul={src_row_mul}]",
               algo_bytes=plan.nnz * (4 + 4 * dim) + plan.n_rows * (4 * dim + 16))
+    return out
+
+
+def two_hop_enabled(n_rows: int, dim: int) -> bool:
+    """Whether the order-1 node -> hyperedge -> node round trip runs as ONE two-hop pass over the
+    node table (2 row gathers per incidence, no [E,dim] intermediate) instead of gather-sum +
+    segmented reduce.  Measured on B200 (profiles/r01_bench_twohop_*.json): 0.33 vs 0.375 ms per
+    round trip at the amazon-full shape (node table L2-resident) and 1.81 vs 2.32 ms at the cikm
+    shape (256 MB table, NOT L2-resident: the Zipf head still hits), so it is the default;
+    IHG_TWO_HOP=0 selects the two-kernel form."""
+    return os.environ.get("IHG_TWO_HOP", "1") != "0"
+
+
+def two_hop_reduce(plan: CsrPlan, nbr: torch.Tensor, src: torch.Tensor, *,
+                   node_scale: Optional[torch.Tensor] = None, alpha: float = 1.0,
+                   row_scale: Optional[torch.Tensor] = None,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r] = row_scale[r] * alpha * sum_{e contains r} sum_{n in e} node_scale[n] * src[n]."""
+    _lib.require_cuda(src, nbr, node_scale, row_scale, out)
+    src = _lib.rows_f32(src)
+    dim = int(src.shape[1])
+    assert src.shape[0] == plan.n_rows, (src.shape, plan.n_rows)
+    if out is None:
+        out = _empty((plan.n_rows, dim), src)
+    _lib.call("ihg_two_hop_reduce", plan.ref(), _lib.ptr(nbr), _lib.ptr(src), _lib.ld(src),
+              _lib.ptr(node_scale), float(alpha), _lib.ptr(row_scale), _lib.ptr(plan.partial(dim)),
+              _lib.ptr(out), _lib.ld(out), dim, _lib.stream_ptr(), tag="two_hop_reduce",
+              # what the pair it replaces must move: gather-sum E(12+16d) + segmented reduce
+              algo_bytes=(plan.nnz // 3) * (12 + 16 * dim) + plan.nnz * (4 + 4 * dim) + plan.n_rows * (4 * dim + 16))
     return out
 
 
@@ -341,3 +371,35 @@ class HemScoreFn(torch.autograd.Function):
 
 def hem_score(user_f, query_f, item_f, items_bias, item_idx, lam):
     return HemScoreFn.apply(user_f, query_f, item_f, items_bias, item_idx, lam)
+
+
+def rank_topk(features: torch.Tensor, users: Optional[torch.Tensor], queries: torch.Tensor,
+              items_bias: torch.Tensor, lam: float, *, query_row0: int, item_row0: int, item_count: int,
+              candidates: Optional[torch.Tensor] = None, k: int = 10):
+    """Batched inference ranking (no autograd): for every (user, query) the k best of the candidate
+    items (`candidates` int64 [B, C]; None = all items) under the HEM score
+    (/root/reference/Models/PredictionLayers.py:21-44), i.e. what
+    `torch.sort(model(users, queries, None), descending=True)[1][:10]`
+    (/root/reference/Helpers/Metrics.py:60-61) yields per query.  Returns (item ids int64 [B, k],
+    scores fp32 [B, k])."""
+    _lib.require_cuda(features, users, queries, items_bias, candidates)
+    features = _lib.rows_f32(features)
+    queries = queries.to(torch.int64).contiguous()
+    if users is not None:
+        users = users.to(torch.int64).contiguous()
+        assert users.numel() == queries.numel()
+    B, D = int(queries.numel()), int(features.shape[1])
+    if candidates is not None:
+        candidates = candidates.to(torch.int64).contiguous()
+        assert candidates.dim() == 2 and candidates.shape[0] == B, (candidates.shape, B)
+        C = int(candidates.shape[1])
+    else:
+        C = int(item_count)
+    items_bias = items_bias.detach().contiguous()
+    top_items = torch.empty((B, k), dtype=torch.int64, device=features.device)
+    top_scores = torch.empty((B, k), dtype=_F32, device=features.device)
+    _lib.call("ihg_rank_topk", _lib.ptr(features), _lib.ld(features), _lib.ptr(users), _lib.ptr(queries), B,
+              int(query_row0), _lib.ptr(candidates), C, int(item_row0), int(item_count), _lib.ptr(items_bias),
+              float(lam), D, int(k), _lib.ptr(top_items), _lib.ptr(top_scores), _lib.stream_ptr(),
+              tag="rank_topk", algo_bytes=B * (8 * D + C * ((8 if candidates is not None else 0) + 4 * D + 4) + 12 * k))
+    return top_items, top_scores

@@ -57,6 +57,7 @@ class CsrPlan:
             n_seg=n_seg, n_split=n_split, n_part=n_part, seg=self.seg.data_ptr(),
             split_row=self.split_row.data_ptr(), split_ptr=self.split_ptr.data_ptr())
         self._partial = {}
+        self._nbr = None
 
     def partial(self, dim: int) -> Optional[torch.Tensor]:
         """Scratch for the partial sums of split rows (cached per feature dimension)."""
@@ -70,6 +71,18 @@ class CsrPlan:
 
     def ref(self):
         return ctypes.byref(self.struct)
+
+    def two_hop_nbr(self, i3: torch.Tensor, bounds=(INT64_MAX, INT64_MAX),
+                    row_slot: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """int32 [nnz, 2]: for every incidence (row r, hyperedge col[j]) the two OTHER nodes of that
+        hyperedge (`ihg_two_hop_index_build`); built once per plan, the graph is static."""
+        if self._nbr is None:
+            _lib.require_cuda(i3, row_slot)
+            nbr = torch.empty((max(self.nnz, 1), 2), dtype=torch.int32, device=self.rowptr.device)
+            _lib.call("ihg_two_hop_index_build", self.ref(), _lib.ptr(i3), bounds[0], bounds[1],
+                      _lib.ptr(row_slot), _lib.ptr(nbr), _lib.stream_ptr())
+            self._nbr = nbr
+        return self._nbr
 
 
 def csr_from_keys(keys: torch.Tensor, num_keys: int, values: Optional[torch.Tensor] = None):

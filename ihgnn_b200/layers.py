@@ -168,6 +168,38 @@ class _EdgeGatherSumFn(torch.autograd.Function):
         return dh, None, None, None, None
 
 
+class _TwoHopFn(torch.autograd.Function):
+    """out[r] = row_scale[r] * alpha * sum_{e contains r} sum_{n in e} node_scale[n] * h[n]:
+    _EdgeGatherSumFn followed by _ScatterMeanFn in one pass over the node table (no [E,d]
+    intermediate).  H H^T is symmetric, so backward is the same kernel with the scales swapped."""
+
+    @staticmethod
+    def forward(ctx, h, graph: PpsHyperGraph, node_scale, alpha: float, row_scale):
+        ctx.graph, ctx.node_scale, ctx.alpha, ctx.row_scale = graph, node_scale, alpha, row_scale
+        return F_.two_hop_reduce(graph.plan, _two_hop_nbr(graph), h, node_scale=node_scale, alpha=alpha,
+                                 row_scale=row_scale)
+
+    @staticmethod
+    def backward(ctx, dout):
+        g = ctx.graph
+        dh = F_.two_hop_reduce(g.plan, _two_hop_nbr(g), dout, node_scale=ctx.row_scale, alpha=ctx.alpha,
+                               row_scale=ctx.node_scale)
+        return dh, None, None, None, None
+
+
+def _two_hop_nbr(graph) -> Tensor:
+    return graph.plan.two_hop_nbr(graph.i3, graph.type_bounds, getattr(graph, "row_slot", None))
+
+
+def _gather_scatter(h: Tensor, graph, node_scale, alpha: float, gather_bwd_scale, row_scale) -> Tensor:
+    """row_scale * H . (alpha * H^T . (node_scale * h)): one two-hop pass when the node table is
+    L2-resident, else gather-sum into [E,d] + segmented reduce."""
+    if F_.two_hop_enabled(int(h.shape[0]), int(h.shape[1])):
+        return _TwoHopFn.apply(h, graph, node_scale, alpha, row_scale)
+    ef = _EdgeGatherSumFn.apply(h, graph, node_scale, alpha, gather_bwd_scale)
+    return _ScatterMeanFn.apply(ef, graph, row_scale)
+
+
 class _EdgeInteractFn(torch.autograd.Function):
     """Order 2/3 hyperedge features (CommonLayers.py:68-85) with the first-order blocks hoisted:
     ef[e] = p[u]+p[q]+p[i] + W_hi . cat(u*q, q*i, i*u [, u*q*i])."""
@@ -360,10 +392,9 @@ class IHGNNLayer(nn.Module):
             b_f = torch.matmul(w_lo, bt)                                         # [3, d]
             b_f = b_f + torch.stack([fi.aggregation.bias, torch.zeros_like(bt), torch.zeros_like(bt)])
             p = F_.typed_linear(input_features, w_f, b_f, g.type_bounds)
-            ef = _EdgeGatherSumFn.apply(p, g, None, 1.0, None)
-        else:
-            xp = F_.typed_linear(input_features, wt.unsqueeze(0), bt.unsqueeze(0), None)   # :224
-            ef = fi(xp)                                                                    # :225
+            return _gather_scatter(p, g, None, 1.0, None, g.dv_inv)                        # :225,:233-234
+        xp = F_.typed_linear(input_features, wt.unsqueeze(0), bt.unsqueeze(0), None)       # :224
+        ef = fi(xp)                                                                        # :225
         return _ScatterMeanFn.apply(ef, g, g.dv_inv)                                       # :233-234
 
 
@@ -387,8 +418,7 @@ class HGCNLayer(nn.Module):
         g = self.graph
         h = F_.typed_linear(input_features, self.feature_transform.weight.unsqueeze(0),
                             self.feature_transform.bias.unsqueeze(0), None)
-        ef = _EdgeGatherSumFn.apply(h, g, g.dv_inv_sqrt, self._alpha, self._bwd_scale)
-        return _ScatterMeanFn.apply(ef, g, g.dv_inv_sqrt)
+        return _gather_scatter(h, g, g.dv_inv_sqrt, self._alpha, self._bwd_scale, g.dv_inv_sqrt)
 
 
 # --------------------------------------------------------------------------------------

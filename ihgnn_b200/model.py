@@ -102,8 +102,59 @@ class RawGnn(nn.Module):
             fi = output_feature[ds.item_start_index_in_graph:]
         return self.prediction_layer(fu, fq, fi, item_indices)
 
+    @torch.no_grad()
+    def rank(self, user_indices: Tensor, query_indices: Tensor, candidates: Optional[Tensor] = None,
+             k: int = 10):
+        """Batched evaluation: the k best items per (user, query) -- all items, or the given
+        candidate lists [B, C] -- in one launch on the saved features.  Equals, per query b,
+        `torch.sort(self(u_b * ones(I), q_b * ones(I), None), descending=True)[1][:k]`
+        (TrainTestHelper.py:56 + Metrics.py:60-61).  Returns (item ids [B, k], scores [B, k])."""
+        ds = self.dataset
+        feat = self._saved_output_feature
+        if feat is None:
+            feat = self.output_features()
+        p = self.prediction_layer
+        return F_.rank_topk(feat, user_indices, query_indices, p.items_bias, p.lambda_muq,
+                            query_row0=ds.query_start_index_in_graph, item_row0=ds.item_start_index_in_graph,
+                            item_count=ds.item_count, candidates=candidates, k=k)
+
     def save_features_for_test(self) -> None:
         self._saved_output_feature = self.output_features()
 
     def clear_saved_feature(self) -> None:
         self._saved_output_feature = None
+
+
+def evaluate_searches(model: RawGnn, logs, batch_size: int = 8192, k: int = 10):
+    """Batched form of `test_and_get_avg_metrics`, Helpers/TrainTestHelper.py:37-102 for RawGnn models: `logs` is a sequence of
+    (user, query, interacted_items[, ...]) tuples (TestSearchLogDataLoader.logs, Dataset.py:297-318).
+    Features are saved once, every search is ranked against all items by `RawGnn.rank` (one launch
+    per `batch_size` searches instead of one forward + full sort + .cpu() per search), and
+    HR@10 / NDCG@10 / MAP@10 follow Helpers/Metrics.py:47-110 (flags all 1) on the host.
+    Returns (hit_ratio, ndcg, map) averaged over the searches."""
+    import math
+    dev = model.embeddings.embedding_user.weight.device
+    logs = [l for l in logs if len(l[2]) > 0]
+    if not logs:
+        return 0.0, 0.0, 0.0
+    hr = ndcg = mp = 0.0
+    with torch.no_grad():
+        model.save_features_for_test()
+        try:
+            for s in range(0, len(logs), batch_size):
+                part = logs[s:s + batch_size]
+                users = torch.tensor([l[0] for l in part], dtype=torch.int64).to(dev)
+                queries = torch.tensor([l[1] for l in part], dtype=torch.int64).to(dev)
+                top, _ = model.rank(users, queries, None, k)
+                top = top.cpu().tolist()                       # one D2H copy per batch
+                for rec, l in zip(top, part):
+                    items = [int(x) for x in l[2]]
+                    hits = [rec.index(it) for it in items if it in rec]                 # Metrics.py:66-68
+                    n10 = min(len(items), 10)                                           # :62
+                    hr += len(hits) / n10                                               # :80
+                    ndcg += sum(math.log(2, i + 2) for i in hits) / sum(math.log(2, i + 2) for i in range(n10))
+                    mp += sum((j + 1) / (i + 1) for j, i in enumerate(hits)) / len(hits) if hits else 0.0
+        finally:
+            model.clear_saved_feature()
+    n = len(logs)
+    return hr / n, ndcg / n, mp / n

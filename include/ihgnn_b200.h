@@ -118,6 +118,25 @@ int ihg_segment_reduce(const ihg_csr* csr_host, const float* src, int64_t src_ld
                        float* out, int64_t out_ld, int32_t dim, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * a5-a8  node -> hyperedge -> node round trip of an order-1 layer in one pass (no [E,dim]
+ *     intermediate):   Models/CommonLayers.py:58-66 (order-1 FeatureInteractor, aggregation
+ *     Linear hoisted to node level) followed by thsp.matmul(incidence, ef) * Dv^-1
+ *     (GnnLayers.py:233-234); HGCN's H De^-1 H^T (GnnLayers.py:148-151); and their backward
+ *     products (H H^T is symmetric).
+ *   out[r,:] = row_scale[r] * alpha * sum_{e contains r} sum_{n in e} node_scale[n] * src[n,:]
+ * ihg_two_hop_index_build fills nbr int32 [nnz,2]: for incidence j of row r (slot(r) as in
+ * ihg_segment_reduce) the two OTHER nodes of hyperedge col[j], slots (slot+1)%3 and (slot+2)%3.
+ * The row's own term is deg(r) * node_scale[r] * src[r].  Deterministic (same chunk plan and
+ * fix-up as ihg_segment_reduce); node_scale / row_scale nullable; `partial` as there.
+ * ------------------------------------------------------------------------------------ */
+int ihg_two_hop_index_build(const ihg_csr* csr_host, const int32_t* i3, int64_t bound0,
+                            int64_t bound1, const int32_t* row_slot, int32_t* nbr, void* stream);
+int ihg_two_hop_reduce(const ihg_csr* csr_host, const int32_t* nbr, const float* src,
+                       int64_t src_ld, const float* node_scale, float alpha,
+                       const float* row_scale, float* partial, float* out, int64_t out_ld,
+                       int32_t dim, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * a6/a8  node -> hyperedge gather-sum.
  *   out[e,:] = alpha * sum_{s<3} node_scale[i3[e,s]] * src[i3[e,s], :]  (+ bias)
  * Order-1 FeatureInteractor after hoisting the aggregation Linear to node level
@@ -229,6 +248,27 @@ int ihg_hem_score_bwd(const float* dscore, const float* user_f, int64_t user_ld,
                       int32_t dim, float* d_user, float* d_query, float* d_item, float* d_bias,
                       int64_t item_count, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t ihg_hem_score_bwd_workspace_bytes(int64_t item_count);
+
+/* ------------------------------------------------------------------------------------
+ * Inference ranking (BASELINE.json configs[4]): per (user, query) score a
+ * candidate item list with the HEM scorer and keep the k best, for a whole batch of queries in
+ * one launch.  Replaces the per-query loop  TestSearchLogDataLoader.__iter__ (Dataset.py:324-329)
+ * -> RawGnn.forward eval branch (Models/RawGnn.py:124-142) -> HemPredictionLayer.forward
+ * (Models/PredictionLayers.py:21-44) -> torch.sort(descending)[:10] (Helpers/Metrics.py:60-61).
+ *   feat       [N, dim] saved output features (RawGnn.save_features_for_test, RawGnn.py:147-155)
+ *   users      int64 [n_queries] user ids (row = id) or null (m = q);  queries int64 [n_queries],
+ *              row = id + query_row0
+ *   cand       int64 [n_queries, n_cand] item ids, or null = all items 0..n_cand-1
+ *              (the reference's "predict on all items"); ids outside [0, item_count) never rank
+ *   score      = sum_D feat[item_row0 + id] * (lambda*q + (1-lambda)*u) + items_bias[id]
+ *   top_items  int64 [n_queries, k], top_scores fp32 [n_queries, k]: descending score, ties to the
+ *              earlier candidate; unfilled places (fewer than k valid candidates) = (-1, -inf).
+ * dim % 4 == 0, dim <= 1024, 1 <= k <= 32.
+ * ------------------------------------------------------------------------------------ */
+int ihg_rank_topk(const float* feat, int64_t feat_ld, const int64_t* users, const int64_t* queries,
+                  int64_t n_queries, int64_t query_row0, const int64_t* cand, int64_t n_cand,
+                  int64_t item_row0, int64_t item_count, const float* items_bias, float lambda_muq,
+                  int32_t dim, int32_t k, int64_t* top_items, float* top_scores, void* stream);
 
 #ifdef __cplusplus
 }

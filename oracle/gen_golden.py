@@ -41,6 +41,7 @@ with contextlib.redirect_stdout(io.StringIO()):
     from Helpers.Graph import PpsHyperGraph  # noqa: E402
     from Dataset import GraphDataset  # noqa: E402
     from Models import RawGnn, IHGNNLayer, HGCNLayer, HemPredictionLayer  # noqa: E402
+    from Helpers.Metrics import Metrics  # noqa: E402
 
 CPU = torch.device("cpu")
 
@@ -91,7 +92,7 @@ def _layer_outputs(model):
     return outs
 
 
-def _run(model, users, queries, items, flags, prefix, out):
+def _run(model, users, queries, items, flags, prefix, out, pos_log):
     model.zero_grad()
     scores = model(users, queries, items)
     loss = torch.nn.BCEWithLogitsLoss()(scores, flags.to(scores.dtype))   # Main.py:191
@@ -110,6 +111,25 @@ def _run(model, users, queries, items, flags, prefix, out):
         u0, q0 = int(users[0]), int(queries[0])
         ev = model(u0 * torch.ones(I, dtype=torch.long), q0 * torch.ones(I, dtype=torch.long), None)
         out[f"{prefix}.eval_scores"] = _np(ev)
+        # the evaluation loop proper (TrainTestHelper.py:53-63): per search, all items scored, the
+        # reference's own torch.sort top-10 and its own Metrics.calculate_on_all_items
+        n_rank = min(8, int(users.numel()) // 11)
+        top, top_s, mets, inter = [], [], [], []
+        for b in range(n_rank):
+            ub, qb = int(users[b]), int(queries[b])
+            outb = model(ub * torch.ones(I, dtype=torch.long), qb * torch.ones(I, dtype=torch.long), None)
+            _, idx = torch.sort(outb, descending=True)                         # Metrics.py:60
+            top.append(_np(idx[:10]))
+            top_s.append(_np(outb[idx[:10]]))
+            sel = (pos_log[0] == ub) & (pos_log[1] == qb)
+            items_b = sorted(set(int(x) for x in pos_log[2][sel]))             # get_interacted_items of that search
+            m = Metrics.calculate_on_all_items(outb, items_b, None, True)
+            mets.append([m.HitRatio_at10, m.NDCG_at10, m.MAP_at10])
+            inter.append(items_b + [-1] * (16 - len(items_b)))
+        out[f"{prefix}.rank_top10"] = np.stack(top).astype(np.int64)
+        out[f"{prefix}.rank_scores"] = np.stack(top_s)
+        out[f"{prefix}.rank_metrics"] = np.asarray(mets, dtype=np.float64)
+        out["rank.interacted"] = np.asarray(inter, dtype=np.int64)
         model.clear_saved_feature()
     # conv-only metric M1: loss = sum(cat(outs,1)) w.r.t. X
     x = torch.cat(model.embeddings(None, None, None)).detach().clone().requires_grad_(True)
@@ -185,7 +205,8 @@ def make_case(name: str, cfg: dict, outdir: str) -> None:
     out["batch.users"], out["batch.queries"], out["batch.items"] = _np(users), _np(queries), _np(items)
     out["batch.flags"] = _np(flags)
 
-    _run(model, users, queries, items, flags, "ref32", out)
+    pos_log = (log.pos_user, log.pos_query, log.pos_item)
+    _run(model, users, queries, items, flags, "ref32", out, pos_log)
 
     # indexed embedding lookups, the Srrl client form (Srrl.py:74-94)
     with torch.no_grad():
@@ -196,7 +217,7 @@ def make_case(name: str, cfg: dict, outdir: str) -> None:
         out["ref32.embed_query_idx"] = _np(model.embeddings.embed_query(qi))
 
     _cast_model_to_double(model)
-    _run(model, users, queries, items, flags, "ref64", out)
+    _run(model, users, queries, items, flags, "ref64", out, pos_log)
 
     path = os.path.join(outdir, f"{name}.npz")
     np.savez_compressed(path, **out)

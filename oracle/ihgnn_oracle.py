@@ -14,6 +14,7 @@ same ATen ops in the same order are the faithful CPU form), of:
   hgcn_layer           Models/GnnLayers.py:142-153    HGCNLayer.forward
   hem_score            Models/PredictionLayers.py:21-44 HemPredictionLayer.forward
   rawgnn_features/forward  Models/RawGnn.py:104-144   RawGnn.forward
+  rank_topk / metrics_at_10  Dataset.py:324-329 + Helpers/Metrics.py:47-110  the evaluation loop
 
 The edge->node reduction of the reference goes through `torch_sparse.matmul`
 (rusty1s/pytorch_sparse, NOT vendored and NOT version-pinned by the reference: it ships no
@@ -268,6 +269,51 @@ class OracleModel:
     def grads(self) -> Dict[str, torch.Tensor]:
         return {k: (v.grad if v.grad is not None else torch.zeros_like(v))
                 for k, v in self.params.items()}
+
+
+def rank_topk(model: "OracleModel", users: torch.Tensor, queries: torch.Tensor,
+              candidates: Optional[torch.Tensor] = None, k: int = 10,
+              features: Optional[torch.Tensor] = None):
+    """The reference's evaluation of one search per loop iteration, restated per query:
+    TestSearchLogDataLoader.__iter__ (Dataset.py:324-329: users = u * ones(I), queries = q * ones(I))
+    -> RawGnn.forward(users, queries, None) on the saved features (RawGnn.py:124-142)
+    -> `_, idx = torch.sort(outputs, descending=True); idx[:10]` (Helpers/Metrics.py:60-61).
+    With `candidates` [B, C] only those items are scored (BASELINE.json configs[4]) and the
+    returned ids are item ids.  Returns (ids int64 [B, k], scores [B, k])."""
+    with torch.no_grad():
+        f = model.features() if features is None else features
+        ids, vals = [], []
+        for b in range(int(queries.numel())):
+            if candidates is None:
+                ones = torch.ones(model.I, dtype=torch.long)
+                out = model.forward(users[b] * ones, queries[b] * ones, None, features=f)      # all items
+                _, order = torch.sort(out, descending=True, stable=True)
+                top = order[:k]
+                ids.append(top)
+                vals.append(out[top])
+            else:
+                c = candidates[b]
+                ones = torch.ones(c.numel(), dtype=torch.long)
+                out = model.forward(users[b] * ones, queries[b] * ones, c, features=f)
+                _, order = torch.sort(out, descending=True, stable=True)
+                top = order[:k]
+                ids.append(c[top])
+                vals.append(out[top])
+        return torch.stack(ids), torch.stack(vals)
+
+
+def metrics_at_10(recommend_indices: Sequence[int], interacted_items: Sequence[int]):
+    """Helpers/Metrics.py:47-88 for flags_are_all_1 (the only form TestSearchLogDataLoader emits,
+    Dataset.py:312): (HR@10, NDCG@10, MAP@10) of one search from its top-10 item ids."""
+    import math
+    rec = [int(x) for x in recommend_indices][:10]
+    hits = [rec.index(int(it)) for it in interacted_items if int(it) in rec]        # :66-68
+    n10 = min(len(interacted_items), 10)                                             # :62
+    hr = len(hits) / n10                                                             # :80
+    dcg = sum(math.log(2, i + 2) for i in hits)                                      # :93
+    idcg = sum(math.log(2, i + 2) for i in range(n10))                               # :97-103
+    ap = sum((j + 1) / (i + 1) for j, i in enumerate(hits)) / len(hits) if hits else 0.0   # :105-109 (hit order = interacted_items order, as the reference)
+    return hr, dcg / idcg, ap
 
 
 def bce_with_logits_mean(scores: torch.Tensor, flags: torch.Tensor) -> torch.Tensor:

@@ -130,6 +130,61 @@ def test_segment_reduce_and_gather_sum_vs_oracle(dim):
     assert max_rel(got_s, want_s.numpy()) < 2e-6
 
 
+@pytest.fixture(params=["0", "1"], ids=["gather+reduce", "two-hop"])
+def two_hop_mode(request, monkeypatch):
+    """Run a model test through both forms of the order-1 node -> hyperedge -> node round trip."""
+    monkeypatch.setenv("IHG_TWO_HOP", request.param)
+    return request.param
+
+
+@pytest.mark.parametrize("dim", [4, 16, 64, 128, 256])
+def test_two_hop_reduce_vs_oracle(dim):
+    """ihg_two_hop_reduce == row_scale * H . (alpha * H^T . (node_scale * x)) (the order-1 IHGNN
+    round trip, HGCN's H De^-1 H^T and their transposes), neighbour index bit-exact."""
+    from ihgnn_b200 import functional as F_
+    from ihgnn_b200 import synth
+    from ihgnn_b200.graph import PpsHyperGraph
+    U, Q, I, E = 400, 30, 200, 9000
+    log = synth.make_search_log(U, Q, I, E, 50, shape="cikm", seed=dim + 1, zipf=1.0)
+    ref = orc.build_hypergraph(log.pos_user, log.pos_query, log.pos_item, U, Q, I)
+    g = PpsHyperGraph.from_tensors(log.pos_user, log.pos_query, log.pos_item, U, Q, I, DEV, chunk_len=64)
+    assert g.plan.n_split > 0
+    nbr = g.plan.two_hop_nbr(g.i3, g.type_bounds)
+    # index parity: incidence j of row r lists the other two nodes of hyperedge col[j]
+    I3, col, rowptr = ref.I3.numpy(), ref.col.numpy(), ref.rowptr.numpy()
+    row_of = np.repeat(np.arange(U + Q + I), np.diff(rowptr))
+    slot = (row_of >= U).astype(np.int64) + (row_of >= U + Q)
+    want_nbr = np.stack([I3[col, (slot + 1) % 3], I3[col, (slot + 2) % 3]], 1)
+    assert np.array_equal(nbr.cpu().numpy().astype(np.int64), want_nbr)
+    assert np.array_equal(I3[col, slot], row_of)
+    # the row_slot form (sharded local tables) builds the same list
+    from ihgnn_b200.graph import CsrPlan
+    plan2 = CsrPlan(g.rowptr, g.col, 64)
+    rows = np.arange(U + Q + I)
+    row_slot = ((rows >= U).astype(np.int32) + (rows >= U + Q)).astype(np.int32)
+    nbr2 = plan2.two_hop_nbr(g.i3, row_slot=torch.from_numpy(row_slot).to(DEV))
+    assert torch.equal(nbr, nbr2)
+    gen = torch.Generator().manual_seed(dim)
+    x = torch.randn(U + Q + I, dim, generator=gen)
+    H = ref.adjacency(torch.float64)
+    ns, rs = ref.VertexDegrees.pow(-0.5).double(), ref.VertexDegrees.pow(-1).double()
+    ef = (x.double() * ns)[ref.I3].sum(1) / 3.0
+    want = (rs * torch.sparse.mm(H, ef)).numpy()
+    got = F_.two_hop_reduce(g.plan, nbr, x.to(DEV), node_scale=g.dv_inv_sqrt, alpha=1.0 / 3.0,
+                            row_scale=g.dv_inv).cpu().numpy()
+    assert max_rel(got, want) < 2e-6
+    iso = (np.diff(rowptr) == 0)
+    assert iso.any() and np.all(got[iso] == 0.0)
+    want_plain = torch.sparse.mm(H, x.double()[ref.I3].sum(1)).numpy()
+    got_plain = F_.two_hop_reduce(g.plan, nbr, x.to(DEV)).cpu().numpy()
+    assert max_rel(got_plain, want_plain) < 2e-6
+    # equals the two-kernel form it replaces to rounding
+    two = F_.segment_reduce(g.plan, F_.edge_gather_sum(x.to(DEV), g.i3), dim).cpu().numpy()
+    assert max_rel(got_plain, two) < 2e-6
+    again = F_.two_hop_reduce(g.plan, nbr, x.to(DEV)).cpu().numpy()
+    assert np.array_equal(got_plain, again)            # fixed summation order
+
+
 def _run_model(m, golden):
     users, queries, items, flags = (t.to(DEV) for t in batch_of(golden))
     m.zero_grad()
@@ -140,7 +195,7 @@ def _run_model(m, golden):
     return scores.detach().cpu().numpy(), float(loss), grads
 
 
-def test_model_forward_backward_matches_reference(golden):
+def test_model_forward_backward_matches_reference(golden, two_hop_mode):
     m = _model(golden)
     scores, loss, grads = _run_model(m, golden)
     worst = {}
@@ -162,7 +217,7 @@ def test_model_forward_backward_matches_reference(golden):
     assert not bad, f"beyond {REL_TOL}: {bad}"
 
 
-def test_conv_stack_gradients_match_reference(golden):
+def test_conv_stack_gradients_match_reference(golden, two_hop_mode):
     """Metric M1's unit of work: loss = sum(cat(outs, 1)), gradient w.r.t. X and conv weights."""
     m = _model(golden)
     x = m.embeddings.embed_all().detach().clone().requires_grad_(True)
@@ -199,7 +254,7 @@ def test_indexed_embedding_lookups(golden):
 
 @pytest.mark.parametrize("order,dim,layers", [(3, 64, 2), (3, 128, 2), (2, 32, 1), (1, 128, 3), (3, 48, 1),
                                               (3, 96, 1), (2, 128, 1), (3, 32, 2)])
-def test_medium_graph_vs_oracle(order, dim, layers):
+def test_medium_graph_vs_oracle(order, dim, layers, two_hop_mode):
     """Seeded medium-size case (heavy Zipf head, split rows, ragged tiles) against the oracle
     in fp64, through the whole RawGnn stack: forward scores, loss and every gradient."""
     from ihgnn_b200 import HemPredictionLayer, IHGNNLayer, RawGnn, synth
@@ -353,3 +408,75 @@ def test_hem_bias_gradient_fixed_point():
         want = torch.zeros(n_items, dtype=torch.float64).index_add_(0, idx.cpu(), g.cpu().double())
         assert max_rel(out[0].cpu().numpy(), want.numpy()) < 1e-6
         assert torch.equal(out[0], out[1])
+
+
+# --------------------------------------------------------------------------------------
+# inference ranking (BASELINE.json configs[4])
+# --------------------------------------------------------------------------------------
+def test_rank_topk_matches_reference_eval_loop(golden):
+    """RawGnn.rank == the reference's per-search loop (all items scored, torch.sort, top-10) and
+    the batched evaluation reproduces the reference's own Metrics values."""
+    from ihgnn_b200.model import evaluate_searches
+    m = _model(golden)
+    users, queries, _, _ = batch_of(golden)
+    n = golden["ref64.rank_top10"].shape[0]
+    with torch.no_grad():
+        m.save_features_for_test()
+        ids, vals = m.rank(users[:n].to(DEV), queries[:n].to(DEV), None, 10)
+        # bit-identical to the training-time scorer on the same rows
+        I = m.dataset.item_count
+        ev = m(users[0].item() * torch.ones(I, dtype=torch.long, device=DEV),
+               queries[0].item() * torch.ones(I, dtype=torch.long, device=DEV), None)
+        m.clear_saved_feature()
+    assert np.array_equal(ids.cpu().numpy(), golden["ref64.rank_top10"])
+    assert max_rel(vals.cpu().numpy(), golden["ref64.rank_scores"]) <= REL_TOL
+    assert torch.equal(vals[0], ev[ids[0]])
+    logs = [(int(users[b]), int(queries[b]), [int(x) for x in golden["rank.interacted"][b] if x >= 0]) for b in range(n)]
+    hr, ndcg, mp = evaluate_searches(m, logs, batch_size=3)
+    want = golden["ref64.rank_metrics"].mean(0)
+    assert np.allclose([hr, ndcg, mp], want, rtol=0, atol=1e-9), ([hr, ndcg, mp], want)
+
+
+@pytest.mark.parametrize("D,I,C,k", [(192, 5000, 1000, 10), (64, 3000, None, 10), (512, 2500, 1500, 32),
+                                     (128, 700, 37, 1), (48, 300, 5, 10)])
+def test_rank_topk_vs_oracle(D, I, C, k):
+    """Candidate lists (one chunk / several chunks / fewer candidates than k), all-items mode,
+    out-of-range candidate ids, users == None -- against torch.sort on the oracle's scores."""
+    from ihgnn_b200 import functional as F_
+    U, Q, B = 400, 60, 257
+    gen = torch.Generator().manual_seed(D + I)
+    feat = torch.randn(U + Q + I, D, generator=gen)
+    bias = torch.randn(I, generator=gen)
+    users = torch.randint(0, U, (B,), generator=gen)
+    queries = torch.randint(0, Q, (B,), generator=gen)
+    lam = 0.3
+    cand = None
+    if C is not None:
+        cand = torch.stack([torch.randperm(I, generator=gen)[:C] for _ in range(B)])
+        cand[::7, 0] = -1                                    # invalid ids never rank
+        cand[::5, -1] = I + 3
+    for with_user in (True, False):
+        u = users if with_user else None
+        ids, vals = F_.rank_topk(feat.to(DEV), u.to(DEV) if u is not None else None, queries.to(DEV),
+                                 bias.to(DEV), lam, query_row0=U, item_row0=U + Q, item_count=I,
+                                 candidates=cand.to(DEV) if cand is not None else None, k=k)
+        ids, vals = ids.cpu(), vals.cpu()
+        f64 = feat.double()
+        for b in range(0, B, 16):
+            mq = f64[queries[b] + U]
+            mvec = lam * mq + (1 - lam) * f64[users[b]] if with_user else mq
+            cb = torch.arange(I) if cand is None else cand[b]
+            ok = (cb >= 0) & (cb < I)
+            cbv = cb[ok]
+            sc = orc.hem_score(None, mvec.expand(cbv.numel(), -1), f64[cbv + U + Q], bias.double(), cbv, lam)
+            order = torch.sort(sc, descending=True, stable=True)[1][:k]
+            nv = int(order.numel())
+            assert ids[b, :nv].tolist() == cbv[order].tolist(), b
+            assert max_rel(vals[b, :nv].numpy(), sc[order].numpy()) <= REL_TOL
+            assert (ids[b, nv:] == -1).all() and torch.isinf(vals[b, nv:]).all()
+    # ties go to the earlier candidate: identical item rows
+    feat2 = feat.clone()
+    feat2[U + Q:] = feat2[U + Q]
+    ids, _ = F_.rank_topk(feat2.to(DEV), None, queries[:4].to(DEV), torch.zeros(I).to(DEV), lam, query_row0=U,
+                          item_row0=U + Q, item_count=I, candidates=None, k=min(k, I))
+    assert ids.cpu().tolist() == [list(range(min(k, I)))] * 4

@@ -79,3 +79,28 @@ def test_indexed_embedding_lookups(golden):
     assert np.array_equal(eu.numpy(), golden["ref32.embed_user_idx"])
     assert np.array_equal(ei.numpy(), golden["ref32.embed_item_idx"])
     assert max_rel(eq.numpy(), golden["ref32.embed_query_idx"]) <= 1e-7
+
+
+def test_ranking_matches_reference_eval_loop(golden):
+    """oracle.rank_topk / metrics_at_10 against the reference's own evaluation loop
+    (TrainTestHelper.py:53-63: all-item scores -> torch.sort top-10 -> Metrics.calculate_on_all_items)."""
+    users, queries, _, _ = batch_of(golden)
+    n = golden["ref64.rank_top10"].shape[0]
+    m = oracle_model(golden, torch.float64)
+    ids, vals = orc.rank_topk(m, users[:n], queries[:n], None, 10)
+    assert np.array_equal(ids.numpy(), golden["ref64.rank_top10"])
+    assert max_rel(vals.numpy(), golden["ref64.rank_scores"]) <= 1e-12
+    for b in range(n):
+        inter = [int(x) for x in golden["rank.interacted"][b] if x >= 0]
+        got = orc.metrics_at_10(golden["ref64.rank_top10"][b], inter)
+        assert np.allclose(got, golden["ref64.rank_metrics"][b], rtol=0, atol=1e-12), (b, got)
+    # candidate-list form == all-items form restricted to the list
+    rng = np.random.default_rng(3)
+    cand = torch.from_numpy(np.stack([rng.permutation(m.I)[: m.I // 2] for _ in range(n)]))
+    ids_c, vals_c = orc.rank_topk(m, users[:n], queries[:n], cand, 5)
+    f = m.features()
+    for b in range(n):
+        full = m.forward(users[b] * torch.ones(m.I, dtype=torch.long), queries[b] * torch.ones(m.I, dtype=torch.long),
+                         None, features=f).detach()
+        want = sorted(cand[b].tolist(), key=lambda i: -float(full[i]))[:5]
+        assert ids_c[b].tolist() == want
