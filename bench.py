@@ -36,23 +36,35 @@ METRIC = "hypergraph_conv_hyperedge_layers_per_sec_fwd_bwd"
 UNIT = "hyperedge-layers/s"
 
 
-# C-ABI call tag -> kernel name in the committed ncu --set full extract
-_TAG_KERNEL = {"segment_reduce[mul=1]": "segment_reduce_kernel", "segment_reduce[mul=3]": "segment_reduce_kernel",
-               "edge_gather_sum": "edge_gather_sum_kernel", "edge_interact_fwd": "feature_interact_fwd_ts_kernel",
-               "node_linear": "node_linear_tc_kernel"}
+# C-ABI call tag -> the kernels that call launches, by name in the committed ncu --set full extract
+_TAG_KERNEL = {"segment_reduce[mul=1]": ["segment_reduce_kernel", "segment_fixup_kernel"],
+               "segment_reduce[mul=3]": ["segment_reduce_kernel", "segment_fixup_kernel"],
+               "two_hop_reduce": ["two_hop_reduce_kernel", "segment_fixup_kernel"],
+               "edge_gather_sum": ["edge_gather_sum_kernel"],
+               "edge_interact_fwd": ["feature_interact_fwd_ts_kernel"],
+               "edge_interact_bwd": ["interact_bwd_slot_ts_kernel", "edge_interact_bwd_wgrad_tc_kernel"],
+               "node_linear": ["node_linear_ts_kernel"],
+               "node_linear_wgrad": ["node_wgrad_tc_kernel", "wgrad_partials_sum_kernel"]}
 
 
 def ncu_traffic(workload, tag):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
-    committed ncu capture of this workload (profiles/r01_ncu_traffic.json); None if not captured."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per C-ABI call of the dominant tag (summed over
+    the kernels the call launches), from the committed ncu capture of this workload
+    (profiles/r01_ncu_traffic.json, written by profiles/ncu_extract.py); None if not captured."""
     try:
         with open(os.path.join(REPO, "profiles", "r01_ncu_traffic.json")) as f:
             t = json.load(f)
         if t.get("workload") != workload or tag not in _TAG_KERNEL:
             return None, None
-        for name, b in t["dram_bytes_per_launch"].items():
-            if _TAG_KERNEL[tag] in name:
-                return float(b), t.get("source")
+        total, found = 0.0, False
+        for kern in _TAG_KERNEL[tag]:
+            for name, b in t["dram_bytes_per_launch"].items():
+                if kern in name:
+                    total += float(b)
+                    found = True
+                    break
+        if found:
+            return total, t.get("source")
     except (OSError, ValueError, KeyError):
         pass
     return None, None
@@ -436,7 +448,9 @@ def main():
 
     w = synth.WORKLOADS[args.workload]
     layers, d = w["layers"], w["dim"]
-    world = int(os.environ.get("WORLD_SIZE", "1")) if args.impl == "ours" else 1
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
+        return                                    # the CPU arm runs on rank 0 alone; the others exit 0 without work
     log = synth.make_workload(args.workload, scale=args.scale * world)   # weak scaling: world x the workload
     if args.impl == "reference":
         run_reference_arm(args, log, layers, d)

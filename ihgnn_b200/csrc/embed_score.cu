@@ -82,27 +82,62 @@ halo_copy_kernel(HaloSegs segs, const int64_t* __restrict__ src_rows, int64_t sr
 
 // One block per source row b.  The first occurrence of an index ("leader") sums every later
 // duplicate in ascending b and adds the total to the destination row once => deterministic.
+// Both scans over idx are block-parallel: windows of 128 positions are tested at once, the matches
+// of a window are compacted IN ORDER (ballot + prefix) into shared memory, then added in that order.
 __global__ void __launch_bounds__(128)
 scatter_add_rows_kernel(const float* __restrict__ g, int64_t g_ld, const int64_t* __restrict__ idx,
                         int64_t idx_offset, int64_t count, float* __restrict__ out,
                         int64_t out_ld, int nvec) {
     __shared__ int dup_before;
+    __shared__ int warp_cnt[4];
+    __shared__ int match[128];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t b = blockIdx.x;
     const int64_t my = __ldg(idx + b);
-    if (threadIdx.x == 0) dup_before = 0;
+    if (tid == 0) dup_before = 0;
     __syncthreads();
     int found = 0;
-    for (int64_t j = threadIdx.x; j < b; j += blockDim.x) found |= (__ldg(idx + j) == my);
+    for (int64_t j = tid; j < b; j += blockDim.x) found |= (__ldg(idx + j) == my);
     if (found) dup_before = 1;   // benign race: every writer stores 1
     __syncthreads();
     if (dup_before) return;
-    for (int c = threadIdx.x; c < nvec; c += blockDim.x) {
-        float4 acc = ldg4(g + b * g_ld + 4 * c);
-        for (int64_t j = b + 1; j < count; ++j)
-            if (__ldg(idx + j) == my) f4_add(acc, ldg4(g + j * g_ld + 4 * c));
+    float4 acc[2];                                   // nvec <= 256 (dim <= 1024): two float4 per thread
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        const int c = tid + 128 * w;
+        acc[w] = c < nvec ? ldg4(g + b * g_ld + 4 * c) : f4_zero();
+    }
+    for (int64_t j0 = b + 1; j0 < count; j0 += 128) {
+        const int64_t j = j0 + tid;
+        const bool hit = j < count && __ldg(idx + j) == my;
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            if (w < warp) base += warp_cnt[w];
+            total += warp_cnt[w];
+        }
+        if (hit) match[base + __popc(bal & ((1u << lane) - 1u))] = (int)(j - j0);
+        __syncthreads();
+        for (int m = 0; m < total; ++m) {
+            const int64_t jj = j0 + match[m];
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const int c = tid + 128 * w;
+                if (c < nvec) f4_add(acc[w], ldg4(g + jj * g_ld + 4 * c));
+            }
+        }
+        __syncthreads();                             // match[] / warp_cnt[] are rewritten by the next window
+    }
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        const int c = tid + 128 * w;
+        if (c >= nvec) continue;
         float* o = out + (my + idx_offset) * out_ld + 4 * c;
         float4 base = *reinterpret_cast<const float4*>(o);
-        f4_add(base, acc);
+        f4_add(base, acc[w]);
         stg4(o, base);
     }
 }
@@ -273,6 +308,7 @@ int ihg_scatter_add_rows(const float* g, int64_t g_ld, const int64_t* idx, int64
     IHG_REQUIRE(dim > 0 && dim % 4 == 0 && g_ld % 4 == 0 && out_ld % 4 == 0,
                 "scatter_add_rows: dim and leading dimensions must be multiples of 4");
     IHG_REQUIRE(count <= 65536, "scatter_add_rows: count=%lld exceeds the 65536-row batch limit", (long long)count);
+    IHG_REQUIRE(dim <= 1024, "scatter_add_rows: dim=%d exceeds 1024", dim);
     if (count <= 0) return IHG_OK;
     scatter_add_rows_kernel<<<(unsigned)count, 128, 0, as_stream(stream)>>>(g, g_ld, idx, idx_offset,
                                                                             count, out, out_ld, dim / 4);

@@ -15,6 +15,8 @@
 //
 // Roofline: HBM.  Algorithmic bytes per incidence: 4 (col) + 4*dim (source row); per row:
 // 16 (plan) + 4 (scale) + 4*dim (output row).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ihg {
@@ -197,6 +199,9 @@ static int launch_segment_reduce(const ihg_csr* g, const float* src, int64_t src
     // cp.async into a per-thread shared-memory ring -- 4x the bytes in flight per group but 64 KB of
     // shared memory per block (3 blocks/SM) and a drain per batch: 1.29 vs 1.07 ms.  Numbering the
     // hyperedges by user (sequential reads for a third of the incidences) moved it by < 1 %.
+    // Launch-bound variants re-measured in situ (profiles/r01_bench_segreduce_variants.txt): unlike the
+    // L2-served two-hop gathers, these DRAM-served 256/512-byte random row reads get SLOWER with more
+    // resident warps or a shorter unroll (unroll 2 with >= 5/6/8 blocks: 2.3 / 2.7 / 3.2 TB/s vs 3.6-4.0).
     segment_reduce_kernel<LPR, VPL, kSegUnroll, SEGS><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
         src, src_ld, mul, b0, b1, row_slot, init, init_ld, src_scale, row_scale, g->col, g->n_seg, n_groups,
         reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
@@ -241,8 +246,8 @@ __global__ void two_hop_index_kernel(const int4* __restrict__ seg, int64_t n_seg
     }
 }
 
-template <int LPR, int VPL, int UNR>
-__global__ void __launch_bounds__(kSegWarpsPerBlock * 32)
+template <int LPR, int VPL, int UNR, int MINB>
+__global__ void __launch_bounds__(kSegWarpsPerBlock * 32, MINB)
 two_hop_reduce_kernel(const float* __restrict__ src, int64_t src_ld,
                       const float* __restrict__ node_scale, float alpha,
                       const float* __restrict__ row_scale, const int2* __restrict__ nbr,
@@ -337,7 +342,10 @@ static int launch_two_hop(const ihg_csr* g, const int32_t* nbr, const float* src
     const int64_t groups_per_block = (int64_t)kSegWarpsPerBlock * G;
     int64_t blocks = ceil_div(g->n_seg, groups_per_block);
     if (blocks < 1) blocks = 1;
-    two_hop_reduce_kernel<LPR, VPL, 4><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
+    // (unroll 2, >= 5 resident blocks = 48 registers) measured best in situ: occupancy beats per-thread
+    // ILP for these L2-served gathers (per call 0.274 vs 0.327 ms for unroll 4 / 80 registers at the
+    // amazon-full shape, 1.59 vs 1.99 ms at cikm; profiles/r01_bench_twohop_variants.txt)
+    two_hop_reduce_kernel<LPR, VPL, 2, 5><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
         src, src_ld, node_scale, alpha, row_scale, reinterpret_cast<const int2*>(nbr), g->n_seg,
         reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
     IHG_LAUNCH_CHECK();
