@@ -32,6 +32,16 @@ if REPO not in sys.path:
 
 from ihgnn_b200 import synth  # noqa: E402
 
+# stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner there) get
+# stderr instead, the result goes to the saved descriptor
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 METRIC = "hypergraph_conv_hyperedge_layers_per_sec_fwd_bwd"
 UNIT = "hyperedge-layers/s"
 
@@ -215,7 +225,7 @@ def run_reference_arm(args, log, layers, d):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------
@@ -428,7 +438,7 @@ def run_gpu_arm(args, log, layers, d):
         "kernels": {k: {"ms_per_step": round(v["ms_per_step"], 4), "calls_per_step": v["calls"] / args.steps,
                         "GBps": round(v["gbs"], 1)} for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -6,18 +6,18 @@ loudly if libihgnn_b200.so is missing (there is no CPU or PyTorch fallback).
 """
 from . import synth  # noqa: F401  (numpy-only)
 
-__all__ = ["synth", "PpsHyperGraph", "GraphDataset", "EmbeddingLayer", "FeatureInteractor",
-           "IHGNNLayer", "HGCNLayer", "HemPredictionLayer", "RawGnn"]
+__all__ = ["synth", "PpsHyperGraph", "Pps2DGraph", "GraphDataset", "EmbeddingLayer", "FeatureInteractor",
+           "IHGNNLayer", "HGCNLayer", "GCNLayer", "HemPredictionLayer", "RawGnn"]
 
 
 def __getattr__(name):
-    if name == "PpsHyperGraph":
-        from .graph import PpsHyperGraph
-        return PpsHyperGraph
+    if name in ("PpsHyperGraph", "Pps2DGraph"):
+        from . import graph
+        return getattr(graph, name)
     if name == "GraphDataset":
         from .dataset import GraphDataset
         return GraphDataset
-    if name in ("EmbeddingLayer", "FeatureInteractor", "IHGNNLayer", "HGCNLayer", "HemPredictionLayer"):
+    if name in ("EmbeddingLayer", "FeatureInteractor", "IHGNNLayer", "HGCNLayer", "GCNLayer", "HemPredictionLayer"):
         from . import layers
         return getattr(layers, name)
     if name == "RawGnn":

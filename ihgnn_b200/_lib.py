@@ -48,7 +48,7 @@ SIGNATURES = {
     "ihg_segment_plan_build": (c_int32, [P, I64, I32, P, P, P, P, P, I64, P]),
     "ihg_segment_reduce": (c_int32, [POINTER(IhgCsr), P, I64, I32, I64, I64, P, P, I64, P, P, P, P, I64, I32, P]),
     "ihg_two_hop_index_build": (c_int32, [POINTER(IhgCsr), P, I64, I64, P, P, P]),
-    "ihg_two_hop_reduce": (c_int32, [POINTER(IhgCsr), P, P, I64, P, F32, P, P, P, I64, I32, P]),
+    "ihg_two_hop_reduce": (c_int32, [POINTER(IhgCsr), P, P, I64, P, F32, F32, F32, P, P, P, I64, I32, P]),
     "ihg_edge_gather_sum": (c_int32, [P, I64, P, F32, P, P, I64, P, I64, I32, P]),
     "ihg_edge_interact_fwd_workspace_bytes": (I64, [I32, I32]),
     "ihg_edge_interact_fwd": (c_int32, [P, I64, P, I64, P, I64, I32, P, I64, P, I64, I32, P, I64, P]),
@@ -66,6 +66,7 @@ SIGNATURES = {
     "ihg_hem_score_bwd": (c_int32, [P, P, I64, P, I64, P, I64, P, F32, I64, I32, P, P, P, P, I64, P, I64, P]),
     "ihg_hem_score_bwd_workspace_bytes": (I64, [I64]),
     "ihg_rank_topk": (c_int32, [P, I64, P, P, I64, I64, P, I64, I64, I64, P, F32, I32, I32, P, P, P]),
+    "ihg_sample_batch": (c_int32, [P, P, P, P, I64, I32, I64, ctypes.c_uint64, ctypes.c_uint64, P, P, P, P, P, P, P, P, P]),
     "ihg_halo_copy": (c_int32, [P, P, P, I32, P, I64, I64, I32, P]),
 }
 

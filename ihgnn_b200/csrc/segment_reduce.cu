@@ -249,8 +249,9 @@ __global__ void two_hop_index_kernel(const int4* __restrict__ seg, int64_t n_seg
 template <int LPR, int VPL, int UNR, int MINB>
 __global__ void __launch_bounds__(kSegWarpsPerBlock * 32, MINB)
 two_hop_reduce_kernel(const float* __restrict__ src, int64_t src_ld,
-                      const float* __restrict__ node_scale, float alpha,
+                      const float* __restrict__ node_scale, float alpha, float own_per_inc, float own_const,
                       const float* __restrict__ row_scale, const int2* __restrict__ nbr,
+                      const int32_t* __restrict__ rowptr,
                       int64_t n_seg, const int4* __restrict__ seg, float* __restrict__ partial,
                       float* __restrict__ out, int64_t out_ld, int dim) {
     constexpr int G = 32 / LPR;
@@ -268,11 +269,15 @@ two_hop_reduce_kernel(const float* __restrict__ src, int64_t src_ld,
     // the row's own term, issued early so that its latency hides behind the gathers
     float4 own[VPL];
     float own_w = 0.0f;
-    if (live && end > begin) own_w = (float)(end - begin) * (node_scale ? __ldg(node_scale + row) : 1.0f);
+    // own weight: own_per_inc per incidence of the chunk; own_const once per row (by the row's first chunk,
+    // including rows without incidences -- a self connection does not need a hyperedge)
+    const bool first_chunk = live && (part < 0 || begin == __ldg(rowptr + row));
+    if (live) own_w = ((float)(end - begin) * own_per_inc + (first_chunk ? own_const : 0.0f)) *
+                      (node_scale ? __ldg(node_scale + row) : 1.0f);
 #pragma unroll
     for (int w = 0; w < VPL; ++w) {
         const int cv = gl + w * LPR;
-        own[w] = (live && end > begin && cv < nvec) ? ldg4(src + (int64_t)row * src_ld + 4 * cv) : f4_zero();
+        own[w] = (own_w != 0.0f && cv < nvec) ? ldg4(src + (int64_t)row * src_ld + 4 * cv) : f4_zero();
     }
 
     float4 acc[VPL];
@@ -336,7 +341,8 @@ two_hop_reduce_kernel(const float* __restrict__ src, int64_t src_ld,
 
 template <int LPR, int VPL>
 static int launch_two_hop(const ihg_csr* g, const int32_t* nbr, const float* src, int64_t src_ld,
-                          const float* node_scale, float alpha, const float* row_scale,
+                          const float* node_scale, float alpha, float own_per_inc, float own_const,
+                          const float* row_scale,
                           float* partial, float* out, int64_t out_ld, int dim, cudaStream_t st) {
     constexpr int G = 32 / LPR;
     const int64_t groups_per_block = (int64_t)kSegWarpsPerBlock * G;
@@ -346,8 +352,8 @@ static int launch_two_hop(const ihg_csr* g, const int32_t* nbr, const float* src
     // ILP for these L2-served gathers (per call 0.274 vs 0.327 ms for unroll 4 / 80 registers at the
     // amazon-full shape, 1.59 vs 1.99 ms at cikm; profiles/r01_bench_twohop_variants.txt)
     two_hop_reduce_kernel<LPR, VPL, 2, 5><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
-        src, src_ld, node_scale, alpha, row_scale, reinterpret_cast<const int2*>(nbr), g->n_seg,
-        reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
+        src, src_ld, node_scale, alpha, own_per_inc, own_const, row_scale, reinterpret_cast<const int2*>(nbr),
+        g->rowptr, g->n_seg, reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
     IHG_LAUNCH_CHECK();
     if (g->n_split > 0) {
         segment_fixup_kernel<LPR, VPL><<<(unsigned)g->n_split, kSegWarpsPerBlock * 32, 0, st>>>(
@@ -407,20 +413,21 @@ extern "C" int ihg_two_hop_index_build(const ihg_csr* g, const int32_t* i3, int6
 
 extern "C" int ihg_two_hop_reduce(const ihg_csr* g, const int32_t* nbr, const float* src,
                                   int64_t src_ld, const float* node_scale, float alpha,
+                                  float own_per_incidence, float own_const,
                                   const float* row_scale, float* partial, float* out,
                                   int64_t out_ld, int32_t dim, void* stream) {
     IHG_REQUIRE(g && src && out, "two_hop_reduce: null pointer");
     IHG_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 256, "two_hop_reduce: dim=%d must be a multiple of 4, <= 256", dim);
     IHG_REQUIRE(src_ld % 4 == 0 && out_ld % 4 == 0 && src_ld >= dim && out_ld >= dim,
                 "two_hop_reduce: leading dimensions must be multiples of 4 and >= dim");
-    IHG_REQUIRE(g->n_rows > 0 && g->n_seg >= g->n_rows && g->seg, "two_hop_reduce: incomplete csr plan");
+    IHG_REQUIRE(g->n_rows > 0 && g->n_seg >= g->n_rows && g->seg && g->rowptr, "two_hop_reduce: incomplete csr plan");
     IHG_REQUIRE(g->nnz == 0 || nbr, "two_hop_reduce: null neighbour list");
     IHG_REQUIRE(g->n_split == 0 || (partial && g->split_row && g->split_ptr),
                 "two_hop_reduce: split rows need the partial buffer");
     cudaStream_t st = as_stream(stream);
     const int nvec = dim / 4;
 #define IHG_TH_CASE(L, V) \
-    return launch_two_hop<L, V>(g, nbr, src, src_ld, node_scale, alpha, row_scale, partial, out, out_ld, dim, st)
+    return launch_two_hop<L, V>(g, nbr, src, src_ld, node_scale, alpha, own_per_incidence, own_const, row_scale, partial, out, out_ld, dim, st)
     if (nvec <= 1) IHG_TH_CASE(1, 1);
     if (nvec <= 2) IHG_TH_CASE(2, 1);
     if (nvec <= 4) IHG_TH_CASE(4, 1);

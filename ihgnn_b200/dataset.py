@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from .graph import PpsHyperGraph
+from .graph import Pps2DGraph, PpsHyperGraph
 from .synth import SearchLogSet
 
 
@@ -48,6 +48,7 @@ class GraphDataset:
         self.pos_item = np.asarray(pos_item, dtype=np.int64)
         self._hgraph: Optional[PpsHyperGraph] = None
         self._cgraph: Optional[PpsHyperGraph] = None
+        self._graph2d: Optional[Pps2DGraph] = None
 
     def __len__(self) -> int:
         return int(self.pos_user.shape[0])
@@ -61,7 +62,18 @@ class GraphDataset:
         return self._hgraph
 
     @property
-    def graph(self) -> PpsHyperGraph:                       # Dataset.py:79-82
+    def graph2d(self) -> Pps2DGraph:                        # Dataset.py:83-90 (no self connection)
+        if self._graph2d is None:
+            self._graph2d = Pps2DGraph.from_hypergraph(self._compute_graph(), False)
+        return self._graph2d
+
+    @property
+    def graph(self):                                        # Dataset.py:79-82
+        if self.graph_type is Pps2DGraph:
+            return self.graph2d
+        return self._compute_graph()
+
+    def _compute_graph(self) -> PpsHyperGraph:
         """The graph the layers convolve over.  Hyperedge ids never leave the layers (their outputs
         are node features), so this copy numbers the hyperedges by ascending user (stable): the
         user third of every edge -> node reduction then reads hyperedge rows sequentially and the
@@ -105,3 +117,50 @@ class GraphDataset:
                         pu.append(int(u)); pq.append(int(q)); pi.append(int(it))
         return cls(U, Q, I, V, np.asarray(words, dtype=np.int64), np.asarray(offsets, dtype=np.int64),
                    np.asarray(pu), np.asarray(pq), np.asarray(pi), device)
+
+
+class DeviceBatchSampler:
+    """Device-side replacement of `DataLoader(dataset, batch_size, shuffle=True,
+    collate_fn=GraphDataset.collate_fn)` (/root/reference/Main.py:152 with Dataset.py:107-119,
+    :260-293): iterating yields the 8-tuple `collate_fn` returns -- (users, queries, items, flags,
+    neg_users, neg_queries, neg_items, neg_flags), all int64 on the device -- one kernel launch per
+    batch (`ihg_sample_batch`), no Python per-positive loop and no host->device copies.  One pass =
+    one epoch over a fresh permutation of the positives (the last batch may be short, as with
+    drop_last=False).  Seeded, hence reproducible; the reference is unseeded, so parity with it is
+    distributional (uniform, distinct negatives per positive; the positive item is not excluded)."""
+
+    def __init__(self, dataset: GraphDataset, batch_size: int = 100, neg_sample_size: int = 10, seed: int = 0):
+        from . import _lib
+        self._lib = _lib
+        dev = GraphDataset.device
+        if torch.device(dev).type != "cuda":
+            raise RuntimeError("DeviceBatchSampler samples on the GPU; there is no CPU fallback")
+        self.dataset, self.batch_size, self.neg = dataset, int(batch_size), int(neg_sample_size)
+        self.seed, self.step, self.device = int(seed), 0, dev
+        self.pos_user = torch.as_tensor(dataset.pos_user, dtype=torch.int64, device=dev)
+        self.pos_query = torch.as_tensor(dataset.pos_query, dtype=torch.int64, device=dev)
+        self.pos_item = torch.as_tensor(dataset.pos_item, dtype=torch.int64, device=dev)
+        self._gen = torch.Generator(device=dev)
+        self._gen.manual_seed(self.seed)
+
+    def __len__(self) -> int:
+        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+
+    def sample(self, pick: torch.Tensor):
+        """The 8-tuple for the positives `pick` (int64 indices into the interaction list)."""
+        L = self._lib
+        L.require_cuda(pick)
+        pick = pick.to(torch.int64).contiguous()
+        B, K = int(pick.numel()), self.neg
+        mk = lambda n: torch.empty(n, dtype=torch.int64, device=self.device)
+        out = [mk(B) for _ in range(4)] + [mk(B * K) for _ in range(4)]
+        L.call("ihg_sample_batch", L.ptr(self.pos_user), L.ptr(self.pos_query), L.ptr(self.pos_item), L.ptr(pick),
+               B, K, self.dataset.item_count, self.seed & (2 ** 64 - 1), self.step, *(L.ptr(t) for t in out),
+               L.stream_ptr())
+        self.step += 1
+        return tuple(out)
+
+    def __iter__(self):
+        perm = torch.randperm(len(self.dataset), generator=self._gen, device=self.device)
+        for s in range(0, int(perm.numel()), self.batch_size):
+            yield self.sample(perm[s:s + self.batch_size])

@@ -599,6 +599,8 @@ class ShardedRawGnn(torch.nn.Module):
             order = feature_interaction_order if (k == 0 or feature_interaction_order == 1) else 1
             self.gnns.append(ShardedIHGNNLayer(graph, d, order))
         self.prediction_layer = HemPredictionLayer(d * (1 + layer_count), lambda_muq, p.I)
+        self.to(dev)
+        self.sync_replicated_parameters()
         # bag CSR of the own queries (+ its transpose) for EmbeddingBag(mean)
         words = np.asarray(bag_words, dtype=np.int64)
         ptr = np.concatenate([np.asarray(bag_offsets, dtype=np.int64), [words.shape[0]]])
@@ -648,6 +650,61 @@ class ShardedRawGnn(torch.nn.Module):
         local_rows = (ids - lo + base)[positions]
         rows = _FetchRowsFn.apply(f_own, local_rows, positions, 3 * B, self.g.group)
         return self.prediction_layer(rows[:B], rows[B:2 * B], rows[2 * B:], items)
+
+    @torch.no_grad()
+    def sync_replicated_parameters(self) -> None:
+        """Rank 0's values for every REPLICATED parameter (conv weights, vocabulary table, item
+        bias): the row-sharded tables differ in size per rank, so the ranks' RNG streams diverge
+        during construction and the replicas would start out different."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        group = self.g.group
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        for q in list(self.gnns.parameters()) + [self.embedding_bag_vocabulary, self.prediction_layer.items_bias]:
+            dist.broadcast(q.data, src=src, group=group)
+
+    @torch.no_grad()
+    def gather_features(self) -> torch.Tensor:
+        """Replicate the output features on every rank in GLOBAL node order [U+Q+I, d(1+L)]
+        (users, queries, items; Helpers/Graph.py:110-111): one padded all-gather of the own rows,
+        then three row-range copies per source rank.  Inference only (BASELINE.json configs[4]:
+        item features replicated, queries split across the GPUs, no per-query communication)."""
+        import torch.distributed as dist
+        from . import functional as F_
+        p = self.g.plan
+        f_own = self.output_features().contiguous()
+        D = int(f_own.shape[1])
+        n_max = max(int(p.ub[r + 1] - p.ub[r]) + int(p.qb[r + 1] - p.qb[r]) + int(p.ib[r + 1] - p.ib[r])
+                    for r in range(p.world))
+        send = torch.zeros((n_max, D), dtype=torch.float32, device=f_own.device)
+        F_.copy_rows_raw(f_own, send[:p.n_own])
+        recv = torch.empty((p.world, n_max, D), dtype=torch.float32, device=f_own.device)
+        dist.all_gather_into_tensor(recv.view(-1, D), send, group=self.g.group)
+        feat = torch.empty((p.U + p.Q + p.I, D), dtype=torch.float32, device=f_own.device)
+        for r in range(p.world):
+            uo, qo, io = int(p.ub[r + 1] - p.ub[r]), int(p.qb[r + 1] - p.qb[r]), int(p.ib[r + 1] - p.ib[r])
+            for n, src0, dst0 in ((uo, 0, int(p.ub[r])), (qo, uo, p.U + int(p.qb[r])),
+                                  (io, uo + qo, p.U + p.Q + int(p.ib[r]))):
+                if n:
+                    F_.copy_rows_raw(recv[r, src0:src0 + n], feat[dst0:dst0 + n])
+        return feat
+
+    @torch.no_grad()
+    def rank(self, users: torch.Tensor, queries: torch.Tensor, candidates: Optional[torch.Tensor] = None,
+             k: int = 10, features: Optional[torch.Tensor] = None):
+        """Rank THIS rank's share of the searches: rows [rank::world] of (users, queries, candidates)
+        against the replicated features (`gather_features`, pass it in to reuse it across batches).
+        Returns (row indices of the share, item ids [n, k], scores [n, k]); no collective per query."""
+        from . import functional as F_
+        p = self.g.plan
+        feat = self.gather_features() if features is None else features
+        share = torch.arange(p.rank, int(queries.numel()), p.world, device=feat.device)
+        cand = candidates[share] if candidates is not None else None
+        pl = self.prediction_layer
+        ids, vals = F_.rank_topk(feat, users[share], queries[share], pl.items_bias, pl.lambda_muq,
+                                 query_row0=p.U, item_row0=p.U + p.Q, item_count=p.I, candidates=cand, k=k)
+        return share, ids, vals
 
     def sync_grads(self) -> None:
         """All-reduce the gradients of the replicated parameters whose per-rank gradients are

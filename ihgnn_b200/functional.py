@@ -69,8 +69,10 @@ def two_hop_enabled(n_rows: int, dim: int) -> bool:
 def two_hop_reduce(plan: CsrPlan, nbr: torch.Tensor, src: torch.Tensor, *,
                    node_scale: Optional[torch.Tensor] = None, alpha: float = 1.0,
                    row_scale: Optional[torch.Tensor] = None,
-                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[r] = row_scale[r] * alpha * sum_{e contains r} sum_{n in e} node_scale[n] * src[n]."""
+                   out: Optional[torch.Tensor] = None, own=(1.0, 0.0)) -> torch.Tensor:
+    """out[r] = row_scale[r] * alpha * sum_{e contains r} sum_{n in e} node_scale[n] * src[n].
+    `own` = (per incidence, constant) weight of the row's own term: (1, 0) hypergraph round trip,
+    (0, 0) / (0, 1) the pairwise adjacency of Pps2DGraph without / with self connections."""
     _lib.require_cuda(src, nbr, node_scale, row_scale, out)
     src = _lib.rows_f32(src)
     dim = int(src.shape[1])
@@ -78,8 +80,8 @@ def two_hop_reduce(plan: CsrPlan, nbr: torch.Tensor, src: torch.Tensor, *,
     if out is None:
         out = _empty((plan.n_rows, dim), src)
     _lib.call("ihg_two_hop_reduce", plan.ref(), _lib.ptr(nbr), _lib.ptr(src), _lib.ld(src),
-              _lib.ptr(node_scale), float(alpha), _lib.ptr(row_scale), _lib.ptr(plan.partial(dim)),
-              _lib.ptr(out), _lib.ld(out), dim, _lib.stream_ptr(), tag="two_hop_reduce",
+              _lib.ptr(node_scale), float(alpha), float(own[0]), float(own[1]), _lib.ptr(row_scale),
+              _lib.ptr(plan.partial(dim)), _lib.ptr(out), _lib.ld(out), dim, _lib.stream_ptr(), tag="two_hop_reduce",
               # what the pair it replaces must move: gather-sum E(12+16d) + segmented reduce
               algo_bytes=(plan.nnz // 3) * (12 + 16 * dim) + plan.nnz * (4 + 4 * dim) + plan.n_rows * (4 * dim + 16))
     return out

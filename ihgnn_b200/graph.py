@@ -212,3 +212,58 @@ class PpsHyperGraph(PpsGraph):
     def type_bounds(self):
         """(U, U+Q): node ids below U are users (slot 0), below U+Q queries (slot 1), else items."""
         return self.user_count, self.user_count + self.query_count
+
+
+class Pps2DGraph(PpsGraph):
+    """Pairwise user-query-item graph, drop-in for `Helpers.Graph.Pps2DGraph`
+    (/root/reference/Helpers/Graph.py:12-81) with `Gs.graph_completeness == graph_uqi` (the
+    reference default): every positive interaction adds u-q, q-i, i-u in both directions, duplicate
+    pairs summed by `coalesce()`; `VertexDegrees` = [self connection] + 2 x interactions of the node
+    (0 stored as 1e-8 without self connections, Graph.py:35,67-68).
+
+    The adjacency is never stored: products with it run on the hypergraph incidence (`hyper`, the
+    same device CSR/CSC the IHGNN layers use) through `ihg_two_hop_reduce`.  Reference attributes
+    `Adjacency` (coalesced sparse COO) and `VertexDegrees` are available; `Adjacency` is materialised
+    lazily, only if something reads it.  Interaction flags above 1 are treated as 1, as the reference
+    does by default (`treat_all_1`, Dataset.py:200; SearchLog.py:204-205)."""
+
+    def __init__(self):
+        super().__init__()
+        self._adjacency = None
+
+    @classmethod
+    def from_interactions(cls, interactions, node_count: int, user_count: int, query_count: int,
+                          use_self_connection: bool, device) -> "Pps2DGraph":
+        """Signature of Graph.py:19-26."""
+        hyper = PpsHyperGraph.from_interactions(interactions, node_count, user_count, query_count, device)
+        return cls.from_hypergraph(hyper, use_self_connection)
+
+    @classmethod
+    def from_hypergraph(cls, hyper: PpsHyperGraph, use_self_connection: bool) -> "Pps2DGraph":
+        g = cls()
+        g.hyper = hyper
+        g.use_self_connection = bool(use_self_connection)
+        g.node_count = hyper.node_count
+        counts = (hyper.rowptr[1:] - hyper.rowptr[:-1]).to(torch.float32)
+        deg = 2.0 * counts + (1.0 if use_self_connection else 0.0)            # Graph.py:29,45
+        if not use_self_connection:
+            deg = torch.where(deg == 0, torch.full_like(deg, 1e-8), deg)      # :67-68
+        g.VertexDegrees = deg.view(-1, 1)                                     # :80
+        g.dv_inv_sqrt = deg.pow(-0.5)                                         # GnnLayers.py:24
+        return g
+
+    @property
+    def Adjacency(self) -> torch.Tensor:
+        """Coalesced sparse COO adjacency [N,N] (Graph.py:71-77), unit weights summed over duplicates."""
+        if self._adjacency is None:
+            i3 = self.hyper.i3.to(torch.int64)
+            u, q, i = i3[:, 0], i3[:, 1], i3[:, 2]
+            rows = torch.cat([u, q, i, i, q, u])                              # Graph.py:42-43
+            cols = torch.cat([q, i, u, q, u, i])
+            if self.use_self_connection:
+                eye = torch.arange(self.node_count, device=i3.device)
+                rows, cols = torch.cat([eye, rows]), torch.cat([eye, cols])
+            vals = torch.ones(rows.numel(), dtype=torch.float32, device=i3.device)
+            self._adjacency = torch.sparse_coo_tensor(torch.stack([rows, cols]), vals,
+                                                      (self.node_count, self.node_count)).coalesce()
+        return self._adjacency

@@ -8,8 +8,8 @@ or, as a launcher that leaves the reference untouched on disk:
     python -m ihgnn_b200.install /path/to/IHGNN/Main.py --device 0 --gnn IHGNN ...
 
 `patch_reference` imports the reference's `Helpers.Graph`, `Models.*` and `Dataset` modules and
-rebinds the hot-path classes -- PpsHyperGraph, EmbeddingLayer, FeatureInteractor, IHGNNLayer,
-HGCNLayer, HemPredictionLayer -- to the CUDA-backed ones in every namespace that holds a
+rebinds the hot-path classes -- PpsHyperGraph, Pps2DGraph, EmbeddingLayer, FeatureInteractor,
+IHGNNLayer, HGCNLayer, GCNLayer, HemPredictionLayer -- to the CUDA-backed ones in every namespace that holds a
 reference to them (`Models/__init__.py:12-24` name maps included), so `Main.py`, `RawGnn` and
 `Srrl` run on top unchanged.  The reference imports `torch_sparse` and `dgl` unconditionally
 (`Helpers/Torches.py:13-18`); they must be importable (the real packages, or the stubs under
@@ -22,16 +22,17 @@ import runpy
 import sys
 from typing import Dict
 
-_REPLACED = ("PpsHyperGraph", "EmbeddingLayer", "FeatureInteractor", "IHGNNLayer", "HGCNLayer",
-             "HemPredictionLayer")
+_REPLACED = ("PpsHyperGraph", "Pps2DGraph", "EmbeddingLayer", "FeatureInteractor", "IHGNNLayer", "HGCNLayer",
+             "GCNLayer", "HemPredictionLayer")
 
 
 def replacement_classes() -> Dict[str, type]:
     from . import layers
-    from .graph import PpsHyperGraph
-    out = {"PpsHyperGraph": PpsHyperGraph}
-    for name in _REPLACED[1:]:
-        out[name] = getattr(layers, name)
+    from .graph import Pps2DGraph, PpsHyperGraph
+    out = {"PpsHyperGraph": PpsHyperGraph, "Pps2DGraph": Pps2DGraph}
+    for name in _REPLACED:
+        if name not in out:
+            out[name] = getattr(layers, name)
     return out
 
 

@@ -20,7 +20,7 @@ from torch.nn.parameter import Parameter
 
 from . import _lib
 from . import functional as F_
-from .graph import CsrPlan, PpsHyperGraph, csr_from_keys
+from .graph import CsrPlan, Pps2DGraph, PpsHyperGraph, csr_from_keys
 from .settings import Gs, Gsv
 
 
@@ -174,17 +174,17 @@ class _TwoHopFn(torch.autograd.Function):
     intermediate).  H H^T is symmetric, so backward is the same kernel with the scales swapped."""
 
     @staticmethod
-    def forward(ctx, h, graph: PpsHyperGraph, node_scale, alpha: float, row_scale):
-        ctx.graph, ctx.node_scale, ctx.alpha, ctx.row_scale = graph, node_scale, alpha, row_scale
+    def forward(ctx, h, graph: PpsHyperGraph, node_scale, alpha: float, row_scale, own=(1.0, 0.0)):
+        ctx.graph, ctx.node_scale, ctx.alpha, ctx.row_scale, ctx.own = graph, node_scale, alpha, row_scale, own
         return F_.two_hop_reduce(graph.plan, _two_hop_nbr(graph), h, node_scale=node_scale, alpha=alpha,
-                                 row_scale=row_scale)
+                                 row_scale=row_scale, own=own)
 
     @staticmethod
     def backward(ctx, dout):
         g = ctx.graph
         dh = F_.two_hop_reduce(g.plan, _two_hop_nbr(g), dout, node_scale=ctx.row_scale, alpha=ctx.alpha,
-                               row_scale=ctx.node_scale)
-        return dh, None, None, None, None
+                               row_scale=ctx.node_scale, own=ctx.own)
+        return dh, None, None, None, None, None
 
 
 def _two_hop_nbr(graph) -> Tensor:
@@ -419,6 +419,38 @@ class HGCNLayer(nn.Module):
         h = F_.typed_linear(input_features, self.feature_transform.weight.unsqueeze(0),
                             self.feature_transform.bias.unsqueeze(0), None)
         return _gather_scatter(h, g, g.dv_inv_sqrt, self._alpha, self._bwd_scale, g.dv_inv_sqrt)
+
+
+class GCNLayer(nn.Module):
+    """out = D^-1/2 A D^-1/2 Linear(X) over the pairwise graph of Pps2DGraph
+    (/root/reference/Models/GnnLayers.py:9-45; the Linear first or last exactly as :33-43).
+    A x is computed from the hypergraph incidence without materialising A: for a node r,
+    (A x)[r] = [self connection] x[r] + sum over its interactions of the two OTHER nodes' rows
+    (`ihg_two_hop_reduce` with the own term switched off), which equals the coalesced adjacency
+    product because duplicate pairs are summed either way."""
+
+    def __init__(self, device, dataset, input_dimension: int, output_dimension: int):
+        super().__init__()
+        self.device = device
+        self.dataset = dataset
+        self.input_dimension = input_dimension
+        self.output_dimension = output_dimension
+        graph2d: Pps2DGraph = dataset.graph2d                          # GnnLayers.py:23
+        self.graph2d = graph2d
+        self.Dv_neg_1_slash_2 = graph2d.dv_inv_sqrt.view(-1, 1)        # :24
+        self.feature_transform = nn.Linear(input_dimension, output_dimension)
+
+    def _propagate(self, h: Tensor) -> Tensor:
+        g2 = self.graph2d
+        own = (0.0, 1.0 if g2.use_self_connection else 0.0)
+        return _TwoHopFn.apply(h, g2.hyper, g2.dv_inv_sqrt, 1.0, g2.dv_inv_sqrt, own)
+
+    def forward(self, input_features: Tensor) -> Tensor:
+        _lib.require_cuda(input_features)
+        w, b = self.feature_transform.weight.unsqueeze(0), self.feature_transform.bias.unsqueeze(0)
+        if self.input_dimension >= self.output_dimension:              # :33-38
+            return self._propagate(F_.typed_linear(input_features, w, b, None))
+        return F_.typed_linear(self._propagate(input_features), w, b, None)   # :39-43
 
 
 # --------------------------------------------------------------------------------------

@@ -17,7 +17,7 @@ import torch.nn as nn
 from torch import Tensor
 
 from . import functional as F_
-from .layers import EmbeddingLayer, HGCNLayer, HemPredictionLayer, IHGNNLayer
+from .layers import EmbeddingLayer, GCNLayer, HGCNLayer, HemPredictionLayer, IHGNNLayer
 
 
 class RawGnn(nn.Module):
@@ -41,9 +41,9 @@ class RawGnn(nn.Module):
         self.embeddings = EmbeddingLayer(dataset=dataset, embedding_size=embedding_size)
         self.gnns = []
         for layer in range(gnn_layer_count):
-            if gnn_layer_type is HGCNLayer:
-                self.gnns.append(HGCNLayer(device=device, dataset=dataset, input_dimension=embedding_size,
-                                           output_dimension=embedding_size))
+            if gnn_layer_type in (HGCNLayer, GCNLayer):                        # RawGnn.py:61-73
+                self.gnns.append(gnn_layer_type(device=device, dataset=dataset, input_dimension=embedding_size,
+                                                output_dimension=embedding_size))
             elif gnn_layer_type is IHGNNLayer:
                 order = feature_interaction_order
                 if order > 1 and layer > 0:                  # RawGnn.py:76-78

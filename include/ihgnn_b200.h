@@ -126,15 +126,19 @@ int ihg_segment_reduce(const ihg_csr* csr_host, const float* src, int64_t src_ld
  *   out[r,:] = row_scale[r] * alpha * sum_{e contains r} sum_{n in e} node_scale[n] * src[n,:]
  * ihg_two_hop_index_build fills nbr int32 [nnz,2]: for incidence j of row r (slot(r) as in
  * ihg_segment_reduce) the two OTHER nodes of hyperedge col[j], slots (slot+1)%3 and (slot+2)%3.
- * The row's own term is deg(r) * node_scale[r] * src[r].  Deterministic (same chunk plan and
- * fix-up as ihg_segment_reduce); node_scale / row_scale nullable; `partial` as there.
+ * The row's own term is (own_per_incidence * deg(r) + own_const) * node_scale[r] * src[r]:
+ * (1, 0) is the hypergraph round trip above; (0, 0) / (0, 1) is the pairwise adjacency of
+ * Pps2DGraph (Helpers/Graph.py:19-81, u-q, q-i, i-u both ways per interaction, duplicates summed
+ * as coalesce() does) without / with self connections, i.e. GCNLayer's D^-1/2 A D^-1/2 product
+ * (Models/GnnLayers.py:33-43).  Deterministic (same chunk plan and fix-up as ihg_segment_reduce);
+ * node_scale / row_scale nullable; `partial` as there.
  * ------------------------------------------------------------------------------------ */
 int ihg_two_hop_index_build(const ihg_csr* csr_host, const int32_t* i3, int64_t bound0,
                             int64_t bound1, const int32_t* row_slot, int32_t* nbr, void* stream);
 int ihg_two_hop_reduce(const ihg_csr* csr_host, const int32_t* nbr, const float* src,
                        int64_t src_ld, const float* node_scale, float alpha,
-                       const float* row_scale, float* partial, float* out, int64_t out_ld,
-                       int32_t dim, void* stream);
+                       float own_per_incidence, float own_const, const float* row_scale,
+                       float* partial, float* out, int64_t out_ld, int32_t dim, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * a6/a8  node -> hyperedge gather-sum.
@@ -269,6 +273,22 @@ int ihg_rank_topk(const float* feat, int64_t feat_ld, const int64_t* users, cons
                   int64_t n_queries, int64_t query_row0, const int64_t* cand, int64_t n_cand,
                   int64_t item_row0, int64_t item_count, const float* items_bias, float lambda_muq,
                   int32_t dim, int32_t k, int64_t* top_items, float* top_scores, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Training-batch sampler on the device.  Replaces GraphDataset.__getitem__
+ * (Dataset.py:107-119, default nonrand_neg_sample_size == 0: the positive plus
+ * random.sample(range(item_count), K) = K distinct uniform items) and GraphDataset.collate_fn
+ * (Dataset.py:260-293) by one launch writing the 8-tuple collate_fn returns, in its order and
+ * dtypes (all int64): positives (users, queries, items, flags == 1) for the interactions
+ * pick[0..batch), then per positive its K negatives (users, queries repeated; items drawn; flags 0).
+ * Draws are a pure function of (seed, step, slot, draw): reproducible; the reference is unseeded, so
+ * parity is distributional.  pos_* : device int64 [E] positive interactions; neg_per_positive <= 64.
+ * ------------------------------------------------------------------------------------ */
+int ihg_sample_batch(const int64_t* pos_user, const int64_t* pos_query, const int64_t* pos_item,
+                     const int64_t* pick, int64_t batch, int32_t neg_per_positive, int64_t item_count,
+                     uint64_t seed, uint64_t step, int64_t* p_users, int64_t* p_queries,
+                     int64_t* p_items, int64_t* p_flags, int64_t* n_users, int64_t* n_queries,
+                     int64_t* n_items, int64_t* n_flags, void* stream);
 
 #ifdef __cplusplus
 }

@@ -40,7 +40,7 @@ with contextlib.redirect_stdout(io.StringIO()):
     IOHelper.warned_about_cannot_log = True
     from Helpers.Graph import PpsHyperGraph  # noqa: E402
     from Dataset import GraphDataset  # noqa: E402
-    from Models import RawGnn, IHGNNLayer, HGCNLayer, HemPredictionLayer  # noqa: E402
+    from Models import RawGnn, IHGNNLayer, HGCNLayer, GCNLayer, HemPredictionLayer  # noqa: E402
     from Helpers.Metrics import Metrics  # noqa: E402
 
 CPU = torch.device("cpu")
@@ -53,6 +53,8 @@ CASES = {
                              gnn="IHGNN", L=1, order=2, d=8, batch=16),
     "ihgnn_o1_L3_cikm": dict(U=45, Q=20, I=70, V=30, E=300, shape="cikm", seed=13,
                              gnn="IHGNN", L=3, order=1, d=32, batch=20),
+    "gcn_L2_cikm": dict(U=40, Q=18, I=60, V=30, E=320, shape="cikm", seed=16,
+                        gnn="GCN", L=2, order=1, d=16, batch=20),
     "hgcn_L2_amazon": dict(U=50, Q=20, I=80, V=30, E=350, shape="amazon", seed=14,
                            gnn="HGCN", L=2, order=1, d=16, batch=20),
     # d=64 / 3 layers at the smallest size that still has heavy (Zipf head) nodes
@@ -74,8 +76,9 @@ def _cast_model_to_double(model):
             gnn.Dv_neg_1 = gnn.Dv_neg_1.double()
         if hasattr(gnn, "Dv_neg_1_slash_2"):
             gnn.Dv_neg_1_slash_2 = gnn.Dv_neg_1_slash_2.double()
+        if hasattr(gnn, "De_neg_1"):
             gnn.De_neg_1 = gnn.De_neg_1.double()
-        for name in ("incidence", "incidence_t"):
+        for name in ("incidence", "incidence_t", "adjacency"):
             if hasattr(gnn, name):
                 setattr(gnn, name, getattr(gnn, name).to(torch.float64))
     return model
@@ -178,7 +181,12 @@ def make_case(name: str, cfg: dict, outdir: str) -> None:
     out["graph.EdgeDegrees"] = _np(g.EdgeDegrees)
     out["graph.EdgeCount"] = np.array(g.EdgeCount, dtype=np.int64)
 
-    layer_type = IHGNNLayer if cfg["gnn"] == "IHGNN" else HGCNLayer
+    layer_type = {"IHGNN": IHGNNLayer, "HGCN": HGCNLayer, "GCN": GCNLayer}[cfg["gnn"]]
+    if cfg["gnn"] == "GCN":
+        g2 = ds.graph2d          # the reference's Pps2DGraph.from_interactions, Graph.py:19-81 (no self connection)
+        out["graph2d.coo_indices"] = _np(g2.Adjacency.indices())
+        out["graph2d.coo_values"] = _np(g2.Adjacency.values())
+        out["graph2d.VertexDegrees"] = _np(g2.VertexDegrees)
     torch.manual_seed(1000 + cfg["seed"])
     model = RawGnn(device=CPU, dataset=ds, embedding_size=cfg["d"], gnn_layer_type=layer_type,
                    gnn_layer_count=cfg["L"], feature_interaction_order=cfg["order"],

@@ -12,6 +12,7 @@ same ATen ops in the same order are the faithful CPU form), of:
   feature_interactor   Models/CommonLayers.py:58-87   FeatureInteractor.forward
   ihgnn_layer          Models/GnnLayers.py:221-236    IHGNNLayer.forward
   hgcn_layer           Models/GnnLayers.py:142-153    HGCNLayer.forward
+  build_graph2d / gcn_layer  Helpers/Graph.py:19-81, Models/GnnLayers.py:9-45  Pps2DGraph, GCNLayer.forward
   hem_score            Models/PredictionLayers.py:21-44 HemPredictionLayer.forward
   rawgnn_features/forward  Models/RawGnn.py:104-144   RawGnn.forward
   rank_topk / metrics_at_10  Dataset.py:324-329 + Helpers/Metrics.py:47-110  the evaluation loop
@@ -175,6 +176,48 @@ def hgcn_layer(x: torch.Tensor, adjacency: torch.Tensor, adjacency_t: torch.Tens
     return dv_neg_half * o                                                  # :152
 
 
+def build_graph2d(user, query, item, user_count: int, query_count: int, item_count: int,
+                  use_self_connection: bool = False):
+    """Pps2DGraph.from_interactions (Helpers/Graph.py:19-81) for graph_completeness == graph_uqi with
+    all flags 1 (treat_all_1, Dataset.py:200): per interaction the six directed pairs u-q, q-i, i-u,
+    i-q, q-u, u-i (:42-44), coalesced (duplicates summed, :71-77); degrees += 2 per interaction per
+    node (:45), 0 -> 1e-8 without self connections (:67-68).  Returns (coalesced COO [N,N] float32,
+    VertexDegrees float32 [N,1])."""
+    u = torch.as_tensor(np.asarray(user, dtype=np.int64))
+    q = torch.as_tensor(np.asarray(query, dtype=np.int64)) + user_count
+    i = torch.as_tensor(np.asarray(item, dtype=np.int64)) + user_count + query_count
+    n = user_count + query_count + item_count
+    rows = torch.stack([u, q, i, i, q, u], 1).reshape(-1)            # insertion order of :42
+    cols = torch.stack([q, i, u, q, u, i], 1).reshape(-1)            # :43
+    deg = torch.zeros(n, dtype=torch.float32)
+    if use_self_connection:
+        eye = torch.arange(n)
+        rows, cols = torch.cat([eye, rows]), torch.cat([eye, cols])  # :28
+        deg += 1                                                     # :29
+    deg += 2 * torch.bincount(torch.cat([u, q, i]), minlength=n).to(torch.float32)   # :45
+    if not use_self_connection:
+        deg[deg == 0] = 1e-8                                         # :67-68
+    vals = torch.ones(rows.numel(), dtype=torch.float32)
+    adj = torch.sparse_coo_tensor(torch.stack([rows, cols]), vals, (n, n)).coalesce()
+    return adj, deg.view(-1, 1)
+
+
+def gcn_layer(x: torch.Tensor, adjacency2d: torch.Tensor, dv_neg_half: torch.Tensor,
+              transform_weight, transform_bias):
+    """GnnLayers.py:27-45: D^-1/2 A D^-1/2 applied after the Linear when d_in >= d_out (:33-38),
+    before it otherwise (:39-43)."""
+    d_out, d_in = transform_weight.shape
+    if d_in >= d_out:
+        h = torch.nn.functional.linear(x, transform_weight, transform_bias)    # :34
+        h = dv_neg_half * h                                                     # :35
+        h = torch.sparse.mm(adjacency2d, h)                                     # :36
+        return dv_neg_half * h                                                  # :37
+    h = dv_neg_half * x                                                         # :40
+    h = torch.sparse.mm(adjacency2d, h)                                         # :41
+    h = dv_neg_half * h                                                         # :42
+    return torch.nn.functional.linear(h, transform_weight, transform_bias)      # :43
+
+
 def hem_score(user_feature: Optional[torch.Tensor], query_feature: torch.Tensor,
               item_feature: torch.Tensor, items_bias: torch.Tensor,
               item_indices: Optional[torch.Tensor], lambda_muq: float):
@@ -217,6 +260,12 @@ class OracleModel:
         self.dv_neg_1 = graph.VertexDegrees.pow(-1).to(dtype)
         self.dv_neg_half = graph.VertexDegrees.pow(-0.5).to(dtype)
         self.de_neg_1 = graph.EdgeDegrees.pow(-1).to(dtype)
+        if layer_type == "GCN":
+            i3 = graph.I3.numpy()
+            adj2d, deg2d = build_graph2d(i3[:, 0], i3[:, 1] - user_count, i3[:, 2] - user_count - query_count,
+                                         user_count, query_count, item_count, False)      # Dataset.py:87: no self connection
+            self.adjacency2d = adj2d.to(dtype)
+            self.dv2d_neg_half = deg2d.pow(-0.5).to(dtype)                                # GnnLayers.py:24 (fp32 pow, then cast)
 
     def layer_order(self, layer: int) -> int:
         """RawGnn.py:76-78: interactions above order 1 apply to layer 0 only."""
@@ -244,6 +293,8 @@ class OracleModel:
             elif self.layer_type == "HGCN":
                 h = hgcn_layer(h, self.adjacency, self.adjacency_t, self.dv_neg_half,
                                self.de_neg_1, tw, tb)
+            elif self.layer_type == "GCN":
+                h = gcn_layer(h, self.adjacency2d, self.dv2d_neg_half, tw, tb)
             else:
                 raise NotImplementedError(self.layer_type)
             outs.append(h)

@@ -24,7 +24,7 @@ import Models, Models.GnnLayers as G, Models.CommonLayers as C, Models.Embedding
 import Helpers.Graph as HG
 ref = {"IHGNNLayer": G.IHGNNLayer, "HGCNLayer": G.HGCNLayer, "FeatureInteractor": C.FeatureInteractor,
        "EmbeddingLayer": Em.EmbeddingLayer, "HemPredictionLayer": P.HemPredictionLayer,
-       "PpsHyperGraph": HG.PpsHyperGraph}
+       "PpsHyperGraph": HG.PpsHyperGraph, "GCNLayer": G.GCNLayer, "Pps2DGraph": HG.Pps2DGraph}
 import ihgnn_b200.install as inst
 new = inst.replacement_classes()
 # identical constructor / forward signatures (parameter names and order)
@@ -38,6 +38,9 @@ for name, cls in ref.items():
 a = list(inspect.signature(HG.PpsHyperGraph.from_interactions).parameters)
 b = list(inspect.signature(new["PpsHyperGraph"].from_interactions).parameters)
 assert a == b, (a, b)
+a = list(inspect.signature(HG.Pps2DGraph.from_interactions).parameters)
+b = list(inspect.signature(new["Pps2DGraph"].from_interactions).parameters)
+assert a == b, (a, b)
 counts = inst.patch_reference()
 assert all(v >= 1 for v in counts.values()), counts
 import Dataset as D
@@ -46,7 +49,8 @@ assert R.IHGNNLayer is new["IHGNNLayer"] and R.HGCNLayer is new["HGCNLayer"]
 assert R.EmbeddingLayer is new["EmbeddingLayer"] and R.HemPredictionLayer is new["HemPredictionLayer"]
 assert D.PpsHyperGraph is new["PpsHyperGraph"] and G.FeatureInteractor is new["FeatureInteractor"]
 assert Models.parse_gnn_layer["IHGNN"] is new["IHGNNLayer"] and Models.parse_gnn_layer["ihgnn"] is new["IHGNNLayer"]
-assert Models.parse_gnn_layer["HGCN"] is new["HGCNLayer"]
+assert Models.parse_gnn_layer["HGCN"] is new["HGCNLayer"] and Models.parse_gnn_layer["GCN"] is new["GCNLayer"]
+assert D.Pps2DGraph is new["Pps2DGraph"] and R.GCNLayer is new["GCNLayer"]
 # the layers read the reference's own settings object once it is importable
 from ihgnn_b200 import settings
 assert settings.Gs is Gs

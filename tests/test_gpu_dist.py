@@ -98,3 +98,64 @@ def test_sharded_stack_matches_single_gpu(dim):
     errs = [v[0] for v in ret.values()]
     assert max(errs) < 5e-6, dict(ret)       # different (but fixed) summation order across ranks
     assert all(v[1] for v in ret.values()), dict(ret)
+
+
+def _rank_worker(rank: int, world: int, port: int, ret):
+    sys.path.insert(0, REPO)
+    import torch.distributed as dist
+    from ihgnn_b200 import functional as F_
+    from ihgnn_b200 import synth
+    from ihgnn_b200.dist import PartitionPlan, ShardedHyperGraph, ShardedRawGnn
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        U, Q, I, E, V, d, L = 3000, 100, 1200, 40_000, 50, 64, 2
+        log = synth.make_search_log(U, Q, I, E, V, shape="cikm", seed=9, zipf=1.0)
+        plan = PartitionPlan(log.pos_user, log.pos_query, log.pos_item, U, Q, I, world, rank)
+        sg = ShardedHyperGraph(plan, dev)
+        words, offsets = log.bag_inputs()
+        torch.manual_seed(3)                                     # same replicated weights on every rank
+        model = ShardedRawGnn(sg, words, offsets, V, d, L, 3).to(dev)
+        feat = model.gather_features()
+        own = torch.from_numpy(plan.own_global_ids()).to(dev)
+        ok_layout = torch.equal(feat[own], model.output_features())
+        # every rank holds the same replicated table
+        chk = feat.double().sum().view(1)
+        lst = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(lst, chk)
+        ok_same = all(float(x) == float(lst[0]) for x in lst)
+        gen = torch.Generator().manual_seed(17)
+        B, C = 301, 200
+        users = torch.randint(0, U, (B,), generator=gen).to(dev)
+        queries = torch.randint(0, Q, (B,), generator=gen).to(dev)
+        cand = torch.stack([torch.randperm(I, generator=gen)[:C] for _ in range(B)]).to(dev)
+        share, ids, vals = model.rank(users, queries, cand, 10, features=feat)
+        pl = model.prediction_layer
+        ids_all, vals_all = F_.rank_topk(feat, users, queries, pl.items_bias, pl.lambda_muq, query_row0=U,
+                                         item_row0=U + Q, item_count=I, candidates=cand, k=10)
+        ok_rank = torch.equal(ids, ids_all[share]) and torch.equal(vals, vals_all[share])
+        ok_share = share.tolist() == list(range(rank, B, world))
+        # float64 check of the scores on the replicated table
+        b0 = int(share[0])
+        m = 0.5 * feat[queries[b0] + U].double() + 0.5 * feat[users[b0]].double()
+        sc = (feat[cand[b0] + U + Q].double() * m).sum(1) + pl.items_bias[cand[b0]].double()
+        top = torch.sort(sc, descending=True)[1][:10]
+        ok_ref = cand[b0][top].tolist() == ids[0].tolist()
+        ret[rank] = (bool(ok_layout), bool(ok_same), bool(ok_rank), bool(ok_share), bool(ok_ref))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_ranking_replicated_features():
+    """BASELINE.json configs[4] layout: features replicated by one all-gather, searches split across
+    the ranks, no per-query communication; each rank's results equal the single-device ranking."""
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_rank_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    assert all(all(v) for v in ret.values()), dict(ret)

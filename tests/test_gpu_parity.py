@@ -24,9 +24,9 @@ def _dataset(golden):
 
 
 def _model(golden, ds=None):
-    from ihgnn_b200 import HGCNLayer, HemPredictionLayer, IHGNNLayer, RawGnn
+    from ihgnn_b200 import GCNLayer, HGCNLayer, HemPredictionLayer, IHGNNLayer, RawGnn
     ds = ds or _dataset(golden)
-    layer = IHGNNLayer if str(golden["cfg.gnn"]) == "IHGNN" else HGCNLayer
+    layer = {"IHGNN": IHGNNLayer, "HGCN": HGCNLayer, "GCN": GCNLayer}[str(golden["cfg.gnn"])]
     m = RawGnn(device=torch.device(DEV), dataset=ds, embedding_size=int(golden["cfg.d"]),
                gnn_layer_type=layer, gnn_layer_count=int(golden["cfg.L"]),
                feature_interaction_order=int(golden["cfg.order"]), phase2_attention=False,
@@ -54,6 +54,56 @@ def test_graph_build_matches_reference_bit_exact(golden):
     assert np.array_equal(adj.values().cpu().numpy(), golden["graph.coo_values"])
     dv = torch.from_numpy(golden["graph.VertexDegrees"]).pow(-1).view(-1).numpy()
     assert np.array_equal(g.dv_inv.cpu().numpy(), dv)      # GnnLayers.py:187, bit-exact reciprocal
+
+
+def test_graph2d_matches_reference_bit_exact(golden):
+    """Pps2DGraph (Helpers/Graph.py:19-81): coalesced pairwise adjacency and degrees, bit-exact."""
+    if "graph2d.coo_indices" not in golden:
+        pytest.skip("fixture without the 2-D graph")
+    from ihgnn_b200.graph import Pps2DGraph
+    ds = _dataset(golden)
+    g2 = Pps2DGraph.from_hypergraph(ds.hypergraph, False)
+    assert np.array_equal(g2.Adjacency.indices().cpu().numpy(), golden["graph2d.coo_indices"])
+    assert np.array_equal(g2.Adjacency.values().cpu().numpy(), golden["graph2d.coo_values"])
+    assert np.array_equal(g2.VertexDegrees.cpu().numpy(), golden["graph2d.VertexDegrees"])
+    assert np.array_equal(ds.graph2d.VertexDegrees.cpu().numpy(), golden["graph2d.VertexDegrees"])
+    # from_interactions keeps the reference signature (tuples stand in for PosInteraction)
+    U, Q, I, V, E = (int(x) for x in golden["counts"])
+    inter = list(zip(golden["pos_user"].tolist(), golden["pos_query"].tolist(), golden["pos_item"].tolist()))
+    g3 = Pps2DGraph.from_interactions(inter, U + Q + I, U, Q, True, torch.device(DEV))
+    adj, deg = orc.build_graph2d(golden["pos_user"], golden["pos_query"], golden["pos_item"], U, Q, I, True)
+    assert torch.equal(g3.Adjacency.indices().cpu(), adj.indices()) and torch.equal(g3.Adjacency.values().cpu(), adj.values())
+    assert torch.equal(g3.VertexDegrees.cpu(), deg)
+
+
+@pytest.mark.parametrize("d_in,d_out,self_conn", [(64, 64, False), (32, 64, True), (128, 48, True)])
+def test_gcn_layer_vs_oracle(d_in, d_out, self_conn):
+    """GCNLayer forward / backward (both Linear placements, with and without self connections,
+    heavy rows) against the fp64 oracle."""
+    from ihgnn_b200 import synth
+    from ihgnn_b200.dataset import GraphDataset
+    from ihgnn_b200.graph import Pps2DGraph
+    from ihgnn_b200.layers import GCNLayer
+    U, Q, I, E = 900, 40, 500, 15_000
+    log = synth.make_search_log(U, Q, I, E, 50, shape="cikm", seed=d_in, zipf=1.0)
+    ds = GraphDataset.from_search_log(log, DEV)
+    ds._graph2d = Pps2DGraph.from_hypergraph(ds.graph, self_conn)
+    torch.manual_seed(d_out)
+    layer = GCNLayer(torch.device(DEV), ds, d_in, d_out).to(DEV)
+    x = torch.randn(U + Q + I, d_in, device=DEV, requires_grad=True)
+    out = layer(x)
+    gout = torch.randn_like(out)
+    out.backward(gout)
+    adj, deg = orc.build_graph2d(log.pos_user, log.pos_query, log.pos_item, U, Q, I, self_conn)
+    x64 = x.detach().cpu().double().requires_grad_(True)
+    w = layer.feature_transform.weight.detach().cpu().double().requires_grad_(True)
+    b = layer.feature_transform.bias.detach().cpu().double().requires_grad_(True)
+    ref = orc.gcn_layer(x64, adj.double(), deg.pow(-0.5).double(), w, b)
+    ref.backward(gout.cpu().double())
+    assert max_rel(out.detach().cpu().numpy(), ref.detach().numpy()) <= REL_TOL
+    assert max_rel(x.grad.cpu().numpy(), x64.grad.numpy()) <= REL_TOL
+    assert max_rel(layer.feature_transform.weight.grad.cpu().numpy(), w.grad.numpy()) <= REL_TOL
+    assert max_rel(layer.feature_transform.bias.grad.cpu().numpy(), b.grad.numpy()) <= REL_TOL
 
 
 @pytest.mark.parametrize("shape,U,Q,I,E,zipf", [
@@ -480,3 +530,50 @@ def test_rank_topk_vs_oracle(D, I, C, k):
     ids, _ = F_.rank_topk(feat2.to(DEV), None, queries[:4].to(DEV), torch.zeros(I).to(DEV), lam, query_row0=U,
                           item_row0=U + Q, item_count=I, candidates=None, k=min(k, I))
     assert ids.cpu().tolist() == [list(range(min(k, I)))] * 4
+
+
+# --------------------------------------------------------------------------------------
+# device-side batch sampler
+# --------------------------------------------------------------------------------------
+def test_device_batch_sampler_matches_collate_fn_contract():
+    """Same 8-tuple layout / dtypes as GraphDataset.collate_fn (Dataset.py:260-293) fed by
+    __getitem__ (Dataset.py:107-119); negatives uniform over the items and distinct per positive;
+    one epoch visits every positive once; reproducible for a fixed seed."""
+    from ihgnn_b200 import synth
+    from ihgnn_b200.dataset import DeviceBatchSampler, GraphDataset
+    U, Q, I, E = 500, 40, 64, 10_007
+    log = synth.make_search_log(U, Q, I, E, 50, shape="amazon", seed=5)
+    ds = GraphDataset.from_search_log(log, DEV)
+    sm = DeviceBatchSampler(ds, batch_size=100, neg_sample_size=10, seed=42)
+    assert len(sm) == (E + 99) // 100
+    seen, neg_hist, batches = [], np.zeros(I, np.int64), []
+    for tup in sm:
+        assert len(tup) == 8 and all(t.dtype == torch.int64 and t.is_cuda for t in tup)
+        pu, pq, pi, pf, nu, nq, ni, nf = (t.cpu().numpy() for t in tup)
+        B = pu.shape[0]
+        assert nu.shape[0] == 10 * B and (pf == 1).all() and (nf == 0).all()
+        assert np.array_equal(nu, np.repeat(pu, 10)) and np.array_equal(nq, np.repeat(pq, 10))
+        assert ni.min() >= 0 and ni.max() < I
+        grp = np.sort(ni.reshape(B, 10), 1)
+        assert (np.diff(grp, axis=1) > 0).all()                 # random.sample: distinct inside a group
+        seen.append(np.stack([pu, pq, pi], 1))
+        neg_hist += np.bincount(ni, minlength=I)
+        batches.append(ni)
+    seen = np.concatenate(seen)
+    assert seen.shape[0] == E
+    want = np.stack([log.pos_user, log.pos_query, log.pos_item], 1)
+    assert np.array_equal(seen[np.lexsort(seen.T[::-1])], want[np.lexsort(want.T[::-1])])   # a permutation of the positives
+    # uniformity: chi-square over I bins, 10 E draws (mean = dof = 63, sd ~ 11)
+    exp = 10 * E / I
+    chi2 = float(((neg_hist - exp) ** 2 / exp).sum())
+    assert chi2 < 63 + 6 * 11.3, chi2
+    # reproducible for a fixed seed, different for another one
+    again = [t[6].cpu().numpy() for t in DeviceBatchSampler(ds, 100, 10, seed=42)]
+    assert all(np.array_equal(a, b) for a, b in zip(batches, again))
+    other = [t[6].cpu().numpy() for t in DeviceBatchSampler(ds, 100, 10, seed=43)]
+    assert not all(np.array_equal(a, b) for a, b in zip(batches, other))
+    # the tuple drives a training step exactly like the reference's loop (TrainTestHelper.py:123-131)
+    tup = next(iter(sm))
+    users, queries, items = (torch.cat([tup[i], tup[i + 4]]) for i in range(3))
+    flags = torch.cat([tup[3], tup[7]]).float()
+    assert users.shape == queries.shape == items.shape == flags.shape == (1100,)

@@ -104,3 +104,15 @@ def test_ranking_matches_reference_eval_loop(golden):
                          None, features=f).detach()
         want = sorted(cand[b].tolist(), key=lambda i: -float(full[i]))[:5]
         assert ids_c[b].tolist() == want
+
+
+def test_graph2d_bit_exact(golden):
+    """oracle.build_graph2d against the reference's Pps2DGraph.from_interactions (Graph.py:19-81)."""
+    import pytest
+    if "graph2d.coo_indices" not in golden:
+        pytest.skip("fixture without the 2-D graph")
+    U, Q, I, V, E = (int(x) for x in golden["counts"])
+    adj, deg = orc.build_graph2d(golden["pos_user"], golden["pos_query"], golden["pos_item"], U, Q, I, False)
+    assert np.array_equal(adj.indices().numpy(), golden["graph2d.coo_indices"])
+    assert np.array_equal(adj.values().numpy(), golden["graph2d.coo_values"])
+    assert np.array_equal(deg.numpy(), golden["graph2d.VertexDegrees"])
