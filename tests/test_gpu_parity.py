@@ -577,3 +577,39 @@ def test_device_batch_sampler_matches_collate_fn_contract():
     users, queries, items = (torch.cat([tup[i], tup[i + 4]]) for i in range(3))
     flags = torch.cat([tup[3], tup[7]]).float()
     assert users.shape == queries.shape == items.shape == flags.shape == (1100,)
+
+
+def test_graphed_train_step_equals_eager(golden):
+    """ihgnn_b200.graphs.GraphedTrainStep (forward + BCE + backward + Adam replayed as one CUDA graph)
+    follows the same trajectory as the eager loop of TrainTestHelper.py:123-143."""
+    from ihgnn_b200.graphs import GraphedTrainStep
+    users, queries, items, flags = batch_of(golden)
+    flags = flags.float()
+    losses = {}
+    for mode in ("eager", "graph"):
+        m = _model(golden)
+        opt = torch.optim.Adam(m.parameters(), 1e-3, fused=True, capturable=(mode == "graph"))
+        out = []
+        if mode == "graph":
+            # warmup=1 runs ONE real step before capture (the capture itself only records): undo it
+            step2 = GraphedTrainStep(m, opt, int(users.numel()), DEV, warmup=1,
+                                     example=(users, queries, items, flags))
+            m.load_state_dict(state_of(golden), strict=True)          # in place: the graph keeps its pointers
+            for st in opt.state.values():                             # Adam moments / step counts, in place
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+            for _ in range(4):
+                out.append(float(step2(users, queries, items, flags)))
+        else:
+            ud, qd, idv, fd = (t.to(DEV) for t in (users, queries, items, flags))
+            for _ in range(4):
+                loss = torch.nn.functional.binary_cross_entropy_with_logits(m(ud, qd, idv), fd)
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                opt.step()
+                out.append(float(loss))
+        losses[mode] = out
+    assert losses["eager"][0] == pytest.approx(float(golden["ref64.loss"]), rel=1e-5)
+    assert losses["graph"] == pytest.approx(losses["eager"], rel=2e-6), losses
+    assert len(set(losses["eager"])) == 4                             # the parameters do move between steps
