@@ -46,7 +46,7 @@ SIGNATURES = {
     "ihg_csr_from_keys": (c_int32, [P, P, I64, I64, P, P, P, P, P, I64, P]),
     "ihg_segment_plan_workspace_bytes": (I64, [I64]),
     "ihg_segment_plan_build": (c_int32, [P, I64, I32, P, P, P, P, P, I64, P]),
-    "ihg_segment_reduce": (c_int32, [POINTER(IhgCsr), P, I64, I32, I64, I64, P, P, I64, P, P, P, P, I64, I32, P]),
+    "ihg_segment_reduce": (c_int32, [POINTER(IhgCsr), P, I64, I32, I64, I64, P, P, I64, P, P, P, P, I64, I32, I32, P]),
     "ihg_two_hop_index_build": (c_int32, [POINTER(IhgCsr), P, I64, I64, P, P, P]),
     "ihg_two_hop_reduce": (c_int32, [POINTER(IhgCsr), P, P, I64, P, F32, F32, F32, P, P, P, I64, I32, P]),
     "ihg_edge_gather_sum": (c_int32, [P, I64, P, F32, P, P, I64, P, I64, I32, P]),

@@ -25,15 +25,16 @@ constexpr int kSegWarpsPerBlock = 8;
 constexpr int kSegUnroll = 4;        // independent 128-bit row gathers in flight per lane group
 constexpr int kSegPerGroup = 1;      // chunks a lane group walks through (strided)
 
-template <int LPR, int VPL, int UNR, int SEGS>
-__global__ void __launch_bounds__(kSegWarpsPerBlock * 32)
+template <int LPR, int VPL, int UNR, int SEGS, int MINB>
+__global__ void __launch_bounds__(kSegWarpsPerBlock * 32, MINB)
 segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src_row_mul,
                       int64_t bound0, int64_t bound1, const int32_t* __restrict__ row_slot,
                       const float* __restrict__ init, int64_t init_ld,
                       const float* __restrict__ src_scale,
                       const float* __restrict__ row_scale, const int32_t* __restrict__ col,
                       int64_t n_seg, int64_t n_groups, const int4* __restrict__ seg,
-                      float* __restrict__ partial, float* __restrict__ out, int64_t out_ld, int dim) {
+                      float* __restrict__ partial, float* __restrict__ out, int64_t out_ld, int dim,
+                      int accumulate) {
     constexpr int G = 32 / LPR;
     constexpr unsigned kFull = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -64,7 +65,7 @@ segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src
         for (int w = 0; w < VPL; ++w) {
             const int cv = gl + w * LPR;
             // an optional initial row (e.g. the rank's own partial sum) opens the ordered sum
-            acc[w] = (init && live && part < 0 && cv < nvec) ? ldg4(init + (int64_t)row * init_ld + 4 * cv) : f4_zero();
+            acc[w] = (init && !accumulate && live && part < 0 && cv < nvec) ? ldg4(init + (int64_t)row * init_ld + 4 * cv) : f4_zero();
         }
         // longest chunk among the groups of this warp drives the (warp-uniform) trip count
         int len = end - begin;
@@ -103,10 +104,23 @@ segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src
         if (live) {
             if (part < 0) {
                 const float rs = row_scale ? __ldg(row_scale + row) : 1.0f;
+                if (!accumulate) {
 #pragma unroll
-                for (int w = 0; w < VPL; ++w) {
-                    const int cv = gl + w * LPR;
-                    if (cv < nvec) stg4(out + (int64_t)row * out_ld + 4 * cv, f4_scale(rs, acc[w]));
+                    for (int w = 0; w < VPL; ++w) {
+                        const int cv = gl + w * LPR;
+                        if (cv < nvec) stg4(out + (int64_t)row * out_ld + 4 * cv, f4_scale(rs, acc[w]));
+                    }
+                } else if (end > begin) {
+                    // accumulate mode: out[row] = init[row] + rs * sum; rows without incidences stay untouched
+                    // (init may alias out: plain loads, not the read-only path)
+#pragma unroll
+                    for (int w = 0; w < VPL; ++w) {
+                        const int cv = gl + w * LPR;
+                        if (cv >= nvec) continue;
+                        float4 o = *reinterpret_cast<const float4*>(init + (int64_t)row * init_ld + 4 * cv);
+                        f4_fma(o, rs, acc[w]);
+                        stg4(out + (int64_t)row * out_ld + 4 * cv, o);
+                    }
                 }
             } else {
 #pragma unroll
@@ -133,7 +147,7 @@ segment_fixup_kernel(const float* __restrict__ partial, const int32_t* __restric
                      const int32_t* __restrict__ split_ptr, int64_t n_split,
                      const float* __restrict__ init, int64_t init_ld,
                      const float* __restrict__ row_scale, float* __restrict__ out, int64_t out_ld,
-                     int dim) {
+                     int dim, int accumulate) {
     constexpr int G = 32 / LPR;
     __shared__ float4 warp_sum[kSegWarpsPerBlock][LPR * VPL];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -170,10 +184,20 @@ segment_fixup_kernel(const float* __restrict__ partial, const int32_t* __restric
 #pragma unroll
         for (int w = 0; w < VPL; ++w) {
             const int cv = gl + w * LPR;
-            float4 t = (init && cv < nvec) ? ldg4(init + (int64_t)row * init_ld + 4 * cv) : f4_zero();
+            if (cv >= nvec) continue;
+            if (!accumulate) {
+                float4 t = init ? ldg4(init + (int64_t)row * init_ld + 4 * cv) : f4_zero();
 #pragma unroll
-            for (int k = 0; k < kSegWarpsPerBlock; ++k) f4_add(t, warp_sum[k][cv]);
-            if (cv < nvec) stg4(out + (int64_t)row * out_ld + 4 * cv, f4_scale(rs, t));
+                for (int k = 0; k < kSegWarpsPerBlock; ++k) f4_add(t, warp_sum[k][cv]);
+                stg4(out + (int64_t)row * out_ld + 4 * cv, f4_scale(rs, t));
+            } else {
+                float4 t = f4_zero();
+#pragma unroll
+                for (int k = 0; k < kSegWarpsPerBlock; ++k) f4_add(t, warp_sum[k][cv]);
+                float4 o = *reinterpret_cast<const float4*>(init + (int64_t)row * init_ld + 4 * cv);
+                f4_fma(o, rs, t);
+                stg4(out + (int64_t)row * out_ld + 4 * cv, o);
+            }
         }
     }
 }
@@ -183,7 +207,7 @@ static int launch_segment_reduce(const ihg_csr* g, const float* src, int64_t src
                                  int64_t b0, int64_t b1, const int32_t* row_slot, const float* init,
                                  int64_t init_ld, const float* src_scale,
                                  const float* row_scale, float* partial, float* out, int64_t out_ld,
-                                 int dim, cudaStream_t st) {
+                                 int dim, int accumulate, int l2_source, cudaStream_t st) {
     constexpr int G = 32 / LPR;
     // (unroll, chunks per group) = (4, 1) measured best on both bench workloads (profiles/
     // microbench_segment.py): 5.3 TB/s at d=128 (82% of the measured copy bandwidth); at d=64 the
@@ -202,13 +226,20 @@ static int launch_segment_reduce(const ihg_csr* g, const float* src, int64_t src
     // Launch-bound variants re-measured in situ (profiles/r01_bench_segreduce_variants.txt): unlike the
     // L2-served two-hop gathers, these DRAM-served 256/512-byte random row reads get SLOWER with more
     // resident warps or a shorter unroll (unroll 2 with >= 5/6/8 blocks: 2.3 / 2.7 / 3.2 TB/s vs 3.6-4.0).
-    segment_reduce_kernel<LPR, VPL, kSegUnroll, SEGS><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
-        src, src_ld, mul, b0, b1, row_slot, init, init_ld, src_scale, row_scale, g->col, g->n_seg, n_groups,
-        reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
+    // A source that is L2-resident (the L2-sized hyperedge ranges of the phased reduction) wants the
+    // opposite: unroll 2 and >= 5 resident blocks, like the two-hop gathers.
+    if (l2_source)
+        segment_reduce_kernel<LPR, VPL, 2, SEGS, 5><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
+            src, src_ld, mul, b0, b1, row_slot, init, init_ld, src_scale, row_scale, g->col, g->n_seg, n_groups,
+            reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim, accumulate);
+    else
+        segment_reduce_kernel<LPR, VPL, kSegUnroll, SEGS, 0><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
+            src, src_ld, mul, b0, b1, row_slot, init, init_ld, src_scale, row_scale, g->col, g->n_seg, n_groups,
+            reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim, accumulate);
     IHG_LAUNCH_CHECK();
     if (g->n_split > 0) {
         segment_fixup_kernel<LPR, VPL><<<(unsigned)g->n_split, kSegWarpsPerBlock * 32, 0, st>>>(
-            partial, g->split_row, g->split_ptr, g->n_split, init, init_ld, row_scale, out, out_ld, dim);
+            partial, g->split_row, g->split_ptr, g->n_split, init, init_ld, row_scale, out, out_ld, dim, accumulate);
         IHG_LAUNCH_CHECK();
     }
     return IHG_OK;
@@ -357,7 +388,7 @@ static int launch_two_hop(const ihg_csr* g, const int32_t* nbr, const float* src
     IHG_LAUNCH_CHECK();
     if (g->n_split > 0) {
         segment_fixup_kernel<LPR, VPL><<<(unsigned)g->n_split, kSegWarpsPerBlock * 32, 0, st>>>(
-            partial, g->split_row, g->split_ptr, g->n_split, nullptr, 0, row_scale, out, out_ld, dim);
+            partial, g->split_row, g->split_ptr, g->n_split, nullptr, 0, row_scale, out, out_ld, dim, 0);
         IHG_LAUNCH_CHECK();
     }
     return IHG_OK;
@@ -371,12 +402,17 @@ extern "C" int ihg_segment_reduce(const ihg_csr* g, const float* src, int64_t sr
                                   int32_t src_row_mul, int64_t bound0, int64_t bound1,
                                   const int32_t* row_slot, const float* init, int64_t init_ld,
                                   const float* src_scale, const float* row_scale, float* partial,
-                                  float* out, int64_t out_ld, int32_t dim, void* stream) {
+                                  float* out, int64_t out_ld, int32_t dim, int32_t flags,
+                                  void* stream) {
     IHG_REQUIRE(g && src && out, "segment_reduce: null pointer");
+    const int accumulate = (flags & IHG_SEG_ACCUMULATE) != 0, l2_source = (flags & IHG_SEG_L2_SOURCE) != 0;
+    IHG_REQUIRE(!accumulate || init, "segment_reduce: accumulate mode needs init (usually == out)");
     IHG_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 256, "segment_reduce: dim=%d must be a multiple of 4, <= 256", dim);
     IHG_REQUIRE(src_ld % 4 == 0 && out_ld % 4 == 0 && src_ld >= dim && out_ld >= dim,
                 "segment_reduce: leading dimensions must be multiples of 4 and >= dim");
-    IHG_REQUIRE(g->n_rows > 0 && g->n_seg >= g->n_rows && g->seg, "segment_reduce: incomplete csr plan");
+    // accumulate mode leaves empty rows untouched, so its plan may list the non-empty rows only
+    IHG_REQUIRE(g->n_rows > 0 && (g->n_seg >= g->n_rows || accumulate) && g->seg, "segment_reduce: incomplete csr plan");
+    if (g->n_seg == 0) return IHG_OK;
     IHG_REQUIRE(g->nnz == 0 || g->col, "segment_reduce: null col");
     IHG_REQUIRE(g->n_split == 0 || (partial && g->split_row && g->split_ptr),
                 "segment_reduce: split rows need the partial buffer");
@@ -385,7 +421,7 @@ extern "C" int ihg_segment_reduce(const ihg_csr* g, const float* src, int64_t sr
     cudaStream_t st = as_stream(stream);
     const int nvec = dim / 4;
 #define IHG_SEG_CASE(L, V) \
-    return launch_segment_reduce<L, V>(g, src, src_ld, src_row_mul, bound0, bound1, row_slot, init, init_ld, src_scale, row_scale, partial, out, out_ld, dim, st)
+    return launch_segment_reduce<L, V>(g, src, src_ld, src_row_mul, bound0, bound1, row_slot, init, init_ld, src_scale, row_scale, partial, out, out_ld, dim, accumulate, l2_source, st)
     if (nvec <= 1) IHG_SEG_CASE(1, 1);
     if (nvec <= 2) IHG_SEG_CASE(2, 1);
     if (nvec <= 4) IHG_SEG_CASE(4, 1);

@@ -34,8 +34,10 @@ def segment_reduce(plan: CsrPlan, src: torch.Tensor, dim: int, *, src_row_mul: i
                    row_scale: Optional[torch.Tensor] = None,
                    out: Optional[torch.Tensor] = None,
                    row_slot: Optional[torch.Tensor] = None,
-                   init: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[r] = row_scale[r] * (init[r] + sum_{j in row r} src_scale[col j] * src[col[j]*mul + slot(r)])."""
+                   init: Optional[torch.Tensor] = None, accumulate: bool = False,
+                   l2_source: bool = False) -> torch.Tensor:
+    """out[r] = row_scale[r] * (init[r] + sum_{j in row r} src_scale[col j] * src[col[j]*mul + slot(r)]);
+    accumulate: out[r] = init[r] + row_scale[r] * sum, empty rows untouched (init may be out)."""
     _lib.require_cuda(src, src_scale, row_scale, out, row_slot, init)
     if init is not None:
         init = _lib.rows_f32(init)
@@ -50,7 +52,7 @@ def segment_reduce(plan: CsrPlan, src: torch.Tensor, dim: int, *, src_row_mul: i
     _lib.call("ihg_segment_reduce", plan.ref(), _lib.ptr(src), src_ld, src_row_mul, bounds[0],
               bounds[1], _lib.ptr(row_slot), _lib.ptr(init), _lib.ld(init) if init is not None else 0,
               _lib.ptr(src_scale), _lib.ptr(row_scale), _lib.ptr(plan.partial(dim)),
-              _lib.ptr(out), _lib.ld(out), dim, _lib.stream_ptr(),
+              _lib.ptr(out), _lib.ld(out), dim, (1 if accumulate else 0) | (2 if l2_source else 0), _lib.stream_ptr(),
               tag=f"segment_reduce[mul={src_row_mul}]",
               algo_bytes=plan.nnz * (4 + 4 * dim) + plan.n_rows * (4 * dim + 16))
     return out
@@ -84,6 +86,25 @@ def two_hop_reduce(plan: CsrPlan, nbr: torch.Tensor, src: torch.Tensor, *,
               _lib.ptr(plan.partial(dim)), _lib.ptr(out), _lib.ld(out), dim, _lib.stream_ptr(), tag="two_hop_reduce",
               # what the pair it replaces must move: gather-sum E(12+16d) + segmented reduce
               algo_bytes=(plan.nnz // 3) * (12 + 16 * dim) + plan.nnz * (4 + 4 * dim) + plan.n_rows * (4 * dim + 16))
+    return out
+
+
+def phased_segment_reduce(plan: CsrPlan, edge_count: int, src: torch.Tensor, dim: int, *,
+                          row_scale: Optional[torch.Tensor] = None,
+                          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """segment_reduce(plan, src [E, dim]) as a few passes over L2-sized hyperedge ranges.
+    Every hyperedge row is read three times (once per slot); in one pass over all hyperedges the
+    second and third read come from DRAM again (E*dim*4 bytes >> L2).  Restricting a pass to a range
+    of hyperedges whose rows fit in L2 turns them into L2 hits: DRAM reads drop from 3x to ~1x.
+    Falls back to the single pass when the table already fits or would need too many passes."""
+    plans = plan.phase_plans(edge_count, dim)
+    if not plans:
+        return segment_reduce(plan, src, dim, row_scale=row_scale, out=out)
+    src = _lib.rows_f32(src)
+    l2 = os.environ.get("IHG_PHASE_L2_VARIANT", "1") != "0"
+    out = segment_reduce(plans[0], src, dim, row_scale=row_scale, out=out, l2_source=l2)
+    for sub in plans[1:]:
+        segment_reduce(sub, src, dim, row_scale=row_scale, out=out, init=out, accumulate=True, l2_source=l2)
     return out
 
 

@@ -110,12 +110,20 @@ int ihg_segment_plan_build(const int32_t* rowptr, int64_t n_rows, int32_t chunk_
  * row stride init_ld) is added first: out = row_scale * (init[r] + sum ...) -- the multi-GPU
  * reduce adds the rank's own partial before the received ones.  row_scale / src_scale may be
  * null (= 1).  `partial` is scratch of csr->n_part * dim floats.  dim % 4 == 0, dim <= 256.
+ * flags & IHG_SEG_ACCUMULATE: out[r] = init[r] + row_scale[r] * sum instead, rows without
+ * incidences are left untouched (the plan may then list the non-empty rows only), and init may
+ * alias out -- used to run one reduction as a few passes over L2-sized hyperedge ranges (each pass
+ * a CSR restricted to the range), so that the three reads of a hyperedge row (one per slot) hit L2
+ * after the first.  flags & IHG_SEG_L2_SOURCE: the source rows are expected in L2 -- launch the
+ * high-occupancy variant (DRAM-served random rows want the opposite).
  * ------------------------------------------------------------------------------------ */
+#define IHG_SEG_ACCUMULATE 1
+#define IHG_SEG_L2_SOURCE 2
 int ihg_segment_reduce(const ihg_csr* csr_host, const float* src, int64_t src_ld,
                        int32_t src_row_mul, int64_t bound0, int64_t bound1,
                        const int32_t* row_slot, const float* init, int64_t init_ld,
                        const float* src_scale, const float* row_scale, float* partial,
-                       float* out, int64_t out_ld, int32_t dim, void* stream);
+                       float* out, int64_t out_ld, int32_t dim, int32_t flags, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * a5-a8  node -> hyperedge -> node round trip of an order-1 layer in one pass (no [E,dim]

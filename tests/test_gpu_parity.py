@@ -613,3 +613,44 @@ def test_graphed_train_step_equals_eager(golden):
     assert losses["eager"][0] == pytest.approx(float(golden["ref64.loss"]), rel=1e-5)
     assert losses["graph"] == pytest.approx(losses["eager"], rel=2e-6), losses
     assert len(set(losses["eager"])) == 4                             # the parameters do move between steps
+
+
+@pytest.mark.parametrize("dim,mb", [(64, 0.5), (128, 1.0), (32, 0.25)])
+def test_phased_segment_reduce_equals_single_pass(dim, mb, monkeypatch):
+    """The edge -> node reduction run as several passes over L2-sized hyperedge ranges
+    (accumulate mode of ihg_segment_reduce) against the fp64 SpMM and the single pass: every
+    incidence lands in exactly one range plan, isolated rows stay exact zeros, split rows included."""
+    from ihgnn_b200 import functional as F_
+    from ihgnn_b200 import synth
+    from ihgnn_b200.graph import PpsHyperGraph
+    monkeypatch.setenv("IHG_PHASE_MB", str(mb))
+    monkeypatch.setenv("IHG_PHASES", "1")                   # opt-in: measured slower than the single pass on B200
+    U, Q, I, E = 400, 30, 200, 9000
+    log = synth.make_search_log(U, Q, I, E, 50, shape="cikm", seed=dim + 7, zipf=1.0)
+    ref = orc.build_hypergraph(log.pos_user, log.pos_query, log.pos_item, U, Q, I)
+    g = PpsHyperGraph.from_tensors(log.pos_user, log.pos_query, log.pos_item, U, Q, I, DEV, chunk_len=64)
+    plans = g.plan.phase_plans(E, dim)
+    assert plans is not None and 2 <= len(plans) <= 6
+    assert sum(p.nnz for p in plans) == 3 * E
+    assert any(p.n_split > 0 for p in plans)
+    per = -(-E // len(plans))
+    for k, p in enumerate(plans):
+        c = p.col.cpu().numpy()
+        assert c.size == 0 or (c.min() >= k * per and c.max() < (k + 1) * per)
+    gen = torch.Generator().manual_seed(dim)
+    ef = torch.randn(E, dim, generator=gen)
+    dv = ref.VertexDegrees.pow(-1)
+    want = (dv.double() * torch.sparse.mm(ref.adjacency(torch.float64), ef.double())).numpy()
+    got = F_.phased_segment_reduce(g.plan, E, ef.to(DEV), dim, row_scale=g.dv_inv).cpu().numpy()
+    assert max_rel(got, want) < 2e-6
+    iso = (np.diff(ref.rowptr.numpy()) == 0)
+    assert iso.any() and np.all(got[iso] == 0.0)
+    one = F_.segment_reduce(g.plan, ef.to(DEV), dim, row_scale=g.dv_inv).cpu().numpy()
+    assert max_rel(got, one) < 2e-6
+    again = F_.phased_segment_reduce(g.plan, E, ef.to(DEV), dim, row_scale=g.dv_inv).cpu().numpy()
+    assert np.array_equal(got, again)
+    # a strided destination (the sharded backward writes next to another block of columns)
+    both = torch.zeros(U + Q + I, 2 * dim, device=DEV)
+    F_.phased_segment_reduce(g.plan, E, ef.to(DEV), dim, out=both[:, dim:])
+    want_raw = torch.sparse.mm(ref.adjacency(torch.float64), ef.double()).numpy()
+    assert max_rel(both[:, dim:].cpu().numpy(), want_raw) < 2e-6 and float(both[:, :dim].abs().max()) == 0.0
