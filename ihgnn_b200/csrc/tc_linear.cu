@@ -177,10 +177,13 @@ node_linear_tc_kernel(const float* __restrict__ x, int64_t x_ld, const float* __
 // SWIZZLE_128B_BASE32B layout (the row index is the MMA K dimension); M is padded to 128 with
 // zero sub-tiles.  One accumulator [128 x n_in] per node type stays in TMEM across all tiles of
 // the CTA; partials go to the workspace and are summed in CTA order (deterministic).
-// Small CTAs (4 producer warps + 1 MMA warp), several resident per SM.
+// 8 producer warps + 1 MMA warp per CTA, two CTAs per SM.  (With 4 producer warps the kernel was
+// issue-latency bound: ncu showed the few resident warps mostly "selected" / waiting on fixed-latency
+// ALU dependencies of the tf32 split, tensor pipe 23 %, DRAM 25 %.)
 // =========================================================================================
 constexpr int kNwTe = 32;
-constexpr int kNwThreads = 5 * 32;
+constexpr int kNwProdWarps = 8;                   // one tile row x one 16-byte chunk column per producer thread
+constexpr int kNwThreads = (kNwProdWarps + 1) * 32;
 constexpr int kNwMaxBlk = 4;
 
 __global__ void __launch_bounds__(kNwThreads)
@@ -197,7 +200,7 @@ node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* _
     const uint32_t a_bytes = 8 * sub_bytes;                               // 4 hi + 4 lo sub-tiles (M = 128)
     const int NB = KB + 1;                                                // + the constant "ones" block (bias gradient)
     const uint32_t stage_bytes = a_bytes + 2 * (uint32_t)NB * sub_bytes;
-    const bool is_mma_warp = warp == 4;
+    const bool is_mma_warp = warp == kNwProdWarps;
     const int acc_cols = n_in + 16;                                       // column n_in accumulates sum_r dy[r][n]
     const uint32_t tmem_cols = tmem_cols_pow2((uint32_t)(n_types * acc_cols));
 
@@ -222,7 +225,7 @@ node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* _
     }
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(smem_u32(&bar_full[s]), 4);
+            mbar_init(smem_u32(&bar_full[s]), kNwProdWarps);
             mbar_init(smem_u32(&bar_empty[s]), 1);
         }
         mbar_init(smem_u32(&bar_done), 1);
@@ -236,62 +239,49 @@ node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* _
     const uint32_t tmem_base = tmem_base_slot;
 
     if (!is_mma_warp) {
-        const int c = tid & 7, r0 = tid >> 3;            // rows r0, r0 + 16; chunk c of every block
+        const int c = tid & 7, r0 = tid >> 3;            // row r0 of the tile; chunk c of every block
         uint32_t it = 0;
         uint32_t started = 0;                            // bit t set once type t's accumulator is live
         // Software pipeline: the loads of tile i+1 are issued BEFORE tile i is split and stored, so
-        // every thread keeps 8-16 independent 128-bit loads in flight across the wait / store phase
-        // (the 112 KB of operand stages allow only two CTAs per SM; without this the kernel was
-        // load-latency bound at ~1.3 TB/s).
-        float4 av[2][kNwMaxBlk], bv[2][kNwMaxBlk];
-        auto load_tile = [&](int64_t tile, float4 (&a)[2][kNwMaxBlk], float4 (&b)[2][kNwMaxBlk]) {
+        // every thread keeps its 128-bit loads in flight across the wait / store phase.
+        float4 av[kNwMaxBlk], bv[kNwMaxBlk];
+        auto load_tile = [&](int64_t tile, float4 (&a)[kNwMaxBlk], float4 (&b)[kNwMaxBlk]) {
             int t = 0;
             while (t < 2 && tile >= tile_base[t + 1]) ++t;
-            const int64_t row0 = lo[t] + (tile - tile_base[t]) * kNwTe;
+            const int64_t r = lo[t] + (tile - tile_base[t]) * kNwTe + r0;
+            const bool ok = tile < n_tiles && r < hi[t];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int64_t r = row0 + r0 + 16 * j;
-                const bool ok = tile < n_tiles && r < hi[t];
-#pragma unroll
-                for (int blk = 0; blk < kNwMaxBlk; ++blk) {
-                    a[j][blk] = (ok && blk < KA) ? ldg4(dy + r * dy_ld + blk * kChunkK + 4 * c) : f4_zero();
-                    b[j][blk] = (ok && blk < KB) ? ldg4(x + r * x_ld + blk * kChunkK + 4 * c) : f4_zero();
-                }
+            for (int blk = 0; blk < kNwMaxBlk; ++blk) {
+                a[blk] = (ok && blk < KA) ? ldg4(dy + r * dy_ld + blk * kChunkK + 4 * c) : f4_zero();
+                b[blk] = (ok && blk < KB) ? ldg4(x + r * x_ld + blk * kChunkK + 4 * c) : f4_zero();
             }
-            return t;
         };
         if ((int64_t)blockIdx.x < n_tiles) load_tile(blockIdx.x, av, bv);
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             int t = 0;
             while (t < 2 && tile >= tile_base[t + 1]) ++t;
             started |= 1u << (n_types > 1 ? t : 0);
-            float4 an[2][kNwMaxBlk], bn[2][kNwMaxBlk];
+            float4 an[kNwMaxBlk], bn[kNwMaxBlk];
             load_tile(tile + gridDim.x, an, bn);
             const int s = it & 1;
             mbar_wait(smem_u32(&bar_empty[s]), ((it >> 1) & 1u) ^ 1u);
             const uint32_t ah = smem_base + (uint32_t)s * stage_bytes;
             const uint32_t bh = ah + a_bytes;
 #pragma unroll
-            for (int blk = 0; blk < kNwMaxBlk; ++blk)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (blk < KA)
-                        store_split_chunk_mn(ah + (uint32_t)blk * sub_bytes, ah + (uint32_t)(4 + blk) * sub_bytes,
-                                             r0 + 16 * j, c, av[j][blk]);
-                    if (blk < KB)
-                        store_split_chunk_mn(bh + (uint32_t)blk * sub_bytes, bh + (uint32_t)(NB + blk) * sub_bytes,
-                                             r0 + 16 * j, c, bv[j][blk]);
-                }
+            for (int blk = 0; blk < kNwMaxBlk; ++blk) {
+                if (blk < KA)
+                    store_split_chunk_mn(ah + (uint32_t)blk * sub_bytes, ah + (uint32_t)(4 + blk) * sub_bytes, r0, c, av[blk]);
+                if (blk < KB)
+                    store_split_chunk_mn(bh + (uint32_t)blk * sub_bytes, bh + (uint32_t)(NB + blk) * sub_bytes, r0, c, bv[blk]);
+            }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int blk = 0; blk < kNwMaxBlk; ++blk) {
-                    av[j][blk] = an[j][blk];
-                    bv[j][blk] = bn[j][blk];
-                }
+            for (int blk = 0; blk < kNwMaxBlk; ++blk) {
+                av[blk] = an[blk];
+                bv[blk] = bn[blk];
+            }
         }
         // final epilogue: warp == TMEM lane quadrant; rows n < n_out of every type's accumulator
         const int n = warp * 32 + lane;
@@ -301,7 +291,7 @@ node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* _
             mbar_wait(smem_u32(&bar_done), 0);
             fence_after_sync();
         }
-        for (int t = 0; t < n_types; ++t)
+        for (int t = 0; t < n_types && warp < 4; ++t)    // warps 0-3 own the four TMEM lane quadrants
             for (int c0 = 0; c0 < acc_cols; c0 += 16) {
                 float acc[16];
                 if (any && ((started >> t) & 1u)) {      // block-uniform: untouched accumulators are undefined
