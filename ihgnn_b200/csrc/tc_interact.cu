@@ -613,7 +613,9 @@ interact_prep_weights_t_kernel(const float* __restrict__ w_hi, int64_t w_ld, int
 // (coalesced (row, chunk) mapping), then every operand sub-tile is produced from registers.
 // blockIdx.y selects a range of feature groups when all groups would not fit TMEM twice.
 constexpr int kWgTe = 32;                       // hyperedges per tile
-constexpr int kWgProducerWarps = 4;
+constexpr int kWgProducerWarps = 8;               // (row, chunk) per thread: 32 rows x 8 chunks = 256 threads
+constexpr int kWgRowsPerThread = kWgTe * 8 / (kWgProducerWarps * 32);
+constexpr int kWgRowStep = kWgProducerWarps * 4;  // rows covered by one pass of the producers
 constexpr int kWgThreads = (kWgProducerWarps + 1) * 32;
 constexpr int kWgMaxKC = 4;                     // dim <= 128
 
@@ -661,23 +663,33 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
     const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
     if (!is_mma_warp) {
-        // (row, chunk) lane mapping: 8 consecutive lanes cover one row's 128-byte slice; 128 threads
-        // cover rows r0 and r0 + 16 of the 32-row tile
+        // (row, chunk) lane mapping: 8 consecutive lanes cover one row's 128-byte slice; the 256
+        // producer threads cover the 32 rows of a tile (8 warps: with 4 the producers' instruction
+        // issue -- products, tf32 splits, swizzled stores -- had too few warps to hide ALU latency)
         const int c = tid & 7, r0 = tid >> 3;
         uint32_t ita = 0, itb = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++itb) {
-            // ---- one burst of loads: def and u/q/i slices for both rows, all 32-column blocks
-            float4 dv[2][NBLK], uv[2][NBLK], qv[2][NBLK], iv[2][NBLK];
+        // node ids of the next tile are fetched one tile ahead: the row gathers of a tile then start
+        // without waiting for their own index loads
+        int nxt_u[kWgRowsPerThread], nxt_q[kWgRowsPerThread], nxt_i[kWgRowsPerThread];
+        auto load_ids = [&](int64_t tile) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int64_t e = tile * kWgTe + r0 + 16 * j;
+            for (int j = 0; j < kWgRowsPerThread; ++j) {
+                const int64_t e = tile * kWgTe + r0 + kWgRowStep * j;
+                const bool ok = tile < n_tiles && e < E;
+                nxt_u[j] = ok ? __ldg(i3 + 3 * e) : 0;
+                nxt_q[j] = ok ? __ldg(i3 + 3 * e + 1) : 0;
+                nxt_i[j] = ok ? __ldg(i3 + 3 * e + 2) : 0;
+            }
+        };
+        load_ids(blockIdx.x);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++itb) {
+            // ---- one burst of loads: def and u/q/i slices of this thread's row(s), all 32-column blocks
+            float4 dv[kWgRowsPerThread][NBLK], uv[kWgRowsPerThread][NBLK], qv[kWgRowsPerThread][NBLK], iv[kWgRowsPerThread][NBLK];
+#pragma unroll
+            for (int j = 0; j < kWgRowsPerThread; ++j) {
+                const int64_t e = tile * kWgTe + r0 + kWgRowStep * j;
                 const bool ok = e < E;
-                int nu_ = 0, nq = 0, ni = 0;
-                if (ok) {
-                    nu_ = __ldg(i3 + 3 * e);
-                    nq = __ldg(i3 + 3 * e + 1);
-                    ni = __ldg(i3 + 3 * e + 2);
-                }
+                const int nu_ = nxt_u[j], nq = nxt_q[j], ni = nxt_i[j];
 #pragma unroll
                 for (int blk = 0; blk < NBLK; ++blk) {
                     const bool okb = ok && blk < KC;
@@ -687,6 +699,7 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                     iv[j][blk] = okb ? ldg4(xp + (int64_t)ni * xp_ld + blk * kChunkK + 4 * c) : f4_zero();
                 }
             }
+            load_ids(tile + gridDim.x);
             // ---- B stage: def tile
             {
                 const int sb = itb % nbs;
@@ -696,9 +709,9 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                 for (int blk = 0; blk < NBLK; ++blk)
                     if (blk < KC) {
 #pragma unroll
-                        for (int j = 0; j < 2; ++j)
+                        for (int j = 0; j < kWgRowsPerThread; ++j)
                             store_split_chunk_mn(bh + (uint32_t)blk * sub_bytes, bh + (uint32_t)(KC + blk) * sub_bytes,
-                                                 r0 + 16 * j, c, dv[j][blk]);
+                                                 r0 + kWgRowStep * j, c, dv[j][blk]);
                     }
                 fence_async_smem();
                 __syncwarp();
@@ -718,7 +731,7 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                     else if (TKC == 1) { b = 4 * g + j4; blk = 0; }
                     else { const int st = 4 * g + j4; b = st / KC; blk = st % KC; }
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
+                    for (int j = 0; j < kWgRowsPerThread; ++j) {
                         float4 u = f4_zero(), q = f4_zero(), v = f4_zero();
                         if (TKC > 0) {
                             // blk is a compile-time constant after unrolling: plain register reads
@@ -736,7 +749,7 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
                         else if (b == 2) z = f4_mul(v, u);
                         else if (b == 3 && nb == 4) z = f4_mul(f4_mul(u, q), v);
                         store_split_chunk_mn(ah + (uint32_t)j4 * sub_bytes, ah + (uint32_t)(4 + j4) * sub_bytes,
-                                             r0 + 16 * j, c, z);
+                                             r0 + kWgRowStep * j, c, z);
                     }
                 }
                 fence_async_smem();
@@ -751,7 +764,7 @@ edge_interact_bwd_wgrad_tc_kernel(const float* __restrict__ xp, int64_t xp_ld,
             mbar_wait(smem_u32(&bar_done), 0);
             fence_after_sync();
         }
-        for (int g = 0; g < ng; ++g)
+        for (int g = 0; g < ng && warp < 4; ++g)            // warps 0-3 own the four TMEM lane quadrants
             for (int c0 = 0; c0 < dim; c0 += 16) {
                 float acc[16];
                 if (my_tiles > 0) {
