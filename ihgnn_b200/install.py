@@ -36,9 +36,12 @@ def replacement_classes() -> Dict[str, type]:
     return out
 
 
-def patch_reference(reference_dir: str = None) -> Dict[str, int]:
+def patch_reference(reference_dir: str = None, fast_eval: bool = True) -> Dict[str, int]:
     """Rebind the hot-path classes inside the imported reference modules.  Returns, per class
-    name, how many module attributes were rebound."""
+    name, how many module attributes were rebound.  `fast_eval` also rebinds
+    `Helpers.TrainTestHelper.test_and_get_avg_metrics` (:37-102) to the batched GPU ranking with the
+    same signature and return value (`model.make_fast_test_and_get_avg_metrics`); Main.py picks it
+    up through its `from Helpers.TrainTestHelper import ...`."""
     if reference_dir and reference_dir not in sys.path:
         sys.path.insert(0, reference_dir)
     mods = [importlib.import_module(m) for m in (
@@ -70,6 +73,14 @@ def patch_reference(reference_dir: str = None) -> Dict[str, int]:
                     for name in _REPLACED:
                         if v in old.get(name, ()):
                             reg[i] = new[name]
+    if fast_eval:
+        tth = importlib.import_module("Helpers.TrainTestHelper")
+        if not getattr(tth.test_and_get_avg_metrics, "_ihgnn_b200", False):
+            from .model import make_fast_test_and_get_avg_metrics
+            metrics_cls = importlib.import_module("Helpers.Metrics").Metrics
+            fast = make_fast_test_and_get_avg_metrics(tth.test_and_get_avg_metrics, metrics_cls)
+            fast._ihgnn_b200 = True
+            tth.test_and_get_avg_metrics = fast
     return counts
 
 

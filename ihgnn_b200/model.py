@@ -125,36 +125,107 @@ class RawGnn(nn.Module):
         self._saved_output_feature = None
 
 
-def evaluate_searches(model: RawGnn, logs, batch_size: int = 8192, k: int = 10):
-    """Batched form of `test_and_get_avg_metrics`, Helpers/TrainTestHelper.py:37-102 for RawGnn models: `logs` is a sequence of
-    (user, query, interacted_items[, ...]) tuples (TestSearchLogDataLoader.logs, Dataset.py:297-318).
-    Features are saved once, every search is ranked against all items by `RawGnn.rank` (one launch
-    per `batch_size` searches instead of one forward + full sort + .cpu() per search), and
-    HR@10 / NDCG@10 / MAP@10 follow Helpers/Metrics.py:47-110 (flags all 1) on the host.
-    Returns (hit_ratio, ndcg, map) averaged over the searches."""
+def rank_searches(model, user_indices: Tensor, query_indices: Tensor, candidates: Optional[Tensor] = None,
+                  k: int = 10):
+    """`RawGnn.rank` for any RawGnn-shaped model -- this package's or the reference's own
+    (Models/RawGnn.py) running on the drop-in layers: needs `_saved_output_feature`
+    (`save_features_for_test()` must have run), `dataset` offsets and a HemPredictionLayer."""
+    feat = model._saved_output_feature
+    if feat is None:
+        raise RuntimeError("rank_searches: call model.save_features_for_test() first")
+    ds, p = model.dataset, model.prediction_layer
+    return F_.rank_topk(feat, user_indices, query_indices, p.items_bias, p.lambda_muq,
+                        query_row0=ds.query_start_index_in_graph, item_row0=ds.item_start_index_in_graph,
+                        item_count=ds.item_count, candidates=candidates, k=k)
+
+
+def search_metrics(model, logs, batch_size: int = 8192):
+    """Per-search (HR@10, NDCG@10, MAP@10) of `logs` = sequence of (user, query, interacted_items, ...)
+    tuples (TestSearchLogDataLoader.logs, Dataset.py:297-318), every search ranked against all items
+    in batches of `batch_size` searches per launch; the metric arithmetic is Helpers/Metrics.py:47-110
+    for flags_are_all_1 (the only form the reference's loader emits).  `model` must hold saved features."""
     import math
-    dev = model.embeddings.embedding_user.weight.device
+    dev = model._saved_output_feature.device
+    out = []
+    for s in range(0, len(logs), batch_size):
+        part = logs[s:s + batch_size]
+        users = torch.tensor([l[0] for l in part], dtype=torch.int64).to(dev)
+        queries = torch.tensor([l[1] for l in part], dtype=torch.int64).to(dev)
+        top, _ = rank_searches(model, users, queries, None, 10)
+        top = top.cpu().tolist()                               # one D2H copy per batch
+        for rec, l in zip(top, part):
+            items = [int(x) for x in l[2]]
+            hits = [rec.index(it) for it in items if it in rec]                         # Metrics.py:66-68
+            n10 = min(len(items), 10)                                                   # :62
+            hr = len(hits) / n10                                                        # :80
+            ndcg = sum(math.log(2, i + 2) for i in hits) / sum(math.log(2, i + 2) for i in range(n10))
+            ap = sum((j + 1) / (i + 1) for j, i in enumerate(hits)) / len(hits) if hits else 0.0
+            out.append((hr, ndcg, ap))
+    return out
+
+
+def evaluate_searches(model, logs, batch_size: int = 8192, k: int = 10):
+    """Batched form of `test_and_get_avg_metrics` (Helpers/TrainTestHelper.py:37-102) for RawGnn
+    models: features are saved once, every search is ranked against all items (one launch per
+    `batch_size` searches instead of one forward + full sort + .cpu() per search) and HR@10 /
+    NDCG@10 / MAP@10 are averaged over the searches.  Returns (hit_ratio, ndcg, map)."""
     logs = [l for l in logs if len(l[2]) > 0]
     if not logs:
         return 0.0, 0.0, 0.0
-    hr = ndcg = mp = 0.0
     with torch.no_grad():
         model.save_features_for_test()
         try:
-            for s in range(0, len(logs), batch_size):
-                part = logs[s:s + batch_size]
-                users = torch.tensor([l[0] for l in part], dtype=torch.int64).to(dev)
-                queries = torch.tensor([l[1] for l in part], dtype=torch.int64).to(dev)
-                top, _ = model.rank(users, queries, None, k)
-                top = top.cpu().tolist()                       # one D2H copy per batch
-                for rec, l in zip(top, part):
-                    items = [int(x) for x in l[2]]
-                    hits = [rec.index(it) for it in items if it in rec]                 # Metrics.py:66-68
-                    n10 = min(len(items), 10)                                           # :62
-                    hr += len(hits) / n10                                               # :80
-                    ndcg += sum(math.log(2, i + 2) for i in hits) / sum(math.log(2, i + 2) for i in range(n10))
-                    mp += sum((j + 1) / (i + 1) for j, i in enumerate(hits)) / len(hits) if hits else 0.0
+            per = search_metrics(model, logs, batch_size)
         finally:
             model.clear_saved_feature()
-    n = len(logs)
-    return hr / n, ndcg / n, mp / n
+    n = len(per)
+    return sum(p[0] for p in per) / n, sum(p[1] for p in per) / n, sum(p[2] for p in per) / n
+
+
+def make_fast_test_and_get_avg_metrics(original, metrics_cls, log_print=None):
+    """A drop-in for the reference's `test_and_get_avg_metrics(model, dataset_train, dataloader,
+    get_long_tail_stat=False)` (Helpers/TrainTestHelper.py:37-102) with the same return value --
+    (per-user averages or None, average Metrics, seconds) -- that ranks the searches in batches on the
+    GPU.  `metrics_cls` is the reference's `Helpers.Metrics.Metrics`; models without saved-feature
+    support (Srrl) go to `original`."""
+    import time
+
+    def test_and_get_avg_metrics(model, dataset_train, dataloader, get_long_tail_stat: bool = False):
+        if not (hasattr(model, "save_features_for_test") and hasattr(model, "prediction_layer")
+                and hasattr(dataloader, "logs")):
+            return original(model, dataset_train, dataloader, get_long_tail_stat)
+        start = time.time()
+        logs = dataloader.logs
+        total = metrics_cls()
+        per_user = [[] for _ in range(dataset_train.user_count)] if get_long_tail_stat else None
+        with torch.no_grad():
+            model.save_features_for_test()                                              # :50-51
+            try:
+                per = search_metrics(model, logs)
+            finally:
+                model.clear_saved_feature()                                             # :87-88
+        for l, (hr, ndcg, ap) in zip(logs, per):
+            m = metrics_cls()
+            m.HitRatio_at10, m.NDCG_at10, m.MAP_at10 = hr, ndcg, ap
+            total.add_to_self(m)                                                        # :65-66
+            if per_user is not None:
+                per_user[int(l[0])].append(m)                                           # :69-70
+        u_metrics = None
+        if per_user is not None:                                                        # :72-81
+            u_metrics = []
+            for ms in per_user:
+                if not ms:
+                    u_metrics.append(None)
+                else:
+                    m0 = metrics_cls()
+                    for m in ms:
+                        m0.add_to_self(m)
+                    u_metrics.append(m0.divide_and_get_new(len(ms)))
+        avg = total.divide_and_get_new(len(logs))                                       # :91
+        elapsed = time.time() - start
+        if log_print is not None:
+            log_print(f"test done in {elapsed:<.2f} s, {len(logs)} search logs (batched GPU ranking).")
+            log_print(avg.to_string(highlight=True))
+        return u_metrics, avg, elapsed
+
+    return test_and_get_avg_metrics

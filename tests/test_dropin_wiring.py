@@ -51,6 +51,10 @@ assert D.PpsHyperGraph is new["PpsHyperGraph"] and G.FeatureInteractor is new["F
 assert Models.parse_gnn_layer["IHGNN"] is new["IHGNNLayer"] and Models.parse_gnn_layer["ihgnn"] is new["IHGNNLayer"]
 assert Models.parse_gnn_layer["HGCN"] is new["HGCNLayer"] and Models.parse_gnn_layer["GCN"] is new["GCNLayer"]
 assert D.Pps2DGraph is new["Pps2DGraph"] and R.GCNLayer is new["GCNLayer"]
+# the evaluation loop is rebound to the batched GPU ranking, same signature
+import Helpers.TrainTestHelper as T
+assert getattr(T.test_and_get_avg_metrics, "_ihgnn_b200", False)
+assert list(inspect.signature(T.test_and_get_avg_metrics).parameters) == ["model", "dataset_train", "dataloader", "get_long_tail_stat"]
 # the layers read the reference's own settings object once it is importable
 from ihgnn_b200 import settings
 assert settings.Gs is Gs

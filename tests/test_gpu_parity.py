@@ -486,6 +486,36 @@ def test_rank_topk_matches_reference_eval_loop(golden):
     want = golden["ref64.rank_metrics"].mean(0)
     assert np.allclose([hr, ndcg, mp], want, rtol=0, atol=1e-9), ([hr, ndcg, mp], want)
 
+    # the drop-in for Helpers/TrainTestHelper.py:37-102 (what install.patch_reference binds), driven with
+    # a stand-in for the reference's Metrics class (Helpers/Metrics.py:8-31) and loader (.logs)
+    from ihgnn_b200.model import make_fast_test_and_get_avg_metrics
+
+    class Metrics:
+        def __init__(self):
+            self.NDCG_at10 = self.HitRatio_at10 = self.MAP_at10 = 0.0
+
+        def add_to_self(self, o):
+            self.NDCG_at10 += o.NDCG_at10; self.HitRatio_at10 += o.HitRatio_at10; self.MAP_at10 += o.MAP_at10
+
+        def divide_and_get_new(self, n):
+            r = Metrics()
+            r.NDCG_at10, r.HitRatio_at10, r.MAP_at10 = self.NDCG_at10 / n, self.HitRatio_at10 / n, self.MAP_at10 / n
+            return r
+
+        def to_string(self, highlight=False):
+            return ""
+
+    class Loader:
+        pass
+    loader = Loader()
+    loader.logs = [(u, q, it, None, True) for u, q, it in logs]
+    fast = make_fast_test_and_get_avg_metrics(None, Metrics)
+    u_metrics, avg, secs = fast(m, m.dataset, loader, True)
+    assert np.allclose([avg.HitRatio_at10, avg.NDCG_at10, avg.MAP_at10], want, rtol=0, atol=1e-9)
+    assert len(u_metrics) == m.dataset.user_count and secs >= 0 and m._saved_output_feature is None
+    seen_users = {u for u, _, _ in logs}
+    assert all((u_metrics[u] is not None) == (u in seen_users) for u in range(m.dataset.user_count))
+
 
 @pytest.mark.parametrize("D,I,C,k", [(192, 5000, 1000, 10), (64, 3000, None, 10), (512, 2500, 1500, 32),
                                      (128, 700, 37, 1), (48, 300, 5, 10)])
