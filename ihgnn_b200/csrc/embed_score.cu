@@ -84,6 +84,9 @@ halo_copy_kernel(HaloSegs segs, const int64_t* __restrict__ src_rows, int64_t sr
 // duplicate in ascending b and adds the total to the destination row once => deterministic.
 // Both scans over idx are block-parallel: windows of 128 positions are tested at once, the matches
 // of a window are compacted IN ORDER (ballot + prefix) into shared memory, then added in that order.
+constexpr int kScatterSmemIdx = 2048;          // batches up to this size keep the whole index list in shared memory
+
+template <bool SMEM_IDX>
 __global__ void __launch_bounds__(128)
 scatter_add_rows_kernel(const float* __restrict__ g, int64_t g_ld, const int64_t* __restrict__ idx,
                         int64_t idx_offset, int64_t count, float* __restrict__ out,
@@ -91,13 +94,19 @@ scatter_add_rows_kernel(const float* __restrict__ g, int64_t g_ld, const int64_t
     __shared__ int dup_before;
     __shared__ int warp_cnt[4];
     __shared__ int match[128];
+    __shared__ int64_t s_idx[SMEM_IDX ? kScatterSmemIdx : 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t b = blockIdx.x;
-    const int64_t my = __ldg(idx + b);
+    if (SMEM_IDX) {
+        // one coalesced sweep: every later scan reads shared memory instead of chaining global loads
+        for (int64_t j = tid; j < count; j += blockDim.x) s_idx[j] = __ldg(idx + j);
+    }
     if (tid == 0) dup_before = 0;
     __syncthreads();
+    auto index_at = [&](int64_t j) -> int64_t { return SMEM_IDX ? s_idx[j] : __ldg(idx + j); };
+    const int64_t my = index_at(b);
     int found = 0;
-    for (int64_t j = tid; j < b; j += blockDim.x) found |= (__ldg(idx + j) == my);
+    for (int64_t j = tid; j < b; j += blockDim.x) found |= (index_at(j) == my);
     if (found) dup_before = 1;   // benign race: every writer stores 1
     __syncthreads();
     if (dup_before) return;
@@ -109,7 +118,7 @@ scatter_add_rows_kernel(const float* __restrict__ g, int64_t g_ld, const int64_t
     }
     for (int64_t j0 = b + 1; j0 < count; j0 += 128) {
         const int64_t j = j0 + tid;
-        const bool hit = j < count && __ldg(idx + j) == my;
+        const bool hit = j < count && index_at(j) == my;
         const unsigned bal = __ballot_sync(0xffffffffu, hit);
         if (lane == 0) warp_cnt[warp] = __popc(bal);
         __syncthreads();
@@ -310,8 +319,12 @@ int ihg_scatter_add_rows(const float* g, int64_t g_ld, const int64_t* idx, int64
     IHG_REQUIRE(count <= 65536, "scatter_add_rows: count=%lld exceeds the 65536-row batch limit", (long long)count);
     IHG_REQUIRE(dim <= 1024, "scatter_add_rows: dim=%d exceeds 1024", dim);
     if (count <= 0) return IHG_OK;
-    scatter_add_rows_kernel<<<(unsigned)count, 128, 0, as_stream(stream)>>>(g, g_ld, idx, idx_offset,
-                                                                            count, out, out_ld, dim / 4);
+    if (count <= kScatterSmemIdx)
+        scatter_add_rows_kernel<true><<<(unsigned)count, 128, 0, as_stream(stream)>>>(g, g_ld, idx, idx_offset,
+                                                                                      count, out, out_ld, dim / 4);
+    else
+        scatter_add_rows_kernel<false><<<(unsigned)count, 128, 0, as_stream(stream)>>>(g, g_ld, idx, idx_offset,
+                                                                                       count, out, out_ld, dim / 4);
     IHG_LAUNCH_CHECK();
     return IHG_OK;
 }

@@ -684,3 +684,33 @@ def test_phased_segment_reduce_equals_single_pass(dim, mb, monkeypatch):
     F_.phased_segment_reduce(g.plan, E, ef.to(DEV), dim, out=both[:, dim:])
     want_raw = torch.sparse.mm(ref.adjacency(torch.float64), ef.double()).numpy()
     assert max_rel(both[:, dim:].cpu().numpy(), want_raw) < 2e-6 and float(both[:, :dim].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,rows,dim", [(1100, 300, 64), (2048, 50, 192), (5000, 700, 128), (7, 3, 8), (3000, 1, 512)])
+def test_gather_rows_backward_scatter_add(B, rows, dim):
+    """gather_rows / its deterministic scatter-add backward (RawGnn.py:128-133 row selects and their
+    index_put_ backward) with heavy duplication, both the shared-memory index path (B <= 2048) and the
+    global one, against fp64 index_add_; bitwise reproducible."""
+    from ihgnn_b200 import functional as F_
+    gen = torch.Generator().manual_seed(B + dim)
+    table = torch.randn(rows + 5, dim, generator=gen)
+    idx = torch.randint(0, rows, (B,), generator=gen)
+    gout = torch.randn(B, dim, generator=gen)
+    t = table.to(DEV).requires_grad_(True)
+    out = F_.gather_rows(t, idx.to(DEV), 2)
+    assert torch.equal(out.detach().cpu(), table[idx + 2])
+    out.backward(gout.to(DEV))
+    want = torch.zeros(rows + 5, dim, dtype=torch.float64).index_add_(0, idx + 2, gout.double())
+    assert max_rel(t.grad.cpu().numpy(), want.numpy()) < 2e-6
+    g1 = t.grad.clone()
+    t.grad = None
+    F_.gather_rows(t, idx.to(DEV), 2).backward(gout.to(DEV))
+    assert torch.equal(g1, t.grad)
+    # several selections out of one table share ONE dense gradient
+    t.grad = None
+    a, b = F_.gather_rows_multi(t, [idx.to(DEV), idx.flip(0).to(DEV)], [2, 0])
+    (a.sum() + 2 * b.sum()).backward()
+    want2 = torch.zeros(rows + 5, dim, dtype=torch.float64)
+    want2.index_add_(0, idx + 2, torch.ones(B, dim, dtype=torch.float64))
+    want2.index_add_(0, idx.flip(0), 2 * torch.ones(B, dim, dtype=torch.float64))
+    assert max_rel(t.grad.cpu().numpy(), want2.numpy()) < 2e-6
