@@ -326,6 +326,9 @@ def run_gpu_arm(args, log, layers, d):
         conv_step()
     n_before = len(sampler.rows)
     use_graph = world == 1 and os.environ.get("IHG_CUDA_GRAPH", "1") != "0"
+    # N > 1: the conv step (halo pushes / pulls, symmetric-memory barriers, the NCCL all-reduce of the
+    # dense gradients) is sync-free as well and can be captured per rank; opt-in until proven at N = 8
+    use_conv_graph = use_graph or (world > 1 and os.environ.get("IHG_DIST_GRAPH", "0") == "1")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     # --- per-kernel breakdown: eager steps with CUDA events around every C-ABI call ------
@@ -346,7 +349,7 @@ def run_gpu_arm(args, log, layers, d):
 
     # --- M1 headline: the same step, captured in a CUDA graph on one GPU (every entry point of the
     # library is sync-free and allocation-free, so the ~30 launches replay as one) -------------
-    if use_graph:
+    if use_conv_graph:
         from ihgnn_b200.graphs import graph_callable
         conv_graph = graph_callable(conv_step, 2)
         run_conv = conv_graph.replay
@@ -461,7 +464,7 @@ def run_gpu_arm(args, log, layers, d):
                    "l2_policy": "inputs larger than L2 (no flush): per step the kernels stream "
                                 f"{conv_bytes / 1e9:.1f} GB algorithmic vs 126 MB L2",
                    "graph_build_s": t_build,
-                   "cuda_graph": bool(use_graph)},
+                   "cuda_graph": bool(use_conv_graph), "cuda_graph_e2e": bool(use_graph)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,

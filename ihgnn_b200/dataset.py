@@ -100,23 +100,79 @@ class GraphDataset:
     def from_files(cls, directory: str, device, train_file: str = "train_data.csv") -> "GraphDataset":
         """Read the reference's on-disk format (graph_info.txt, queries_multihot.txt,
         train_data.csv; Dataset.py:141-200, Helpers/SearchLog.py:63-71)."""
-        with open(os.path.join(directory, "graph_info.txt"), encoding="utf-8") as f:
-            U, Q, I, V = (int(p) for p in f.readline().split())
-        words, offsets = [], []
-        with open(os.path.join(directory, "queries_multihot.txt"), encoding="utf-8") as f:
-            for line in f:
-                offsets.append(len(words))
-                words.extend(int(p) + 1 for p in line.split())
-        pu, pq, pi = [], [], []
-        with open(os.path.join(directory, train_file), encoding="utf-8") as f:
-            f.readline()
-            for line in f:
-                u, q, _t, items, _pages, _pos, flags, _times = line.strip().split(",")
-                for it, fl in zip(items.split(), flags.split()):
-                    if int(fl) > 0:
-                        pu.append(int(u)); pq.append(int(q)); pi.append(int(it))
-        return cls(U, Q, I, V, np.asarray(words, dtype=np.int64), np.asarray(offsets, dtype=np.int64),
-                   np.asarray(pu), np.asarray(pq), np.asarray(pi), device)
+        d = read_reference_files(directory, train_file)
+        return cls(d["user_count"], d["query_count"], d["item_count"], d["vocab_size"], d["bag_words"],
+                   d["bag_offsets"], d["pos_user"], d["pos_query"], d["pos_item"], device)
+
+
+def _split_ints(fields) -> np.ndarray:
+    """All space-separated integers of a sequence of strings, concatenated (one C-level split)."""
+    text = " ".join(fields)
+    return np.array(text.split(), dtype=np.int64) if text.strip() else np.zeros(0, dtype=np.int64)
+
+
+def read_search_logs(path: str):
+    """One search-log CSV of the reference (header, then `user,query,search_time,items,pages,positions,
+    interactions,times` with space-separated list fields; Helpers/SearchLog.py:63-75,
+    SearchLogCollection.py:26-32), read column-wise instead of one Python object per row:
+    (log_user [n], log_query [n], log_ptr [n+1], items [nnz], flags [nnz])."""
+    users, queries, items_f, flags_f = [], [], [], []
+    with open(path, encoding="utf-8") as f:
+        f.readline()                                               # header (SearchLogCollection.py:29)
+        for line in f:
+            if not line.strip():
+                continue
+            parts = line.rstrip("\n").split(",")
+            users.append(parts[0]); queries.append(parts[1]); items_f.append(parts[3]); flags_f.append(parts[6])
+    n = len(users)
+    log_user = np.array(users, dtype=np.int64) if n else np.zeros(0, np.int64)
+    log_query = np.array(queries, dtype=np.int64) if n else np.zeros(0, np.int64)
+    counts = np.fromiter((len(s.split()) for s in items_f), dtype=np.int64, count=n)
+    log_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(counts, out=log_ptr[1:])
+    items, flags = _split_ints(items_f), _split_ints(flags_f)
+    if items.shape[0] != log_ptr[-1] or flags.shape[0] != log_ptr[-1]:
+        raise ValueError(f"{path}: items / interactions lists of unequal length")
+    return log_user, log_query, log_ptr, items, flags
+
+
+def read_reference_files(directory: str, train_file: str = "train_data.csv") -> dict:
+    """Host-side reader of a reference dataset directory (Dataset.py:141-212): counts from
+    graph_info.txt, EmbeddingBag inputs from queries_multihot.txt (word ids + 1, :165-176), the
+    positive (user, query, item) interactions of `train_file` in file order (flag > 0, one per
+    interacted item, :196-200 / SearchLog.py:199-207), plus the raw logs for negative-item lookups."""
+    with open(os.path.join(directory, "graph_info.txt"), encoding="utf-8") as f:
+        U, Q, I, V = (int(p) for p in f.readline().split())
+    with open(os.path.join(directory, "queries_multihot.txt"), encoding="utf-8") as f:
+        lines = [ln.strip() for ln in f]
+    while lines and len(lines) > Q and not lines[-1]:
+        lines.pop()                                                # trailing blank lines are not queries
+    lens = np.fromiter((len(ln.split()) for ln in lines), dtype=np.int64, count=len(lines))
+    offsets = np.zeros(len(lines), dtype=np.int64)
+    if len(lines) > 1:
+        np.cumsum(lens[:-1], out=offsets[1:])
+    words = _split_ints(lines) + 1                                 # Dataset.py:169: index + 1, row 0 is padding
+    log_user, log_query, log_ptr, items, flags = read_search_logs(os.path.join(directory, train_file))
+    per_log = np.diff(log_ptr)
+    keep = flags > 0
+    return {"user_count": U, "query_count": Q, "item_count": I, "vocab_size": V,
+            "bag_words": words, "bag_offsets": offsets,
+            "pos_user": np.repeat(log_user, per_log)[keep], "pos_query": np.repeat(log_query, per_log)[keep],
+            "pos_item": items[keep],
+            "log_user": log_user, "log_query": log_query, "log_ptr": log_ptr, "log_items": items, "log_flags": flags}
+
+
+def read_test_logs(path: str):
+    """`TestSearchLogDataLoader.logs` (Dataset.py:301-318): (user, query, interacted items, None, True)
+    for every search log with at least one interaction."""
+    log_user, log_query, log_ptr, items, flags = read_search_logs(path)
+    logs = []
+    for k in range(log_user.shape[0]):
+        a, b = int(log_ptr[k]), int(log_ptr[k + 1])
+        hit = items[a:b][flags[a:b] > 0]
+        if hit.size:
+            logs.append((int(log_user[k]), int(log_query[k]), [int(x) for x in hit], None, True))
+    return logs
 
 
 class DeviceBatchSampler:

@@ -139,12 +139,26 @@ def rank_searches(model, user_indices: Tensor, query_indices: Tensor, candidates
                         item_count=ds.item_count, candidates=candidates, k=k)
 
 
+def metrics_at_10(recommended, interacted_items):
+    """(HR@10, NDCG@10, MAP@10) of one search from its top-10 item ids: the arithmetic of
+    `Metrics.calculate_on_all_items` for flags_are_all_1 (Helpers/Metrics.py:60-110), including its
+    MAP convention (hits enumerated in `interacted_items` order, :105-109).  Pure host code."""
+    import math
+    rec = [int(x) for x in recommended][:10]
+    items = [int(x) for x in interacted_items]
+    hits = [rec.index(it) for it in items if it in rec]                                 # Metrics.py:66-68
+    n10 = min(len(items), 10)                                                           # :62
+    hr = len(hits) / n10                                                                # :80
+    ndcg = sum(math.log(2, i + 2) for i in hits) / sum(math.log(2, i + 2) for i in range(n10))   # :84, :93-103
+    ap = sum((j + 1) / (i + 1) for j, i in enumerate(hits)) / len(hits) if hits else 0.0          # :81, :105-109
+    return hr, ndcg, ap
+
+
 def search_metrics(model, logs, batch_size: int = 8192):
     """Per-search (HR@10, NDCG@10, MAP@10) of `logs` = sequence of (user, query, interacted_items, ...)
     tuples (TestSearchLogDataLoader.logs, Dataset.py:297-318), every search ranked against all items
     in batches of `batch_size` searches per launch; the metric arithmetic is Helpers/Metrics.py:47-110
     for flags_are_all_1 (the only form the reference's loader emits).  `model` must hold saved features."""
-    import math
     dev = model._saved_output_feature.device
     out = []
     for s in range(0, len(logs), batch_size):
@@ -153,14 +167,7 @@ def search_metrics(model, logs, batch_size: int = 8192):
         queries = torch.tensor([l[1] for l in part], dtype=torch.int64).to(dev)
         top, _ = rank_searches(model, users, queries, None, 10)
         top = top.cpu().tolist()                               # one D2H copy per batch
-        for rec, l in zip(top, part):
-            items = [int(x) for x in l[2]]
-            hits = [rec.index(it) for it in items if it in rec]                         # Metrics.py:66-68
-            n10 = min(len(items), 10)                                                   # :62
-            hr = len(hits) / n10                                                        # :80
-            ndcg = sum(math.log(2, i + 2) for i in hits) / sum(math.log(2, i + 2) for i in range(n10))
-            ap = sum((j + 1) / (i + 1) for j, i in enumerate(hits)) / len(hits) if hits else 0.0
-            out.append((hr, ndcg, ap))
+        out.extend(metrics_at_10(rec, l[2]) for rec, l in zip(top, part))
     return out
 
 
