@@ -537,40 +537,34 @@ def allreduce_dense_grads(module: torch.nn.Module, group=None) -> None:
 # sharded model: row-sharded embedding tables + sharded conv stack + replicated scorer
 # ----------------------------------------------------------------------------------------
 class _FetchRowsFn(torch.autograd.Function):
-    """Rows of a row-sharded matrix by GLOBAL id, available on every rank:
-    out[j] = F[global_ids[j]].  Each rank fills the rows it owns into a zero buffer, one
-    all-reduce(sum) completes it (the batch head needs only B x 3 rows, SURVEY 8e "tiny").
-    Backward: every rank already holds the full gradient; it scatter-adds the rows it owns
-    (duplicates summed in ascending j: deterministic)."""
+    """Rows of a row-sharded matrix by GLOBAL id, available on every rank: out[j] = F[global_ids[j]].
+    Fixed-shape and sync-free: every rank gathers ONE row per requested id -- its own row when it owns
+    the id (mask 1), an arbitrary own row otherwise (mask 0) -- zeroes the rows it does not own and one
+    all-reduce(sum) completes the matrix (the batch head needs only B x 3 rows, SURVEY 8e "tiny").
+    Backward: every rank already holds the full gradient; it scatter-adds the masked rows (the ones it
+    does not own contribute exact zeros; duplicates summed in ascending j: deterministic)."""
 
     @staticmethod
-    def forward(ctx, f_own, local_rows, positions, total: int, group):
+    def forward(ctx, f_own, local_rows, mask, group):
         import torch.distributed as dist
         from . import functional as F_
-        from . import _lib
-        d = int(f_own.shape[1])
-        out = torch.zeros((total, d), dtype=torch.float32, device=f_own.device)
-        if positions.numel():
-            mine = F_.gather_rows_raw(f_own, local_rows, 0)
-            _lib.call("ihg_scatter_add_rows", _lib.ptr(mine), d, _lib.ptr(positions), 0, int(positions.numel()),
-                      _lib.ptr(out), d, d, _lib.stream_ptr())
+        out = F_.gather_rows_raw(f_own, local_rows, 0)
+        out.mul_(mask.view(-1, 1))
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
-        ctx.save_for_backward(local_rows, positions)
+        ctx.save_for_backward(local_rows, mask)
         ctx.shape = tuple(f_own.shape)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        from . import functional as F_
         from . import _lib
-        local_rows, positions = ctx.saved_tensors
+        local_rows, mask = ctx.saved_tensors
         d = int(dout.shape[1])
+        g = (dout * mask.view(-1, 1)).contiguous()
         df = torch.zeros(ctx.shape, dtype=torch.float32, device=dout.device)
-        if positions.numel():
-            mine = F_.gather_rows_raw(dout.contiguous(), positions, 0)
-            _lib.call("ihg_scatter_add_rows", _lib.ptr(mine), d, _lib.ptr(local_rows), 0, int(local_rows.numel()),
-                      _lib.ptr(df), d, d, _lib.stream_ptr())
-        return df, None, None, None, None
+        _lib.call("ihg_scatter_add_rows", _lib.ptr(g), d, _lib.ptr(local_rows), 0, int(local_rows.numel()),
+                  _lib.ptr(df), d, d, _lib.stream_ptr())
+        return df, None, None, None
 
 
 class ShardedRawGnn(torch.nn.Module):
@@ -641,14 +635,16 @@ class ShardedRawGnn(torch.nn.Module):
         cache = getattr(self, "_range_cache", None)
         if cache is None or cache[0] != B:
             mk = lambda a, b_, c: torch.tensor([a] * B + [b_] * B + [c] * B, device=ids.device)
+            # ids this rank does not own read a spread-out dummy own row (masked to zero afterwards):
+            # distinct rows keep the duplicate chains of the deterministic scatter-add short
+            dummy = torch.arange(3 * B, device=ids.device) % max(p.n_own, 1)
             cache = (B, mk(p.ub[r], p.qb[r], p.ib[r]), mk(p.ub[r + 1], p.qb[r + 1], p.ib[r + 1]),
-                     mk(0, p.Uo, p.Uo + p.Qo))
+                     mk(0, p.Uo, p.Uo + p.Qo), dummy)
             self._range_cache = cache
-        _, lo, hi, base = cache
+        _, lo, hi, base, dummy = cache
         mine = (ids >= lo) & (ids < hi)
-        positions = torch.nonzero(mine).view(-1)
-        local_rows = (ids - lo + base)[positions]
-        rows = _FetchRowsFn.apply(f_own, local_rows, positions, 3 * B, self.g.group)
+        local_rows = torch.where(mine, ids - lo + base, dummy)
+        rows = _FetchRowsFn.apply(f_own, local_rows, mine.to(torch.float32), self.g.group)
         return self.prediction_layer(rows[:B], rows[B:2 * B], rows[2 * B:], items)
 
     @torch.no_grad()

@@ -27,8 +27,8 @@ PINNING: the reference has no tests or golden vectors of its own (SURVEY.md sect
 This oracle is pinned against outputs of the reference itself, executed in the build
 container by oracle/gen_golden.py (fixtures under tests/golden/), by
 tests/test_oracle_golden.py -- indices bit-exact, fp32 values to ~1 ulp-level agreement
--- and against the live reference where /root/reference is present
-(tests/test_oracle_live_reference.py).
+-- and the host-side readers / drop-in wiring are checked against the live reference where
+/root/reference is present (tests/test_loaders.py, tests/test_dropin_wiring.py).
 """
 from __future__ import annotations
 

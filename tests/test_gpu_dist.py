@@ -159,3 +159,86 @@ def test_sharded_ranking_replicated_features():
     mp.spawn(_rank_worker, args=(world, port, ret), nprocs=world, join=True)
     assert len(ret) == world
     assert all(all(v) for v in ret.values()), dict(ret)
+
+
+def _train_worker(rank: int, world: int, port: int, ret):
+    sys.path.insert(0, REPO)
+    import torch.distributed as dist
+    from ihgnn_b200 import HemPredictionLayer, IHGNNLayer, RawGnn, synth
+    from ihgnn_b200.dataset import GraphDataset
+    from ihgnn_b200.dist import PartitionPlan, ShardedHyperGraph, ShardedRawGnn
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        U, Q, I, E, V, d, L = 3000, 100, 1200, 40_000, 50, 64, 2
+        log = synth.make_search_log(U, Q, I, E, V, shape="cikm", seed=9, zipf=1.0)
+        # ---- the single-GPU model on the global graph: identical on every rank (same seed)
+        ds = GraphDataset.from_search_log(log, dev)
+        torch.manual_seed(5)
+        ref = RawGnn(device=dev, dataset=ds, embedding_size=d, gnn_layer_type=IHGNNLayer, gnn_layer_count=L,
+                     feature_interaction_order=3, phase2_attention=False, predictions=HemPredictionLayer,
+                     lambda_muq=0.5).to(dev)
+        # ---- the sharded model with the same parameters
+        plan = PartitionPlan(log.pos_user, log.pos_query, log.pos_item, U, Q, I, world, rank)
+        sg = ShardedHyperGraph(plan, dev)
+        words, offsets = log.bag_inputs()
+        sh = ShardedRawGnn(sg, words, offsets, V, d, L, 3).to(dev)
+        u0, u1, i0, i1 = int(plan.ub[rank]), int(plan.ub[rank + 1]), int(plan.ib[rank]), int(plan.ib[rank + 1])
+        with torch.no_grad():
+            sh.embedding_user.copy_(ref.embeddings.embedding_user.weight[1:][u0:u1])
+            sh.embedding_item.copy_(ref.embeddings.embedding_item.weight[1:][i0:i1])
+            sh.embedding_bag_vocabulary.copy_(ref.embeddings.embedding_bag_vocabulary.weight)
+            sh.prediction_layer.items_bias.copy_(ref.prediction_layer.items_bias)
+            for a, b in zip(sh.gnns, ref.gnns):
+                a.load_state_dict(b.state_dict(), strict=True)
+        rng = np.random.default_rng(3)
+        B = 64
+        pick = rng.choice(E, size=B, replace=False)
+        users = torch.from_numpy(np.concatenate([log.pos_user[pick], np.repeat(log.pos_user[pick], 10)])).to(dev)
+        queries = torch.from_numpy(np.concatenate([log.pos_query[pick], np.repeat(log.pos_query[pick], 10)])).to(dev)
+        items = torch.from_numpy(np.concatenate([log.pos_item[pick], rng.integers(0, I, size=10 * B)])).to(dev)
+        flags = torch.cat([torch.ones(B), torch.zeros(10 * B)]).to(dev)
+
+        def step(m, sync=None):
+            m.zero_grad(set_to_none=True)
+            sc = m(users, queries, items)
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(sc, flags)
+            loss.backward()
+            if sync:
+                sync()
+            return sc.detach(), float(loss)
+
+        sc_r, loss_r = step(ref)
+        sc_s, loss_s = step(sh, sh.sync_grads)
+        rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+        errs = {"scores": rel(sc_s, sc_r), "loss": abs(loss_s - loss_r) / abs(loss_r),
+                "user": rel(sh.embedding_user.grad, ref.embeddings.embedding_user.weight.grad[1:][u0:u1]),
+                "item": rel(sh.embedding_item.grad, ref.embeddings.embedding_item.weight.grad[1:][i0:i1]),
+                "vocab": rel(sh.embedding_bag_vocabulary.grad, ref.embeddings.embedding_bag_vocabulary.weight.grad),
+                "bias": rel(sh.prediction_layer.items_bias.grad, ref.prediction_layer.items_bias.grad)}
+        for k, (a, b) in enumerate(zip(sh.gnns, ref.gnns)):
+            for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+                errs[f"gnn{k}.{n}"] = rel(pa.grad, pb.grad)
+        sc_s2, loss_s2 = step(sh, sh.sync_grads)
+        ret[rank] = (errs, bool(torch.equal(sc_s, sc_s2)) and loss_s == loss_s2)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_training_step_matches_single_gpu():
+    """ShardedRawGnn.forward -> BCE -> backward -> sync_grads (what bench.py's e2e leg runs at N > 1)
+    against the single-GPU RawGnn with the same parameters: scores, loss, the sharded embedding
+    gradients and the all-reduced replicated gradients; deterministic."""
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_train_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r, (errs, same) in ret.items():
+        bad = {k: v for k, v in errs.items() if not v < 1e-5}
+        assert not bad, (r, bad)
+        assert same, r
