@@ -16,7 +16,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libihgnn_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lib: Optional[ctypes.CDLL] = None
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define IHG_ABI_VERSION 1
+#define IHG_ABI_VERSION 2   /* 2: ihg_segment_reduce gained `flags`, two-hop / ranking / sampler entry points */
 
 #define IHG_OK 0
 #define IHG_ERR_INVALID_ARGUMENT 1   /* bad shape / null pointer / unsupported dimension   */

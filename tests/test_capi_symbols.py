@@ -35,13 +35,37 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_error_channel(lib):
-    assert lib.ihg_abi_version() == 1
+    assert lib.ihg_abi_version() == 2
     assert lib.ihg_last_error() is not None
     # argument validation happens before any CUDA call, so it can be exercised without a GPU
     rc = lib.ihg_node_linear(None, 0, None, 1, 64, 64, 0, None, None, 0, 10, 0, 0, None, 0, None)
     assert rc == 1 and b"null pointer" in lib.ihg_last_error()
     rc = lib.ihg_edge_interact_fwd(1, 64, 1, 64, 1, 64, 5, 1, 10, 1, 64, 64, None, 0, None)
     assert rc == 1 and b"order" in lib.ihg_last_error()
+
+
+def test_new_entry_points_validate_arguments(lib):
+    """ihg_rank_topk / ihg_sample_batch / ihg_two_hop_reduce / ihg_segment_reduce flags: the argument checks
+    run before any CUDA call."""
+    rc = lib.ihg_rank_topk(1, 64, None, 1, 4, 0, None, 10, 0, 10, 1, 0.5, 64, 33, 1, 1, None)
+    assert rc == 1 and b"k=33" in lib.ihg_last_error()
+    rc = lib.ihg_rank_topk(1, 64, None, 1, 4, 0, None, 10, 0, 10, 1, 0.5, 62, 10, 1, 1, None)
+    assert rc == 1 and b"dim=62" in lib.ihg_last_error()
+    rc = lib.ihg_rank_topk(None, 64, None, 1, 4, 0, None, 10, 0, 10, 1, 0.5, 64, 10, 1, 1, None)
+    assert rc == 1 and b"null pointer" in lib.ihg_last_error()
+    rc = lib.ihg_sample_batch(1, 1, 1, 1, 8, 65, 100, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, None)
+    assert rc == 1 and b"neg_per_positive=65" in lib.ihg_last_error()
+    rc = lib.ihg_sample_batch(1, 1, 1, 1, 8, 10, 5, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, None)
+    assert rc == 1 and b"distinct" in lib.ihg_last_error()
+    rc = lib.ihg_two_hop_reduce(None, None, None, 64, None, 1.0, 1.0, 0.0, None, None, None, 64, 64, None)
+    assert rc == 1 and b"null pointer" in lib.ihg_last_error()
+    from ihgnn_b200 import _lib
+    import ctypes
+    csr = _lib.IhgCsr(n_rows=4, nnz=0, rowptr=1, col=None, chunk_len=128, n_seg=4, n_split=0, n_part=0, seg=1,
+                      split_row=None, split_ptr=None)
+    # accumulate mode without an init row
+    rc = lib.ihg_segment_reduce(ctypes.byref(csr), 1, 64, 1, 0, 0, None, None, 0, None, None, None, 1, 64, 64, 1, None)
+    assert rc == 1 and b"accumulate" in lib.ihg_last_error()
 
 
 def test_workspace_queries_are_pure(lib):

@@ -37,7 +37,7 @@ def _model(golden, ds=None):
 
 def test_library_loaded():
     from ihgnn_b200 import _lib
-    assert _lib.lib().ihg_abi_version() == 1
+    assert _lib.lib().ihg_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_graph_build_matches_reference_bit_exact(golden):
