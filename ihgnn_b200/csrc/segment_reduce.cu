@@ -22,14 +22,10 @@
 namespace ihg {
 
 constexpr int kSegWarpsPerBlock = 8;
-
-// dev A/B switches (read once): source rows through ld.global.nc.L1::no_allocate
-static bool seg_stream_loads() { static const bool v = getenv("IHG_SEG_STREAM") != nullptr; return v; }
-static bool th_stream_loads() { static const bool v = getenv("IHG_TH_STREAM") != nullptr; return v; }
 constexpr int kSegUnroll = 4;        // independent 128-bit row gathers in flight per lane group
 constexpr int kSegPerGroup = 1;      // chunks a lane group walks through (strided)
 
-template <int LPR, int VPL, int UNR, int SEGS, int MINB, bool STREAM = false>
+template <int LPR, int VPL, int UNR, int SEGS, int MINB>
 __global__ void __launch_bounds__(kSegWarpsPerBlock * 32, MINB)
 segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src_row_mul,
                       int64_t bound0, int64_t bound1, const int32_t* __restrict__ row_slot,
@@ -93,7 +89,7 @@ segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src
 #pragma unroll
                     for (int w = 0; w < VPL; ++w) {
                         const int cv = gl + w * LPR;
-                        v[u][w] = (ok && cv < nvec) ? (STREAM ? ldg4_stream(src + sr * src_ld + 4 * cv) : ldg4(src + sr * src_ld + 4 * cv)) : f4_zero();
+                        v[u][w] = (ok && cv < nvec) ? ldg4(src + sr * src_ld + 4 * cv) : f4_zero();
                     }
                 }
 #pragma unroll
@@ -236,10 +232,6 @@ static int launch_segment_reduce(const ihg_csr* g, const float* src, int64_t src
         segment_reduce_kernel<LPR, VPL, 2, SEGS, 5><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
             src, src_ld, mul, b0, b1, row_slot, init, init_ld, src_scale, row_scale, g->col, g->n_seg, n_groups,
             reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim, accumulate);
-    else if (seg_stream_loads())
-        segment_reduce_kernel<LPR, VPL, kSegUnroll, SEGS, 0, true><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
-            src, src_ld, mul, b0, b1, row_slot, init, init_ld, src_scale, row_scale, g->col, g->n_seg, n_groups,
-            reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim, accumulate);
     else
         segment_reduce_kernel<LPR, VPL, kSegUnroll, SEGS, 0><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
             src, src_ld, mul, b0, b1, row_slot, init, init_ld, src_scale, row_scale, g->col, g->n_seg, n_groups,
@@ -285,7 +277,7 @@ __global__ void two_hop_index_kernel(const int4* __restrict__ seg, int64_t n_seg
     }
 }
 
-template <int LPR, int VPL, int UNR, int MINB, bool STREAM = false>
+template <int LPR, int VPL, int UNR, int MINB>
 __global__ void __launch_bounds__(kSegWarpsPerBlock * 32, MINB)
 two_hop_reduce_kernel(const float* __restrict__ src, int64_t src_ld,
                       const float* __restrict__ node_scale, float alpha, float own_per_inc, float own_const,
@@ -346,8 +338,8 @@ two_hop_reduce_kernel(const float* __restrict__ src, int64_t src_ld,
                 for (int w = 0; w < VPL; ++w) {
                     const int cv = gl + w * LPR;
                     const bool okc = ok && cv < nvec;
-                    v[u][0][w] = okc ? (STREAM ? ldg4_stream(src + (int64_t)na * src_ld + 4 * cv) : ldg4(src + (int64_t)na * src_ld + 4 * cv)) : f4_zero();
-                    v[u][1][w] = okc ? (STREAM ? ldg4_stream(src + (int64_t)nb * src_ld + 4 * cv) : ldg4(src + (int64_t)nb * src_ld + 4 * cv)) : f4_zero();
+                    v[u][0][w] = okc ? ldg4(src + (int64_t)na * src_ld + 4 * cv) : f4_zero();
+                    v[u][1][w] = okc ? ldg4(src + (int64_t)nb * src_ld + 4 * cv) : f4_zero();
                 }
             }
 #pragma unroll
@@ -390,11 +382,6 @@ static int launch_two_hop(const ihg_csr* g, const int32_t* nbr, const float* src
     // (unroll 2, >= 5 resident blocks = 48 registers) measured best in situ: occupancy beats per-thread
     // ILP for these L2-served gathers (per call 0.274 vs 0.327 ms for unroll 4 / 80 registers at the
     // amazon-full shape, 1.59 vs 1.99 ms at cikm; profiles/r01_bench_twohop_variants.txt)
-    if (th_stream_loads())
-        two_hop_reduce_kernel<LPR, VPL, 2, 5, true><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
-            src, src_ld, node_scale, alpha, own_per_inc, own_const, row_scale, reinterpret_cast<const int2*>(nbr),
-            g->rowptr, g->n_seg, reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
-    else
     two_hop_reduce_kernel<LPR, VPL, 2, 5><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
         src, src_ld, node_scale, alpha, own_per_inc, own_const, row_scale, reinterpret_cast<const int2*>(nbr),
         g->rowptr, g->n_seg, reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
