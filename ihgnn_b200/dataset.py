@@ -46,6 +46,7 @@ class GraphDataset:
         self.pos_user = np.asarray(pos_user, dtype=np.int64)
         self.pos_query = np.asarray(pos_query, dtype=np.int64)
         self.pos_item = np.asarray(pos_item, dtype=np.int64)
+        self.raw_logs = None               # (log_user, log_query, log_ptr, log_items, log_flags) when known
         self._hgraph: Optional[PpsHyperGraph] = None
         self._cgraph: Optional[PpsHyperGraph] = None
         self._graph2d: Optional[Pps2DGraph] = None
@@ -93,16 +94,21 @@ class GraphDataset:
     @classmethod
     def from_search_log(cls, log: SearchLogSet, device) -> "GraphDataset":
         words, offsets = log.bag_inputs()
-        return cls(log.user_count, log.query_count, log.item_count, log.vocab_size, words, offsets,
-                   log.pos_user, log.pos_query, log.pos_item, device)
+        ds = cls(log.user_count, log.query_count, log.item_count, log.vocab_size, words, offsets,
+                 log.pos_user, log.pos_query, log.pos_item, device)
+        if getattr(log, "log_ptr", None) is not None:
+            ds.raw_logs = (log.log_user, log.log_query, log.log_ptr, log.log_items, log.log_flags)
+        return ds
 
     @classmethod
     def from_files(cls, directory: str, device, train_file: str = "train_data.csv") -> "GraphDataset":
         """Read the reference's on-disk format (graph_info.txt, queries_multihot.txt,
         train_data.csv; Dataset.py:141-200, Helpers/SearchLog.py:63-71)."""
         d = read_reference_files(directory, train_file)
-        return cls(d["user_count"], d["query_count"], d["item_count"], d["vocab_size"], d["bag_words"],
-                   d["bag_offsets"], d["pos_user"], d["pos_query"], d["pos_item"], device)
+        ds = cls(d["user_count"], d["query_count"], d["item_count"], d["vocab_size"], d["bag_words"],
+                 d["bag_offsets"], d["pos_user"], d["pos_query"], d["pos_item"], device)
+        ds.raw_logs = (d["log_user"], d["log_query"], d["log_ptr"], d["log_items"], d["log_flags"])
+        return ds
 
 
 def _split_ints(fields) -> np.ndarray:
@@ -162,6 +168,27 @@ def read_reference_files(directory: str, train_file: str = "train_data.csv") -> 
             "log_user": log_user, "log_query": log_query, "log_ptr": log_ptr, "log_items": items, "log_flags": flags}
 
 
+def logged_negative_lists(log_user, log_query, log_ptr, log_items, log_flags, pos_user, pos_query,
+                          query_count: int):
+    """`neg_items_for_user_query_pair` (Dataset.py:196-209) as a CSR: for every (user, query) pair that
+    occurs in the logs, the items it was shown without interacting (flag <= 0), in log order, duplicates
+    kept.  Returns (pos_pair [E] = pair id of every positive, neg_ptr [P+1], neg_items)."""
+    log_key = np.asarray(log_user, dtype=np.int64) * int(query_count) + np.asarray(log_query, dtype=np.int64)
+    keys, log_pair = np.unique(log_key, return_inverse=True)
+    per_log = np.diff(np.asarray(log_ptr, dtype=np.int64))
+    inc_pair = np.repeat(log_pair, per_log)
+    neg = np.asarray(log_flags) <= 0
+    order = np.argsort(inc_pair[neg], kind="stable")
+    neg_items = np.asarray(log_items, dtype=np.int64)[neg][order]
+    neg_ptr = np.zeros(keys.shape[0] + 1, dtype=np.int64)
+    np.cumsum(np.bincount(inc_pair[neg], minlength=keys.shape[0]), out=neg_ptr[1:])
+    pos_key = np.asarray(pos_user, dtype=np.int64) * int(query_count) + np.asarray(pos_query, dtype=np.int64)
+    pos_pair = np.searchsorted(keys, pos_key)
+    if pos_pair.size and not np.array_equal(keys[np.minimum(pos_pair, keys.shape[0] - 1)], pos_key):
+        raise ValueError("a positive interaction's (user, query) pair does not occur in the logs")
+    return pos_pair.astype(np.int64), neg_ptr, neg_items
+
+
 def read_test_logs(path: str):
     """`TestSearchLogDataLoader.logs` (Dataset.py:301-318): (user, query, interacted items, None, True)
     for every search log with at least one interaction."""
@@ -185,13 +212,29 @@ class DeviceBatchSampler:
     drop_last=False).  Seeded, hence reproducible; the reference is unseeded, so parity with it is
     distributional (uniform, distinct negatives per positive; the positive item is not excluded)."""
 
-    def __init__(self, dataset: GraphDataset, batch_size: int = 100, neg_sample_size: int = 10, seed: int = 0):
+    def __init__(self, dataset: GraphDataset, batch_size: int = 100, neg_sample_size: int = 10, seed: int = 0,
+                 nonrandom_neg_sample_size: int = 0):
+        """`neg_sample_size` random negatives per positive (Gs.random_negative_sample_size) plus
+        `nonrandom_neg_sample_size` taken from the items the (user, query) pair was shown without
+        interacting (Gs.non_random_negative_sample_size, 0 in the reference's defaults; Dataset.py:110-119);
+        the latter needs the raw logs (`dataset.raw_logs`: `from_files`, or a synthetic log with negatives)."""
         from . import _lib
         self._lib = _lib
         dev = GraphDataset.device
         if torch.device(dev).type != "cuda":
             raise RuntimeError("DeviceBatchSampler samples on the GPU; there is no CPU fallback")
-        self.dataset, self.batch_size, self.neg = dataset, int(batch_size), int(neg_sample_size)
+        self.dataset, self.batch_size = dataset, int(batch_size)
+        self.nonrand = int(nonrandom_neg_sample_size)
+        self.neg = int(neg_sample_size) + self.nonrand                      # Dataset.py:139
+        self.pos_pair = self.neg_ptr = self.neg_items = None
+        if self.nonrand > 0:
+            if dataset.raw_logs is None:
+                raise ValueError("nonrandom_neg_sample_size > 0 needs dataset.raw_logs (the logged non-interactions)")
+            pp, nptr, nit = logged_negative_lists(*dataset.raw_logs, dataset.pos_user, dataset.pos_query,
+                                                  dataset.query_count)
+            self.pos_pair = torch.as_tensor(pp, dtype=torch.int64, device=dev)
+            self.neg_ptr = torch.as_tensor(nptr, dtype=torch.int64, device=dev)
+            self.neg_items = torch.as_tensor(nit if nit.size else np.zeros(1, np.int64), dtype=torch.int64, device=dev)
         self.seed, self.step, self.device = int(seed), 0, dev
         self.pos_user = torch.as_tensor(dataset.pos_user, dtype=torch.int64, device=dev)
         self.pos_query = torch.as_tensor(dataset.pos_query, dtype=torch.int64, device=dev)
@@ -212,7 +255,7 @@ class DeviceBatchSampler:
         out = [mk(B) for _ in range(4)] + [mk(B * K) for _ in range(4)]
         L.call("ihg_sample_batch", L.ptr(self.pos_user), L.ptr(self.pos_query), L.ptr(self.pos_item), L.ptr(pick),
                B, K, self.dataset.item_count, self.seed & (2 ** 64 - 1), self.step, *(L.ptr(t) for t in out),
-               L.stream_ptr())
+               L.ptr(self.pos_pair), L.ptr(self.neg_ptr), L.ptr(self.neg_items), self.nonrand, L.stream_ptr())
         self.step += 1
         return tuple(out)
 

@@ -291,12 +291,17 @@ int ihg_rank_topk(const float* feat, int64_t feat_ld, const int64_t* users, cons
  * pick[0..batch), then per positive its K negatives (users, queries repeated; items drawn; flags 0).
  * Draws are a pure function of (seed, step, slot, draw): reproducible; the reference is unseeded, so
  * parity is distributional.  pos_* : device int64 [E] positive interactions; neg_per_positive <= 64.
+ * nonrandom_per_positive > 0 (Dataset.py:110-119): neg_items / neg_ptr = CSR, by (user, query) pair,
+ * of the items that pair was shown without interacting (log order, duplicates kept), pos_pair [E] =
+ * pair id of every positive.  A pair with fewer logged negatives than requested gets
+ * [random fill | all of them]; otherwise [nonrandom distinct list positions | the remaining random].
  * ------------------------------------------------------------------------------------ */
 int ihg_sample_batch(const int64_t* pos_user, const int64_t* pos_query, const int64_t* pos_item,
                      const int64_t* pick, int64_t batch, int32_t neg_per_positive, int64_t item_count,
                      uint64_t seed, uint64_t step, int64_t* p_users, int64_t* p_queries,
                      int64_t* p_items, int64_t* p_flags, int64_t* n_users, int64_t* n_queries,
-                     int64_t* n_items, int64_t* n_flags, void* stream);
+                     int64_t* n_items, int64_t* n_flags, const int64_t* pos_pair, const int64_t* neg_ptr,
+                     const int64_t* neg_items, int32_t nonrandom_per_positive, void* stream);
 
 #ifdef __cplusplus
 }

@@ -714,3 +714,48 @@ def test_gather_rows_backward_scatter_add(B, rows, dim):
     want2.index_add_(0, idx + 2, torch.ones(B, dim, dtype=torch.float64))
     want2.index_add_(0, idx.flip(0), 2 * torch.ones(B, dim, dtype=torch.float64))
     assert max_rel(t.grad.cpu().numpy(), want2.numpy()) < 2e-6
+
+
+def test_device_batch_sampler_logged_negatives():
+    """non_random_negative_sample_size > 0 (Dataset.py:110-119): a positive whose (user, query) pair has
+    enough logged non-interactions gets [nonrandom of them, distinct list positions | random items];
+    one with fewer gets [random fill | all of them, in log order]."""
+    from ihgnn_b200 import synth
+    from ihgnn_b200.dataset import DeviceBatchSampler, GraphDataset, logged_negative_lists
+    U, Q, I, E = 300, 40, 500, 4000
+    log = synth.make_search_log(U, Q, I, E, 50, shape="cikm", seed=8, with_negatives=True)
+    ds = GraphDataset.from_search_log(log, DEV)
+    assert ds.raw_logs is not None
+    R, NR = 7, 5
+    sm = DeviceBatchSampler(ds, batch_size=128, neg_sample_size=R, nonrandom_neg_sample_size=NR, seed=1)
+    pp, nptr, nit = logged_negative_lists(*ds.raw_logs, ds.pos_user, ds.pos_query, Q)
+    lists = {}
+    for e in range(len(ds)):
+        lists[(int(ds.pos_user[e]), int(ds.pos_query[e]))] = nit[nptr[pp[e]]:nptr[pp[e] + 1]].tolist()
+    seen_short = seen_long = 0
+    for tup in sm:
+        pu, pq, pi, pf, nu, nq, ni, nf = (t.cpu().numpy() for t in tup)
+        B = pu.shape[0]
+        K = R + NR
+        assert ni.shape[0] == B * K and np.array_equal(nu, np.repeat(pu, K)) and (nf == 0).all()
+        assert ni.min() >= 0 and ni.max() < I
+        for b in range(B):
+            lst = lists[(int(pu[b]), int(pq[b]))]
+            grp = ni[b * K:(b + 1) * K].tolist()
+            if len(lst) < NR:
+                seen_short += 1
+                n_rand = K - len(lst)
+                assert grp[n_rand:] == lst                          # all logged negatives, log order, last
+                assert len(set(grp[:n_rand])) == n_rand             # random.sample: distinct
+            else:
+                seen_long += 1
+                picked, rest = grp[:NR], grp[NR:]
+                pool = list(lst)
+                for it in picked:                                   # a sub-multiset of the logged list
+                    assert it in pool
+                    pool.remove(it)
+                assert len(set(rest)) == R
+    assert seen_short > 0 and seen_long > 0
+    with pytest.raises(ValueError):
+        DeviceBatchSampler(GraphDataset.from_search_log(synth.make_search_log(U, Q, I, 500, 50, seed=1), DEV), 10, 5,
+                           nonrandom_neg_sample_size=2)

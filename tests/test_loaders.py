@@ -80,3 +80,45 @@ def test_metrics_at_10_matches_reference_metrics(golden):
         inter = [int(x) for x in golden["rank.interacted"][b] if x >= 0]
         got = metrics_at_10(golden["ref64.rank_top10"][b], inter)
         assert np.allclose(got, golden["ref64.rank_metrics"][b], rtol=0, atol=1e-12), (b, got)
+
+
+def test_logged_negative_lists_match_reference_dict(tmp_path):
+    """`neg_items_for_user_query_pair` (Dataset.py:196-209): brute-force dict, and -- where the reference
+    tree is present -- the dict the reference's own GraphDataset builds from the same files."""
+    import json
+    import subprocess
+    from ihgnn_b200.dataset import logged_negative_lists
+    log = synth.make_search_log(40, 18, 60, 320, 30, shape="cikm", seed=16, with_negatives=True)
+    pp, nptr, nit = logged_negative_lists(log.log_user, log.log_query, log.log_ptr, log.log_items, log.log_flags,
+                                          log.pos_user, log.pos_query, 18)
+    want = {}
+    for k in range(len(log.log_user)):
+        a, b = int(log.log_ptr[k]), int(log.log_ptr[k + 1])
+        lst = want.setdefault((int(log.log_user[k]), int(log.log_query[k])), [])
+        lst.extend(int(it) for it, fl in zip(log.log_items[a:b], log.log_flags[a:b]) if fl <= 0)
+    assert nptr[-1] == nit.shape[0] == sum(len(v) for v in want.values())
+    for e in range(len(log.pos_user)):
+        got = nit[nptr[pp[e]]:nptr[pp[e] + 1]].tolist()
+        assert got == want[(int(log.pos_user[e]), int(log.pos_query[e]))]
+    if not os.path.isdir(REFERENCE):
+        return
+    synth.write_reference_files(log, str(tmp_path))
+    code = r'''
+import sys, json, contextlib, io
+sys.dont_write_bytecode = True
+sys.path.insert(0, "%(repo)s/oracle/stubs"); sys.path.insert(0, "%(ref)s")
+import torch
+with contextlib.redirect_stdout(io.StringIO()):
+    from Helpers.GlobalSettings import Gs, Gsv
+    Gs.graph_completeness = Gsv.graph_uqi
+    from Helpers.IOHelper import IOHelper
+    IOHelper.warned_about_cannot_log = True
+    from Helpers.Graph import PpsHyperGraph
+    from Dataset import GraphDataset
+    ds = GraphDataset("%(d)s/graph_info.txt", "%(d)s/queries_multihot.txt", "%(d)s/train_data.csv", PpsHyperGraph, 8, 2, torch.device("cpu"))
+print(json.dumps([[k[0], k[1], v] for k, v in ds.neg_items_for_user_query_pair.items()]))
+''' % {"repo": REPO, "ref": REFERENCE, "d": str(tmp_path)}
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path))
+    assert res.returncode == 0, res.stderr[-2000:]
+    ref = {(u, q): v for u, q, v in json.loads(res.stdout.strip().splitlines()[-1])}
+    assert ref == want
