@@ -19,7 +19,7 @@ import torch
 from . import _lib
 
 INT64_MAX = (1 << 63) - 1
-DEFAULT_CHUNK_LEN = 128
+DEFAULT_CHUNK_LEN = int(os.environ.get("IHG_CHUNK_LEN", "128"))   # incidences per work item; 128 measured best (dev switch)
 
 
 class CsrPlan:
