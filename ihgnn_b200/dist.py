@@ -151,6 +151,26 @@ class PartitionPlan:
         self.vertex_degrees_own = deg
         self.dv_inv_own = (np.float32(1.0) / deg).astype(np.float32)
 
+    def batch_rows(self, users: torch.Tensor, queries: torch.Tensor, items: torch.Tensor):
+        """Fixed-shape lookup plan of the batch head (RawGnn.py:128-133 over a row-sharded feature
+        matrix): for the 3B requested rows [users | queries | items] (per-type GLOBAL ids, any device)
+        returns (local_rows int64 [3B], mine bool [3B]) -- the own-layout row of every id this rank owns,
+        and for the others a spread-out dummy own row (they are masked to zero before the all-reduce;
+        distinct dummies keep the duplicate chains of the deterministic scatter-add short).
+        Sync-free: no data-dependent shapes."""
+        r, B, dev = self.rank, int(users.numel()), users.device
+        ids = torch.cat([users, queries, items]).to(torch.int64)
+        cache = getattr(self, "_batch_cache", None)
+        if cache is None or cache[0] != (B, dev):
+            mk = lambda a, b_, c: torch.tensor([int(a)] * B + [int(b_)] * B + [int(c)] * B, dtype=torch.int64, device=dev)
+            cache = ((B, dev), mk(self.ub[r], self.qb[r], self.ib[r]),
+                     mk(self.ub[r + 1], self.qb[r + 1], self.ib[r + 1]), mk(0, self.Uo, self.Uo + self.Qo),
+                     torch.arange(3 * B, dtype=torch.int64, device=dev) % max(self.n_own, 1))
+            self._batch_cache = cache
+        _, lo, hi, base, dummy = cache
+        mine = (ids >= lo) & (ids < hi)
+        return torch.where(mine, ids - lo + base, dummy), mine
+
     def own_global_ids(self) -> np.ndarray:
         """Global node ids of the own rows, in own-layout order."""
         r = self.rank
@@ -631,19 +651,7 @@ class ShardedRawGnn(torch.nn.Module):
         f_own = self.output_features()
         B = int(users.numel())
         r = p.rank
-        ids = torch.cat([users, queries, items])                       # per-type global ids, [3B]
-        cache = getattr(self, "_range_cache", None)
-        if cache is None or cache[0] != B:
-            mk = lambda a, b_, c: torch.tensor([a] * B + [b_] * B + [c] * B, device=ids.device)
-            # ids this rank does not own read a spread-out dummy own row (masked to zero afterwards):
-            # distinct rows keep the duplicate chains of the deterministic scatter-add short
-            dummy = torch.arange(3 * B, device=ids.device) % max(p.n_own, 1)
-            cache = (B, mk(p.ub[r], p.qb[r], p.ib[r]), mk(p.ub[r + 1], p.qb[r + 1], p.ib[r + 1]),
-                     mk(0, p.Uo, p.Uo + p.Qo), dummy)
-            self._range_cache = cache
-        _, lo, hi, base, dummy = cache
-        mine = (ids >= lo) & (ids < hi)
-        local_rows = torch.where(mine, ids - lo + base, dummy)
+        local_rows, mine = p.batch_rows(users, queries, items)
         rows = _FetchRowsFn.apply(f_own, local_rows, mine.to(torch.float32), self.g.group)
         return self.prediction_layer(rows[:B], rows[B:2 * B], rows[2 * B:], items)
 

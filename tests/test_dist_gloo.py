@@ -104,3 +104,56 @@ def test_partition_plan_single_rank_is_identity():
     assert np.array_equal(p.i3_local[:, 0], log.pos_user)
     assert np.array_equal(p.i3_local[:, 1], log.pos_query + 20)
     assert np.array_equal(p.i3_local[:, 2], log.pos_item + 25)
+
+
+def _fetch_worker(rank: int, world: int, port: int, ret):
+    sys.path.insert(0, REPO)
+    import torch.distributed as dist
+    from ihgnn_b200 import synth
+    from ihgnn_b200.dist import PartitionPlan
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        U, Q, I, E, D = 61, 13, 47, 900, 6
+        log = synth.make_search_log(U, Q, I, E, 30, shape="cikm", seed=5, zipf=0.9)
+        plan = PartitionPlan(log.pos_user, log.pos_query, log.pos_item, U, Q, I, world, rank)
+        gen = torch.Generator().manual_seed(7)
+        feat = torch.randn(U + Q + I, D, generator=gen, dtype=torch.float64)      # the global matrix
+        f_own = feat[torch.from_numpy(plan.own_global_ids())]
+        B = 37
+        users = torch.randint(0, U, (B,), generator=gen)
+        queries = torch.randint(0, Q, (B,), generator=gen)
+        items = torch.randint(0, I, (B,), generator=gen)
+        local_rows, mine = plan.batch_rows(users, queries, items)
+        assert local_rows.shape == mine.shape == (3 * B,) and int(local_rows.min()) >= 0 \
+            and int(local_rows.max()) < plan.n_own
+        # the choreography of _FetchRowsFn.forward with CPU ops: gather, mask, all-reduce
+        rows = f_own[local_rows] * mine.to(torch.float64).view(-1, 1)
+        dist.all_reduce(rows)
+        want = torch.cat([feat[users], feat[queries + U], feat[items + U + Q]])
+        ok_fwd = torch.equal(rows, want)
+        # every requested id is owned by exactly one rank
+        cnt = mine.to(torch.int64)
+        dist.all_reduce(cnt)
+        ok_own = bool((cnt == 1).all())
+        # backward: masked scatter-add of the (replicated) gradient == the owner's slice of the global one
+        gout = torch.randn(3 * B, D, generator=gen, dtype=torch.float64)
+        df = torch.zeros_like(f_own).index_add_(0, local_rows, gout * mine.to(torch.float64).view(-1, 1))
+        gidx = torch.cat([users, queries + U, items + U + Q])
+        dglobal = torch.zeros_like(feat).index_add_(0, gidx, gout)
+        ok_bwd = torch.allclose(df, dglobal[torch.from_numpy(plan.own_global_ids())], rtol=0, atol=1e-12)
+        # a second call with the same batch size reuses the cached range tensors
+        lr2, m2 = plan.batch_rows(users, queries, items)
+        ret[rank] = (bool(ok_fwd), ok_own, bool(ok_bwd), bool(torch.equal(lr2, local_rows) and torch.equal(m2, mine)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_fixed_shape_batch_row_fetch(world):
+    """PartitionPlan.batch_rows + the gather / mask / all-reduce choreography of the sharded batch head
+    (dist._FetchRowsFn) reproduce the global row selects of RawGnn.py:128-133 and their backward."""
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_fetch_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world and all(all(v) for v in ret.values()), dict(ret)
