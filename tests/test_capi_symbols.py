@@ -53,10 +53,14 @@ def test_new_entry_points_validate_arguments(lib):
     assert rc == 1 and b"dim=62" in lib.ihg_last_error()
     rc = lib.ihg_rank_topk(None, 64, None, 1, 4, 0, None, 10, 0, 10, 1, 0.5, 64, 10, 1, 1, None)
     assert rc == 1 and b"null pointer" in lib.ihg_last_error()
-    rc = lib.ihg_sample_batch(1, 1, 1, 1, 8, 65, 100, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, None)
+    rc = lib.ihg_sample_batch(1, 1, 1, 1, 8, 65, 100, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, None, None, None, 0, None)
     assert rc == 1 and b"neg_per_positive=65" in lib.ihg_last_error()
-    rc = lib.ihg_sample_batch(1, 1, 1, 1, 8, 10, 5, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, None)
+    rc = lib.ihg_sample_batch(1, 1, 1, 1, 8, 10, 5, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, None, None, None, 0, None)
     assert rc == 1 and b"distinct" in lib.ihg_last_error()
+    rc = lib.ihg_sample_batch(1, 1, 1, 1, 8, 10, 100, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, None, None, None, 3, None)
+    assert rc == 1 and b"logged negatives" in lib.ihg_last_error()
+    rc = lib.ihg_sample_batch(1, 1, 1, 1, 8, 10, 100, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 11, None)
+    assert rc == 1 and b"nonrandom_per_positive=11" in lib.ihg_last_error()
     rc = lib.ihg_two_hop_reduce(None, None, None, 64, None, 1.0, 1.0, 0.0, None, None, None, 64, 64, None)
     assert rc == 1 and b"null pointer" in lib.ihg_last_error()
     from ihgnn_b200 import _lib
