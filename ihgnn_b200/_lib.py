@@ -62,10 +62,10 @@ SIGNATURES = {
     "ihg_copy_rows": (c_int32, [P, I64, P, I64, I64, I32, P]),
     "ihg_gather_rows": (c_int32, [P, I64, P, I64, I64, P, I64, I32, P]),
     "ihg_scatter_add_rows": (c_int32, [P, I64, P, I64, I64, P, I64, I32, P]),
-    "ihg_hem_score_fwd": (c_int32, [P, I64, P, I64, P, I64, P, P, F32, I64, I32, P, P]),
-    "ihg_hem_score_bwd": (c_int32, [P, P, I64, P, I64, P, I64, P, F32, I64, I32, P, P, P, P, I64, P, I64, P]),
+    "ihg_hem_score_fwd": (c_int32, [P, I64, P, I64, P, I64, P, P, F32, I64, I32, P, I32, P, P]),
+    "ihg_hem_score_bwd": (c_int32, [P, P, I64, P, I64, P, I64, P, F32, I64, I32, P, P, P, P, I64, P, I64, P, P]),
     "ihg_hem_score_bwd_workspace_bytes": (I64, [I64]),
-    "ihg_rank_topk": (c_int32, [P, I64, P, P, I64, I64, P, I64, I64, I64, P, F32, I32, I32, P, P, P]),
+    "ihg_rank_topk": (c_int32, [P, I64, P, P, I64, I64, P, I64, I64, I64, P, F32, I32, I32, I32, P, P, P]),
     "ihg_sample_batch": (c_int32, [P, P, P, P, I64, I32, I64, ctypes.c_uint64, ctypes.c_uint64, P, P, P, P, P, P, P, P,
                                    P, P, P, I32, P]),
     "ihg_halo_copy": (c_int32, [P, P, P, I32, P, I64, I64, I32, P]),

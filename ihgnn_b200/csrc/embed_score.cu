@@ -151,6 +151,8 @@ scatter_add_rows_kernel(const float* __restrict__ g, int64_t g_ld, const int64_t
     }
 }
 
+constexpr float kCosEps = 1e-8f;
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -161,13 +163,14 @@ __global__ void __launch_bounds__(256)
 hem_score_fwd_kernel(const float* __restrict__ uf, int64_t u_ld, const float* __restrict__ qf,
                      int64_t q_ld, const float* __restrict__ itf, int64_t i_ld,
                      const float* __restrict__ items_bias, const int64_t* __restrict__ item_idx,
-                     float lam, int64_t count, int nvec, float* __restrict__ score) {
+                     float lam, int64_t count, int nvec, float* __restrict__ score, int cosine,
+                     float* __restrict__ norms) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const float oml = 1.0f - lam;
     for (int64_t b = warp; b < count; b += nwarps) {
-        float s = 0.f;
+        float s = 0.f, ni2 = 0.f, nm2 = 0.f;
         for (int c = lane; c < nvec; c += 32) {
             const float4 q = ldg4(qf + b * q_ld + 4 * c);
             const float4 it = ldg4(itf + b * i_ld + 4 * c);
@@ -178,11 +181,23 @@ hem_score_fwd_kernel(const float* __restrict__ uf, int64_t u_ld, const float* __
                                 lam * q.z + oml * u.z, lam * q.w + oml * u.w);
             }
             s += it.x * m.x + it.y * m.y + it.z * m.z + it.w * m.w;
+            if (cosine) {
+                ni2 += it.x * it.x + it.y * it.y + it.z * it.z + it.w * it.w;
+                nm2 += m.x * m.x + m.y * m.y + m.z * m.z + m.w * m.w;
+            }
         }
         s = warp_sum(s);
+        if (cosine) { ni2 = warp_sum(ni2); nm2 = warp_sum(nm2); }
         if (lane == 0) {
             const int64_t bi = item_idx ? __ldg(item_idx + b) : b;
-            score[b] = s + __ldg(items_bias + bi);
+            if (cosine) {
+                // torch.cosine_similarity (PredictionLayers.py:39): x.y / (max(|x|, eps) max(|y|, eps)), eps = 1e-8
+                const float a = fmaxf(sqrtf(ni2), kCosEps), bm = fmaxf(sqrtf(nm2), kCosEps);
+                norms[3 * b] = s; norms[3 * b + 1] = a; norms[3 * b + 2] = bm;
+                score[b] = s / (a * bm) + __ldg(items_bias + bi);
+            } else {
+                score[b] = s + __ldg(items_bias + bi);
+            }
         }
     }
 }
@@ -191,7 +206,8 @@ __global__ void __launch_bounds__(256)
 hem_score_bwd_kernel(const float* __restrict__ dscore, const float* __restrict__ uf, int64_t u_ld,
                      const float* __restrict__ qf, int64_t q_ld, const float* __restrict__ itf,
                      int64_t i_ld, float lam, int64_t count, int nvec, float* __restrict__ d_user,
-                     float* __restrict__ d_query, float* __restrict__ d_item) {
+                     float* __restrict__ d_query, float* __restrict__ d_item,
+                     const float* __restrict__ norms) {
     const int64_t total = count * nvec;
     const float oml = 1.0f - lam;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -208,12 +224,20 @@ hem_score_bwd_kernel(const float* __restrict__ dscore, const float* __restrict__
                             lam * q.z + oml * u.z, lam * q.w + oml * u.w);
         }
         const int64_t o = b * (int64_t)nvec * 4 + 4 * c;   // gradients are dense [count, dim]
-        if (d_item) stg4(d_item + o, f4_scale(gsc, m));
+        float4 gi = f4_scale(gsc, m), gm = f4_scale(gsc, it);            // d score / d item, d score / d m  (dot product)
+        if (norms) {
+            // cosine: s = dot / (a bm);  ds/d item = m/(a bm) - dot item/(a^3 bm);  ds/d m symmetric
+            const float dot = __ldg(norms + 3 * b), a = __ldg(norms + 3 * b + 1), bm = __ldg(norms + 3 * b + 2);
+            const float inv = gsc / (a * bm), ci = dot / (a * a), cm = dot / (bm * bm);
+            gi = make_float4(inv * (m.x - ci * it.x), inv * (m.y - ci * it.y), inv * (m.z - ci * it.z), inv * (m.w - ci * it.w));
+            gm = make_float4(inv * (it.x - cm * m.x), inv * (it.y - cm * m.y), inv * (it.z - cm * m.z), inv * (it.w - cm * m.w));
+        }
+        if (d_item) stg4(d_item + o, gi);
         if (uf) {
-            if (d_query) stg4(d_query + o, f4_scale(gsc * lam, it));
-            if (d_user) stg4(d_user + o, f4_scale(gsc * oml, it));
+            if (d_query) stg4(d_query + o, f4_scale(lam, gm));
+            if (d_user) stg4(d_user + o, f4_scale(oml, gm));
         } else {
-            if (d_query) stg4(d_query + o, f4_scale(gsc, it));
+            if (d_query) stg4(d_query + o, gm);
         }
     }
 }
@@ -332,14 +356,15 @@ int ihg_scatter_add_rows(const float* g, int64_t g_ld, const int64_t* idx, int64
 int ihg_hem_score_fwd(const float* user_f, int64_t user_ld, const float* query_f, int64_t query_ld,
                       const float* item_f, int64_t item_ld, const float* items_bias,
                       const int64_t* item_idx, float lambda_muq, int64_t count, int32_t dim,
-                      float* score, void* stream) {
+                      float* score, int32_t cosine, float* norms, void* stream) {
     IHG_REQUIRE(query_f && item_f && items_bias && score, "hem_score_fwd: null pointer");
+    IHG_REQUIRE(!cosine || norms, "hem_score_fwd: the cosine scorer needs the norms buffer [count, 3]");
     IHG_REQUIRE(dim > 0 && dim % 4 == 0 && query_ld % 4 == 0 && item_ld % 4 == 0 && (!user_f || user_ld % 4 == 0),
                 "hem_score_fwd: dim and leading dimensions must be multiples of 4");
     if (count <= 0) return IHG_OK;
     hem_score_fwd_kernel<<<blocks_for(count, 8), 256, 0, as_stream(stream)>>>(
         user_f, user_ld, query_f, query_ld, item_f, item_ld, items_bias, item_idx, lambda_muq, count,
-        dim / 4, score);
+        dim / 4, score, cosine, norms);
     IHG_LAUNCH_CHECK();
     return IHG_OK;
 }
@@ -352,7 +377,8 @@ int ihg_hem_score_bwd(const float* dscore, const float* user_f, int64_t user_ld,
                       const float* query_f, int64_t query_ld, const float* item_f, int64_t item_ld,
                       const int64_t* item_idx, float lambda_muq, int64_t count, int32_t dim,
                       float* d_user, float* d_query, float* d_item, float* d_bias,
-                      int64_t item_count, void* workspace, int64_t workspace_bytes, void* stream) {
+                      int64_t item_count, void* workspace, int64_t workspace_bytes, const float* norms,
+                      void* stream) {
     IHG_REQUIRE(dscore && query_f && item_f, "hem_score_bwd: null pointer");
     IHG_REQUIRE(dim > 0 && dim % 4 == 0 && query_ld % 4 == 0 && item_ld % 4 == 0 && (!user_f || user_ld % 4 == 0),
                 "hem_score_bwd: dim and leading dimensions must be multiples of 4");
@@ -381,7 +407,7 @@ int ihg_hem_score_bwd(const float* dscore, const float* user_f, int64_t user_ld,
     if (count <= 0) return IHG_OK;
     hem_score_bwd_kernel<<<blocks_for(count * (dim / 4), 256), 256, 0, st>>>(
         dscore, user_f, user_ld, query_f, query_ld, item_f, item_ld, lambda_muq, count, dim / 4,
-        d_user, d_query, d_item);
+        d_user, d_query, d_item, norms);
     IHG_LAUNCH_CHECK();
     return IHG_OK;
 }

@@ -43,7 +43,7 @@ rank_topk_kernel(const float* __restrict__ feat, int64_t feat_ld, const int64_t*
                  const int64_t* __restrict__ queries, int64_t query_row0,
                  const int64_t* __restrict__ cand, int64_t n_cand, int64_t item_row0,
                  int64_t item_count, const float* __restrict__ items_bias, float lam, int nvec, int k,
-                 int64_t* __restrict__ top_items, float* __restrict__ top_scores) {
+                 int cosine, int64_t* __restrict__ top_items, float* __restrict__ top_scores) {
     // positions [0, kRankMaxK): the running top-k; [kRankMaxK, kRankMaxK + kRankChunk): this chunk
     __shared__ float s_val[kRankMaxK + kRankChunk];
     __shared__ int64_t s_id[kRankMaxK + kRankChunk];
@@ -75,6 +75,13 @@ rank_topk_kernel(const float* __restrict__ feat, int64_t feat_ld, const int64_t*
                 }
             }
         }
+    }
+    float norm_m = 1.0f;                             // max(|m|, eps) for the cosine scorer
+    if (cosine) {
+        float nm2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < VPL; ++w) nm2 += m[w].x * m[w].x + m[w].y * m[w].y + m[w].z * m[w].z + m[w].w * m[w].w;
+        norm_m = fmaxf(sqrtf(rank_warp_sum(nm2)), 1e-8f);
     }
     for (int i = tid; i < kRankMaxK; i += blockDim.x) {
         s_val[i] = -CUDART_INF_F;
@@ -108,6 +115,13 @@ rank_topk_kernel(const float* __restrict__ feat, int64_t feat_ld, const int64_t*
                 for (int w = 0; w < VPL; ++w)
                     s += v[u][w].x * m[w].x + v[u][w].y * m[w].y + v[u][w].z * m[w].z + v[u][w].w * m[w].w;
                 s = rank_warp_sum(s);
+                if (cosine) {                        // PredictionLayers.py:39: cosine_similarity(item, m)
+                    float ni2 = 0.f;
+#pragma unroll
+                    for (int w = 0; w < VPL; ++w)
+                        ni2 += v[u][w].x * v[u][w].x + v[u][w].y * v[u][w].y + v[u][w].z * v[u][w].z + v[u][w].w * v[u][w].w;
+                    s = s / (fmaxf(sqrtf(rank_warp_sum(ni2)), 1e-8f) * norm_m);      // same expression as hem_score_fwd_kernel
+                }
                 const int j = j0 + u;
                 if (lane == 0 && j < n) {
                     s_val[kRankMaxK + j] = id[u] >= 0 ? s + __ldg(items_bias + id[u]) : -CUDART_INF_F;
@@ -172,8 +186,8 @@ extern "C" int ihg_rank_topk(const float* feat, int64_t feat_ld, const int64_t* 
                              const int64_t* queries, int64_t n_queries, int64_t query_row0,
                              const int64_t* cand, int64_t n_cand, int64_t item_row0,
                              int64_t item_count, const float* items_bias, float lambda_muq,
-                             int32_t dim, int32_t k, int64_t* top_items, float* top_scores,
-                             void* stream) {
+                             int32_t dim, int32_t k, int32_t cosine, int64_t* top_items,
+                             float* top_scores, void* stream) {
     IHG_REQUIRE(feat && queries && items_bias && top_items && top_scores, "rank_topk: null pointer");
     IHG_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 1024 && feat_ld % 4 == 0 && feat_ld >= dim,
                 "rank_topk: dim=%d must be a multiple of 4, <= 1024, leading dimension a multiple of 4", dim);
@@ -185,7 +199,7 @@ extern "C" int ihg_rank_topk(const float* feat, int64_t feat_ld, const int64_t* 
     const unsigned grid = (unsigned)n_queries;
 #define IHG_RANK_CASE(V)                                                                              \
     rank_topk_kernel<V><<<grid, kRankWarps * 32, 0, st>>>(feat, feat_ld, users, queries, query_row0, \
-        cand, n_cand, item_row0, item_count, items_bias, lambda_muq, nvec, k, top_items, top_scores)
+        cand, n_cand, item_row0, item_count, items_bias, lambda_muq, nvec, k, cosine, top_items, top_scores)
     if (nvec <= 32) IHG_RANK_CASE(1);
     else if (nvec <= 64) IHG_RANK_CASE(2);
     else if (nvec <= 128) IHG_RANK_CASE(4);

@@ -706,8 +706,10 @@ class ShardedRawGnn(torch.nn.Module):
         share = torch.arange(p.rank, int(queries.numel()), p.world, device=feat.device)
         cand = candidates[share] if candidates is not None else None
         pl = self.prediction_layer
+        from .settings import Gs
         ids, vals = F_.rank_topk(feat, users[share], queries[share], pl.items_bias, pl.lambda_muq,
-                                 query_row0=p.U, item_row0=p.U + p.Q, item_count=p.I, candidates=cand, k=k)
+                                 query_row0=p.U, item_row0=p.U + p.Q, item_count=p.I, candidates=cand, k=k,
+                                 cosine=bool(Gs.Prediction.use_cosine_similarity))
         return share, ids, vals
 
     def sync_grads(self) -> None:

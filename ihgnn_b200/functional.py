@@ -350,7 +350,7 @@ class HemScoreFn(torch.autograd.Function):
     (/root/reference/Models/PredictionLayers.py:21-44)."""
 
     @staticmethod
-    def forward(ctx, user_f, query_f, item_f, items_bias, item_idx, lam: float):
+    def forward(ctx, user_f, query_f, item_f, items_bias, item_idx, lam: float, cosine: bool = False):
         _lib.require_cuda(user_f, query_f, item_f, items_bias, item_idx)
         query_f, item_f = _lib.rows_f32(query_f), _lib.rows_f32(item_f)
         if user_f is not None:
@@ -360,10 +360,12 @@ class HemScoreFn(torch.autograd.Function):
         items_bias = items_bias.contiguous()
         B, D = int(item_f.shape[0]), int(item_f.shape[1])
         score = torch.empty(B, dtype=_F32, device=item_f.device)
+        norms = torch.empty((B, 3), dtype=_F32, device=item_f.device) if cosine else None   # (item.m, |item|, |m|)
         _lib.call("ihg_hem_score_fwd", _lib.ptr(user_f), _lib.ld(user_f) if user_f is not None else 0,
                   _lib.ptr(query_f), _lib.ld(query_f), _lib.ptr(item_f), _lib.ld(item_f),
                   _lib.ptr(items_bias), _lib.ptr(item_idx), float(lam), B, D, _lib.ptr(score),
-                  _lib.stream_ptr())
+                  1 if cosine else 0, _lib.ptr(norms), _lib.stream_ptr())
+        ctx.norms = norms
         ctx.lam, ctx.n_items = float(lam), int(items_bias.numel())
         ctx.has_user, ctx.has_idx = user_f is not None, item_idx is not None
         ctx.save_for_backward(*(t for t in (user_f, query_f, item_f, item_idx) if t is not None))
@@ -388,17 +390,17 @@ class HemScoreFn(torch.autograd.Function):
                   _lib.ld(user_f) if user_f is not None else 0, _lib.ptr(query_f), _lib.ld(query_f),
                   _lib.ptr(item_f), _lib.ld(item_f), _lib.ptr(item_idx), ctx.lam, B, D,
                   _lib.ptr(d_user), _lib.ptr(d_query), _lib.ptr(d_item), _lib.ptr(d_bias),
-                  ctx.n_items, _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
-        return d_user, d_query, d_item, d_bias, None, None
+                  ctx.n_items, _lib.ptr(ws), ws_bytes, _lib.ptr(ctx.norms), _lib.stream_ptr())
+        return d_user, d_query, d_item, d_bias, None, None, None
 
 
-def hem_score(user_f, query_f, item_f, items_bias, item_idx, lam):
-    return HemScoreFn.apply(user_f, query_f, item_f, items_bias, item_idx, lam)
+def hem_score(user_f, query_f, item_f, items_bias, item_idx, lam, cosine: bool = False):
+    return HemScoreFn.apply(user_f, query_f, item_f, items_bias, item_idx, lam, bool(cosine))
 
 
 def rank_topk(features: torch.Tensor, users: Optional[torch.Tensor], queries: torch.Tensor,
               items_bias: torch.Tensor, lam: float, *, query_row0: int, item_row0: int, item_count: int,
-              candidates: Optional[torch.Tensor] = None, k: int = 10):
+              candidates: Optional[torch.Tensor] = None, k: int = 10, cosine: bool = False):
     """Batched inference ranking (no autograd): for every (user, query) the k best of the candidate
     items (`candidates` int64 [B, C]; None = all items) under the HEM score
     (/root/reference/Models/PredictionLayers.py:21-44), i.e. what
@@ -423,6 +425,6 @@ def rank_topk(features: torch.Tensor, users: Optional[torch.Tensor], queries: to
     top_scores = torch.empty((B, k), dtype=_F32, device=features.device)
     _lib.call("ihg_rank_topk", _lib.ptr(features), _lib.ld(features), _lib.ptr(users), _lib.ptr(queries), B,
               int(query_row0), _lib.ptr(candidates), C, int(item_row0), int(item_count), _lib.ptr(items_bias),
-              float(lam), D, int(k), _lib.ptr(top_items), _lib.ptr(top_scores), _lib.stream_ptr(),
+              float(lam), D, int(k), 1 if cosine else 0, _lib.ptr(top_items), _lib.ptr(top_scores), _lib.stream_ptr(),
               tag="rank_topk", algo_bytes=B * (8 * D + C * ((8 if candidates is not None else 0) + 4 * D + 4) + 12 * k))
     return top_items, top_scores

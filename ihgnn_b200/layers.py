@@ -457,7 +457,8 @@ class GCNLayer(nn.Module):
 # prediction
 # --------------------------------------------------------------------------------------
 class HemPredictionLayer(nn.Module):
-    """score = sum_D item * (lambda*query + (1-lambda)*user) + bias[item]  (PredictionLayers.py:21-44)."""
+    """score = sum_D item * (lambda*query + (1-lambda)*user) + bias[item]  (PredictionLayers.py:21-44);
+    with Gs.Prediction.use_cosine_similarity the dot product becomes cosine_similarity(item, m) (:38-40)."""
 
     def __init__(self, feature_dimension: int, lambda_muq: float, item_count: int):
         super().__init__()
@@ -468,8 +469,5 @@ class HemPredictionLayer(nn.Module):
 
     def forward(self, user_feature: Optional[Tensor], query_feature: Tensor, item_feature: Tensor,
                 item_indices: Optional[Tensor] = None) -> Tensor:
-        if Gs.Prediction.use_cosine_similarity:
-            raise NotImplementedError("ihgnn_b200.HemPredictionLayer implements the dot-product scorer "
-                                      "(Gs.Prediction.use_cosine_similarity == False, the reference default)")
         return F_.hem_score(user_feature, query_feature, item_feature, self.items_bias, item_indices,
-                            self.lambda_muq)
+                            self.lambda_muq, cosine=bool(Gs.Prediction.use_cosine_similarity))   # :38-43

@@ -18,6 +18,7 @@ from torch import Tensor
 
 from . import functional as F_
 from .layers import EmbeddingLayer, GCNLayer, HGCNLayer, HemPredictionLayer, IHGNNLayer
+from .settings import Gs
 
 
 class RawGnn(nn.Module):
@@ -116,7 +117,8 @@ class RawGnn(nn.Module):
         p = self.prediction_layer
         return F_.rank_topk(feat, user_indices, query_indices, p.items_bias, p.lambda_muq,
                             query_row0=ds.query_start_index_in_graph, item_row0=ds.item_start_index_in_graph,
-                            item_count=ds.item_count, candidates=candidates, k=k)
+                            item_count=ds.item_count, candidates=candidates, k=k,
+                            cosine=bool(Gs.Prediction.use_cosine_similarity))
 
     def save_features_for_test(self) -> None:
         self._saved_output_feature = self.output_features()
@@ -136,7 +138,8 @@ def rank_searches(model, user_indices: Tensor, query_indices: Tensor, candidates
     ds, p = model.dataset, model.prediction_layer
     return F_.rank_topk(feat, user_indices, query_indices, p.items_bias, p.lambda_muq,
                         query_row0=ds.query_start_index_in_graph, item_row0=ds.item_start_index_in_graph,
-                        item_count=ds.item_count, candidates=candidates, k=k)
+                        item_count=ds.item_count, candidates=candidates, k=k,
+                        cosine=bool(Gs.Prediction.use_cosine_similarity))
 
 
 def metrics_at_10(recommended, interacted_items):

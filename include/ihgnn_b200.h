@@ -244,7 +244,10 @@ int ihg_halo_copy(const void* const* seg_src, void* const* seg_dst, const int64_
 /* ------------------------------------------------------------------------------------
  * a10 HemPredictionLayer.forward                   Models/PredictionLayers.py:21-44
  *   m = lambda*q + (1-lambda)*u   (u null: m = q);  score[b] = sum_D item[b]*m[b] + bias[b']
- *   b' = item_idx[b] (item_idx null: b' = b, "all items").  Dot-product branch only.
+ *   b' = item_idx[b] (item_idx null: b' = b, "all items").
+ *   cosine != 0 (Gs.Prediction.use_cosine_similarity, PredictionLayers.py:38-40):
+ *   score[b] = item.m / (max(|item|, 1e-8) max(|m|, 1e-8)) + bias[b'];  fwd then fills norms [count,3] =
+ *   (item.m, |item|, |m|) which bwd takes back (norms null in bwd = dot-product branch).
  * bwd: d_item = g*m, d_query = g*lambda*item, d_user = g*(1-lambda)*item (null = skip),
  *      d_bias[i] = sum_{b: idx[b]==i} g[b], summed in 64-bit fixed point (order-independent,
  *      bit-reproducible; resolution 2^-38 of max|g|).  workspace: 8-byte aligned device scratch of
@@ -253,12 +256,14 @@ int ihg_halo_copy(const void* const* seg_src, void* const* seg_dst, const int64_
 int ihg_hem_score_fwd(const float* user_f, int64_t user_ld, const float* query_f,
                       int64_t query_ld, const float* item_f, int64_t item_ld,
                       const float* items_bias, const int64_t* item_idx, float lambda_muq,
-                      int64_t count, int32_t dim, float* score, void* stream);
+                      int64_t count, int32_t dim, float* score, int32_t cosine, float* norms,
+                      void* stream);
 int ihg_hem_score_bwd(const float* dscore, const float* user_f, int64_t user_ld,
                       const float* query_f, int64_t query_ld, const float* item_f,
                       int64_t item_ld, const int64_t* item_idx, float lambda_muq, int64_t count,
                       int32_t dim, float* d_user, float* d_query, float* d_item, float* d_bias,
-                      int64_t item_count, void* workspace, int64_t workspace_bytes, void* stream);
+                      int64_t item_count, void* workspace, int64_t workspace_bytes,
+                      const float* norms, void* stream);
 int64_t ihg_hem_score_bwd_workspace_bytes(int64_t item_count);
 
 /* ------------------------------------------------------------------------------------
@@ -273,6 +278,7 @@ int64_t ihg_hem_score_bwd_workspace_bytes(int64_t item_count);
  *   cand       int64 [n_queries, n_cand] item ids, or null = all items 0..n_cand-1
  *              (the reference's "predict on all items"); ids outside [0, item_count) never rank
  *   score      = sum_D feat[item_row0 + id] * (lambda*q + (1-lambda)*u) + items_bias[id]
+ *                (cosine != 0: the cosine scorer of ihg_hem_score_fwd instead of the dot product)
  *   top_items  int64 [n_queries, k], top_scores fp32 [n_queries, k]: descending score, ties to the
  *              earlier candidate; unfilled places (fewer than k valid candidates) = (-1, -inf).
  * dim % 4 == 0, dim <= 1024, 1 <= k <= 32.
@@ -280,7 +286,8 @@ int64_t ihg_hem_score_bwd_workspace_bytes(int64_t item_count);
 int ihg_rank_topk(const float* feat, int64_t feat_ld, const int64_t* users, const int64_t* queries,
                   int64_t n_queries, int64_t query_row0, const int64_t* cand, int64_t n_cand,
                   int64_t item_row0, int64_t item_count, const float* items_bias, float lambda_muq,
-                  int32_t dim, int32_t k, int64_t* top_items, float* top_scores, void* stream);
+                  int32_t dim, int32_t k, int32_t cosine, int64_t* top_items, float* top_scores,
+                  void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Training-batch sampler on the device.  Replaces GraphDataset.__getitem__

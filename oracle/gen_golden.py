@@ -55,6 +55,9 @@ CASES = {
                              gnn="IHGNN", L=3, order=1, d=32, batch=20),
     "gcn_L2_cikm": dict(U=40, Q=18, I=60, V=30, E=320, shape="cikm", seed=16,
                         gnn="GCN", L=2, order=1, d=16, batch=20),
+    # Gs.Prediction.use_cosine_similarity = True (PredictionLayers.py:38-40)
+    "ihgnn_o3_L1_cosine": dict(U=35, Q=14, I=55, V=25, E=260, shape="amazon", seed=17,
+                               gnn="IHGNN", L=1, order=3, d=16, batch=18, cosine=True),
     "hgcn_L2_amazon": dict(U=50, Q=20, I=80, V=30, E=350, shape="amazon", seed=14,
                            gnn="HGCN", L=2, order=1, d=16, batch=20),
     # d=64 / 3 layers at the smallest size that still has heavy (Zipf head) nodes
@@ -150,6 +153,14 @@ def _run(model, users, queries, items, flags, prefix, out, pos_log):
 
 
 def make_case(name: str, cfg: dict, outdir: str) -> None:
+    Gs.Prediction.use_cosine_similarity = bool(cfg.get("cosine", False))
+    try:
+        _make_case(name, cfg, outdir)
+    finally:
+        Gs.Prediction.use_cosine_similarity = False
+
+
+def _make_case(name: str, cfg: dict, outdir: str) -> None:
     log = synth.make_search_log(cfg["U"], cfg["Q"], cfg["I"], cfg["E"], cfg["V"],
                                 shape=cfg["shape"], seed=cfg["seed"], with_negatives=True)
     out = {}
@@ -198,6 +209,7 @@ def make_case(name: str, cfg: dict, outdir: str) -> None:
     out["cfg.order"] = np.array(cfg["order"])
     out["cfg.d"] = np.array(cfg["d"])
     out["cfg.lambda_muq"] = np.array(0.5)
+    out["cfg.cosine"] = np.array(bool(cfg.get("cosine", False)))
 
     # a training batch in TrainTestHelper.py:126-129 form: positives then 10 negatives each
     rng = np.random.default_rng(cfg["seed"] + 500)

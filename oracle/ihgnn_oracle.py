@@ -220,13 +220,16 @@ def gcn_layer(x: torch.Tensor, adjacency2d: torch.Tensor, dv_neg_half: torch.Ten
 
 def hem_score(user_feature: Optional[torch.Tensor], query_feature: torch.Tensor,
               item_feature: torch.Tensor, items_bias: torch.Tensor,
-              item_indices: Optional[torch.Tensor], lambda_muq: float):
-    """PredictionLayers.py:21-44, dot-product branch (use_cosine_similarity False)."""
+              item_indices: Optional[torch.Tensor], lambda_muq: float, cosine: bool = False):
+    """PredictionLayers.py:21-44: dot-product branch (:41-43) or, with
+    Gs.Prediction.use_cosine_similarity, torch.cosine_similarity(item, m) + bias (:38-40)."""
     bias = items_bias if item_indices is None else items_bias[item_indices]   # :30-31
     if user_feature is not None:
         m = lambda_muq * query_feature + (1 - lambda_muq) * user_feature      # :35
     else:
         m = query_feature                                                     # :37
+    if cosine:
+        return torch.cosine_similarity(item_feature, m) + bias                # :39-40
     return (item_feature * m).sum(1) + bias                                   # :42-43
 
 
@@ -242,8 +245,10 @@ class OracleModel:
                  bag_words: torch.Tensor, bag_offsets: torch.Tensor,
                  user_count: int, query_count: int, item_count: int,
                  layer_type: str = "IHGNN", layer_count: int = 2, order: int = 3,
-                 lambda_muq: float = 0.5, dtype=torch.float32, requires_grad: bool = True):
+                 lambda_muq: float = 0.5, dtype=torch.float32, requires_grad: bool = True,
+                 cosine: bool = False):
         self.dtype = dtype
+        self.cosine = cosine
         self.graph = graph
         self.layer_type = layer_type
         self.layer_count = layer_count
@@ -315,7 +320,7 @@ class OracleModel:
         else:
             fi = f[self.U + self.Q:]                           # :133
         return hem_score(fu, fq, fi, self.params["prediction_layer.items_bias"], items,
-                         self.lambda_muq)
+                         self.lambda_muq, self.cosine)
 
     def grads(self) -> Dict[str, torch.Tensor]:
         return {k: (v.grad if v.grad is not None else torch.zeros_like(v))

@@ -24,9 +24,12 @@ def golden_names():
 
 
 @pytest.fixture(params=golden_names())
-def golden(request):
+def golden(request, monkeypatch):
     import numpy as np
     with np.load(os.path.join(GOLDEN_DIR, request.param + ".npz")) as z:
         data = {k: z[k] for k in z.files}
     data["__name__"] = request.param
+    # fixtures generated with Gs.Prediction.use_cosine_similarity = True run the product with it too
+    from ihgnn_b200 import settings
+    monkeypatch.setattr(settings.Gs.Prediction, "use_cosine_similarity", bool(data.get("cfg.cosine", False)))
     return data

@@ -44,7 +44,7 @@ def oracle_model(golden, dtype=torch.float32) -> "orc.OracleModel":
                            torch.from_numpy(golden["bag_words"]), torch.from_numpy(golden["bag_offsets"]),
                            U, Q, I, layer_type=str(golden["cfg.gnn"]), layer_count=int(golden["cfg.L"]),
                            order=int(golden["cfg.order"]), lambda_muq=float(golden["cfg.lambda_muq"]),
-                           dtype=dtype)
+                           dtype=dtype, cosine=bool(golden.get("cfg.cosine", False)))
 
 
 def batch_of(golden):

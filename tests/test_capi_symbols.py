@@ -47,11 +47,11 @@ def test_abi_version_and_error_channel(lib):
 def test_new_entry_points_validate_arguments(lib):
     """ihg_rank_topk / ihg_sample_batch / ihg_two_hop_reduce / ihg_segment_reduce flags: the argument checks
     run before any CUDA call."""
-    rc = lib.ihg_rank_topk(1, 64, None, 1, 4, 0, None, 10, 0, 10, 1, 0.5, 64, 33, 1, 1, None)
+    rc = lib.ihg_rank_topk(1, 64, None, 1, 4, 0, None, 10, 0, 10, 1, 0.5, 64, 33, 0, 1, 1, None)
     assert rc == 1 and b"k=33" in lib.ihg_last_error()
-    rc = lib.ihg_rank_topk(1, 64, None, 1, 4, 0, None, 10, 0, 10, 1, 0.5, 62, 10, 1, 1, None)
+    rc = lib.ihg_rank_topk(1, 64, None, 1, 4, 0, None, 10, 0, 10, 1, 0.5, 62, 10, 0, 1, 1, None)
     assert rc == 1 and b"dim=62" in lib.ihg_last_error()
-    rc = lib.ihg_rank_topk(None, 64, None, 1, 4, 0, None, 10, 0, 10, 1, 0.5, 64, 10, 1, 1, None)
+    rc = lib.ihg_rank_topk(None, 64, None, 1, 4, 0, None, 10, 0, 10, 1, 0.5, 64, 10, 0, 1, 1, None)
     assert rc == 1 and b"null pointer" in lib.ihg_last_error()
     rc = lib.ihg_sample_batch(1, 1, 1, 1, 8, 65, 100, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, None, None, None, 0, None)
     assert rc == 1 and b"neg_per_positive=65" in lib.ihg_last_error()
