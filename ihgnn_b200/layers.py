@@ -73,9 +73,15 @@ class EmbeddingLayer(nn.Module):
         self.embedding_user = EmbeddingLayer.create_embedding(len(self.users) + 1, embedding_size, padding_idx=0)
         self.embedding_item = EmbeddingLayer.create_embedding(len(self.items) + 1, embedding_size, padding_idx=0)
         self.embedding_bag_vocabulary = EmbeddingLayer.create_embedding_bag(len(self.vocabulary) + 1, embedding_size)
-        if Gs.Query.transform != Gsv.mean:                  # EmbeddingLayers.py:38-48
-            raise NotImplementedError(
-                "ihgnn_b200.EmbeddingLayer implements Gs.Query.transform == 'mean' (the reference default)")
+        if Gs.Query.transform == Gsv.mean:                  # EmbeddingLayers.py:38-48
+            pass
+        elif Gs.Query.transform == Gsv.activation:
+            self.query_transform = nn.Sequential(nn.Linear(embedding_size, embedding_size),
+                                                 Gs.Query.transform_activation())
+        elif Gs.Query.transform == Gsv.rnn:
+            raise NotImplementedError()                     # as the reference (:45-46)
+        else:
+            raise ValueError()
         self._tables: Optional[_BagTables] = None
 
     @property
@@ -94,6 +100,8 @@ class EmbeddingLayer(nn.Module):
 
     def embed_all(self) -> Tensor:
         """[users; queries; items] feature matrix [N, d] in one pass (what RawGnn.py:112 cats)."""
+        if Gs.Query.transform == Gsv.activation:            # the transformed query rows are a separate tensor
+            return torch.cat([self.embed_user(), self.embed_query(), self.embed_item()])
         return F_.EmbedAllFn.apply(self.embedding_user.weight, self.embedding_bag_vocabulary.weight,
                                    self.embedding_item.weight, self.tables)
 
@@ -118,6 +126,9 @@ class EmbeddingLayer(nn.Module):
         q = _BagMeanFn.apply(w, t)
         if query_indices is not None:                       # EmbeddingLayers.py:80-81
             q = F_.gather_rows(q, query_indices, 0)
+        if Gs.Query.transform == Gsv.activation:            # :83-84: Linear on the node-Linear kernel, then the activation module
+            lin, act = self.query_transform[0], self.query_transform[1]
+            q = act(F_.typed_linear(q, lin.weight.unsqueeze(0), lin.bias.unsqueeze(0), None))
         return q
 
     @staticmethod

@@ -29,6 +29,11 @@ except Exception:  # reference not on sys.path: standalone mirror
         class Query:
             transform = Gsv.mean
 
+            @staticmethod
+            def transform_activation():              # GlobalSettings.py:75-76 (last assignment wins: nn.ReLU)
+                import torch.nn as nn
+                return nn.ReLU()
+
         class Prediction:
             use_cosine_similarity = False
 

@@ -58,6 +58,9 @@ CASES = {
     # Gs.Prediction.use_cosine_similarity = True (PredictionLayers.py:38-40)
     "ihgnn_o3_L1_cosine": dict(U=35, Q=14, I=55, V=25, E=260, shape="amazon", seed=17,
                                gnn="IHGNN", L=1, order=3, d=16, batch=18, cosine=True),
+    # Gs.Query.transform = activation (EmbeddingLayers.py:40-44, :83-84), activation = the reference's nn.ReLU
+    "ihgnn_o1_L2_qact": dict(U=32, Q=15, I=48, V=22, E=240, shape="cikm", seed=18,
+                             gnn="IHGNN", L=2, order=1, d=32, batch=16, query_transform="activation"),
     "hgcn_L2_amazon": dict(U=50, Q=20, I=80, V=30, E=350, shape="amazon", seed=14,
                            gnn="HGCN", L=2, order=1, d=16, batch=20),
     # d=64 / 3 layers at the smallest size that still has heavy (Zipf head) nodes
@@ -154,10 +157,12 @@ def _run(model, users, queries, items, flags, prefix, out, pos_log):
 
 def make_case(name: str, cfg: dict, outdir: str) -> None:
     Gs.Prediction.use_cosine_similarity = bool(cfg.get("cosine", False))
+    Gs.Query.transform = Gsv.activation if cfg.get("query_transform") == "activation" else Gsv.mean
     try:
         _make_case(name, cfg, outdir)
     finally:
         Gs.Prediction.use_cosine_similarity = False
+        Gs.Query.transform = Gsv.mean
 
 
 def _make_case(name: str, cfg: dict, outdir: str) -> None:
@@ -210,6 +215,10 @@ def _make_case(name: str, cfg: dict, outdir: str) -> None:
     out["cfg.d"] = np.array(cfg["d"])
     out["cfg.lambda_muq"] = np.array(0.5)
     out["cfg.cosine"] = np.array(bool(cfg.get("cosine", False)))
+    act = ""
+    if cfg.get("query_transform") == "activation":
+        act = type(model.embeddings.query_transform[1]).__name__.lower()       # 'relu' (GlobalSettings.py:76)
+    out["cfg.query_activation"] = np.array(act)
 
     # a training batch in TrainTestHelper.py:126-129 form: positives then 10 negatives each
     rng = np.random.default_rng(cfg["seed"] + 500)

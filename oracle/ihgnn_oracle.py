@@ -111,19 +111,23 @@ def embed_item(weight_item: torch.Tensor, item_indices: Optional[torch.Tensor] =
 
 
 def embed_query(weight_vocab: torch.Tensor, bag_words: torch.Tensor, bag_offsets: torch.Tensor,
-                query_indices: Optional[torch.Tensor] = None):
-    """EmbeddingLayers.py:76-91 with Gs.Query.transform == mean: EmbeddingBag(mean) over all
-    Q queries, then an optional row select.  Empty bags give zeros."""
+                query_indices: Optional[torch.Tensor] = None, transform=None):
+    """EmbeddingLayers.py:76-91: EmbeddingBag(mean) over all Q queries, then an optional row select
+    (empty bags give zeros).  Gs.Query.transform == activation (:83-84, :40-44) applies
+    `transform` = (Linear weight, Linear bias, activation name 'relu' | 'tanh') afterwards."""
     out = torch.nn.functional.embedding_bag(bag_words, weight_vocab, bag_offsets, mode="mean")
     if query_indices is not None:
         out = out[query_indices]
+    if transform is not None:
+        w, b, act = transform
+        out = getattr(torch, act)(torch.nn.functional.linear(out, w, b))
     return out
 
 
-def embed_all(weight_user, weight_vocab, weight_item, bag_words, bag_offsets):
+def embed_all(weight_user, weight_vocab, weight_item, bag_words, bag_offsets, transform=None):
     """EmbeddingLayer.forward(None, None, None) followed by RawGnn's cat (RawGnn.py:112)."""
     return torch.cat([embed_user(weight_user),
-                      embed_query(weight_vocab, bag_words, bag_offsets),
+                      embed_query(weight_vocab, bag_words, bag_offsets, None, transform),
                       embed_item(weight_item)])
 
 
@@ -246,9 +250,10 @@ class OracleModel:
                  user_count: int, query_count: int, item_count: int,
                  layer_type: str = "IHGNN", layer_count: int = 2, order: int = 3,
                  lambda_muq: float = 0.5, dtype=torch.float32, requires_grad: bool = True,
-                 cosine: bool = False):
+                 cosine: bool = False, query_activation: Optional[str] = None):
         self.dtype = dtype
         self.cosine = cosine
+        self.query_activation = query_activation          # None (mean) | 'relu' | 'tanh'  (Gs.Query.transform)
         self.graph = graph
         self.layer_type = layer_type
         self.layer_count = layer_count
@@ -278,10 +283,14 @@ class OracleModel:
 
     def input_features(self) -> torch.Tensor:
         p = self.params
+        transform = None
+        if self.query_activation is not None:
+            transform = (p["embeddings.query_transform.0.weight"], p["embeddings.query_transform.0.bias"],
+                         self.query_activation)
         return embed_all(p["embeddings.embedding_user.weight"],
                          p["embeddings.embedding_bag_vocabulary.weight"],
                          p["embeddings.embedding_item.weight"],
-                         self.bag_words, self.bag_offsets)
+                         self.bag_words, self.bag_offsets, transform)
 
     def conv_stack(self, x: torch.Tensor) -> List[torch.Tensor]:
         """RawGnn.py:113-118: outputs of every layer, input first."""

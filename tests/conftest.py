@@ -32,4 +32,6 @@ def golden(request, monkeypatch):
     # fixtures generated with Gs.Prediction.use_cosine_similarity = True run the product with it too
     from ihgnn_b200 import settings
     monkeypatch.setattr(settings.Gs.Prediction, "use_cosine_similarity", bool(data.get("cfg.cosine", False)))
+    act = str(data["cfg.query_activation"]) if "cfg.query_activation" in data else ""
+    monkeypatch.setattr(settings.Gs.Query, "transform", settings.Gsv.activation if act else settings.Gsv.mean)
     return data

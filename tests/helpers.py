@@ -44,7 +44,9 @@ def oracle_model(golden, dtype=torch.float32) -> "orc.OracleModel":
                            torch.from_numpy(golden["bag_words"]), torch.from_numpy(golden["bag_offsets"]),
                            U, Q, I, layer_type=str(golden["cfg.gnn"]), layer_count=int(golden["cfg.L"]),
                            order=int(golden["cfg.order"]), lambda_muq=float(golden["cfg.lambda_muq"]),
-                           dtype=dtype, cosine=bool(golden.get("cfg.cosine", False)))
+                           dtype=dtype, cosine=bool(golden.get("cfg.cosine", False)),
+                           query_activation=(str(golden["cfg.query_activation"]) or None)
+                           if "cfg.query_activation" in golden else None)
 
 
 def batch_of(golden):

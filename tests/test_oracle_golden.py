@@ -74,8 +74,12 @@ def test_indexed_embedding_lookups(golden):
     with torch.no_grad():
         eu = orc.embed_user(p["embeddings.embedding_user.weight"], users[:9])
         ei = orc.embed_item(p["embeddings.embedding_item.weight"], items[:9])
+        transform = None
+        if m.query_activation:                          # Gs.Query.transform == activation fixtures
+            transform = (p["embeddings.query_transform.0.weight"], p["embeddings.query_transform.0.bias"],
+                         m.query_activation)
         eq = orc.embed_query(p["embeddings.embedding_bag_vocabulary.weight"], m.bag_words,
-                             m.bag_offsets, torch.from_numpy(golden["embed.query_indices"]))
+                             m.bag_offsets, torch.from_numpy(golden["embed.query_indices"]), transform)
     assert np.array_equal(eu.numpy(), golden["ref32.embed_user_idx"])
     assert np.array_equal(ei.numpy(), golden["ref32.embed_item_idx"])
     assert max_rel(eq.numpy(), golden["ref32.embed_query_idx"]) <= 1e-7
