@@ -282,6 +282,11 @@ class Pps2DGraph(PpsGraph):
 
     @classmethod
     def from_hypergraph(cls, hyper: PpsHyperGraph, use_self_connection: bool) -> "Pps2DGraph":
+        from .settings import Gs, Gsv
+        completeness = getattr(Gs, "graph_completeness", Gsv.graph_uqi)
+        if completeness != Gsv.graph_uqi:                                      # Graph.py:46-65: uq / ui / qi only
+            raise NotImplementedError(f"ihgnn_b200.Pps2DGraph implements graph_completeness == 'uqi' "
+                                      f"(the reference default, ArgsParser.py:85); got {completeness!r}")
         g = cls()
         g.hyper = hyper
         g.use_self_connection = bool(use_self_connection)

@@ -97,3 +97,13 @@ def test_product_does_not_import_the_oracle():
                 with open(os.path.join(root, f)) as fh:
                     src = fh.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_pps2dgraph_rejects_partial_completeness(monkeypatch):
+    """--completeness uq / ui / qi (Helpers/Graph.py:46-65) is not implemented: fail loudly instead of
+    silently convolving over the full u-q-i pair set."""
+    from ihgnn_b200 import settings
+    from ihgnn_b200.graph import Pps2DGraph
+    monkeypatch.setattr(settings.Gs, "graph_completeness", "uq", raising=False)
+    with pytest.raises(NotImplementedError):
+        Pps2DGraph.from_hypergraph(None, False)
