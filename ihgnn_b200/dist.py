@@ -24,7 +24,7 @@ CUDA only (NCCL).  The planner is pure numpy and is exercised on CPU by tests/te
 from __future__ import annotations
 
 import os
-from typing import List, Optional, Tuple
+from typing import List, Optional
 
 import numpy as np
 import torch
@@ -650,7 +650,6 @@ class ShardedRawGnn(torch.nn.Module):
         p = self.g.plan
         f_own = self.output_features()
         B = int(users.numel())
-        r = p.rank
         local_rows, mine = p.batch_rows(users, queries, items)
         rows = _FetchRowsFn.apply(f_own, local_rows, mine.to(torch.float32), self.g.group)
         return self.prediction_layer(rows[:B], rows[B:2 * B], rows[2 * B:], items)

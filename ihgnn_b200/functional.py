@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from .graph import INT64_MAX, CsrPlan, PpsHyperGraph
+from .graph import INT64_MAX, CsrPlan
 
 _F32 = torch.float32
 

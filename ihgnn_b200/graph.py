@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from typing import Optional, Sequence
+from typing import Optional
 
 import numpy as np
 import torch
