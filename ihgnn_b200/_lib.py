@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_void_p
 from typing import Optional
 
@@ -103,10 +104,48 @@ def check(status: int, what: str) -> None:
         raise RuntimeError(f"{what} failed (status {status}): {msg}")
 
 
+class _CurrentStream:
+    """Placeholder for "the current torch stream of the device the tensor arguments live on";
+    `call` resolves it once that device is known."""
+
+    def __repr__(self):
+        return "<current CUDA stream>"
+
+
+CURRENT_STREAM = _CurrentStream()
+_tls = threading.local()
+
+
+def _take_arg_device() -> Optional[int]:
+    dev = getattr(_tls, "device", None)
+    _tls.device = None
+    return dev
+
+
 def call(name: str, *args, tag: Optional[str] = None, algo_bytes: int = 0) -> None:
     """Invoke a status-returning entry point and raise on error.  `tag` / `algo_bytes`
-    (algorithmic bytes the call must move) only feed the optional profiler."""
+    (algorithmic bytes the call must move) only feed the optional profiler.
+
+    Device guard: the launch goes to the device the tensor arguments live on (recorded by `ptr`
+    while the argument list was evaluated) and to THAT device's current torch stream, whatever
+    torch's current device is -- the reference builds `torch.device('cuda:N')` and never calls
+    `set_device` (Main.py:61-64), so the current device is usually 0."""
     fn = getattr(lib(), name)
+    dev = _take_arg_device()
+    cur = torch.cuda.current_device()
+    if dev is None:
+        dev = cur
+    if any(a is CURRENT_STREAM for a in args):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        args = tuple(st if a is CURRENT_STREAM else a for a in args)
+    if dev != cur:
+        with torch.cuda.device(dev):
+            _call_on_current_device(fn, name, args, tag, algo_bytes)
+    else:
+        _call_on_current_device(fn, name, args, tag, algo_bytes)
+
+
+def _call_on_current_device(fn, name, args, tag, algo_bytes) -> None:
     if profiler is None:
         check(fn(*args), name)
         return
@@ -124,15 +163,25 @@ def launch_count() -> int:
     return int(lib().ihg_launch_count())
 
 
-def stream_ptr() -> int:
-    """The current torch CUDA stream as a cudaStream_t value."""
-    return torch.cuda.current_stream().cuda_stream
+def stream_ptr() -> _CurrentStream:
+    """The stream argument of an entry point: the current torch CUDA stream of the device the
+    call's tensors live on (resolved inside `call`)."""
+    return CURRENT_STREAM
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
-    """Device pointer of a tensor (None -> NULL)."""
+    """Device pointer of a tensor (None -> NULL).  Records the tensor's device for the device guard
+    of the `call` whose argument list is being evaluated; tensors of two devices in one call raise."""
     if t is None:
         return None
+    if t.is_cuda:
+        idx = t.device.index
+        seen = getattr(_tls, "device", None)
+        if seen is None:
+            _tls.device = idx
+        elif seen != idx:
+            _tls.device = None
+            raise RuntimeError(f"ihgnn_b200: tensors of one call live on different devices (cuda:{seen} and cuda:{idx})")
     return t.data_ptr()
 
 

@@ -2,8 +2,8 @@
 
     python -m ihgnn_b200.build [--force]
 
-The shared library lands in ihgnn_b200/lib/ (git-ignored, but it travels with the repo
-snapshot to the GPU box).  nvcc cross-compiles without a GPU.
+The shared library and its digest stamp land in ihgnn_b200/lib/ (both git-ignored via `*.so` /
+`ihgnn_b200/lib/`, but they travel with the repo snapshot to the GPU box).  nvcc cross-compiles without a GPU.
 """
 from __future__ import annotations
 
@@ -43,10 +43,10 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
+    files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     files.append(os.path.join(REPO, "include", "ihgnn_b200.h"))
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.relpath(f, REPO).encode())      # location-independent: a checkout elsewhere matches
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())

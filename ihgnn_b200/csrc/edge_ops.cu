@@ -390,11 +390,7 @@ int ihg_edge_interact_fwd(const float* xp, int64_t xp_ld, const float* p, int64_
     if (E == 0) return IHG_OK;
     const int nb = order == 3 ? 4 : 3;
     cudaStream_t st = as_stream(stream);
-    if (interact_tc_eligible(dim) && xp_ld % 4 == 0 && p_ld % 4 == 0 && ef_ld % 4 == 0) {
-        IHG_REQUIRE(workspace && workspace_bytes >= ihg_edge_interact_fwd_workspace_bytes(dim, order),
-                    "edge_interact_fwd: workspace too small");
-        return launch_interact_fwd_tc(xp, xp_ld, p, p_ld, w_hi, w_ld, nb, i3, E, ef, ef_ld, dim, workspace, st);
-    }
+    (void)workspace; (void)workspace_bytes;      // the hoisted form is the exact-fp32 FFMA kernel for every dim
     const unsigned blocks = (unsigned)ceil_div(E, kTileRows);
 #define IHG_IF_CASE(D) edge_interact_fwd_kernel<D><<<blocks, kGemmThreads, 0, st>>>(xp, xp_ld, p, p_ld, w_hi, w_ld, nb, i3, E, ef, ef_ld, dim)
     if (dim <= 16) IHG_IF_CASE(1);
@@ -407,8 +403,7 @@ int ihg_edge_interact_fwd(const float* xp, int64_t xp_ld, const float* p, int64_
 }
 
 int ihg_feature_interact_supported(int32_t dim) {
-    static const bool hoisted_only = getenv("IHG_HOISTED_FWD") != nullptr;     // A/B switch for measurements
-    return (!hoisted_only && interact_tc_eligible(dim)) ? 1 : 0;
+    return interact_tc_eligible(dim) ? 1 : 0;
 }
 
 int ihg_feature_interact_fwd(const float* xp, int64_t xp_ld, const float* w_agg, int64_t w_ld,
@@ -422,10 +417,6 @@ int ihg_feature_interact_fwd(const float* xp, int64_t xp_ld, const float* w_agg,
     IHG_REQUIRE(workspace && workspace_bytes >= ihg_edge_interact_fwd_workspace_bytes(dim, order),
                 "feature_interact_fwd: workspace too small");
     if (E == 0) return IHG_OK;
-    static const bool smem_operand = getenv("IHG_FWD_SS") != nullptr;          // A/B switch: A operand in shared memory
-    if (smem_operand)
-        return launch_interact_fwd_full_tc(xp, xp_ld, w_agg, w_ld, bias, order == 3 ? 4 : 3, i3, E, ef, ef_ld, dim,
-                                           workspace, as_stream(stream));
     return launch_interact_fwd_full_ts(xp, xp_ld, w_agg, w_ld, bias, order == 3 ? 4 : 3, i3, E, ef, ef_ld, dim,
                                        workspace, as_stream(stream));
 }

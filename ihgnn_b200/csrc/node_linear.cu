@@ -181,12 +181,9 @@ int ihg_node_linear(const float* x, int64_t x_ld, const float* w, int32_t n_type
     if (n_types == 1) bound0 = bound1 = n_rows;
     IHG_REQUIRE(0 <= bound0 && bound0 <= bound1 && bound1 <= n_rows, "node_linear: bad type bounds");
     cudaStream_t st = as_stream(stream);
-    if (node_linear_tc_eligible(n_out, n_in, x_ld, y_ld, addend, addend_ld) && node_linear_ts_eligible(n_out, n_in))
+    if (node_linear_ts_eligible(n_out, n_in, x_ld, y_ld, addend, addend_ld))
         return launch_node_linear_ts(x, x_ld, w, n_types, n_out, n_in, transpose_w, bias, addend, addend_ld, n_rows,
                                      bound0, bound1, y, y_ld, st);
-    if (node_linear_tc_eligible(n_out, n_in, x_ld, y_ld, addend, addend_ld))
-        return launch_node_linear_tc(x, x_ld, w, n_types, n_out, n_in, transpose_w, bias, addend,
-                                     addend_ld, n_rows, bound0, bound1, y, y_ld, st);
     TypeTiles tt{bound0, bound1, n_rows};
     const int64_t blocks = tt.tiles(0) + tt.tiles(1) + tt.tiles(2);
 #define IHG_NL_CASE(D)                                                                              \

@@ -1,13 +1,6 @@
-// Node-level typed Linear on the 5th-generation tensor cores (tcgen05.mma kind::tf32, 3xTF32
-// split precision, fp32 accumulators in TMEM).  Same contract as the SIMT kernel in
-// node_linear.cu -- y[r,:] = x[r,:] . W[t]^T (+bias[t]) (+addend[r,:]) -- selected when
-// n_in % 32 == 0 and n_out % 16 == 0.
-//
-// One CTA owns one tile of 128 rows (tiles never straddle a node-type boundary): row slices of x
-// are split into tf32 hi/lo and written into the UMMA K-major SWIZZLE_128B layout together with
-// the weight rows; one elected thread issues the MMAs; completion is tracked with an mbarrier via
-// tcgen05.commit; the epilogue reads the accumulator with tcgen05.ld.  Several CTAs are resident
-// per SM, so staging, MMA and epilogue of different tiles overlap.
+// Weight gradient of the node-level typed Linear on the 5th-generation tensor cores (tcgen05.mma
+// kind::tf32, 3xTF32 split precision, fp32 accumulators in TMEM).  The forward / input-gradient
+// product lives in tc_linear_ts.cu (A operand in tensor memory, weights resident in shared memory).
 //
 // Roofline: HBM (4*(n_in+n_out) bytes per row vs 6*n_in*n_out tf32 flops per row).
 #include "tc_common.cuh"
@@ -16,159 +9,6 @@
 namespace ihg {
 
 using namespace tc;
-
-struct TcTypeTiles {
-    int64_t b0, b1, n_rows;
-    __host__ __device__ int64_t lo(int t) const { return t == 0 ? 0 : (t == 1 ? b0 : b1); }
-    __host__ __device__ int64_t hi(int t) const { return t == 0 ? b0 : (t == 1 ? b1 : n_rows); }
-    __host__ __device__ int64_t tiles(int t) const { return (hi(t) - lo(t) + kTileM - 1) / kTileM; }
-};
-
-// 256 threads per CTA, one 128-row tile per CTA, K processed in phases of at most 64 features
-// (2 chunks): per phase every thread issues all of its 128-bit row loads in one burst with the
-// coalesced (row, chunk) mapping (8 lanes = one 128-byte row slice), splits to tf32 hi/lo and
-// stages A and the weight rows; one thread issues the MMAs; the epilogue transposes the
-// accumulator through shared memory (reusing the A region) so that bias / addend reads and the
-// stores of y are full-line coalesced.  96 KB of shared memory per CTA => two CTAs per SM
-// overlap each other's load latency.
-constexpr int kNlThreads = 256;
-constexpr int kNlPhaseChunks = 2;
-
-__global__ void __launch_bounds__(kNlThreads)
-node_linear_tc_kernel(const float* __restrict__ x, int64_t x_ld, const float* __restrict__ w,
-                      int n_types, int n_out, int n_in, int transpose_w,
-                      const float* __restrict__ bias, const float* __restrict__ addend,
-                      int64_t addend_ld, TcTypeTiles tt, float* __restrict__ y, int64_t y_ld) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    // per chunk: A hi, A lo (16 KB each); then per chunk: B hi, B lo (n_out x 128 B each)
-    const uint32_t b_tile = (uint32_t)n_out * kChunkBytesPerRow;
-    const uint32_t a_base = base, b_base = base + kNlPhaseChunks * 2 * 16384;
-    __shared__ __align__(8) uint64_t mbar_storage;
-    __shared__ uint32_t tmem_base_slot;
-    const uint32_t mbar = smem_u32(&mbar_storage);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    int64_t bid = blockIdx.x;
-    int type = 0;
-    while (type < 2 && bid >= tt.tiles(type)) { bid -= tt.tiles(type); ++type; }
-    const int64_t row0 = tt.lo(type) + bid * kTileM;
-    const int rows = (int)min((int64_t)kTileM, tt.hi(type) - row0);
-    const int wt = n_types > 1 ? type : 0;
-    const float* W = w + (int64_t)wt * n_out * n_in;
-
-    const uint32_t tmem_cols = tmem_cols_pow2((uint32_t)n_out);
-    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols);
-    if (tid == 0) {
-        mbar_init(mbar, 1);
-        mbar_init_fence();
-    }
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tmem_d = tmem_base_slot;
-    const uint32_t idesc = make_idesc_tf32(n_out);
-
-    const int c = tid & 7, r0 = tid >> 3;               // rows r0 + 32 j, chunk c
-    uint32_t phase = 0;
-    const int n_chunks = n_in / kChunkK;
-    for (int kc0 = 0; kc0 < n_chunks; kc0 += kNlPhaseChunks) {
-        const int nch = min(kNlPhaseChunks, n_chunks - kc0);
-        // ---- one burst of loads: A rows and weight rows of this phase
-        float4 av[kNlPhaseChunks][4], bv[kNlPhaseChunks][4];
-#pragma unroll
-        for (int ch = 0; ch < kNlPhaseChunks; ++ch) {
-            const int k0 = (kc0 + ch) * kChunkK + 4 * c;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int r = r0 + 32 * j;
-                av[ch][j] = (ch < nch && r < rows) ? ldg4(x + (row0 + r) * x_ld + k0) : f4_zero();
-                float4 v = f4_zero();
-                if (ch < nch && r < n_out) {
-                    if (!transpose_w) {
-                        v = ldg4(W + (int64_t)r * n_in + k0);
-                    } else {
-                        const float* p = W + (int64_t)k0 * n_out + r;
-                        v = make_float4(__ldg(p), __ldg(p + n_out), __ldg(p + 2 * n_out), __ldg(p + 3 * n_out));
-                    }
-                }
-                bv[ch][j] = v;
-            }
-        }
-#pragma unroll
-        for (int ch = 0; ch < kNlPhaseChunks; ++ch)
-            if (ch < nch) {
-                const uint32_t a_hi = a_base + (uint32_t)ch * 32768, a_lo = a_hi + 16384;
-                const uint32_t b_hi = b_base + (uint32_t)ch * 2 * b_tile, b_lo = b_hi + b_tile;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int r = r0 + 32 * j;
-                    store_split_chunk(a_hi, a_lo, r, c, av[ch][j]);
-                    if (r < n_out) store_split_chunk(b_hi, b_lo, r, c, bv[ch][j]);
-                }
-            }
-        fence_async_smem();
-        __syncthreads();
-        if (warp == 0) {
-            // warp-uniform issue, one elected lane (tc_common.cuh: MMA issue discipline)
-            fence_after_sync();
-            const uint32_t tmu = warp_uniform(tmem_d);
-            for (int ch = 0; ch < nch; ++ch) {
-                const uint32_t a_hi = a_base + (uint32_t)ch * 32768;
-                const uint32_t b_hi = b_base + (uint32_t)ch * 2 * b_tile;
-                const uint64_t dah = make_kmajor_sw128_desc(a_hi), dal = make_kmajor_sw128_desc(a_hi + 16384);
-                const uint64_t dbh = make_kmajor_sw128_desc(b_hi), dbl = make_kmajor_sw128_desc(b_hi + b_tile);
-                if (elect_one()) {
-#pragma unroll
-                    for (int ks = 0; ks < kChunkK / 8; ++ks)
-                        mma_3xtf32(tmu, advance_desc_k(dah, 8 * ks), advance_desc_k(dal, 8 * ks),
-                                   advance_desc_k(dbh, 8 * ks), advance_desc_k(dbl, 8 * ks), idesc,
-                                   (kc0 + ch > 0 || ks > 0) ? 1u : 0u);
-                    if (ch == nch - 1) mma_commit(mbar);
-                }
-                __syncwarp();
-            }
-        }
-        // the operand tiles are reused by the next phase / the epilogue: wait for the MMAs
-        mbar_wait(mbar, phase);
-        phase ^= 1u;
-    }
-    fence_after_sync();
-    // ---- epilogue: warps (q, half) read 32-column slabs of quadrant q, transpose through a
-    // per-warp staging tile (the A region is free now) and write coalesced rows
-    const int q4 = warp & 3, half = warp >> 2;
-    const uint32_t stg = a_base + (uint32_t)warp * kEpiStageBytes;
-    const int rs = lane >> 3;
-    for (int c0 = 32 * half; c0 < n_out; c0 += 64) {
-        const int ncol = min(32, n_out - c0);
-        __syncwarp();
-        for (int hc = 0; hc < ncol; hc += 16) {
-            float v[16];
-            tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c0 + hc), v);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                sts4(stg + epi_off(lane, hc / 4 + j), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-        }
-        __syncwarp();
-        if (4 * c < ncol) {
-            float4 bb = f4_zero();
-            if (bias) bb = ldg4(bias + (int64_t)wt * n_out + c0 + 4 * c);
-#pragma unroll
-            for (int itr = 0; itr < 8; ++itr) {
-                const int r = q4 * 32 + itr * 4 + rs;
-                if (r < rows) {
-                    float4 o = lds4(stg + epi_off(itr * 4 + rs, c));
-                    f4_add(o, bb);
-                    if (addend) f4_add(o, ldg4(addend + (row0 + r) * addend_ld + c0 + 4 * c));
-                    stg4(y + (row0 + r) * y_ld + c0 + 4 * c, o);
-                }
-            }
-        }
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
-}
 
 // =========================================================================================
 // Weight gradient of the typed node Linear on tensor cores:
@@ -347,8 +187,6 @@ node_wgrad_tc_kernel(const float* __restrict__ dy, int64_t dy_ld, const float* _
 }
 
 bool node_wgrad_tc_eligible(int n_types, int n_out, int n_in) {
-    static const bool disabled = getenv("IHG_DISABLE_TC") != nullptr;
-    if (disabled) return false;
     return n_out % 32 == 0 && n_in % 32 == 0 && n_out <= 128 && n_in <= 128 && n_types * (n_in + 16) <= 512;
 }
 constexpr int kNwCtas = 2 * kNumSMs;
@@ -407,34 +245,6 @@ int launch_node_wgrad_tc(const float* dy, int64_t dy_ld, const float* x, int64_t
     IHG_LAUNCH_CHECK();
     const int64_t total = (int64_t)n_types * n_out * (n_in + 1);
     wgrad_partials_sum_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(ws_dw, grid, n_types, n_out, n_in, dw, db);
-    IHG_LAUNCH_CHECK();
-    return IHG_OK;
-}
-
-bool node_linear_tc_eligible(int n_out, int n_in, int64_t x_ld, int64_t y_ld, const float* addend,
-                             int64_t addend_ld) {
-    static const bool disabled = getenv("IHG_DISABLE_TC") != nullptr;
-    if (disabled) return false;
-    if (n_in % 32 != 0 || n_out % 16 != 0 || n_out < 16 || n_out > 128 || n_in > 128) return false;
-    if (x_ld % 4 != 0 || y_ld % 4 != 0) return false;
-    if (addend && addend_ld % 4 != 0) return false;
-    return true;
-}
-
-int launch_node_linear_tc(const float* x, int64_t x_ld, const float* w, int n_types, int n_out,
-                          int n_in, int transpose_w, const float* bias, const float* addend,
-                          int64_t addend_ld, int64_t n_rows, int64_t bound0, int64_t bound1,
-                          float* y, int64_t y_ld, cudaStream_t st) {
-    TcTypeTiles tt{bound0, bound1, n_rows};
-    const int64_t blocks = tt.tiles(0) + tt.tiles(1) + tt.tiles(2);
-    const int smem = kNlPhaseChunks * (2 * 16384 + 2 * n_out * kChunkBytesPerRow) + 1024;
-    static int attr_smem = 0;
-    if (attr_smem < smem) {
-        IHG_CUDA(cudaFuncSetAttribute(node_linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
-    }
-    node_linear_tc_kernel<<<(unsigned)blocks, kNlThreads, smem, st>>>(x, x_ld, w, n_types, n_out, n_in, transpose_w,
-                                                               bias, addend, addend_ld, tt, y, y_ld);
     IHG_LAUNCH_CHECK();
     return IHG_OK;
 }

@@ -320,10 +320,11 @@ node_linear_ts_kernel(const float* __restrict__ x, int64_t x_ld, const float* __
 
 }  // namespace
 
-bool node_linear_ts_eligible(int n_out, int n_in) {
-    static const bool disabled = getenv("IHG_LINEAR_SS") != nullptr;        // A/B switch: the one-tile-per-CTA kernel
+bool node_linear_ts_eligible(int n_out, int n_in, int64_t x_ld, int64_t y_ld, const float* addend, int64_t addend_ld) {
+    if (n_in % 32 != 0 || n_out % 16 != 0 || n_out < 16 || n_out > 128 || n_in > 128) return false;
+    if (x_ld % 4 != 0 || y_ld % 4 != 0 || (addend && addend_ld % 4 != 0)) return false;
     const int64_t smem = (int64_t)8 * n_in * n_out + 3 * kLtGranuleBytes + kLtEpiWarps * kEpiStageBytes + 1024;
-    return !disabled && n_in % 32 == 0 && n_out % 16 == 0 && n_out >= 16 && n_out <= 128 && smem <= 226 * 1024;
+    return smem <= 226 * 1024;
 }
 
 int launch_node_linear_ts(const float* x, int64_t x_ld, const float* w, int n_types, int n_out, int n_in,

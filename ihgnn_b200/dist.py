@@ -452,6 +452,7 @@ def _halo_reduce(s_local: torch.Tensor, g: ShardedHyperGraph, row_scale: Optiona
         peers = [r for r in range(g.plan.world) if r != g.plan.rank]
         dst = (ctypes.c_void_p * n)(*[recv.data_ptr() + int(g._send_off[r]) * d * 4 for r in peers])
         hdl.barrier(channel=0)                      # every rank's partial sums are complete
+        _lib.ptr(recv)                              # records the device for the call's device guard
         _lib.call("ihg_halo_copy", chunk, dst, off, n, None, d, d, d, _lib.stream_ptr(),
                   tag="halo_pull", algo_bytes=g.S * 8 * d)
         out = F_.segment_reduce(g.reduce_csr, recv, d, row_scale=row_scale, init=s_local[:g.n_own])

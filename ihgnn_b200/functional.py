@@ -237,11 +237,11 @@ class EmbedAllFn(torch.autograd.Function):
         w_user, w_vocab, w_item = (_lib.rows_f32(t) for t in (w_user, w_vocab, w_item))
         x = _empty((U + Q + I, d), w_user)
         st = _lib.stream_ptr()
-        _lib.call("ihg_copy_rows", w_user.data_ptr() + 4 * _lib.ld(w_user), _lib.ld(w_user),
+        _lib.call("ihg_copy_rows", _lib.ptr(w_user) + 4 * _lib.ld(w_user), _lib.ld(w_user),
                   _lib.ptr(x), d, U, d, st)
         segment_reduce(tables.bag_plan, w_vocab, d, row_scale=tables.bag_inv_len, out=x[U:U + Q])
-        _lib.call("ihg_copy_rows", w_item.data_ptr() + 4 * _lib.ld(w_item), _lib.ld(w_item),
-                  x.data_ptr() + 4 * d * (U + Q), d, I, d, st)
+        _lib.call("ihg_copy_rows", _lib.ptr(w_item) + 4 * _lib.ld(w_item), _lib.ld(w_item),
+                  _lib.ptr(x) + 4 * d * (U + Q), d, I, d, st)
         ctx.tables = tables
         ctx.shapes = (tuple(w_user.shape), tuple(w_vocab.shape), tuple(w_item.shape))
         return x
@@ -259,15 +259,15 @@ class EmbedAllFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dwu = _empty(su, dx)
             dwu[0].zero_()                                   # padding_idx=0 row: zero gradient
-            _lib.call("ihg_copy_rows", _lib.ptr(dx), ldx, dwu.data_ptr() + 4 * d, d, U, d, st)
+            _lib.call("ihg_copy_rows", _lib.ptr(dx), ldx, _lib.ptr(dwu) + 4 * d, d, U, d, st)
         if ctx.needs_input_grad[1]:
             # dW_vocab[w] = sum over occurrences (q, w) of dX[U+q] / len(q)
             dwv = segment_reduce(t.word_plan, dx[U:U + Q], d, src_scale=t.bag_inv_len)
         if ctx.needs_input_grad[2]:
             dwi = _empty(si, dx)
             dwi[0].zero_()
-            _lib.call("ihg_copy_rows", dx.data_ptr() + 4 * ldx * (U + Q), ldx,
-                      dwi.data_ptr() + 4 * d, d, I, d, st)
+            _lib.call("ihg_copy_rows", _lib.ptr(dx) + 4 * ldx * (U + Q), ldx,
+                      _lib.ptr(dwi) + 4 * d, d, I, d, st)
         return dwu, dwv, dwi, None
 
 

@@ -11,7 +11,8 @@ graph launch: the host cost per step becomes four small index copies plus the lo
 batch into them, replays the graph and returns the (static) loss tensor.  The batch shape is fixed at
 construction (the reference's batches are fixed-size except the last one of an epoch -- run that one
 eagerly).  `graph_callable` captures any argument-less closure (bench.py uses it for the conv-only
-metric).
+metric).  Construction has no side effect on the model or the optimizer: the warm-up steps that
+precede the capture are undone (parameters and optimizer state are restored in place).
 """
 from __future__ import annotations
 
@@ -34,6 +35,40 @@ def graph_callable(fn: Callable[[], None], warmup: int = 3) -> torch.cuda.CUDAGr
     with torch.cuda.graph(g):
         fn()
     return g
+
+
+def _snapshot(model: torch.nn.Module, optimizer: torch.optim.Optimizer):
+    params = [p.detach().clone() for p in model.parameters()]
+    had_state = {id(p) for group in optimizer.param_groups for p in group["params"] if p in optimizer.state}
+    state = {id(p): {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in optimizer.state[p].items()}
+             for group in optimizer.param_groups for p in group["params"] if p in optimizer.state}
+    return params, had_state, state
+
+
+@torch.no_grad()
+def _restore(model: torch.nn.Module, optimizer: torch.optim.Optimizer, snap) -> None:
+    """Copy the snapshot back IN PLACE (the captured graph holds the addresses of the parameters and
+    of the optimizer's state tensors); state the warm-up created is reset to its initial value."""
+    params, had_state, state = snap
+    for p, v in zip(model.parameters(), params):
+        p.copy_(v)
+    for group in optimizer.param_groups:
+        for p in group["params"]:
+            st = optimizer.state.get(p)
+            if st is None:
+                continue
+            old = state.get(id(p))
+            for k, v in st.items():
+                if not torch.is_tensor(v):
+                    if old is not None:
+                        st[k] = old[k]
+                    elif k == "step":
+                        st[k] = 0
+                elif old is not None:
+                    v.copy_(old[k])
+                else:
+                    v.zero_()           # exp_avg / exp_avg_sq / step of a fresh Adam
+    torch.cuda.synchronize()
 
 
 class GraphedTrainStep:
@@ -68,7 +103,12 @@ class GraphedTrainStep:
             self.optimizer.step()
             self.loss.copy_(loss.detach())
 
+        # warm-up and capture run real optimizer steps (capture itself executes nothing, the warm-up does):
+        # snapshot the parameters and the optimizer state first and put them back afterwards, so that
+        # building a GraphedTrainStep leaves the caller's model and optimizer exactly as they were
+        snap = _snapshot(model, optimizer)
         self.graph = graph_callable(step, warmup)
+        _restore(model, optimizer, snap)
 
     def _load(self, users, queries, items, flags) -> None:
         self.users.copy_(users, non_blocking=True)

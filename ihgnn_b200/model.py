@@ -196,13 +196,17 @@ def make_fast_test_and_get_avg_metrics(original, metrics_cls, log_print=None):
     """A drop-in for the reference's `test_and_get_avg_metrics(model, dataset_train, dataloader,
     get_long_tail_stat=False)` (Helpers/TrainTestHelper.py:37-102) with the same return value --
     (per-user averages or None, average Metrics, seconds) -- that ranks the searches in batches on the
-    GPU.  `metrics_cls` is the reference's `Helpers.Metrics.Metrics`; models without saved-feature
-    support (Srrl) go to `original`."""
+    GPU.  `metrics_cls` is the reference's `Helpers.Metrics.Metrics`; models that are not RawGnn-shaped
+    (Srrl: no `_saved_output_feature`) and logs whose flags are not all 1 go to `original`."""
     import time
 
     def test_and_get_avg_metrics(model, dataset_train, dataloader, get_long_tail_stat: bool = False):
+        # RawGnn-shaped models only: Srrl also has save_features_for_test / prediction_layer but saves
+        # `_saved_u_ps` etc. (Models/Srrl.py), and logs with flags above 1 need the graded NDCG of
+        # Metrics.py:84-103 -- both go to the reference's own loop
         if not (hasattr(model, "save_features_for_test") and hasattr(model, "prediction_layer")
-                and hasattr(dataloader, "logs")):
+                and hasattr(model, "_saved_output_feature") and hasattr(dataloader, "logs")
+                and all(len(l) < 5 or bool(l[4]) for l in dataloader.logs)):
             return original(model, dataset_train, dataloader, get_long_tail_stat)
         start = time.time()
         logs = dataloader.logs

@@ -609,7 +609,8 @@ def test_device_batch_sampler_matches_collate_fn_contract():
     assert users.shape == queries.shape == items.shape == flags.shape == (1100,)
 
 
-def test_graphed_train_step_equals_eager(golden):
+@pytest.mark.parametrize("with_example", [True, False])
+def test_graphed_train_step_equals_eager(golden, with_example):
     """ihgnn_b200.graphs.GraphedTrainStep (forward + BCE + backward + Adam replayed as one CUDA graph)
     follows the same trajectory as the eager loop of TrainTestHelper.py:123-143."""
     from ihgnn_b200.graphs import GraphedTrainStep
@@ -621,14 +622,16 @@ def test_graphed_train_step_equals_eager(golden):
         opt = torch.optim.Adam(m.parameters(), 1e-3, fused=True, capturable=(mode == "graph"))
         out = []
         if mode == "graph":
-            # warmup=1 runs ONE real step before capture (the capture itself only records): undo it
-            step2 = GraphedTrainStep(m, opt, int(users.numel()), DEV, warmup=1,
-                                     example=(users, queries, items, flags))
-            m.load_state_dict(state_of(golden), strict=True)          # in place: the graph keeps its pointers
-            for st in opt.state.values():                             # Adam moments / step counts, in place
+            # construction must leave the model and the optimizer untouched (the default 3 warm-up steps
+            # before the capture are undone in place), with and without an example batch
+            step2 = GraphedTrainStep(m, opt, int(users.numel()), DEV,
+                                     example=(users, queries, items, flags) if with_example else None)
+            for k, v in state_of(golden).items():
+                assert torch.equal(m.state_dict()[k].cpu(), v), f"GraphedTrainStep construction changed {k}"
+            for st in opt.state.values():
                 for v in st.values():
                     if torch.is_tensor(v):
-                        v.zero_()
+                        assert float(v.abs().max()) == 0.0
             for _ in range(4):
                 out.append(float(step2(users, queries, items, flags)))
         else:
