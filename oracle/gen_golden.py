@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE.  Run in the build container only (the reference cannot travel):
 
-    python oracle/gen_golden.py            # rewrites tests/golden/*.npz
+    python oracle/gen_golden.py [case ...]   # rewrites tests/golden/*.npz (all cases, or the named ones)
 
 The reference's own classes are imported from /root/reference with the two import stubs of
 oracle/stubs/ (torch_sparse -> torch.sparse.mm, dgl -> unused) and fed
@@ -66,6 +66,9 @@ CASES = {
     # d=64 / 3 layers at the smallest size that still has heavy (Zipf head) nodes
     "ihgnn_o3_L3_d64": dict(U=100, Q=30, I=90, V=40, E=1200, shape="cikm", seed=15,
                             gnn="IHGNN", L=3, order=3, d=64, batch=33),
+    # the cikm model shape (BASELINE.json configs[2]: d=128, 3 layers, order 3) on a small CIKM-shaped log
+    "ihgnn_o3_L3_d128": dict(U=110, Q=36, I=84, V=36, E=1000, shape="cikm", seed=19,
+                             gnn="IHGNN", L=3, order=3, d=128, batch=30),
 }
 
 
@@ -258,8 +261,10 @@ def _make_case(name: str, cfg: dict, outdir: str) -> None:
 def main():
     outdir = os.path.join(REPO, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
+    only = set(sys.argv[1:])                      # optional: names of the cases to (re)generate
     for name, cfg in CASES.items():
-        make_case(name, cfg, outdir)
+        if not only or name in only:
+            make_case(name, cfg, outdir)
 
 
 if __name__ == "__main__":

@@ -196,3 +196,154 @@ def test_ranking_at_config5_shape_properties():
     assert float(agree) > 0.999                            # fp32 vs fp64 near-ties may swap neighbours
     again, _ = F_.rank_topk(feat, users, queries, bias, 0.5, candidates=cand, k=k, **kw)
     assert torch.equal(again, ids)
+
+
+# ----------------------------------------------------------------------------------------------
+# direct comparison with the oracle at BASELINE's own sizes (the oracle needs seconds to tens of
+# seconds and ~13 GB of host memory for these; everything below runs once per session)
+# ----------------------------------------------------------------------------------------------
+def test_graph_build_bit_exact_vs_oracle_at_full_size(workload):
+    """`ihg_graph_build` at the amazon-full (E = 1.2 M) and cikm (E = 5 M) shapes against the oracle's
+    restatement of Helpers/Graph.py:94-134 (numpy lexsort by (node, hyperedge) = what `coalesce()`
+    yields): I3, CSR row pointers and columns, degrees and the fp32 reciprocals, all bit-exact."""
+    from helpers import orc
+    name, log, ds, d = workload
+    g = ds.hypergraph                                     # the reference's (file) hyperedge order
+    og = orc.build_hypergraph(log.pos_user, log.pos_query, log.pos_item, log.user_count, log.query_count,
+                              log.item_count)
+    assert g.EdgeCount == og.EdgeCount and g.node_count == og.node_count
+    assert torch.equal(g.i3.cpu().to(torch.int64), og.I3)
+    assert torch.equal(g.rowptr.cpu().to(torch.int64), og.rowptr)
+    assert torch.equal(g.col.cpu().to(torch.int64), og.col)
+    assert torch.equal(g.VertexDegrees.cpu(), og.VertexDegrees)
+    assert torch.equal(g.dv_inv.cpu(), og.VertexDegrees.pow(-1).view(-1))            # GnnLayers.py:187
+    assert float((g.dv_inv_sqrt.cpu() / og.VertexDegrees.pow(-0.5).view(-1) - 1).abs().max()) < 2e-7
+    assert torch.equal(g.I3.cpu(), og.I3) and g.I3.dtype == torch.int64              # the lazily built reference views
+    adj = g.Adjacency
+    assert torch.equal(adj.indices().cpu(), torch.stack([og.row, og.col]))
+    assert bool((adj.values() == 1).all())
+
+
+def _seeded_conv_state(layers: int, d: int, seed: int = 0):
+    """Weights of an L-layer IHGNN stack (order 3 on layer 0, order 1 after: RawGnn.py:76-78) with the
+    reference's key names, drawn with nn.Linear's default init bounds."""
+    gen = torch.Generator().manual_seed(seed)
+    state = {}
+    for k in range(layers):
+        K = 7 if k == 0 else 3
+        for name, shape, fan_in in ((f"gnn_{k}.feature_interactor.aggregation.weight", (d, K * d), K * d),
+                                    (f"gnn_{k}.feature_interactor.aggregation.bias", (d,), K * d),
+                                    (f"gnn_{k}.feature_transform.weight", (d, d), d),
+                                    (f"gnn_{k}.feature_transform.bias", (d,), d)):
+            state[name] = (torch.rand(*shape, generator=gen) * 2 - 1) / fan_in ** 0.5
+    return state
+
+
+def _oracle_conv(log, state, x, layers: int, dtype, edges: int):
+    from helpers import orc
+    og = orc.build_hypergraph(log.pos_user[:edges], log.pos_query[:edges], log.pos_item[:edges],
+                              log.user_count, log.query_count, log.item_count)
+    words, offsets = log.bag_inputs()
+    om = orc.OracleModel(state, og, torch.from_numpy(words), torch.from_numpy(offsets), log.user_count,
+                         log.query_count, log.item_count, layer_type="IHGNN", layer_count=layers, order=3,
+                         dtype=dtype)
+    xo = x.to(dtype).clone().requires_grad_(True)
+    outs = om.conv_stack(xo)
+    torch.cat(outs, 1).sum().backward()                                   # metric M1's loss (SURVEY 8d)
+    grads = {k: v.grad for k, v in om.params.items() if k.startswith("gnn_")}
+    return [o.detach() for o in outs[1:]], xo.grad, grads
+
+
+@pytest.mark.parametrize("name,edges", [("amazon-small", None), ("amazon-full", None), ("cikm", 600_000)])
+def test_conv_fwd_bwd_vs_oracle_at_baseline_configs(name, edges):
+    """BASELINE.json configs[0] / configs[1] verbatim ("forward/backward parity vs reference torch.sparse.mm
+    path at full Amazon-subset shape") and the cikm model (d = 128, 3 layers) on the first 600 K of its
+    5 M hyperedges over its full node set (the fp64 oracle's [E, 7d] concatenation would need 36 GB at 5 M):
+    every layer output, dX and every weight / bias gradient of the conv stack against the oracle run in
+    fp64 (<= 1e-5 max-norm relative, the north_star bar); the oracle's own fp32 run is measured against
+    the same arbiter so the noise floor is on record."""
+    from helpers import REL_TOL, max_rel
+    from ihgnn_b200 import synth
+    from ihgnn_b200.dataset import GraphDataset
+    from ihgnn_b200.layers import IHGNNLayer
+    log = synth.make_workload(name)
+    w = synth.WORKLOADS[name]
+    layers, d = w["layers"], w["dim"]
+    E = log.edge_count if edges is None else edges
+    words, offsets = log.bag_inputs()
+    ds = GraphDataset(log.user_count, log.query_count, log.item_count, log.vocab_size, words, offsets,
+                      log.pos_user[:E], log.pos_query[:E], log.pos_item[:E], DEV)
+    state = _seeded_conv_state(layers, d)
+    x = torch.randn(log.node_count, d, generator=torch.Generator().manual_seed(1)) * 0.1
+
+    gnns = []
+    for k in range(layers):
+        layer = IHGNNLayer(torch.device(DEV), ds, d, d, 3 if k == 0 else 1, False)
+        layer.load_state_dict({kk[len(f"gnn_{k}."):]: v for kk, v in state.items() if kk.startswith(f"gnn_{k}.")},
+                              strict=True)
+        gnns.append(layer.to(DEV))
+    xg = x.to(DEV).requires_grad_(True)
+    outs, h = [xg], xg
+    for layer in gnns:
+        h = layer(h)
+        outs.append(h)
+    torch.cat(outs, 1).sum().backward()
+    torch.cuda.synchronize()
+
+    o64, dx64, g64 = _oracle_conv(log, state, x, layers, torch.float64, E)
+    worst = {}
+    for k in range(layers):
+        worst[f"out{k}"] = max_rel(outs[k + 1].detach().cpu().numpy(), o64[k].numpy())
+    worst["dx"] = max_rel(xg.grad.cpu().numpy(), dx64.numpy())
+    for k, layer in enumerate(gnns):
+        for pn, p in layer.named_parameters():
+            worst[f"gnn_{k}.{pn}"] = max_rel(p.grad.cpu().numpy(), g64[f"gnn_{k}.{pn}"].numpy())
+    bad = {k: v for k, v in worst.items() if not v <= REL_TOL}
+    assert not bad, f"{name}: beyond {REL_TOL}: {bad} (all: {worst})"
+    if name != "cikm":                                     # the oracle's own fp32 run: the reference's noise floor
+        o32, dx32, g32 = _oracle_conv(log, state, x, layers, torch.float32, E)
+        floor = max([max_rel(o32[k].numpy(), o64[k].numpy()) for k in range(layers)]
+                    + [max_rel(dx32.numpy(), dx64.numpy())]
+                    + [max_rel(g32[k].numpy(), g64[k].numpy()) for k in g64])
+        print(f"{name}: CUDA path worst {max(worst.values()):.2e}, oracle-fp32 worst {floor:.2e} (vs oracle fp64)")
+        assert floor <= REL_TOL
+
+
+def test_training_step_vs_oracle_at_amazon_small():
+    """configs[0] end to end: embeddings -> 2 IHGNN layers -> batch scores -> BCE -> every parameter
+    gradient, against the fp64 oracle, on the amazon-small workload itself (E = 100 K, N = 35 K, d = 64)."""
+    from helpers import REL_TOL, max_rel, orc
+    from ihgnn_b200 import HemPredictionLayer, IHGNNLayer, RawGnn, synth
+    from ihgnn_b200.dataset import GraphDataset
+    log = synth.make_workload("amazon-small")
+    ds = GraphDataset.from_search_log(log, DEV)
+    torch.manual_seed(7)
+    model = RawGnn(device=torch.device(DEV), dataset=ds, embedding_size=64, gnn_layer_type=IHGNNLayer,
+                   gnn_layer_count=2, feature_interaction_order=3, phase2_attention=False,
+                   predictions=HemPredictionLayer, lambda_muq=0.5).to(DEV)
+    rng = np.random.default_rng(7)
+    pick = rng.integers(0, log.edge_count, size=100)
+    users = np.concatenate([log.pos_user[pick], np.repeat(log.pos_user[pick], 10)])
+    queries = np.concatenate([log.pos_query[pick], np.repeat(log.pos_query[pick], 10)])
+    items = np.concatenate([log.pos_item[pick], rng.integers(0, log.item_count, size=1000)])
+    flags = np.concatenate([np.ones(100), np.zeros(1000)])
+    u, q, i = (torch.from_numpy(a) for a in (users, queries, items))
+    f = torch.from_numpy(flags)
+    scores = model(u.to(DEV), q.to(DEV), i.to(DEV))
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(scores, f.float().to(DEV))
+    loss.backward()
+    og = orc.build_hypergraph(log.pos_user, log.pos_query, log.pos_item, log.user_count, log.query_count, log.item_count)
+    words, offsets = log.bag_inputs()
+    om = orc.OracleModel({k: v.detach().cpu() for k, v in model.state_dict().items()}, og, torch.from_numpy(words),
+                         torch.from_numpy(offsets), log.user_count, log.query_count, log.item_count,
+                         layer_type="IHGNN", layer_count=2, order=3, dtype=torch.float64)
+    so = om.forward(u, q, i)
+    lo = orc.bce_with_logits_mean(so, f.double())
+    lo.backward()
+    worst = {"scores": max_rel(scores.detach().cpu().numpy(), so.detach().numpy()),
+             "loss": abs(float(loss) - float(lo)) / abs(float(lo))}
+    ograds = om.grads()
+    for k, p in model.named_parameters():
+        worst[k] = max_rel(p.grad.cpu().numpy(), ograds[k].numpy())
+    bad = {k: v for k, v in worst.items() if not v <= REL_TOL}
+    assert not bad, f"beyond {REL_TOL}: {bad}"

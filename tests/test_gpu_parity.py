@@ -267,6 +267,86 @@ def test_model_forward_backward_matches_reference(golden, two_hop_mode):
     assert not bad, f"beyond {REL_TOL}: {bad}"
 
 
+class _StockTorchCaller(torch.nn.Module):
+    """What the reference's OWN RawGnn executes on top of the drop-in layers (Models/RawGnn.py:52-99 for the
+    construction by keyword, :104-144 for forward, :147-155 for the saved features): stock `torch.cat` of
+    the three embedding blocks and of the layer outputs into the [N, d(1+L)] matrix, stock advanced
+    indexing for the batch rows -- none of this package's fused caller paths (model.py).  Same submodule
+    names, so the reference `state_dict` loads with strict=True."""
+
+    def __init__(self, device, dataset, embedding_size, layer_type, layer_count, order, lambda_muq):
+        super().__init__()
+        from ihgnn_b200 import EmbeddingLayer, HemPredictionLayer, IHGNNLayer
+        self.dataset = dataset
+        self.embeddings = EmbeddingLayer(dataset=dataset, embedding_size=embedding_size)
+        self.gnns = []
+        for layer in range(layer_count):
+            if layer_type is IHGNNLayer:
+                o = 1 if (order > 1 and layer > 0) else order                      # RawGnn.py:76-78
+                gnn = layer_type(device=device, dataset=dataset, input_dimension=embedding_size,
+                                 output_dimension=embedding_size, feature_interaction_order=o,
+                                 phase2_attention=False)
+            else:
+                gnn = layer_type(device=device, dataset=dataset, input_dimension=embedding_size,
+                                 output_dimension=embedding_size)
+            self.gnns.append(gnn)
+            self.add_module(f"gnn_{layer}", gnn)
+        self.prediction_layer = HemPredictionLayer(feature_dimension=embedding_size * (1 + layer_count),
+                                                   lambda_muq=lambda_muq, item_count=dataset.item_count)
+        self._saved = None
+
+    def _features(self):
+        x = torch.cat(self.embeddings(None, None, None))                           # :112
+        outs, h = [x], x
+        for gnn in self.gnns:                                                      # :116-118
+            h = gnn(h)
+            outs.append(h)
+        return torch.cat(outs, 1)                                                  # :122
+
+    def forward(self, user_indices, query_indices, item_indices=None):
+        f = self._features() if self._saved is None else self._saved
+        fu = f[user_indices]                                                       # :128
+        fq = f[query_indices + self.dataset.query_start_index_in_graph]            # :129
+        if item_indices is not None:
+            fi = f[item_indices + self.dataset.item_start_index_in_graph]          # :131
+        else:
+            fi = f[self.dataset.item_start_index_in_graph:]                        # :133
+        return self.prediction_layer(fu, fq, fi, item_indices)                     # :137-142
+
+
+def test_stock_torch_caller_over_dropin_layers_matches_reference(golden):
+    """north_star: "Main.py and the RawGnn/Srrl models use them unchanged".  The reference tree cannot
+    travel to the GPU box, so its caller is restated with the stock torch ops it uses and run over the
+    drop-in layers: scores, loss, every parameter gradient, the evaluation scores and the top-10 of
+    the reference's own sort must match the reference's numbers."""
+    from ihgnn_b200 import GCNLayer, HGCNLayer, IHGNNLayer
+    ds = _dataset(golden)
+    layer = {"IHGNN": IHGNNLayer, "HGCN": HGCNLayer, "GCN": GCNLayer}[str(golden["cfg.gnn"])]
+    m = _StockTorchCaller(torch.device(DEV), ds, int(golden["cfg.d"]), layer, int(golden["cfg.L"]),
+                          int(golden["cfg.order"]), float(golden["cfg.lambda_muq"]))
+    m.load_state_dict(state_of(golden), strict=True)
+    m = m.to(DEV)
+    scores, loss, grads = _run_model(m, golden)
+    worst = {"scores": max_rel(scores, golden["ref64.scores"]),
+             "loss": abs(loss - float(golden["ref64.loss"])) / abs(float(golden["ref64.loss"]))}
+    for k, g in grads.items():
+        worst["grad." + k] = max_rel(g, golden[f"ref64.grad.{k}"])
+    with torch.no_grad():
+        m._saved = m._features()                                                   # save_features_for_test, :147-155
+        I = ds.item_count
+        ones = torch.ones(I, dtype=torch.long, device=DEV)
+        u0, q0 = int(golden["batch.users"][0]), int(golden["batch.queries"][0])
+        worst["eval_scores"] = max_rel(m(u0 * ones, q0 * ones, None).cpu().numpy(), golden["ref64.eval_scores"])
+        top = golden["ref64.rank_top10"]
+        for b in range(top.shape[0]):                                              # Dataset.py:324-329 + Metrics.py:60-61
+            out = m(int(golden["batch.users"][b]) * ones, int(golden["batch.queries"][b]) * ones, None)
+            _, idx = torch.sort(out, descending=True)
+            got = idx[:10].cpu().numpy()                                           # fp32 here: either precision of the reference's sort
+            assert np.array_equal(got, top[b]) or np.array_equal(got, golden["ref32.rank_top10"][b]), f"search {b}"
+    bad = {k: v for k, v in worst.items() if not v <= REL_TOL}
+    assert not bad, f"beyond {REL_TOL}: {bad}"
+
+
 def test_conv_stack_gradients_match_reference(golden, two_hop_mode):
     """Metric M1's unit of work: loss = sum(cat(outs, 1)), gradient w.r.t. X and conv weights."""
     m = _model(golden)
