@@ -1,21 +1,30 @@
 #!/usr/bin/env python
-"""bench.py -- hypergraph-conv throughput of the IHGNN hot path (BASELINE.json metric).
+"""bench.py -- throughput of the IHGNN hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload amazon-full|cikm|amazon-small]
+    python bench.py [--gpus N] [--steps K] [--warmup W]
+                    [--workload cikm|amazon-full|amazon-small|rank] [--also amazon-full|none]
+                    [--scaling weak|strong]
     python bench.py --impl reference ...      # the CPU arm: oracle port of the reference path
 
-One "step" = one fwd+bwd pass of the L-layer IHGNN stack over the whole hypergraph (metric M1,
-SURVEY.md section 8d: input X [N,d] requires grad, loss = sum(cat(outs,1)), order 3 on layer 0
-and order 1 after, as Models/RawGnn.py:76-78).  `value` = E*L / t in hyperedge-layers/s with
-everything resident in HBM; `e2e` = the same E*L divided by the time of a full training step
-through the public API (RawGnn.forward -> BCE -> backward -> Adam) with the batch indices
-coming from pinned host memory and the loss read back every step.
+Conv workloads (metric M1): one "step" = one fwd+bwd pass of the L-layer IHGNN
+stack over the whole hypergraph (input X [N,d] requires grad, order 3 on layer 0 and order 1 after, as
+Models/RawGnn.py:76-78).  `value` = E*L / t in hyperedge-layers/s with everything resident in HBM;
+`e2e` = the same E*L divided by the time of a full training step through the public API
+(RawGnn.forward -> BCE -> backward -> Adam) with the batch indices coming from pinned host memory and
+the loss read back every step.  The default workload is BASELINE.json configs[2] (`cikm`, the largest
+single-GPU configuration); at N = 1 the line also carries configs[1] (`amazon-full`) under "also".
 
-Prints ONE JSON line (rank 0).
+`--workload rank` is BASELINE.json configs[4]: one step = one evaluation pass (conv forward over the
+graph, then 131 072 searches per GPU, each scoring 1 000 candidate items and keeping the top 10);
+`value` = searches/s.
+
+N > 1 (torchrun): weak scaling by default (the global log is N x the workload, the global training batch
+N x 1 100 rows); `--scaling strong` keeps the workload fixed.  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -44,40 +53,59 @@ def emit(line: dict) -> None:
 
 METRIC = "hypergraph_conv_hyperedge_layers_per_sec_fwd_bwd"
 UNIT = "hyperedge-layers/s"
+RANK_METRIC = "inference_ranking_searches_per_sec"
+RANK_UNIT = "searches/s"
+B_POS, NEG = 100, 10                                  # GlobalSettings.py:26,39: 100 positives + 10 negatives each
 
+# bounded CPU sample of a workload = the same generator at a smaller scale (every count multiplied, so
+# nodes per hyperedge, degree skew and the model are those of the workload itself)
+CPU_SCALE = {"amazon-small": 1.0, "amazon-full": 0.125, "cikm": 0.02}
 
 # C-ABI call tag -> the kernels that call launches, by name in the committed ncu --set full extract
-_TAG_KERNEL = {"segment_reduce[mul=1]": ["segment_reduce_kernel", "segment_fixup_kernel"],
-               "segment_reduce[mul=3]": ["segment_reduce_kernel", "segment_fixup_kernel"],
+_TAG_KERNEL = {"segment_reduce": ["segment_reduce_kernel", "segment_fixup_kernel"],
                "two_hop_reduce": ["two_hop_reduce_kernel", "segment_fixup_kernel"],
                "edge_gather_sum": ["edge_gather_sum_kernel"],
                "edge_interact_fwd": ["feature_interact_fwd_ts_kernel"],
                "edge_interact_bwd": ["interact_bwd_slot_ts_kernel", "edge_interact_bwd_wgrad_tc_kernel"],
                "node_linear": ["node_linear_ts_kernel"],
-               "node_linear_wgrad": ["node_wgrad_tc_kernel", "wgrad_partials_sum_kernel"]}
+               "node_linear_wgrad": ["node_wgrad_tc_kernel", "wgrad_partials_sum_kernel"],
+               "rank_topk": ["rank_topk_kernel"]}
+# gathers served by L2 (node table resident / Zipf-hot): charged the HBM bytes of the kernels they
+# replace, so their "GB/s" is not an HBM fraction -- an L2 figure is reported beside it
+_L2_SERVED = ("two_hop_reduce", "rank_topk")
+L2_BYTES_PER_CLK = 6300.0                             # full-chip LTS cap, B300_MICROARCH.md "L2 cache"
 
 
-def ncu_traffic(workload, tag):
-    """dram__bytes_read.sum + dram__bytes_write.sum per C-ABI call of the dominant tag (summed over
-    the kernels the call launches), from the committed ncu capture of this workload
-    (profiles/r01_ncu_traffic.json, written by profiles/ncu_extract.py); None if not captured."""
-    try:
-        with open(os.path.join(REPO, "profiles", "r01_ncu_traffic.json")) as f:
+def ncu_traffic_file(workload: str):
+    """The committed ncu --set full extract of one eager step of this workload
+    (profiles/ncu_extract.py --traffic): DRAM bytes per launch of every kernel and per step."""
+    for rnd in ("r02", "r01"):
+        path = os.path.join(REPO, "profiles", f"{rnd}_ncu_traffic_{workload}.json")
+        if os.path.exists(path):
+            with open(path) as f:
+                return json.load(f)
+    legacy = os.path.join(REPO, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(legacy):
+        with open(legacy) as f:
             t = json.load(f)
-        if t.get("workload") != workload or tag not in _TAG_KERNEL:
-            return None, None
-        total, found = 0.0, False
-        for kern in _TAG_KERNEL[tag]:
-            for name, b in t["dram_bytes_per_launch"].items():
-                if kern in name:
-                    total += float(b)
-                    found = True
-                    break
-        if found:
-            return total, t.get("source")
-    except (OSError, ValueError, KeyError):
-        pass
-    return None, None
+        if t.get("workload") == workload:
+            return t
+    return None
+
+
+def ncu_traffic(traffic, tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum per C-ABI call of `tag` (summed over the kernels
+    the call launches); None if not captured."""
+    if not traffic or tag not in _TAG_KERNEL:
+        return None
+    total, found = 0.0, False
+    for kern in _TAG_KERNEL[tag]:
+        for name, b in traffic["dram_bytes_per_launch"].items():
+            if kern in name:
+                total += float(b)
+                found = True
+                break
+    return total if found else None
 
 
 def measured_peaks():
@@ -119,7 +147,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def mark(self) -> int:
+        return len(self.rows)
+
+    def stop(self, since: int = 0):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -130,7 +161,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[max(since - 1, 0):]:
             parts = [p.strip() for p in r.split(",")]
             if len(parts) < 6:
                 continue
@@ -168,16 +199,25 @@ class KernelProfiler:
         return agg
 
 
+def conv_config(name: str, layers: int, d: int, E: int, N: int, scaling: str) -> dict:
+    """The workload description, identical in both arms (the CPU arm times a bounded sample of THIS
+    workload and says so in cpu_baseline.sample)."""
+    return {"workload": name, "layers": layers, "dim": d, "hyperedges": E, "nodes": N, "interaction_order": 3,
+            "scaling": scaling, "batch_rows": B_POS * (1 + NEG)}
+
+
 # ----------------------------------------------------------------------------------------
 # the CPU arm: oracle port of the reference path, all host threads
 # ----------------------------------------------------------------------------------------
-def cpu_sample_model(log, layers: int, d: int, sample_edges: int):
-    """Oracle model over a bounded sample of the workload: the same node tables, the first
-    `sample_edges` positive interactions of the same log."""
+def cpu_sample_model(name: str, cpu_scale: float):
+    """Oracle model over a bounded sample of the workload: the same generator, every count multiplied
+    by `cpu_scale` (same nodes-per-hyperedge ratio, degree skew, layer count and width)."""
     from oracle import ihgnn_oracle as orc
-    Es = min(sample_edges, log.edge_count)
-    g = orc.build_hypergraph(log.pos_user[:Es], log.pos_query[:Es], log.pos_item[:Es],
-                             log.user_count, log.query_count, log.item_count)
+    w = synth.WORKLOADS[name]
+    layers, d = w["layers"], w["dim"]
+    log = synth.make_workload(name, scale=cpu_scale)
+    g = orc.build_hypergraph(log.pos_user, log.pos_query, log.pos_item, log.user_count, log.query_count,
+                             log.item_count)
     gen = torch.Generator().manual_seed(0)
     state = {}
     for k in range(layers):
@@ -191,68 +231,144 @@ def cpu_sample_model(log, layers: int, d: int, sample_edges: int):
                         log.user_count, log.query_count, log.item_count, layer_type="IHGNN",
                         layer_count=layers, order=3, dtype=torch.float32)
     x = torch.randn(log.node_count, d, generator=gen) * 0.05
-    return orc, m, x, Es
+    return orc, m, x, log
 
 
-def time_cpu(log, layers, d, sample_edges, steps, warmup):
+def time_cpu(name: str, cpu_scale: float, steps: int, warmup: int):
     torch.set_num_threads(os.cpu_count() or 1)
-    orc, m, x, Es = cpu_sample_model(log, layers, d, sample_edges)
+    orc, m, x, log = cpu_sample_model(name, cpu_scale)
+    layers = synth.WORKLOADS[name]["layers"]
     for _ in range(warmup):
         orc.conv_fwd_bwd(m, x)
     t0 = time.perf_counter()
     for _ in range(steps):
         orc.conv_fwd_bwd(m, x)
     dt = (time.perf_counter() - t0) / steps
-    return Es * layers / dt, dt, Es
+    sample = (f"'{name}' generated at scale {cpu_scale:g} ({log.edge_count} hyperedges, {log.node_count} nodes: the "
+              f"workload's own nodes-per-hyperedge ratio, Zipf skew, {layers} layers, d={synth.WORKLOADS[name]['dim']}), "
+              f"whole conv fwd+bwd per step ({dt * 1e3:.0f} ms), oracle port (torch {torch.__version__} CPU ops), fp32")
+    return log.edge_count * layers / dt, dt, sample
 
 
-def run_reference_arm(args, log, layers, d):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+def rank_cpu(searches: int, steps: int, warmup: int):
+    """The reference's evaluation loop (Dataset.py:324-329, RawGnn.py:124-142, Metrics.py:60-61) restated
+    by the oracle, on `searches` searches x 1 000 candidates over amazon-full-sized saved features."""
+    from oracle import ihgnn_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = synth.WORKLOADS["amazon-full"]
+    U, Q, I, D = w["user_count"], w["query_count"], w["item_count"], w["dim"] * (1 + w["layers"])
+    gen = torch.Generator().manual_seed(0)
+    feat = torch.randn(U + Q + I, D, generator=gen)
+
+    class _M:                                             # what orc.rank_topk reads of a model
+        pass
+    m = _M()
+    m.U, m.Q, m.I, m.lambda_muq, m.cosine = U, Q, I, 0.5, False
+    m.params = {"prediction_layer.items_bias": torch.randn(I, generator=gen)}
+    m.forward = lambda u, q, i, features=None: orc.OracleModel.forward(m, u, q, i, features=features)
+    users = torch.randint(0, U, (searches,), generator=gen)
+    queries = torch.randint(0, Q, (searches,), generator=gen)
+    cand = torch.randint(0, I, (searches, 1000), generator=gen)
+    for _ in range(warmup):
+        orc.rank_topk(m, users[:64], queries[:64], cand[:64], 10, features=feat)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.rank_topk(m, users, queries, cand, 10, features=feat)
+    dt = (time.perf_counter() - t0) / steps
+    sample = (f"{searches} searches x 1000 candidates over saved features [{U + Q + I}, {D}] per step ({dt * 1e3:.0f} ms): "
+              f"per search gather + HEM score + torch.sort + top-10, oracle port (torch CPU ops), fp32; the conv "
+              f"forward that produces the features is not in the CPU sample")
+    return searches / dt, dt, sample
+
+
+def run_reference_arm(args):
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    value, dt, Es = time_cpu(log, layers, d, args.cpu_sample_edges, args.steps, max(args.warmup, 1))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
-    sample = (f"first {Es} of {log.edge_count} hyperedges of '{args.workload}' over the full node set "
-              f"(N={log.node_count}), conv fwd+bwd, fp32, torch {torch.__version__} CPU")
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    if args.workload == "rank":
+        value, dt, sample = rank_cpu(args.cpu_rank_searches, args.steps, max(args.warmup, 1))
+        metric, unit, config = RANK_METRIC, RANK_UNIT, rank_config(world, args.scaling)
+    else:
+        w = synth.WORKLOADS[args.workload]
+        mult = world if args.scaling == "weak" else 1
+        cpu_scale = args.cpu_scale or CPU_SCALE[args.workload]
+        value, dt, sample = time_cpu(args.workload, cpu_scale, args.steps, max(args.warmup, 1))
+        E = int(round(w["edge_count"] * mult))
+        N = sum(max(4, int(round(w[k] * mult))) for k in ("user_count", "query_count", "item_count"))
+        metric, unit, config = METRIC, UNIT, conv_config(args.workload, w["layers"], w["dim"], E, N, args.scaling)
+    emit({
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": args.workload, "layers": layers, "dim": d, "hyperedges": log.edge_count,
-                   "nodes": log.node_count, "interaction_order": 3},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config,
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }
-    emit(line)
+        "note": "rate of the CPU port on a bounded sample of the workload named in config (a rate, not a time: "
+                "the sample keeps the workload's per-hyperedge cost); conv fwd+bwd only, no embedding / scoring / Adam",
+    })
 
 
 # ----------------------------------------------------------------------------------------
-# the GPU arm
+# the GPU arm: conv workloads
 # ----------------------------------------------------------------------------------------
-def run_gpu_arm(args, log, layers, d):
+class Ctx:
+    """Process-wide bench state: device, ranks, process group, clock sampler."""
+
+    def __init__(self, args):
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device: ihgnn_b200 has no CPU fallback "
+                               "(use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist_mod
+            self.dist = dist_mod
+            self.dist.init_process_group("nccl", device_id=self.dev)
+        self.sampler = ClockSampler(self.local_rank)
+        self.sampler.start()
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def all_agree(self, done: bool) -> bool:
+        if self.dist is None:
+            return done
+        flag = torch.tensor([1 if done else 0], device=self.dev, dtype=torch.int32)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+        return bool(int(flag.item()))
+
+    def max_over_ranks(self, *vals):
+        if self.dist is None:
+            return vals
+        tt = torch.tensor(list(vals), device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(tt, op=self.dist.ReduceOp.MAX)
+        return tuple(float(v) for v in tt)
+
+
+def measure_conv(ctx: Ctx, name: str, with_cpu: bool, profile_step: bool = False) -> dict:
+    """Everything bench.py reports for one conv workload; returns the dict on rank 0 (None elsewhere)."""
     from ihgnn_b200 import HemPredictionLayer, IHGNNLayer, RawGnn, _lib
     from ihgnn_b200.dataset import GraphDataset
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: ihgnn_b200 has no CPU fallback "
-                           "(use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=dev)
+    args, dev, world, rank, dist = ctx.args, ctx.dev, ctx.world, ctx.rank, ctx.dist
+    w = synth.WORKLOADS[name]
+    layers, d = w["layers"], w["dim"]
+    mult = world if args.scaling == "weak" else 1
+    rows_per_step = B_POS * (1 + NEG) * mult              # the global training batch grows with the workload
 
     # --- build: graph indices on the device, model with the reference's own initialisers
     t_build0 = time.perf_counter()
+    log = synth.make_workload(name, scale=args.scale * mult)
+    t_synth = time.perf_counter() - t_build0
     torch.manual_seed(0)
-    B, NEG = 100, 10                                                      # GlobalSettings.py:26,39
     if world == 1:
         ds = GraphDataset.from_search_log(log, dev)
         graph = ds.hypergraph
@@ -265,9 +381,10 @@ def run_gpu_arm(args, log, layers, d):
         sync_conv = lambda: None
         sync_all = lambda: None
         parallelism = "single"
+        plan = None
     else:
-        # weak scaling: the global log is `world` x the workload; hyperedges live with their user's
-        # owner, node rows are sharded per type, boundary rows travel by all-to-all (ihgnn_b200/dist.py)
+        # the global log is partitioned: hyperedges live with their user's owner, node rows are sharded per
+        # type, boundary rows travel over NVLink peer memory (ihgnn_b200/dist.py)
         from ihgnn_b200.dist import PartitionPlan, ShardedHyperGraph, ShardedRawGnn, allreduce_dense_grads
         plan = PartitionPlan(log.pos_user, log.pos_query, log.pos_item, log.user_count, log.query_count,
                              log.item_count, world, rank)
@@ -280,16 +397,14 @@ def run_gpu_arm(args, log, layers, d):
         sync_conv = lambda: [allreduce_dense_grads(g) for g in conv_layers]
         sync_all = model.sync_grads
         parallelism = (f"hyperedges partitioned by user owner x{world}, node rows sharded per type, "
-                       f"halo all-to-all (rank0: {plan.n_own} own + {plan.R} halo rows, {plan.edge_count} hyperedges)")
+                       f"halo rows over NVLink peer memory (rank0: {plan.n_own} own + {plan.R} halo rows, "
+                       f"{plan.edge_count} hyperedges)")
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build0
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     # --- M1: conv stack fwd+bwd, inputs resident in HBM -------------------------------
+    gout = torch.ones_like(x)
+
     def conv_step():
         x.grad = None
         for p in model.parameters():
@@ -305,51 +420,43 @@ def run_gpu_arm(args, log, layers, d):
         torch.autograd.backward(outs, [gout] * len(outs))
         sync_conv()
 
-    gout = torch.ones_like(x)
-
-    # nvidia-smi needs a moment to start: launch it before the warm-up, keep warming up (untimed)
-    # until its first sample has arrived, and let it run through both timed regions so that the
-    # reported clocks are the clocks under this load even when the timed region is ~100 ms
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # keep warming up (untimed) until nvidia-smi's first sample has arrived, so that the reported clocks
+    # are the clocks under this load even when the timed region is ~100 ms
     for _ in range(args.warmup):
         conv_step()
     t_wait = time.time()
-    while True:                                   # every rank must run the same number of steps
-        done = 1 if (sampler.proc is None or sampler.rows or time.time() - t_wait > 5.0) else 0
-        if dist is not None:
-            flag = torch.tensor([done], device=dev, dtype=torch.int32)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            done = int(flag.item())
-        if done:
-            break
+    while not ctx.all_agree(ctx.sampler.proc is None or bool(ctx.sampler.rows) or time.time() - t_wait > 5.0):
         conv_step()
-    n_before = len(sampler.rows)
-    use_graph = world == 1 and os.environ.get("IHG_CUDA_GRAPH", "1") != "0"
-    # N > 1: the conv step (halo pushes / pulls, symmetric-memory barriers, the NCCL all-reduce of the
-    # dense gradients) is sync-free as well and can be captured per rank; opt-in until proven at N = 8
-    use_conv_graph = use_graph or (world > 1 and os.environ.get("IHG_DIST_GRAPH", "0") == "1")
+    n_before = ctx.sampler.mark()
+    use_graph = (world == 1 or args.dist_graph) and not args.no_graph
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     # --- per-kernel breakdown: eager steps with CUDA events around every C-ABI call ------
     prof = KernelProfiler()
     prof_steps = max(3, min(args.steps, 10))
-    barrier()
+    ctx.barrier()
     _lib.profiler = prof
     launches0 = _lib.launch_count()
     ev0.record()
     for _ in range(prof_steps):
         conv_step()
     ev1.record()
-    barrier()
+    ctx.barrier()
     launches_per_step = (_lib.launch_count() - launches0) / prof_steps
     _lib.profiler = None
     t_eager = ev0.elapsed_time(ev1) * 1e-3 / prof_steps
     kern = prof.summary(prof_steps)
+    if profile_step:                                      # one eager step between cudaProfilerStart/Stop (ncu --profile-from-start off)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        conv_step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
 
-    # --- M1 headline: the same step, captured in a CUDA graph on one GPU (every entry point of the
-    # library is sync-free and allocation-free, so the ~30 launches replay as one) -------------
-    if use_conv_graph:
+    # --- M1 headline: the same step, captured in a CUDA graph (every entry point of the library is
+    # sync-free and allocation-free, so the launches replay as one) ------------------------------
+    conv_graph = None
+    if use_graph:
         from ihgnn_b200.graphs import graph_callable
         conv_graph = graph_callable(conv_step, 2)
         run_conv = conv_graph.replay
@@ -357,37 +464,40 @@ def run_gpu_arm(args, log, layers, d):
         run_conv = conv_step
     for _ in range(3):
         run_conv()
-    barrier()
+    ctx.barrier()
     ev0.record()
     for _ in range(args.steps):
         run_conv()
     ev1.record()
-    barrier()
+    ctx.barrier()
     launches = int(round(launches_per_step * args.steps))
     t_conv = ev0.elapsed_time(ev1) * 1e-3 / args.steps
 
     # --- e2e: a full training step through the public API, host batch in, loss out -----
-    # Main.py:192 builds torch.optim.Adam(params, lr); fused / capturable are the same update in one
-    # kernel with the step count kept on the device (needed for graph capture)
-    opt = torch.optim.Adam(model.parameters(), 1e-3, fused=os.environ.get("IHG_ADAM", "fused") == "fused",
-                           capturable=use_graph)
+    # Main.py:192 builds torch.optim.Adam(params, lr); ihgnn_b200.optim.FusedAdam is the same update as
+    # one multi-tensor kernel of this library with the step count kept on the device (graph-capturable)
+    from ihgnn_b200.optim import make_adam
+    opt = make_adam(model.parameters(), 1e-3, capturable=use_graph)
     rng = np.random.default_rng(123)                                     # same batches on every rank
     n_batches = 8
     host_batches = []
+    Bp = B_POS * mult
     for _ in range(n_batches):
-        pick = rng.integers(0, log.edge_count, size=B)
+        pick = rng.integers(0, log.edge_count, size=Bp)
         pu, pq, pi = log.pos_user[pick], log.pos_query[pick], log.pos_item[pick]
         users = np.concatenate([pu, np.repeat(pu, NEG)])
         queries = np.concatenate([pq, np.repeat(pq, NEG)])
-        items = np.concatenate([pi, rng.integers(0, log.item_count, size=B * NEG)])
-        flags = np.concatenate([np.ones(B, np.float32), np.zeros(B * NEG, np.float32)])
+        items = np.concatenate([pi, rng.integers(0, log.item_count, size=Bp * NEG)])
+        flags = np.concatenate([np.ones(Bp, np.float32), np.zeros(Bp * NEG, np.float32)])
         host_batches.append(tuple(torch.from_numpy(a).pin_memory() for a in (users, queries, items, flags)))
     h2d_bytes = sum(t.numel() * t.element_size() for t in host_batches[0])
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
+    graphed = None
     if use_graph:
         from ihgnn_b200.graphs import GraphedTrainStep
-        graphed = GraphedTrainStep(model, opt, B * (1 + NEG), dev, example=host_batches[0])
+        graphed = GraphedTrainStep(model, opt, rows_per_step, dev, example=host_batches[0],
+                                   after_backward=sync_all if world > 1 else None)
 
         def train_step(i):
             loss = graphed(*host_batches[i % n_batches])                  # 4 pinned-host -> device copies + one replay
@@ -409,78 +519,265 @@ def run_gpu_arm(args, log, layers, d):
     e2e_steps = max(3, min(args.steps, 20))
     for i in range(e2e_warm):
         train_step(i)
-    barrier()
+    ctx.barrier()
     ev0.record()
     for i in range(e2e_steps):
         train_step(i)
     ev1.record()
-    barrier()
+    ctx.barrier()
     t_e2e = ev0.elapsed_time(ev1) * 1e-3 / e2e_steps
-    sampler.rows = sampler.rows[max(n_before - 1, 0):]       # samples from the timed regions (conv + e2e) on
-    clocks = sampler.stop()
+    clocks = ctx.sampler.stop(n_before) if name == ctx.args.workload else None
 
-    # --- max over ranks ---------------------------------------------------------------
-    if dist is not None:
-        tt = torch.tensor([t_conv, t_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_conv, t_e2e = float(tt[0]), float(tt[1])
-    total_units = E * layers                  # E is the GLOBAL hyperedge count (world x the workload at N > 1)
-    value = total_units / t_conv
-    e2e_value = total_units / t_e2e
+    t_conv, t_e2e = ctx.max_over_ranks(t_conv, t_e2e)
+    total_units = E * layers                  # E is the GLOBAL hyperedge count
+    out = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        traffic_file = ncu_traffic_file(name) if world == 1 else None
+        dom_tag = max(kern, key=lambda k: kern[k]["ms"])
+        dom = kern[dom_tag]
+        traffic = ncu_traffic(traffic_file, dom_tag)
+        conv_bytes = layers * conv_algorithmic_bytes(E, N, d)       # global E, N: aggregate over all ranks
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        l2_peak = L2_BYTES_PER_CLK * sm_mhz * 1e6 / 1e9
+        roofline = {
+            "bound": "hbm", "kernel": dom_tag, "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
+            "frac": dom["gbs"] / peak, "traffic": traffic,
+            "traffic_source": traffic_file.get("source") if traffic_file else None, "peak_source": peak_src,
+            "kernel_avg_ms": dom["avg_ms"], "kernel_calls_per_step": dom["calls"] / prof_steps,
+            "kernel_share_of_step": dom["ms_per_step"] / (t_eager * 1e3),
+            "timed_with": f"CUDA events around every C-ABI call over {prof_steps} eager steps ({t_eager * 1e3:.3f} ms/step)",
+            "algorithmic_bytes_per_launch": dom["bytes"] / dom["calls"],
+            # whole conv step against SURVEY 8(d)'s E(60+76d)+N(28d+12) bytes per layer
+            "conv_step": {"algorithmic_bytes": conv_bytes, "achieved": conv_bytes / t_conv / 1e9,
+                          "frac": conv_bytes / t_conv / 1e9 / (peak * world),
+                          "note": "aggregate over all ranks against n_gpus x the measured single-GPU peak"},
+        }
+        if traffic_file and traffic_file.get("dram_bytes_per_step"):
+            db = float(traffic_file["dram_bytes_per_step"])
+            roofline["dram_step"] = {"bytes": db, "achieved": db / t_conv / 1e9, "frac": db / t_conv / 1e9 / peak,
+                                     "note": "ncu dram__bytes_read+write summed over ONE eager step's launches, divided by "
+                                             "the timed step: what HBM actually moved (the L2-served gathers move less "
+                                             "than the SURVEY 8(d) bytes they are charged)"}
+        for tag in _L2_SERVED:
+            if tag in kern and world == 1:
+                k = kern[tag]
+                g = getattr(graph, "plan", None)
+                l2_bytes = g.nnz * (8 + 8 * d) + N * (8 * d + 16)           # two row gathers + nbr ids per incidence
+                roofline["l2"] = {"kernel": tag, "l2_bytes_per_launch": l2_bytes,
+                                  "achieved": l2_bytes / (k["avg_ms"] * 1e-3) / 1e9, "peak": l2_peak, "unit": "GB/s",
+                                  "frac": l2_bytes / (k["avg_ms"] * 1e-3) / 1e9 / l2_peak,
+                                  "dram_bytes_per_launch": ncu_traffic(traffic_file, tag),
+                                  "peak_source": f"{L2_BYTES_PER_CLK:.0f} B/clk full-chip L2 cap (B300_MICROARCH.md) x "
+                                                 f"{sm_mhz:.0f} MHz observed"}
+        cpu = None
+        if with_cpu and not args.no_cpu_baseline:
+            v, dt, sample = time_cpu(name, args.cpu_scale or CPU_SCALE[name], 3, 1)
+            cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
+        kernels = {}
+        for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"]):
+            kernels[k] = {"ms_per_step": round(v["ms_per_step"], 4), "calls_per_step": v["calls"] / prof_steps,
+                          "GBps": round(v["gbs"], 1), "hbm_frac": round(v["gbs"] / peak, 3)}
+            tb = ncu_traffic(traffic_file, k)
+            if tb is not None:
+                kernels[k]["dram_GBps"] = round(tb / (v["avg_ms"] * 1e-3) / 1e9, 1)
+        out = {
+            "value": total_units / t_conv, "ms_per_step": t_conv * 1e3,
+            "config": conv_config(name, layers, d, E, N, args.scaling),
+            "run": {"parallelism": parallelism,
+                    "l2_policy": "inputs larger than L2 (no flush): per step the kernels stream "
+                                 f"{conv_bytes / 1e9 / world:.1f} GB algorithmic per GPU vs 126 MB L2",
+                    "m1_step": "fwd+bwd of the L conv layers; a ones gradient is fed to every layer output directly "
+                               "(the caller's torch.cat / sum of SURVEY 8(d)'s loss are not timed)",
+                    "synth_s": t_synth, "graph_build_s": t_build - t_synth,
+                    "cuda_graph": bool(use_graph), "eager_ms_per_step": t_eager * 1e3,
+                    "global_batch_rows": rows_per_step},
+            "e2e": {"value": total_units / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
+                    "train_samples_per_s": rows_per_step / t_e2e,
+                    "what": "RawGnn.forward(batch) -> BCEWithLogits -> backward -> Adam step (ihgnn_b200.optim.FusedAdam), batch "
+                            "indices from pinned host memory, loss copied back every step"
+                            + (" (ihgnn_b200.graphs.GraphedTrainStep: the step replays as one CUDA graph)" if use_graph else "")},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
+            "clocks": clocks,
+        }
+    # CUDA graphs that hold NCCL work must be gone before the process group is torn down
+    del graphed, conv_graph, run_conv, train_step
+    del model, opt, x, gout, conv_layers, host_batches
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
 
+
+# ----------------------------------------------------------------------------------------
+# the GPU arm: inference ranking (BASELINE.json configs[4])
+# ----------------------------------------------------------------------------------------
+RANK_SEARCHES_PER_GPU, RANK_CANDIDATES, RANK_K = 131_072, 1_000, 10
+
+
+def rank_config(world: int, scaling: str) -> dict:
+    w = synth.WORKLOADS["amazon-full"]
+    mult = world if scaling == "weak" else 1
+    return {"workload": "rank", "model": "amazon-full", "layers": w["layers"], "dim": w["dim"],
+            "feature_dim": w["dim"] * (1 + w["layers"]), "searches": RANK_SEARCHES_PER_GPU * mult,
+            "candidates": RANK_CANDIDATES, "k": RANK_K, "items": int(round(w["item_count"] * mult)), "scaling": scaling}
+
+
+def measure_rank(ctx: Ctx) -> dict:
+    """One step = one evaluation pass: conv forward over the (sharded) graph -> output features
+    (replicated with one all-gather at N > 1) -> every GPU ranks its share of the searches, 1 000
+    candidates each, top 10 (ihg_rank_topk).  e2e: candidate lists from pinned host memory, top-10
+    ids back to the host, every step."""
+    from ihgnn_b200 import HemPredictionLayer, IHGNNLayer, RawGnn, _lib
+    from ihgnn_b200 import functional as F_
+    from ihgnn_b200.dataset import GraphDataset
+    args, dev, world, rank = ctx.args, ctx.dev, ctx.world, ctx.rank
+    w = synth.WORKLOADS["amazon-full"]
+    layers, d = w["layers"], w["dim"]
+    mult = world if args.scaling == "weak" else 1
+    log = synth.make_workload("amazon-full", scale=mult)
+    torch.manual_seed(0)
+    S = RANK_SEARCHES_PER_GPU * mult // world             # this rank's searches
+    C, K = RANK_CANDIDATES, RANK_K
+    D = d * (1 + layers)
+    gen = torch.Generator().manual_seed(1000 + rank)
+    users_h = torch.randint(0, log.user_count, (S,), generator=gen).pin_memory()
+    queries_h = torch.randint(0, log.query_count, (S,), generator=gen).pin_memory()
+    cand_h = torch.randint(0, log.item_count, (S, C), generator=gen).pin_memory()
+    users, queries, cand = users_h.to(dev), queries_h.to(dev), cand_h.to(dev)
+    if world == 1:
+        ds = GraphDataset.from_search_log(log, dev)
+        model = RawGnn(device=dev, dataset=ds, embedding_size=d, gnn_layer_type=IHGNNLayer, gnn_layer_count=layers,
+                       feature_interaction_order=3, phase2_attention=False, predictions=HemPredictionLayer,
+                       lambda_muq=0.5).to(dev)
+        bias = model.prediction_layer.items_bias
+        kw = dict(query_row0=ds.query_start_index_in_graph, item_row0=ds.item_start_index_in_graph, item_count=ds.item_count)
+        features = model.output_features
+    else:
+        from ihgnn_b200.dist import PartitionPlan, ShardedHyperGraph, ShardedRawGnn
+        plan = PartitionPlan(log.pos_user, log.pos_query, log.pos_item, log.user_count, log.query_count,
+                             log.item_count, world, rank)
+        words, offsets = log.bag_inputs()
+        model = ShardedRawGnn(ShardedHyperGraph(plan, dev), words, offsets, log.vocab_size, d, layers, 3).to(dev)
+        bias = model.prediction_layer.items_bias
+        kw = dict(query_row0=log.user_count, item_row0=log.user_count + log.query_count, item_count=log.item_count)
+        features = model.gather_features
+
+    @torch.no_grad()
+    def step(u, q, c):
+        feat = features()
+        return F_.rank_topk(feat, u, q, bias, 0.5, candidates=c, k=K, **kw)
+
+    for _ in range(max(args.warmup, 3)):
+        step(users, queries, cand)
+    t_wait = time.time()
+    while not ctx.all_agree(ctx.sampler.proc is None or bool(ctx.sampler.rows) or time.time() - t_wait > 5.0):
+        step(users, queries, cand)
+    n_before = ctx.sampler.mark()
+    prof = KernelProfiler()
+    ctx.barrier()
+    _lib.profiler = prof
+    launches0 = _lib.launch_count()
+    for _ in range(3):
+        step(users, queries, cand)
+    ctx.barrier()
+    launches_per_step = (_lib.launch_count() - launches0) / 3
+    _lib.profiler = None
+    kern = prof.summary(3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step(users, queries, cand)
+    ev1.record()
+    ctx.barrier()
+    t_rank = ev0.elapsed_time(ev1) * 1e-3 / args.steps
+    # e2e: host candidate lists in, top-k ids out
+    top_h = torch.empty((S, K), dtype=torch.int64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        ids, _ = step(users_h.to(dev, non_blocking=True), queries_h.to(dev, non_blocking=True),
+                      cand_h.to(dev, non_blocking=True))
+        top_h.copy_(ids, non_blocking=False)
+    for _ in range(2):
+        e2e_step()
+    ctx.barrier()
+    ev0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record()
+    ctx.barrier()
+    t_e2e = ev0.elapsed_time(ev1) * 1e-3 / e2e_steps
+    clocks = ctx.sampler.stop(n_before)
+    t_rank, t_e2e = ctx.max_over_ranks(t_rank, t_e2e)
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-
+        return None
     peak, peak_src = measured_peaks()
-    dom_tag = max(kern, key=lambda k: kern[k]["ms"])
-    dom = kern[dom_tag]
-    traffic, traffic_src = ncu_traffic(args.workload, dom_tag)
-    conv_bytes = layers * conv_algorithmic_bytes(E, N, d)       # global E, N: aggregate over all ranks
-    roofline = {
-        "bound": "hbm", "kernel": dom_tag, "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
-        "frac": dom["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-        "kernel_avg_ms": dom["avg_ms"], "kernel_share_of_step": dom["ms_per_step"] / (t_eager * 1e3),
-        "timed_with": f"CUDA events around every C-ABI call over {prof_steps} eager steps ({t_eager * 1e3:.3f} ms/step)",
-        "algorithmic_bytes_per_launch": dom["bytes"] / dom["calls"],
-        # whole conv step against SURVEY 8(d)'s E(60+76d)+N(28d+12) bytes per layer
-        "conv_step": {"algorithmic_bytes": conv_bytes, "achieved": conv_bytes / t_conv / 1e9,
-                      "frac": conv_bytes / t_conv / 1e9 / (peak * world),
-                      "note": "aggregate over all ranks against n_gpus x the measured single-GPU peak"},
-    }
+    total = S * world
+    k = kern["rank_topk"]
+    algo = S * (8 * D + C * (8 + 4 * D + 4) + 12 * K)
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    l2_peak = L2_BYTES_PER_CLK * sm_mhz * 1e6 / 1e9
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, dt, Es = time_cpu(log, layers, d, args.cpu_sample_edges, 3, 1)
-        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"first {Es} of {E} hyperedges over the full node set, 3 timed conv fwd+bwd steps "
-                         f"({dt * 1e3:.0f} ms/step), oracle port (torch CPU ops), fp32"}
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t_conv * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "layers": layers, "dim": d, "hyperedges": E, "nodes": N,
-                   "interaction_order": 3, "parallelism": parallelism,
-                   "l2_policy": "inputs larger than L2 (no flush): per step the kernels stream "
-                                f"{conv_bytes / 1e9:.1f} GB algorithmic vs 126 MB L2",
-                   "graph_build_s": t_build,
-                   "cuda_graph": bool(use_conv_graph), "cuda_graph_e2e": bool(use_graph)},
+        v, dt, sample = rank_cpu(args.cpu_rank_searches, 2, 1)
+        cpu = {"value": v, "unit": RANK_UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
+    h2d = users_h.numel() * 8 * 2 + cand_h.numel() * 8
+    return {
+        "metric": RANK_METRIC, "value": total / t_rank, "unit": RANK_UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_rank * 1e3, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": rank_config(world, args.scaling),
+        "run": {"step": "conv forward (features) + all-gather of the features at N > 1 + ihg_rank_topk over this GPU's searches",
+                "l2_policy": f"inputs larger than L2: {cand.numel() * 8 / 1e9:.2f} GB of candidate ids per GPU per step"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+        "e2e": {"value": total / t_e2e, "unit": RANK_UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": top_h.numel() * 8,
                 "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
-                "train_samples_per_s": B * (1 + NEG) / t_e2e,
-                "what": "RawGnn.forward(batch) -> BCEWithLogits -> backward -> Adam(fused).step, batch indices "
-                        "from pinned host memory, loss copied back every step"
-                        + (" (ihgnn_b200.graphs.GraphedTrainStep: the step replays as one CUDA graph)" if use_graph else "")},
-        "gpu_launches": int(launches),
-        "roofline": roofline,
+                "what": "per step: users / queries / int64 candidate lists copied from pinned host memory, features "
+                        "recomputed, searches ranked, top-10 ids copied back (PCIe-bound: 8 KB of candidate ids per search)"},
+        "gpu_launches": int(round(launches_per_step * args.steps)),
+        "roofline": {"bound": "hbm", "kernel": "rank_topk", "achieved": algo / (k["avg_ms"] * 1e-3) / 1e9, "peak": peak,
+                     "unit": "GB/s", "frac": algo / (k["avg_ms"] * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                     "traffic": ncu_traffic(ncu_traffic_file("rank"), "rank_topk"), "kernel_avg_ms": k["avg_ms"],
+                     "algorithmic_bytes_per_launch": algo,
+                     "note": "per search 8D + C(8 + 4D + 4) + 12k bytes, candidate rows charged with no cache credit; the item "
+                             "table is L2-resident, so HBM moves mostly the candidate ids",
+                     "l2": {"achieved": algo / (k["avg_ms"] * 1e-3) / 1e9, "peak": l2_peak, "frac": algo / (k["avg_ms"] * 1e-3) / 1e9 / l2_peak,
+                            "peak_source": f"{L2_BYTES_PER_CLK:.0f} B/clk x {sm_mhz:.0f} MHz observed"}},
         "cpu_baseline": cpu,
-        "kernels": {k: {"ms_per_step": round(v["ms_per_step"], 4), "calls_per_step": v["calls"] / prof_steps,
-                        "GBps": round(v["gbs"], 1)} for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])},
+        "kernels": {t: {"ms_per_step": round(v["ms_per_step"], 4), "calls_per_step": v["calls"] / 3, "GBps": round(v["gbs"], 1)}
+                    for t, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])},
     }
-    emit(line)
-    if dist is not None:
-        dist.destroy_process_group()
+
+
+def run_gpu_arm(args):
+    ctx = Ctx(args)
+    try:
+        if args.workload == "rank":
+            line = measure_rank(ctx)
+        else:
+            main_res = measure_conv(ctx, args.workload, with_cpu=ctx.world == 1, profile_step=args.profile_step)
+            line = None
+            if ctx.rank == 0:
+                line = {"metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": ctx.world,
+                        "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
+                        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+                        "data": "synthetic"}
+                line.update({k: main_res[k] for k in ("config", "run", "clocks", "e2e", "gpu_launches", "roofline",
+                                                      "cpu_baseline", "kernels")})
+            also = args.also if (ctx.world == 1 and args.also not in ("none", args.workload)) else None
+            if also:
+                sub = measure_conv(ctx, also, with_cpu=False)
+                if ctx.rank == 0:
+                    sub.pop("clocks", None)
+                    line["also"] = {also: sub}
+        if ctx.rank == 0:
+            emit(line)
+    finally:
+        if ctx.dist is not None:
+            gc.collect()
+            torch.cuda.synchronize()
+            ctx.dist.destroy_process_group()
 
 
 def main():
@@ -489,23 +786,26 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="amazon-full", choices=sorted(synth.WORKLOADS))
+    ap.add_argument("--workload", default="cikm", choices=sorted(synth.WORKLOADS) + ["rank"])
+    ap.add_argument("--also", default="amazon-full", choices=sorted(synth.WORKLOADS) + ["none"],
+                    help="second conv workload reported under 'also' (N = 1 only)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = N x the workload (default), strong = the workload itself over N GPUs")
     ap.add_argument("--scale", type=float, default=1.0, help="multiply every workload count")
-    ap.add_argument("--cpu-sample-edges", type=int, default=200_000)
+    ap.add_argument("--cpu-scale", type=float, default=0.0, help="scale of the CPU arm's bounded sample (0 = per-workload default)")
+    ap.add_argument("--cpu-rank-searches", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
+    ap.add_argument("--dist-graph", action="store_true", default=True, help="N > 1: capture the sharded step per rank")
+    ap.add_argument("--no-dist-graph", dest="dist_graph", action="store_false")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run ONE extra eager conv step between cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-
-    w = synth.WORKLOADS[args.workload]
-    layers, d = w["layers"], w["dim"]
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
-        return                                    # the CPU arm runs on rank 0 alone; the others exit 0 without work
-    log = synth.make_workload(args.workload, scale=args.scale * world)   # weak scaling: world x the workload
     if args.impl == "reference":
-        run_reference_arm(args, log, layers, d)
+        run_reference_arm(args)
     else:
-        run_gpu_arm(args, log, layers, d)
+        run_gpu_arm(args)
 
 
 if __name__ == "__main__":

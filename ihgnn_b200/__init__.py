@@ -7,7 +7,7 @@ loudly if libihgnn_b200.so is missing (there is no CPU or PyTorch fallback).
 from . import synth  # noqa: F401  (numpy-only)
 
 __all__ = ["synth", "PpsHyperGraph", "Pps2DGraph", "GraphDataset", "EmbeddingLayer", "FeatureInteractor",
-           "IHGNNLayer", "HGCNLayer", "GCNLayer", "HemPredictionLayer", "RawGnn"]
+           "IHGNNLayer", "HGCNLayer", "GCNLayer", "HemPredictionLayer", "RawGnn", "FusedAdam"]
 
 
 def __getattr__(name):
@@ -23,4 +23,7 @@ def __getattr__(name):
     if name == "RawGnn":
         from .model import RawGnn
         return RawGnn
+    if name == "FusedAdam":
+        from .optim import FusedAdam
+        return FusedAdam
     raise AttributeError(name)

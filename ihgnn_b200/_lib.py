@@ -17,7 +17,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libihgnn_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -31,6 +31,12 @@ class IhgCsr(Structure):
         ("n_seg", c_int64), ("n_split", c_int64), ("n_part", c_int64),
         ("seg", c_void_p), ("split_row", c_void_p), ("split_ptr", c_void_p),
     ]
+
+
+class IhgAdamTensor(Structure):
+    """Mirror of `struct ihg_adam_tensor` (include/ihgnn_b200.h)."""
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+                ("step", c_void_p), ("numel", c_int64)]
 
 
 P = c_void_p
@@ -70,6 +76,7 @@ SIGNATURES = {
     "ihg_sample_batch": (c_int32, [P, P, P, P, I64, I32, I64, ctypes.c_uint64, ctypes.c_uint64, P, P, P, P, P, P, P, P,
                                    P, P, P, I32, P]),
     "ihg_halo_copy": (c_int32, [P, P, P, I32, P, I64, I64, I32, P]),
+    "ihg_adam_step": (c_int32, [POINTER(IhgAdamTensor), I32, P, F32, F32, F32, F32, P]),
 }
 
 # Optional per-call profiler (bench.py installs one): an object with

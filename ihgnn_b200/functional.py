@@ -53,7 +53,7 @@ def segment_reduce(plan: CsrPlan, src: torch.Tensor, dim: int, *, src_row_mul: i
               bounds[1], _lib.ptr(row_slot), _lib.ptr(init), _lib.ld(init) if init is not None else 0,
               _lib.ptr(src_scale), _lib.ptr(row_scale), _lib.ptr(plan.partial(dim)),
               _lib.ptr(out), _lib.ld(out), dim, (1 if accumulate else 0) | (2 if l2_source else 0), _lib.stream_ptr(),
-              tag=f"segment_reduce[mul={src_row_mul}]",
+              tag="segment_reduce",
               algo_bytes=plan.nnz * (4 + 4 * dim) + plan.n_rows * (4 * dim + 16))
     return out
 

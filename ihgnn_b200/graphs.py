@@ -74,9 +74,9 @@ def _restore(model: torch.nn.Module, optimizer: torch.optim.Optimizer, snap) -> 
 class GraphedTrainStep:
     """forward -> BCEWithLogits(mean) -> backward -> optimizer.step(), captured once.
 
-    model(users, queries, items) -> scores [B];  optimizer must be capturable
-    (`torch.optim.Adam(params, lr, fused=True, capturable=True)` is the reference's Adam,
-    Main.py:192, in capturable form)."""
+    model(users, queries, items) -> scores [B];  optimizer must be capturable:
+    `ihgnn_b200.optim.FusedAdam(params, lr)` (the reference's Adam, Main.py:192, as one kernel of this
+    library) or `torch.optim.Adam(params, lr, fused=True, capturable=True)`."""
 
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, batch_rows: int,
                  device, loss_fn: Optional[Callable] = None, warmup: int = 3,
@@ -91,6 +91,7 @@ class GraphedTrainStep:
             self._load(*example)
         self.loss_fn = loss_fn or torch.nn.functional.binary_cross_entropy_with_logits
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.loss_sum = torch.zeros((), dtype=torch.float64, device=dev)      # accumulated on the device, see pop_loss_sum
         self._after_backward = after_backward
 
         def step():
@@ -102,6 +103,7 @@ class GraphedTrainStep:
                 self._after_backward()
             self.optimizer.step()
             self.loss.copy_(loss.detach())
+            self.loss_sum.add_(loss.detach())
 
         # warm-up and capture run real optimizer steps (capture itself executes nothing, the warm-up does):
         # snapshot the parameters and the optimizer state first and put them back afterwards, so that
@@ -109,6 +111,7 @@ class GraphedTrainStep:
         snap = _snapshot(model, optimizer)
         self.graph = graph_callable(step, warmup)
         _restore(model, optimizer, snap)
+        self.loss_sum.zero_()
 
     def _load(self, users, queries, items, flags) -> None:
         self.users.copy_(users, non_blocking=True)
@@ -118,5 +121,15 @@ class GraphedTrainStep:
 
     def __call__(self, users, queries, items, flags) -> torch.Tensor:
         self._load(users, queries, items, flags)
+        refresh = getattr(self.optimizer, "refresh_lr", None)
+        if refresh is not None:
+            refresh()                  # param_group['lr'] edits (TrainTestHelper.py:155-159) reach the device scalar
         self.graph.replay()
         return self.loss
+
+    def pop_loss_sum(self) -> float:
+        """Sum of the losses of all steps since the last call (ONE device -> host read): the epoch average of
+        TrainTestHelper.py:133-147 without the reference's `loss.item()` synchronisation in every step."""
+        total = float(self.loss_sum)
+        self.loss_sum.zero_()
+        return total

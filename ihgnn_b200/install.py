@@ -36,12 +36,15 @@ def replacement_classes() -> Dict[str, type]:
     return out
 
 
-def patch_reference(reference_dir: str = None, fast_eval: bool = True) -> Dict[str, int]:
+def patch_reference(reference_dir: str = None, fast_eval: bool = True, fused_adam: bool = True) -> Dict[str, int]:
     """Rebind the hot-path classes inside the imported reference modules.  Returns, per class
     name, how many module attributes were rebound.  `fast_eval` also rebinds
     `Helpers.TrainTestHelper.test_and_get_avg_metrics` (:37-102) to the batched GPU ranking with the
     same signature and return value (`model.make_fast_test_and_get_avg_metrics`); Main.py picks it
-    up through its `from Helpers.TrainTestHelper import ...`."""
+    up through its `from Helpers.TrainTestHelper import ...`.  `fused_adam` makes `torch.optim.Adam(...)`
+    (Main.py:192) return `ihgnn_b200.optim.FusedAdam` -- the same update, bit-identical with torch's fused
+    CUDA Adam, as one kernel of this library -- whenever every parameter is a dense fp32 CUDA tensor and only
+    lr / betas / eps / weight_decay are given; any other call goes to torch's own class."""
     if reference_dir and reference_dir not in sys.path:
         sys.path.insert(0, reference_dir)
     mods = [importlib.import_module(m) for m in (
@@ -81,7 +84,31 @@ def patch_reference(reference_dir: str = None, fast_eval: bool = True) -> Dict[s
             fast = make_fast_test_and_get_avg_metrics(tth.test_and_get_avg_metrics, metrics_cls)
             fast._ihgnn_b200 = True
             tth.test_and_get_avg_metrics = fast
+    if fused_adam:
+        _install_fused_adam()
     return counts
+
+
+def _install_fused_adam() -> None:
+    import torch
+    original = torch.optim.Adam
+    if getattr(original, "_ihgnn_b200", False):
+        return
+    from .optim import FusedAdam
+
+    class Adam(original):                                  # isinstance(opt, torch.optim.Adam) keeps holding for torch's own
+        _ihgnn_b200 = True
+
+        def __new__(cls, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, **kw):
+            params = list(params)
+            flat = [p for g in params for p in g["params"]] if params and isinstance(params[0], dict) else params
+            plain = not kw and not isinstance(lr, torch.Tensor) and flat and all(
+                isinstance(p, torch.Tensor) and p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() for p in flat)
+            if plain:
+                return FusedAdam(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+            return original(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, **kw)
+
+    torch.optim.Adam = Adam
 
 
 def main(argv=None) -> None:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define IHG_ABI_VERSION 2   /* 2: ihg_segment_reduce gained `flags`, two-hop / ranking / sampler entry points */
+#define IHG_ABI_VERSION 3   /* 3: ihg_adam_step; 2: ihg_segment_reduce gained `flags`, two-hop / ranking / sampler */
 
 #define IHG_OK 0
 #define IHG_ERR_INVALID_ARGUMENT 1   /* bad shape / null pointer / unsupported dimension   */
@@ -228,6 +228,26 @@ int ihg_gather_rows(const float* table, int64_t table_ld, const int64_t* idx,
                     void* stream);
 int ihg_scatter_add_rows(const float* g, int64_t g_ld, const int64_t* idx, int64_t idx_offset,
                          int64_t count, float* out, int64_t out_ld, int32_t dim, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * f2  optimizer.step()                              Main.py:192, Helpers/TrainTestHelper.py:142-143
+ *   torch.optim.Adam(params, lr, weight_decay) over a list of fp32 parameter tensors in one launch:
+ *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps),
+ *   g += weight_decay * p first when weight_decay != 0 (L2 form, not AdamW).  Bit-identical with
+ *   torch's fused CUDA Adam.  t = step[0] + 1; the fp32 step counters live on the device and are
+ *   incremented by the call, `lr` is a device scalar: nothing host-side changes between replays of
+ *   a captured graph.  `tensors_host` is a HOST array; all pointers inside are device pointers.
+ * ------------------------------------------------------------------------------------ */
+typedef struct ihg_adam_tensor {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    float* step;               /* fp32 [1] */
+    int64_t numel;
+} ihg_adam_tensor;
+int ihg_adam_step(const ihg_adam_tensor* tensors_host, int32_t n_tensors, const float* lr,
+                  float beta1, float beta2, float eps, float weight_decay, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Multi-GPU halo exchange over NVLink peer memory (no reference counterpart: the reference is

@@ -19,7 +19,7 @@ def _run(*args, env=None):
 
 def test_reference_arm_prints_one_contract_line():
     res = _run("--impl", "reference", "--workload", "amazon-small", "--steps", "1", "--warmup", "1",
-               "--cpu-sample-edges", "20000")
+               "--cpu-scale", "0.2")
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, res.stdout
@@ -30,9 +30,27 @@ def test_reference_arm_prints_one_contract_line():
         assert k in d, k
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["data"] == "synthetic"
     assert d["config"]["workload"] == "amazon-small" and d["value"] > 0
+    # config names the WORKLOAD (identical in both arms); the bounded sample is described in cpu_baseline
+    assert d["config"] == {"workload": "amazon-small", "layers": 2, "dim": 64, "hyperedges": 100_000, "nodes": 35_000,
+                           "interaction_order": 3, "scaling": "weak", "batch_rows": 1100}
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "hyperedges" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_rank_workload():
+    res = _run("--impl", "reference", "--workload", "rank", "--steps", "1", "--warmup", "1", "--cpu-rank-searches", "128")
+    assert res.returncode == 0, res.stderr[-2000:]
+    d = json.loads(res.stdout.strip())
+    assert d["metric"] == "inference_ranking_searches_per_sec" and d["unit"] == "searches/s" and d["value"] > 0
+    assert d["config"]["candidates"] == 1000 and d["config"]["searches"] == 131072 and d["cpu_baseline"]["kind"] == "port"
+
+
+def test_default_workload_is_the_largest_single_gpu_config():
+    res = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-scale", "0.004")
+    assert res.returncode == 0, res.stderr[-2000:]
+    d = json.loads(res.stdout.strip())
+    assert d["config"]["workload"] == "cikm" and d["config"]["hyperedges"] == 5_000_000 and d["config"]["dim"] == 128
 
 
 def test_reference_arm_other_ranks_exit_without_work():

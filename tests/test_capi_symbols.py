@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_error_channel(lib):
-    assert lib.ihg_abi_version() == 2
+    assert lib.ihg_abi_version() == 3
     assert lib.ihg_last_error() is not None
     # argument validation happens before any CUDA call, so it can be exercised without a GPU
     rc = lib.ihg_node_linear(None, 0, None, 1, 64, 64, 0, None, None, 0, 10, 0, 0, None, 0, None)

@@ -37,7 +37,7 @@ def _model(golden, ds=None):
 
 def test_library_loaded():
     from ihgnn_b200 import _lib
-    assert _lib.lib().ihg_abi_version() == _lib.ABI_VERSION == 2
+    assert _lib.lib().ihg_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_graph_build_matches_reference_bit_exact(golden):
@@ -842,3 +842,64 @@ def test_device_batch_sampler_logged_negatives():
     with pytest.raises(ValueError):
         DeviceBatchSampler(GraphDataset.from_search_log(synth.make_search_log(U, Q, I, 500, 50, seed=1), DEV), 10, 5,
                            nonrandom_neg_sample_size=2)
+
+
+@pytest.mark.parametrize("weight_decay", [0.0, 0.01])
+def test_fused_adam_bit_identical_with_torch(weight_decay):
+    """ihgnn_b200.optim.FusedAdam (ihg_adam_step) against torch.optim.Adam -- the optimizer of Main.py:192 --
+    for 10 steps over tensors of awkward sizes: bit-identical with torch's fused CUDA implementation
+    (parameters, both moments, step counters), within fp32 rounding of torch's default implementation, and
+    the learning-rate decay of TrainTestHelper.py:155-159 (param_group['lr'] edited between steps) is honoured."""
+    from ihgnn_b200.optim import FusedAdam
+    shapes = [(1000, 64), (7,), (3, 5), (200_001,), (129, 192), (1,)]
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    base = [torch.randn(*s, device=DEV, generator=gen) for s in shapes]
+    sets = {name: [torch.nn.Parameter(b.clone()) for b in base] for name in ("ours", "fused", "default")}
+    opts = {"ours": FusedAdam(sets["ours"], lr=1e-3, weight_decay=weight_decay),
+            "fused": torch.optim.Adam(sets["fused"], lr=1e-3, weight_decay=weight_decay, fused=True),
+            "default": torch.optim.Adam(sets["default"], lr=1e-3, weight_decay=weight_decay)}
+    for step in range(10):
+        if step == 6:
+            for o in opts.values():
+                for g in o.param_groups:
+                    g["lr"] *= 0.5
+        grads = [torch.randn(*s, device=DEV, generator=gen) * (10.0 ** (step % 3 - 1)) for s in shapes]
+        for name, ps in sets.items():
+            for p, g in zip(ps, grads):
+                p.grad = g.clone()
+            opts[name].step()
+    for k, (a, b, c) in enumerate(zip(sets["ours"], sets["fused"], sets["default"])):
+        assert torch.equal(a.detach(), b.detach()), f"tensor {k}: parameters differ from torch fused Adam"
+        sa, sb = opts["ours"].state[a], opts["fused"].state[b]
+        assert torch.equal(sa["exp_avg"], sb["exp_avg"]) and torch.equal(sa["exp_avg_sq"], sb["exp_avg_sq"])
+        assert float(sa["step"]) == float(sb["step"]) == 10.0
+        assert max_rel(a.detach().cpu().numpy(), c.detach().cpu().numpy()) < 1e-6
+    # state_dict layout is torch.optim.Adam's: a checkpoint of one loads into the other
+    opts["fused"].load_state_dict(opts["ours"].state_dict())
+    opts["ours"].load_state_dict(opts["default"].state_dict())
+
+
+def test_fused_adam_in_graphed_train_step(golden):
+    """The whole training step with this library's Adam inside ONE CUDA graph equals the eager loop with
+    torch.optim.Adam(fused=True), step for step; the device-side loss accumulator equals the sum of the losses."""
+    from ihgnn_b200.graphs import GraphedTrainStep
+    from ihgnn_b200.optim import FusedAdam
+    users, queries, items, flags = batch_of(golden)
+    flags = flags.float()
+    m1, m2 = _model(golden), _model(golden)
+    graphed = GraphedTrainStep(m1, FusedAdam(m1.parameters(), 1e-3), int(users.numel()), DEV,
+                               example=(users, queries, items, flags))
+    opt2 = torch.optim.Adam(m2.parameters(), 1e-3, fused=True)
+    ud, qd, idv, fd = (t.to(DEV) for t in (users, queries, items, flags))
+    got, want = [], []
+    for _ in range(4):
+        got.append(float(graphed(users, queries, items, flags)))
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(m2(ud, qd, idv), fd)
+        opt2.zero_grad(set_to_none=True)
+        loss.backward()
+        opt2.step()
+        want.append(float(loss))
+    assert got == pytest.approx(want, rel=2e-6), (got, want)
+    assert graphed.pop_loss_sum() == pytest.approx(sum(got), rel=1e-6)
+    for (k, a), b in zip(m1.named_parameters(), m2.parameters()):
+        assert max_rel(a.detach().cpu().numpy(), b.detach().cpu().numpy()) < 1e-5, k
