@@ -33,7 +33,7 @@ struct AdamArgs {
 
 __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float wd, float b1, float b2,
                                           float step_size, float bc2_sqrt, float eps) {
-    if (wd != 0.f) g = __fadd_rn(g, __fmul_rn(p, wd));
+    if (wd != 0.f) g = __fmaf_rn(p, wd, g);      // `grad += param * weight_decay`, contracted by nvcc in torch's build
     m = __fmaf_rn(b1, m, __fmaf_rn(-b1, g, g));
     const float gg = __fmul_rn(g, g);
     v = __fmaf_rn(b2, v, __fmaf_rn(-b2, gg, gg));

@@ -1,7 +1,10 @@
 """Turn an `ncu --set full` report into the per-kernel summary + DRAM-traffic json kept under profiles/.
 
-    python profiles/ncu_extract.py gpurun_out/prof.ncu-rep profiles/r01_ncu_full_v8_amazon-full.txt \
-        [--traffic profiles/r01_ncu_traffic.json --workload amazon-full] [--note "..."]
+    python profiles/ncu_extract.py gpurun_out/prof.ncu-rep profiles/r02_ncu_full_cikm.txt \
+        [--traffic profiles/r02_ncu_traffic_cikm.json --workload cikm --steps-captured 1] [--note "..."]
+
+(`--steps-captured`: the report was taken with `ncu --profile-from-start off ... bench.py --profile-step`, i.e. it
+holds the launches of exactly one eager conv step; bench.py reads `dram_bytes_per_step` for roofline.dram_step.)
 
 Reads the report with `ncu -i <rep> --page raw --csv` (works without a GPU) and averages every
 metric of interest over the captured launches of each kernel.
@@ -40,6 +43,8 @@ def main():
     ap.add_argument("--traffic")
     ap.add_argument("--workload", default="amazon-full")
     ap.add_argument("--note", default="")
+    ap.add_argument("--steps-captured", type=int, default=0,
+                    help="the report holds exactly this many whole steps: also write dram_bytes_per_step")
     a = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", a.rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -54,6 +59,7 @@ def main():
                 d[m].append(float(r[col[m]].replace(",", "")))
     lines = [f"ncu --set full --clock-control none; per-kernel means over the captured launches. {a.note}".rstrip(), ""]
     traffic = {}
+    total_bytes, total_launches = 0.0, 0
     for k, d in per.items():
         n = len(d["gpu__time_duration.sum"])
         lines.append(f"{k}  ({n} launches)")
@@ -65,11 +71,17 @@ def main():
             ur, uw = units[col["dram__bytes_read.sum"]], units[col["dram__bytes_write.sum"]]
             traffic[k] = (sum(d["dram__bytes_read.sum"]) / n) * _TO_BYTES.get(ur, 1.0) + \
                          (sum(d["dram__bytes_write.sum"]) / n) * _TO_BYTES.get(uw, 1.0)
+            total_bytes += traffic[k] * n
+            total_launches += n
     with open(a.out, "w") as f:
         f.write("\n".join(lines))
     if a.traffic:
         with open(a.traffic, "w") as f:
-            json.dump({"workload": a.workload, "source": a.out, "dram_bytes_per_launch": traffic}, f, indent=1)
+            doc = {"workload": a.workload, "source": a.out, "dram_bytes_per_launch": traffic}
+            if a.steps_captured > 0:
+                doc["dram_bytes_per_step"] = total_bytes / a.steps_captured
+                doc["launches_per_step"] = total_launches / a.steps_captured
+            json.dump(doc, f, indent=1)
     print("\n".join(lines[:60]))
 
 
