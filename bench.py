@@ -387,7 +387,7 @@ def measure_conv(ctx: Ctx, name: str, with_cpu: bool, profile_step: bool = False
         # type, boundary rows travel over NVLink peer memory (ihgnn_b200/dist.py)
         from ihgnn_b200.dist import PartitionPlan, ShardedHyperGraph, ShardedRawGnn, allreduce_dense_grads
         plan = PartitionPlan(log.pos_user, log.pos_query, log.pos_item, log.user_count, log.query_count,
-                             log.item_count, world, rank)
+                             log.item_count, world, rank, device=dev)      # planned on this rank's GPU
         sg = ShardedHyperGraph(plan, dev)
         words, offsets = log.bag_inputs()
         model = ShardedRawGnn(sg, words, offsets, log.vocab_size, d, layers, 3).to(dev)
@@ -656,7 +656,7 @@ def measure_rank(ctx: Ctx) -> dict:
     else:
         from ihgnn_b200.dist import PartitionPlan, ShardedHyperGraph, ShardedRawGnn
         plan = PartitionPlan(log.pos_user, log.pos_query, log.pos_item, log.user_count, log.query_count,
-                             log.item_count, world, rank)
+                             log.item_count, world, rank, device=dev)
         words, offsets = log.bag_inputs()
         model = ShardedRawGnn(ShardedHyperGraph(plan, dev), words, offsets, log.vocab_size, d, layers, 3).to(dev)
         bias = model.prediction_layer.items_bias
@@ -752,6 +752,7 @@ def measure_rank(ctx: Ctx) -> dict:
 
 def run_gpu_arm(args):
     ctx = Ctx(args)
+    ok = False
     try:
         if args.workload == "rank":
             line = measure_rank(ctx)
@@ -773,11 +774,17 @@ def run_gpu_arm(args):
                     line["also"] = {also: sub}
         if ctx.rank == 0:
             emit(line)
+        ok = True
     finally:
         if ctx.dist is not None:
+            # the captured graphs (NCCL work inside) are gone by now; if the process group still refuses to
+            # shut down, do not hang the launcher: the result line is already out
+            threading.Timer(30.0, lambda: os._exit(0 if ok else 1)).start()
             gc.collect()
-            torch.cuda.synchronize()
-            ctx.dist.destroy_process_group()
+            if ok:
+                torch.cuda.synchronize()
+                ctx.dist.destroy_process_group()
+                os._exit(0)
 
 
 def main():

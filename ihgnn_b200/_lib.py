@@ -76,6 +76,7 @@ SIGNATURES = {
     "ihg_sample_batch": (c_int32, [P, P, P, P, I64, I32, I64, ctypes.c_uint64, ctypes.c_uint64, P, P, P, P, P, P, P, P,
                                    P, P, P, I32, P]),
     "ihg_halo_copy": (c_int32, [P, P, P, I32, P, I64, I64, I32, P]),
+    "ihg_halo_reduce": (c_int32, [P, I64, P, P, P, I32, I64, P, P, I64, I64, I32, P]),
     "ihg_adam_step": (c_int32, [POINTER(IhgAdamTensor), I32, P, F32, F32, F32, F32, P]),
 }
 

@@ -34,23 +34,33 @@ def _splits(n: int, world: int) -> np.ndarray:
     return np.array([(n * r) // world for r in range(world + 1)], dtype=np.int64)
 
 
-def _balanced_splits(weight: np.ndarray, world: int) -> np.ndarray:
+def _balanced_splits(weight: torch.Tensor, world: int) -> np.ndarray:
     """Boundaries b[0..world] of contiguous ranges with ~equal total weight (prefix-sum cut)."""
     n = int(weight.shape[0])
-    cum = np.cumsum(weight, dtype=np.int64)
+    cum = torch.cumsum(weight.to(torch.int64), 0)
     total = int(cum[-1]) if n else 0
+    if total == 0:
+        return _splits(n, world)
+    targets = torch.tensor([(total * r) // world for r in range(1, world)], dtype=torch.int64, device=weight.device)
+    cuts = (torch.searchsorted(cum, targets, right=False) + 1).cpu().numpy() if world > 1 else np.zeros(0, np.int64)
     b = np.zeros(world + 1, dtype=np.int64)
     b[world] = n
     for r in range(1, world):
-        b[r] = int(np.searchsorted(cum, (total * r) // world, side="left")) + (1 if total else 0)
-        b[r] = min(max(b[r], b[r - 1]), n)
-    if total == 0:
-        return _splits(n, world)
+        b[r] = min(max(int(cuts[r - 1]), int(b[r - 1])), n)
     return b
 
 
+def _owner_of(ids: torch.Tensor, bounds: np.ndarray) -> torch.Tensor:
+    """Index r of the range [bounds[r], bounds[r+1]) holding each id (last r with bounds[r] <= id)."""
+    inner = torch.as_tensor(bounds[1:-1], dtype=torch.int64, device=ids.device)
+    return torch.bucketize(ids, inner, right=True)
+
+
 class PartitionPlan:
-    """Index plan of one rank.  All arrays are numpy int64 unless noted.
+    """Index plan of one rank, computed with torch ops on `device` (the rank's GPU in production: a few
+    sorts over the rank's own hyperedges, so 100 M-hyperedge logs plan in well under a second; CPU in the
+    gloo tests).  No communication: every rank derives, from the same global log, what it needs from the
+    others AND what the others need from it.
 
     Node id spaces:
       global   u, U+q, U+Q+i                                   (Helpers/Graph.py:110-111)
@@ -59,97 +69,113 @@ class PartitionPlan:
                the chunk received from a rank holds its queries (ascending id) then its items,
                i.e. the local table IS the all-to-all receive layout: no unpack pass, and the
                halo partial sums travelling back are a contiguous slice.
-    """
+
+    Index arrays are kept as torch tensors on `device` (`plan.t["name"]`); reading `plan.name` returns the
+    numpy copy (host-side tests and the CPU replay of the choreography use those)."""
+
+    _TENSORS = ("edge_ids", "i3_local", "row_slot", "send_rows", "reduce_rowptr", "reduce_col", "reduce_entries",
+                "vertex_degrees_own", "dv_inv_own")
 
     def __init__(self, user, query, item, user_count: int, query_count: int, item_count: int,
-                 world: int, rank: int):
-        user = np.asarray(user, dtype=np.int64)
-        query = np.asarray(query, dtype=np.int64)
-        item = np.asarray(item, dtype=np.int64)
-        self.world, self.rank = world, rank
+                 world: int, rank: int, device=None):
+        dev = torch.device(device) if device is not None else torch.device("cpu")
+        as_ids = lambda a: (a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64))).to(
+            device=dev, dtype=torch.int64)
+        user, query, item = as_ids(user), as_ids(query), as_ids(item)
+        self.world, self.rank, self.device = world, rank, dev
         self.U, self.Q, self.I = user_count, query_count, item_count
+        r = rank
         # users: contiguous ranges holding ~E / world hyperedges each (a hyperedge lives with its
         # user, so equal user COUNTS leave the ranks up to ~11 % apart on Zipf-skewed logs and every
         # barrier waits for the slowest); queries / items: equal row counts
-        self.ub = _balanced_splits(np.bincount(user, minlength=user_count), world)
+        deg_u = torch.bincount(user, minlength=user_count)
+        self.ub = _balanced_splits(deg_u, world)
         self.qb, self.ib = _splits(query_count, world), _splits(item_count, world)
-        r = rank
-        self.Uo = int(self.ub[r + 1] - self.ub[r])
-        self.Qo = int(self.qb[r + 1] - self.qb[r])
-        self.Io = int(self.ib[r + 1] - self.ib[r])
+        ub, qb, ib = (int(self.ub[r]), int(self.ub[r + 1])), (int(self.qb[r]), int(self.qb[r + 1])), \
+            (int(self.ib[r]), int(self.ib[r + 1]))
+        self.Uo, self.Qo, self.Io = ub[1] - ub[0], qb[1] - qb[0], ib[1] - ib[0]
         self.n_own = self.Uo + self.Qo + self.Io
         self.own_bounds = (self.Uo, self.Uo + self.Qo)
+        t = {}
 
-        edge_owner = np.searchsorted(self.ub, user, side="right") - 1
-        self.edge_ids = np.nonzero(edge_owner == r)[0]            # ascending global hyperedge ids
-        eu, eq, ei = user[self.edge_ids], query[self.edge_ids], item[self.edge_ids]
-        self.edge_count = int(self.edge_ids.shape[0])
+        edge_owner = _owner_of(user, self.ub)
+        t["edge_ids"] = torch.nonzero(edge_owner == r).view(-1)           # ascending global hyperedge ids
+        eu, eq, ei = user[t["edge_ids"]], query[t["edge_ids"]], item[t["edge_ids"]]
+        self.edge_count = int(t["edge_ids"].numel())
 
-        # halo = remote queries / items referenced by local hyperedges
-        q_need = np.unique(eq[(eq < self.qb[r]) | (eq >= self.qb[r + 1])])
-        i_need = np.unique(ei[(ei < self.ib[r]) | (ei >= self.ib[r + 1])])
-        q_owner = np.searchsorted(self.qb, q_need, side="right") - 1
-        i_owner = np.searchsorted(self.ib, i_need, side="right") - 1
-        self.recv_counts = np.zeros(world, dtype=np.int64)
-        q_local = np.zeros(q_need.shape[0], dtype=np.int64)      # local row of every needed query
-        i_local = np.zeros(i_need.shape[0], dtype=np.int64)
-        slot = [np.zeros(self.Uo, np.int32), np.ones(self.Qo, np.int32), np.full(self.Io, 2, np.int32)]
-        off = self.n_own
-        for s in range(world):
-            qs = np.nonzero(q_owner == s)[0]
-            is_ = np.nonzero(i_owner == s)[0]
-            q_local[qs] = off + np.arange(qs.shape[0])
-            i_local[is_] = off + qs.shape[0] + np.arange(is_.shape[0])
-            slot += [np.ones(qs.shape[0], np.int32), np.full(is_.shape[0], 2, np.int32)]
-            self.recv_counts[s] = qs.shape[0] + is_.shape[0]
-            off += int(self.recv_counts[s])
+        # ---- halo = remote queries / items referenced by local hyperedges; ids ascend with the owner rank
+        # (contiguous ownership ranges), so the sorted unique lists are already grouped by source rank
+        q_mine, i_mine = (eq >= qb[0]) & (eq < qb[1]), (ei >= ib[0]) & (ei < ib[1])
+        q_need, i_need = torch.unique(eq[~q_mine]), torch.unique(ei[~i_mine])
+        q_owner, i_owner = _owner_of(q_need, self.qb), _owner_of(i_need, self.ib)
+        qc = torch.bincount(q_owner, minlength=world)
+        ic = torch.bincount(i_owner, minlength=world)
+        recv = qc + ic
+        self.recv_counts = recv.cpu().numpy().astype(np.int64)
         self.R = int(self.recv_counts.sum())
         self.n_local = self.n_own + self.R
-        self.row_slot = np.concatenate(slot).astype(np.int32)    # node type (= hyperedge slot) of every local row
+        chunk0 = self.n_own + torch.cumsum(recv, 0) - recv                # first local row of the chunk from rank s
+        qstart, istart = torch.cumsum(qc, 0) - qc, torch.cumsum(ic, 0) - ic
+        q_local = chunk0[q_owner] + torch.arange(q_need.numel(), device=dev) - qstart[q_owner]
+        i_local = chunk0[i_owner] + qc[i_owner] + torch.arange(i_need.numel(), device=dev) - istart[i_owner]
+        slot_own = torch.repeat_interleave(torch.arange(3, device=dev), torch.tensor([self.Uo, self.Qo, self.Io], device=dev))
+        slot_halo = torch.repeat_interleave(torch.tensor([1, 2], device=dev).repeat(world),
+                                            torch.stack([qc, ic], 1).reshape(-1))
+        t["row_slot"] = torch.cat([slot_own, slot_halo]).to(torch.int32)  # node type (= hyperedge slot) of every local row
 
         # ---- local ids of the hyperedges' nodes
-        lu = eu - self.ub[r]
-        q_own = (eq >= self.qb[r]) & (eq < self.qb[r + 1])
-        lq = np.where(q_own, self.Uo + (eq - self.qb[r]),
-                      q_local[np.minimum(np.searchsorted(q_need, eq), max(q_need.shape[0] - 1, 0))] if q_need.shape[0] else 0)
-        i_own = (ei >= self.ib[r]) & (ei < self.ib[r + 1])
-        li = np.where(i_own, self.Uo + self.Qo + (ei - self.ib[r]),
-                      i_local[np.minimum(np.searchsorted(i_need, ei), max(i_need.shape[0] - 1, 0))] if i_need.shape[0] else 0)
-        self.i3_local = np.stack([lu, lq, li], axis=1) if self.edge_count else np.zeros((0, 3), np.int64)
+        lu = eu - ub[0]
+        lq = self.Uo + (eq - qb[0])
+        if q_need.numel():
+            pos = torch.searchsorted(q_need, eq).clamp_(max=q_need.numel() - 1)
+            lq = torch.where(q_mine, lq, q_local[pos])
+        li = self.Uo + self.Qo + (ei - ib[0])
+        if i_need.numel():
+            pos = torch.searchsorted(i_need, ei).clamp_(max=i_need.numel() - 1)
+            li = torch.where(i_mine, li, i_local[pos])
+        t["i3_local"] = torch.stack([lu, lq, li], 1) if self.edge_count else torch.zeros((0, 3), dtype=torch.int64, device=dev)
 
-        # ---- what I send: rank d's request list for rows I own (same rule, evaluated for d)
-        send_rows: List[np.ndarray] = []             # own (= local) row index of every sent row
-        self.send_counts = np.zeros(world, dtype=np.int64)
-        for d in range(world):
-            if d == r:
-                send_rows.append(np.zeros(0, np.int64))
-                continue
-            dm = edge_owner == d
-            dq = np.unique(query[dm])
-            dq = dq[(dq >= self.qb[r]) & (dq < self.qb[r + 1])]
-            di = np.unique(item[dm])
-            di = di[(di >= self.ib[r]) & (di < self.ib[r + 1])]
-            send_rows.append(np.concatenate([self.Uo + (dq - self.qb[r]), self.Uo + self.Qo + (di - self.ib[r])]))
-            self.send_counts[d] = dq.shape[0] + di.shape[0]
-        self.send_rows = np.concatenate(send_rows)
+        # ---- what I send: for every other rank d the own rows it references, queries (ascending) then items,
+        # i.e. d's request list evaluated here.  One sort of the keys (d, own-layout row) over the hyperedges
+        # of OTHER ranks that touch my query / item ranges.
+        width = max(self.Qo + self.Io, 1)
+        foreign = edge_owner != r
+        mq = foreign & (query >= qb[0]) & (query < qb[1])
+        mi = foreign & (item >= ib[0]) & (item < ib[1])
+        keys = torch.cat([edge_owner[mq] * width + (query[mq] - qb[0]),
+                          edge_owner[mi] * width + (self.Qo + item[mi] - ib[0])])
+        keys = torch.unique(keys)                                          # sorted by (destination rank, type, id)
+        dest = torch.div(keys, width, rounding_mode="floor")
+        t["send_rows"] = self.Uo + (keys - dest * width)                   # own (= local) row index of every sent row
+        self.send_counts = torch.bincount(dest, minlength=world).cpu().numpy().astype(np.int64)
         self.S = int(self.send_counts.sum())
 
-        # ---- ordered sum of halo_reduce: own row v <- its own partial (the `init` row), then the
-        # rows received for it in ascending source rank; CSR over the receive buffer [S rows]
-        order = np.argsort(self.send_rows, kind="stable")
-        self.reduce_col = order.astype(np.int64)
-        counts = np.bincount(self.send_rows, minlength=self.n_own)
-        self.reduce_rowptr = np.zeros(self.n_own + 1, dtype=np.int64)
-        np.cumsum(counts, out=self.reduce_rowptr[1:])
+        # ---- ordered sum of halo_reduce: own row v <- its own partial, then the partials held for it by the
+        # other ranks in ascending rank.  `reduce_col` indexes the flat receive layout [S rows, by source rank]
+        # (NCCL path); `reduce_entries` = (peer slot, row inside that peer's chunk) for the fused peer-memory pull.
+        _, order = torch.sort(t["send_rows"], stable=True)
+        t["reduce_col"] = order
+        counts = torch.bincount(t["send_rows"], minlength=self.n_own) if self.S else torch.zeros(self.n_own, dtype=torch.int64, device=dev)
+        t["reduce_rowptr"] = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(counts, 0)])
+        send_off = torch.as_tensor(np.concatenate([[0], np.cumsum(self.send_counts)]), dtype=torch.int64, device=dev)
+        src_rank = dest[order]
+        peer_slot = src_rank - (src_rank > r).to(torch.int64)              # index among the ranks other than me
+        t["reduce_entries"] = torch.stack([peer_slot, order - send_off[src_rank]], 1).to(torch.int32)
 
         # ---- global degrees of the rows I own (Graph.py:112,120 on the whole hypergraph)
-        deg = np.concatenate([
-            np.bincount(user, minlength=user_count)[self.ub[r]:self.ub[r + 1]],
-            np.bincount(query, minlength=query_count)[self.qb[r]:self.qb[r + 1]],
-            np.bincount(item, minlength=item_count)[self.ib[r]:self.ib[r + 1]]]).astype(np.float32)
-        deg[deg == 0] = np.float32(1e-8)
-        self.vertex_degrees_own = deg
-        self.dv_inv_own = (np.float32(1.0) / deg).astype(np.float32)
+        deg = torch.cat([deg_u[ub[0]:ub[1]],
+                         torch.bincount(query, minlength=query_count)[qb[0]:qb[1]],
+                         torch.bincount(item, minlength=item_count)[ib[0]:ib[1]]]).to(torch.float32)
+        deg[deg == 0] = 1e-8
+        t["vertex_degrees_own"] = deg
+        t["dv_inv_own"] = deg.pow(-1)                                      # GnnLayers.py:187: fp32 reciprocal
+        self.t = t
+
+    def __getattr__(self, name):
+        t = self.__dict__.get("t")
+        if t is not None and name in t:
+            return t[name].cpu().numpy()
+        raise AttributeError(name)
 
     def batch_rows(self, users: torch.Tensor, queries: torch.Tensor, items: torch.Tensor):
         """Fixed-shape lookup plan of the batch head (RawGnn.py:128-133 over a row-sharded feature
@@ -192,22 +218,24 @@ class ShardedHyperGraph:
         if dev.type != "cuda":
             raise RuntimeError("ihgnn_b200.dist runs on CUDA (NCCL) only; the planner (PartitionPlan) is the host part")
         self.device = dev
-        t = lambda a, dt=torch.int64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+        t = lambda name, dt=torch.int64: plan.t[name].to(device=dev, dtype=dt).contiguous()
         self.EdgeCount = plan.edge_count
         self.node_count = plan.n_local
         self.n_own, self.n_local, self.S, self.R = plan.n_own, plan.n_local, plan.S, plan.R
-        self.i3 = t(plan.i3_local, torch.int32).contiguous()
+        self.i3 = t("i3_local", torch.int32)
         edge_of = torch.arange(plan.edge_count, device=dev, dtype=torch.int32).repeat_interleave(3)
         rowptr, _perm, col = csr_from_keys(self.i3.reshape(-1), plan.n_local, values=edge_of)
         self.rowptr, self.col = rowptr, col
         self.plan_csr = CsrPlan(rowptr, col)
-        self.row_slot = t(plan.row_slot, torch.int32)  # slot(row) for the per-slot gradient reduce
+        self.row_slot = t("row_slot", torch.int32)     # slot(row) for the per-slot gradient reduce
         self.own_bounds = plan.own_bounds              # node types of the own rows (typed Linear)
-        self.dv_inv_own = t(plan.dv_inv_own, torch.float32)
-        self.send_rows = t(plan.send_rows)
+        self.dv_inv_own = t("dv_inv_own", torch.float32)
+        self.send_rows = t("send_rows")
         self.send_counts = [int(x) for x in plan.send_counts]
         self.recv_counts = [int(x) for x in plan.recv_counts]
-        self.reduce_csr = CsrPlan(t(plan.reduce_rowptr, torch.int32), t(plan.reduce_col, torch.int32))
+        self.reduce_rowptr = t("reduce_rowptr", torch.int32)
+        self.reduce_csr = CsrPlan(self.reduce_rowptr, t("reduce_col", torch.int32))
+        self.reduce_entries = t("reduce_entries", torch.int32)    # (peer slot, row in that peer's chunk) per reduce_col entry
         self.p2p = None                                # set by enable_peer_memory()
         # Dv^-1 of every local row (own + halo): exchanged once, the graph is static
         self.dv_inv_local = HaloExchangeFn.apply(self.dv_inv_own.view(-1, 1).expand(-1, 4).contiguous(), self)[:, 0].contiguous()
@@ -444,20 +472,18 @@ def _halo_reduce(s_local: torch.Tensor, g: ShardedHyperGraph, row_scale: Optiona
     from . import functional as F_
     from . import _lib
     d = int(s_local.shape[1])
-    recv = torch.empty((g.S, d), dtype=torch.float32, device=s_local.device)
     if g.p2p and key is not None:
         buf, hdl, chunk, own, off, n = g.peer_buffer(("s", key), d)
         assert s_local.data_ptr() == buf.data_ptr(), "halo_reduce: s_local must be the call site's peer buffer"
-        import ctypes
-        peers = [r for r in range(g.plan.world) if r != g.plan.rank]
-        dst = (ctypes.c_void_p * n)(*[recv.data_ptr() + int(g._send_off[r]) * d * 4 for r in peers])
+        out = torch.empty((g.n_own, d), dtype=torch.float32, device=s_local.device)
         hdl.barrier(channel=0)                      # every rank's partial sums are complete
-        _lib.ptr(recv)                              # records the device for the call's device guard
-        _lib.call("ihg_halo_copy", chunk, dst, off, n, None, d, d, d, _lib.stream_ptr(),
-                  tag="halo_pull", algo_bytes=g.S * 8 * d)
-        out = F_.segment_reduce(g.reduce_csr, recv, d, row_scale=row_scale, init=s_local[:g.n_own])
+        # one kernel: own partial + the holders' partials read straight over NVLink, ascending rank, scaled
+        _lib.call("ihg_halo_reduce", _lib.ptr(s_local), d, _lib.ptr(g.reduce_rowptr), _lib.ptr(g.reduce_entries),
+                  chunk, n, d, _lib.ptr(row_scale), _lib.ptr(out), d, g.n_own, d, _lib.stream_ptr(),
+                  tag="halo_reduce", algo_bytes=g.S * 4 * d + g.n_own * 8 * d)
         hdl.barrier(channel=0)                      # holders may overwrite their buffers again
         return out
+    recv = torch.empty((g.S, d), dtype=torch.float32, device=s_local.device)
     _all_to_all(recv, s_local[g.n_own:], g.send_counts, g.recv_counts, g.group)
     return F_.segment_reduce(g.reduce_csr, recv, d, row_scale=row_scale, init=s_local[:g.n_own])
 

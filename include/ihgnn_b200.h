@@ -261,6 +261,16 @@ int ihg_halo_copy(const void* const* seg_src, void* const* seg_dst, const int64_
                   int32_t n_seg, const int64_t* src_rows, int64_t src_ld, int64_t dst_ld,
                   int32_t dim, void* stream);
 
+/* Owner side of the halo reduce-scatter, fused with the pull over NVLink:
+ *   out[v] = row_scale[v] * (own[v] + sum_{j in [rowptr[v], rowptr[v+1])} peer_base[e.peer][e.row])   e = entries[j]
+ * `entries` int32 [nnz][2] = {peer slot, row inside that peer's chunk}, ascending source rank inside a
+ * row (fixed summation order); `peer_base_host` is a HOST array of n_peers <= 16 peer-mapped device
+ * pointers (row stride peer_ld).  own / row_scale may be null (0 / 1). */
+int ihg_halo_reduce(const float* own, int64_t own_ld, const int32_t* rowptr, const int32_t* entries,
+                    const void* const* peer_base_host, int32_t n_peers, int64_t peer_ld,
+                    const float* row_scale, float* out, int64_t out_ld, int64_t n_rows, int32_t dim,
+                    void* stream);
+
 /* ------------------------------------------------------------------------------------
  * a10 HemPredictionLayer.forward                   Models/PredictionLayers.py:21-44
  *   m = lambda*q + (1-lambda)*u   (u null: m = q);  score[b] = sum_D item[b]*m[b] + bias[b']

@@ -49,7 +49,10 @@ def _worker(rank: int, world: int, port: int, dim: int, ret):
             outs_g.append(h)
         torch.cat(outs_g, 1).sum().backward()
         # ---- sharded stack with the same weights
-        plan = PartitionPlan(log.pos_user, log.pos_query, log.pos_item, U, Q, I, world, rank)
+        plan = PartitionPlan(log.pos_user, log.pos_query, log.pos_item, U, Q, I, world, rank, device=dev)   # planned on the GPU
+        host_plan = PartitionPlan(log.pos_user, log.pos_query, log.pos_item, U, Q, I, world, rank)          # ... equals the CPU plan
+        for name in PartitionPlan._TENSORS:
+            assert np.array_equal(getattr(plan, name), getattr(host_plan, name)), name
         sg = ShardedHyperGraph(plan, dev)
         sh_layers = []
         for L, o in zip(ref_layers, orders):
