@@ -518,6 +518,39 @@ def test_halo_copy_segments():
     assert torch.equal(flat, table[rows])
 
 
+@pytest.mark.parametrize("dim,with_own,with_scale", [(64, True, True), (128, True, False), (256, False, True), (8, True, True)])
+def test_halo_reduce_fused_pull(dim, with_own, with_scale):
+    """ihg_halo_reduce (owner side of the reduce-scatter, fused with the NVLink pull) with local buffers
+    standing in for the peers: out[v] = scale[v] * (own[v] + partials in ascending source order), bit-exact
+    against the same sums formed sequentially in fp32, rows nobody else holds being a scaled copy."""
+    import ctypes
+    from ihgnn_b200 import _lib
+    gen = torch.Generator().manual_seed(dim)
+    n_rows, n_peers = 700, 5
+    chunk_rows = [60, 0, 411, 150, 33]
+    peers = [torch.randn(max(c, 1), dim, generator=gen).to(DEV) for c in chunk_rows]
+    own = torch.randn(n_rows, dim, generator=gen).to(DEV)
+    scale = (torch.rand(n_rows, generator=gen) + 0.5).to(DEV)
+    # every peer row is a partial of one own row; a few hot rows are held by every peer
+    owner_of = [torch.randint(0, n_rows, (c,), generator=gen) for c in chunk_rows]
+    for p in (0, 2, 3, 4):
+        owner_of[p][:20] = torch.arange(20)
+    ent = sorted((int(v), p, k) for p in range(n_peers) for k, v in enumerate(owner_of[p].tolist()))
+    counts = np.bincount([e[0] for e in ent], minlength=n_rows)
+    rowptr = torch.tensor(np.concatenate([[0], np.cumsum(counts)]), dtype=torch.int32, device=DEV)
+    entries = torch.tensor([[e[1], e[2]] for e in ent], dtype=torch.int32, device=DEV)
+    out = torch.empty(n_rows, dim, device=DEV)
+    base = (ctypes.c_void_p * n_peers)(*[t.data_ptr() for t in peers])
+    _lib.call("ihg_halo_reduce", _lib.ptr(own if with_own else None), dim, _lib.ptr(rowptr), _lib.ptr(entries), base,
+              n_peers, dim, _lib.ptr(scale if with_scale else None), _lib.ptr(out), dim, n_rows, dim, _lib.stream_ptr())
+    want = own.clone() if with_own else torch.zeros_like(own)
+    for v, p, k in ent:                                   # ascending (row, peer): the kernel's summation order
+        want[v] += peers[p][k]
+    if with_scale:
+        want *= scale.view(-1, 1)
+    assert torch.equal(out, want)
+
+
 def test_hem_bias_gradient_fixed_point():
     """d_bias = index_add of dscore by item: 64-bit fixed-point atomics must match fp64 to fp32
     rounding for duplicate-heavy batches and tiny gradients, and be bit-reproducible."""
