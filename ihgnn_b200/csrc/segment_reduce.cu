@@ -410,8 +410,9 @@ extern "C" int ihg_segment_reduce(const ihg_csr* g, const float* src, int64_t sr
     IHG_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 256, "segment_reduce: dim=%d must be a multiple of 4, <= 256", dim);
     IHG_REQUIRE(src_ld % 4 == 0 && out_ld % 4 == 0 && src_ld >= dim && out_ld >= dim,
                 "segment_reduce: leading dimensions must be multiples of 4 and >= dim");
-    // accumulate mode leaves empty rows untouched, so its plan may list the non-empty rows only
-    IHG_REQUIRE(g->n_rows > 0 && (g->n_seg >= g->n_rows || accumulate) && g->seg, "segment_reduce: incomplete csr plan");
+    // a plan may list a subset of the rows (accumulate mode: the non-empty rows; multi-GPU: the halo rows or
+    // the own rows of a local table): rows without work items are left untouched
+    IHG_REQUIRE(g->n_rows > 0 && g->n_seg >= 0 && g->seg, "segment_reduce: incomplete csr plan");
     if (g->n_seg == 0) return IHG_OK;
     IHG_REQUIRE(g->nnz == 0 || g->col, "segment_reduce: null col");
     IHG_REQUIRE(g->n_split == 0 || (partial && g->split_row && g->split_ptr),
@@ -456,7 +457,8 @@ extern "C" int ihg_two_hop_reduce(const ihg_csr* g, const int32_t* nbr, const fl
     IHG_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 256, "two_hop_reduce: dim=%d must be a multiple of 4, <= 256", dim);
     IHG_REQUIRE(src_ld % 4 == 0 && out_ld % 4 == 0 && src_ld >= dim && out_ld >= dim,
                 "two_hop_reduce: leading dimensions must be multiples of 4 and >= dim");
-    IHG_REQUIRE(g->n_rows > 0 && g->n_seg >= g->n_rows && g->seg && g->rowptr, "two_hop_reduce: incomplete csr plan");
+    IHG_REQUIRE(g->n_rows > 0 && g->n_seg >= 0 && g->seg && g->rowptr, "two_hop_reduce: incomplete csr plan");
+    if (g->n_seg == 0) return IHG_OK;                 // a row-range view may be empty
     IHG_REQUIRE(g->nnz == 0 || nbr, "two_hop_reduce: null neighbour list");
     IHG_REQUIRE(g->n_split == 0 || (partial && g->split_row && g->split_ptr),
                 "two_hop_reduce: split rows need the partial buffer");

@@ -209,17 +209,78 @@ WORKLOADS: Dict[str, Dict] = {
     "cikm": dict(user_count=250_000, query_count=60_000, item_count=190_000,
                  edge_count=5_000_000, vocab_size=50_000, shape="cikm",
                  layers=3, dim=128, seed=3),
+    # configs[3]: scaled synthetic hypergraph, 100 M hyperedges over 50 M table rows, multi-GPU only
+    # (generated on the device: `make_workload(..., device=...)`)
+    "scaled": dict(user_count=38_000_000, query_count=200_000, item_count=11_800_000,
+                   edge_count=100_000_000, vocab_size=50_000, shape="amazon",
+                   layers=2, dim=64, seed=4),
 }
 
 
-def make_workload(name: str, scale: float = 1.0, with_negatives: bool = False) -> SearchLogSet:
+def make_search_log_on_device(user_count: int, query_count: int, item_count: int, edge_count: int, device,
+                              vocab_size: int = 1000, shape: str = "amazon", seed: int = 0,
+                              zipf: float = 0.8) -> SearchLogSet:
+    """The same kind of log as `make_search_log` -- Zipf(s) popularity per node type under a random
+    rank -> id permutation, Amazon (one positive per log) or CIKM (1..3 clicked items per log) shape --
+    drawn with torch on `device` for logs too large for the host generator (BASELINE.json configs[3]:
+    10^8 hyperedges take minutes in numpy, ~0.1 s on the GPU).  `pos_user / pos_query / pos_item` are int64
+    torch tensors ON THE DEVICE; the (small) query texts are numpy as usual.  Seeded: every rank of a
+    multi-GPU job draws the identical log on its own GPU.  A different stream than the numpy generator's,
+    so the two produce different logs of the same distribution."""
+    import torch
+    assert shape in ("amazon", "cikm")
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed))
+
+    def sampler(n: int):
+        if zipf <= 0:
+            return lambda k: torch.randint(0, n, (k,), generator=gen, device=dev)
+        w = torch.arange(1, n + 1, dtype=torch.float64, device=dev).pow_(-zipf)
+        cdf = torch.cumsum(w, 0)
+        cdf /= cdf[-1].clone()
+        perm = torch.randperm(n, generator=gen, device=dev)
+
+        def sample(k: int):
+            r = torch.searchsorted(cdf, torch.rand(k, generator=gen, device=dev, dtype=torch.float64), right=True)
+            return perm[r.clamp_(max=n - 1)]
+        return sample
+
+    su, sq, si = sampler(user_count), sampler(query_count), sampler(item_count)
+    rng = np.random.default_rng(seed)
+    qlen = rng.integers(1, 8, size=query_count, dtype=np.int64)
+    qptr = np.zeros(query_count + 1, dtype=np.int64)
+    np.cumsum(qlen, out=qptr[1:])
+    qwords = rng.integers(0, vocab_size, size=int(qptr[-1]), dtype=np.int64)
+    E = int(edge_count)
+    if shape == "amazon":
+        pos_user, pos_query = su(E), sq(E)
+    else:
+        n_logs = E                                           # >= E positives for sure; trimmed below
+        clicks = torch.randint(1, 4, (n_logs,), generator=gen, device=dev)
+        csum = torch.cumsum(clicks, 0)
+        n_logs = int(torch.searchsorted(csum, torch.tensor([E], device=dev), right=False)) + 1
+        clicks = clicks[:n_logs].clone()
+        clicks[-1] -= int(csum[n_logs - 1]) - E
+        lu, lq = su(n_logs), sq(n_logs)
+        pos_user, pos_query = torch.repeat_interleave(lu, clicks), torch.repeat_interleave(lq, clicks)
+    pos_item = si(E)
+    return SearchLogSet(user_count, query_count, item_count, vocab_size, qwords, qptr,
+                        pos_user, pos_query, pos_item, shape=shape, seed=seed)
+
+
+def make_workload(name: str, scale: float = 1.0, with_negatives: bool = False, device=None) -> SearchLogSet:
     """Instantiate a named workload; `scale` multiplies every count (multi-GPU weak scaling
-    and bounded CPU-baseline samples use it)."""
+    and bounded CPU-baseline samples use it).  `device`: draw the log with torch on that device
+    (`make_search_log_on_device`) instead of numpy on the host."""
     w = dict(WORKLOADS[name])
     layers, dim, seed = w.pop("layers"), w.pop("dim"), w.pop("seed")
     if scale != 1.0:
         for k in ("user_count", "query_count", "item_count", "edge_count"):
             w[k] = max(4, int(round(w[k] * scale)))
-    log = make_search_log(seed=seed, with_negatives=with_negatives, **w)
+    if device is not None:
+        log = make_search_log_on_device(device=device, seed=seed, **w)
+    else:
+        log = make_search_log(seed=seed, with_negatives=with_negatives, **w)
     log.extra.update(layers=layers, dim=dim, name=name, scale=scale)
     return log
