@@ -59,7 +59,7 @@ B_POS, NEG = 100, 10                                  # GlobalSettings.py:26,39:
 
 # bounded CPU sample of a workload = the same generator at a smaller scale (every count multiplied, so
 # nodes per hyperedge, degree skew and the model are those of the workload itself)
-CPU_SCALE = {"amazon-small": 1.0, "amazon-full": 0.125, "cikm": 0.02}
+CPU_SCALE = {"amazon-small": 1.0, "amazon-full": 0.125, "cikm": 0.02, "scaled": 0.0015}
 
 # C-ABI call tag -> the kernels that call launches, by name in the committed ncu --set full extract
 _TAG_KERNEL = {"segment_reduce": ["segment_reduce_kernel", "segment_fixup_kernel"],
@@ -291,6 +291,8 @@ def run_reference_arm(args):
         metric, unit, config = RANK_METRIC, RANK_UNIT, rank_config(world, args.scaling)
     else:
         w = synth.WORKLOADS[args.workload]
+        if args.workload == "scaled":
+            args.scaling = "strong"
         mult = world if args.scaling == "weak" else 1
         cpu_scale = args.cpu_scale or CPU_SCALE[args.workload]
         value, dt, sample = time_cpu(args.workload, cpu_scale, args.steps, max(args.warmup, 1))
@@ -361,12 +363,17 @@ def measure_conv(ctx: Ctx, name: str, with_cpu: bool, profile_step: bool = False
     args, dev, world, rank, dist = ctx.args, ctx.dev, ctx.world, ctx.rank, ctx.dist
     w = synth.WORKLOADS[name]
     layers, d = w["layers"], w["dim"]
-    mult = world if args.scaling == "weak" else 1
+    fixed = name == "scaled"                              # configs[3]: ONE 100 M-hyperedge workload over 2 / 4 / 8 GPUs
+    scaling = "strong" if fixed else args.scaling
+    mult = world if scaling == "weak" else 1
     rows_per_step = B_POS * (1 + NEG) * mult              # the global training batch grows with the workload
 
     # --- build: graph indices on the device, model with the reference's own initialisers
     t_build0 = time.perf_counter()
-    log = synth.make_workload(name, scale=args.scale * mult)
+    # `scaled` is drawn with torch on the rank's own GPU (identical on every rank: same seed, same generator);
+    # the host generator needs minutes for 10^8 hyperedges
+    log = synth.make_workload(name, scale=args.scale * mult, device=dev if fixed else None)
+    torch.cuda.synchronize()
     t_synth = time.perf_counter() - t_build0
     torch.manual_seed(0)
     if world == 1:
@@ -484,7 +491,8 @@ def measure_conv(ctx: Ctx, name: str, with_cpu: bool, profile_step: bool = False
     Bp = B_POS * mult
     for _ in range(n_batches):
         pick = rng.integers(0, log.edge_count, size=Bp)
-        pu, pq, pi = log.pos_user[pick], log.pos_query[pick], log.pos_item[pick]
+        pu, pq, pi = (np.asarray(a[pick].cpu()) if torch.is_tensor(a) else a[pick]
+                      for a in (log.pos_user, log.pos_query, log.pos_item))
         users = np.concatenate([pu, np.repeat(pu, NEG)])
         queries = np.concatenate([pq, np.repeat(pq, NEG)])
         items = np.concatenate([pi, rng.integers(0, log.item_count, size=Bp * NEG)])
@@ -571,7 +579,7 @@ def measure_conv(ctx: Ctx, name: str, with_cpu: bool, profile_step: bool = False
                                   "peak_source": f"{L2_BYTES_PER_CLK:.0f} B/clk full-chip L2 cap (B300_MICROARCH.md) x "
                                                  f"{sm_mhz:.0f} MHz observed"}
         cpu = None
-        if with_cpu and not args.no_cpu_baseline:
+        if with_cpu and not args.no_cpu_baseline and name in CPU_SCALE:
             v, dt, sample = time_cpu(name, args.cpu_scale or CPU_SCALE[name], 3, 1)
             cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
         kernels = {}
@@ -583,7 +591,7 @@ def measure_conv(ctx: Ctx, name: str, with_cpu: bool, profile_step: bool = False
                 kernels[k]["dram_GBps"] = round(tb / (v["avg_ms"] * 1e-3) / 1e9, 1)
         out = {
             "value": total_units / t_conv, "ms_per_step": t_conv * 1e3,
-            "config": conv_config(name, layers, d, E, N, args.scaling),
+            "config": conv_config(name, layers, d, E, N, scaling),
             "run": {"parallelism": parallelism,
                     "l2_policy": "inputs larger than L2 (no flush): per step the kernels stream "
                                  f"{conv_bytes / 1e9 / world:.1f} GB algorithmic per GPU vs 126 MB L2",
@@ -762,7 +770,7 @@ def run_gpu_arm(args):
             if ctx.rank == 0:
                 line = {"metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": ctx.world,
                         "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
-                        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+                        "higher_is_better": True, "scaling": main_res["config"]["scaling"], "vs_baseline": None, "dtype": "f32",
                         "data": "synthetic"}
                 line.update({k: main_res[k] for k in ("config", "run", "clocks", "e2e", "gpu_launches", "roofline",
                                                       "cpu_baseline", "kernels")})

@@ -247,7 +247,8 @@ class ShardedHyperGraph:
         self.reduce_rowptr = t("reduce_rowptr", torch.int32)
         self.reduce_csr = CsrPlan(self.reduce_rowptr, t("reduce_col", torch.int32))
         self.reduce_entries = t("reduce_entries", torch.int32)    # (peer slot, row in that peer's chunk) per reduce_col entry
-        # overlap of the NVLink transfers with local work (IHG_OVERLAP=0 switches it off): the halo rows of a
+        # overlap of the NVLink transfers with local work (opt-in, IHG_OVERLAP=1; measured at N = 2 it does not
+        # pay: the extra pass that adds the pulled sums costs more than the hidden transfer): the halo rows of a
         # local reduction are produced first, the owners pull them on a high-priority side stream while the own
         # rows are still being reduced, a last pass adds the two
         self.n_rem = plan.n_rem
@@ -256,7 +257,7 @@ class ShardedHyperGraph:
         self.comb_entries = t("comb_entries", torch.int32)
         self.plan_own = self.plan_csr.row_range(0, plan.n_own)
         self.plan_halo = self.plan_csr.row_range(plan.n_own, plan.n_local)
-        self.overlap = os.environ.get("IHG_OVERLAP", "1") != "0"
+        self.overlap = os.environ.get("IHG_OVERLAP", "0") == "1"
         self.side = torch.cuda.Stream(device=dev, priority=-1)
         self.p2p = None                                # set by enable_peer_memory()
         # Dv^-1 of every local row (own + halo): exchanged once, the graph is static
@@ -312,6 +313,14 @@ class ShardedHyperGraph:
     def peer_buffer(self, key, cols: int):
         """Persistent symmetric [max n_local, cols] fp32 buffer for call site `key` (allocated and
         rendezvoused on first use -- a collective, so every rank must reach it in the same order)."""
+        if not self.overlap:
+            # serial mode: the exchanges of a step are strictly ordered by barriers, so every call site can use
+            # the same two buffers -- one local table, one partial-sum table -- except the projected rows of an
+            # order-2/3 layer, which its backward reads again (ShardedFeatureInteractFn / _EdgeInteractFn save them).  At
+            # 10^8 hyperedges a table is several GB; per-site buffers would not fit.
+            role, site = key
+            keep = isinstance(site, tuple) and len(site) == 2 and (site[0] == "fi" or site[1] == "xpp")
+            key = (role, site if keep else "shared")
         k = (key, cols)
         if k not in self._bufs:
             buf = self._symm.empty((self._max_local, cols), dtype=torch.float32, device=self.device)
