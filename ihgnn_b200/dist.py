@@ -258,6 +258,8 @@ class ShardedHyperGraph:
         self.plan_own = self.plan_csr.row_range(0, plan.n_own)
         self.plan_halo = self.plan_csr.row_range(plan.n_own, plan.n_local)
         self.overlap = os.environ.get("IHG_OVERLAP", "0") == "1"
+        # one buffer pair for all call sites when per-site tables (about a dozen per model) would be too large
+        self.share_buffers = False
         self.side = torch.cuda.Stream(device=dev, priority=-1)
         self.p2p = None                                # set by enable_peer_memory()
         # Dv^-1 of every local row (own + halo): exchanged once, the graph is static
@@ -297,6 +299,7 @@ class ShardedHyperGraph:
         self._send_off = np.concatenate([[0], np.cumsum(self.send_counts)]).astype(np.int64)
         self._symm = symm_mem
         self._bufs = {}
+        self.share_buffers = (not self.overlap) and self._max_local * 128 * 4 * 14 > (40 << 30)
         # probe once (allocation + rendezvous + barrier); every rank must agree on the outcome
         ok = 1
         try:
@@ -310,11 +313,18 @@ class ShardedHyperGraph:
         self.p2p = True if int(flag.item()) == 1 else None
         return self.p2p is True
 
+    def table_head(self, key, cols: int) -> Optional[torch.Tensor]:
+        """The own-row part [n_own, cols] of call site `key`'s local table (peer memory only): a producer
+        that writes there saves `halo_exchange` the copy of the own rows."""
+        if not self.p2p:
+            return None
+        return self.peer_buffer(("x", key), cols)[0][:self.n_own]
+
     def peer_buffer(self, key, cols: int):
         """Persistent symmetric [max n_local, cols] fp32 buffer for call site `key` (allocated and
         rendezvoused on first use -- a collective, so every rank must reach it in the same order)."""
-        if not self.overlap:
-            # serial mode: the exchanges of a step are strictly ordered by barriers, so every call site can use
+        if self.share_buffers:
+            # the exchanges of a step are strictly ordered by barriers, so every call site can use
             # the same two buffers -- one local table, one partial-sum table -- except the projected rows of an
             # order-2/3 layer, which its backward reads again (ShardedFeatureInteractFn / _EdgeInteractFn save them).  At
             # 10^8 hyperedges a table is several GB; per-site buffers would not fit.
@@ -442,12 +452,14 @@ def _halo_exchange(x_own: torch.Tensor, g: "ShardedHyperGraph", key=None) -> tor
                 _lib.call("ihg_halo_copy", src, chunk, off, n, _lib.ptr(g.send_rows), _lib.ld(x_own), d, d,
                           _lib.stream_ptr(), tag="halo_push", algo_bytes=g.S * (8 + 8 * d))
                 hdl.barrier(channel=0)              # every rank's pushes have landed
-            F_.copy_rows_raw(x_own, x_local[:g.n_own])
+            if x_own.data_ptr() != x_local.data_ptr():
+                F_.copy_rows_raw(x_own, x_local[:g.n_own])
             main.wait_stream(g.side)
             return x_local
         _lib.call("ihg_halo_copy", src, chunk, off, n, _lib.ptr(g.send_rows), _lib.ld(x_own), d, d,
                   _lib.stream_ptr(), tag="halo_push", algo_bytes=g.S * (8 + 8 * d))
-        F_.copy_rows_raw(x_own, x_local[:g.n_own])
+        if x_own.data_ptr() != x_local.data_ptr():  # producers may have written the own rows in place (table_head)
+            F_.copy_rows_raw(x_own, x_local[:g.n_own])
         hdl.barrier(channel=0)                      # every rank's pushes have landed
         return x_local
     send = F_.gather_rows_raw(x_own, g.send_rows, 0)
@@ -538,8 +550,9 @@ def _halo_reduce(s_local: torch.Tensor, g: ShardedHyperGraph, row_scale: Optiona
         _lib.call("ihg_halo_reduce", _lib.ptr(s_local), d, _lib.ptr(g.reduce_rowptr), _lib.ptr(g.reduce_entries),
                   chunk, n, d, _lib.ptr(row_scale), _lib.ptr(out), d, g.n_own, d, _lib.stream_ptr(),
                   tag="halo_reduce", algo_bytes=g.S * 4 * d + g.n_own * 8 * d)
-        hdl.barrier(channel=0)                      # holders may overwrite their buffers again
-        return out
+        if g.share_buffers:
+            hdl.barrier(channel=0)                  # holders may overwrite the (shared) buffer again; a per-site buffer
+        return out                                  # is next written a whole step -- many barriers -- later
     recv = torch.empty((g.S, d), dtype=torch.float32, device=s_local.device)
     _all_to_all(recv, s_local[g.n_own:], g.send_counts, g.recv_counts, g.group)
     return F_.segment_reduce(g.reduce_csr, recv, d, row_scale=row_scale, init=s_local[:g.n_own])
@@ -642,15 +655,17 @@ class ShardedIHGNNLayer(torch.nn.Module):
         if self.order == 1:
             w_f = torch.matmul(w_lo, wt)
             b_f = torch.matmul(w_lo, bt) + torch.stack([fi.aggregation.bias, zeros, zeros])
-            p_own = F_.typed_linear(x_own, w_f, b_f, g.own_bounds)
+            p_own = F_.typed_linear(x_own, w_f, b_f, g.own_bounds, out=g.table_head((self.uid, "p"), d))
             p = halo_exchange(p_own, g, (self.uid, "p"))
             if F_.two_hop_enabled(g.n_local, d):
                 return ShardedTwoHopFn.apply(p, g, self.uid)
             ef = _EdgeGatherSumFn.apply(p, self.view, None, 1.0, None)
         else:
             from . import _lib
-            xp_own = F_.typed_linear(x_own, wt.unsqueeze(0), bt.unsqueeze(0), None)
-            if _lib.lib().ihg_feature_interact_supported(d):
+            tc = bool(_lib.lib().ihg_feature_interact_supported(d))
+            xp_own = F_.typed_linear(x_own, wt.unsqueeze(0), bt.unsqueeze(0), None,
+                                     out=g.table_head(("fi", self.uid), d) if tc else None)
+            if tc:
                 ef = ShardedFeatureInteractFn.apply(xp_own, fi.aggregation.weight, fi.aggregation.bias, g, self.order, self.uid)
             else:
                 b_lo = torch.stack([fi.aggregation.bias, zeros, zeros])

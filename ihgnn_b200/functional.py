@@ -123,7 +123,7 @@ def edge_gather_sum(src: torch.Tensor, i3: torch.Tensor, *, node_scale: Optional
 
 def node_linear(x: torch.Tensor, w: torch.Tensor, *, transpose_w: bool = False,
                 bias: Optional[torch.Tensor] = None, addend: Optional[torch.Tensor] = None,
-                bounds: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+                bounds: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Typed Linear.  w: [T, n_out, n_in] (transpose_w False) -> y = x W[t]^T + bias[t] + addend;
     transpose_w True -> y = x W[t] (n_out = w.shape[2])."""
     _lib.require_cuda(x, w, bias, addend)
@@ -143,10 +143,11 @@ def node_linear(x: torch.Tensor, w: torch.Tensor, *, transpose_w: bool = False,
         bias = bias.contiguous()
     if addend is not None:
         addend = _lib.rows_f32(addend)
-    y = _empty((n_rows, n_out), x)
+    y = _empty((n_rows, n_out), x) if out is None else out
+    assert tuple(y.shape) == (n_rows, n_out) and y.dtype == _F32 and y.stride(1) == 1 and y.data_ptr() % 16 == 0
     _lib.call("ihg_node_linear", _lib.ptr(x), _lib.ld(x), _lib.ptr(w), T, n_out, n_in,
               1 if transpose_w else 0, _lib.ptr(bias), _lib.ptr(addend),
-              _lib.ld(addend) if addend is not None else 0, n_rows, b0, b1, _lib.ptr(y), n_out,
+              _lib.ld(addend) if addend is not None else 0, n_rows, b0, b1, _lib.ptr(y), _lib.ld(y),
               _lib.stream_ptr(), tag="node_linear",
               algo_bytes=n_rows * 4 * (n_in + n_out + (n_out if addend is not None else 0)))
     return y
@@ -198,13 +199,13 @@ class TypedLinearFn(torch.autograd.Function):
     """y = x W[type(row)]^T + b[type(row)];  w [T, n_out, n_in], b [T, n_out] or None."""
 
     @staticmethod
-    def forward(ctx, x, w, b, bounds):
+    def forward(ctx, x, w, b, bounds, out=None):
         ctx.bounds = bounds
         ctx.has_bias = b is not None
         x = _lib.rows_f32(x)
         w = w.contiguous()
         ctx.save_for_backward(x, w)
-        return node_linear(x, w, bias=b, bounds=bounds)
+        return node_linear(x, w, bias=b, bounds=bounds, out=out.tensor if out is not None else None)
 
     @staticmethod
     def backward(ctx, dy):
@@ -215,11 +216,21 @@ class TypedLinearFn(torch.autograd.Function):
             dx = node_linear(dy, w, transpose_w=True, bounds=ctx.bounds)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw, db = node_linear_wgrad(dy, x, int(w.shape[0]), ctx.bounds, ctx.has_bias)
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
-def typed_linear(x, w, b=None, bounds=None):
-    return TypedLinearFn.apply(x, w, b, bounds)
+class OutBuffer:
+    """Wraps a preallocated result tensor handed to an autograd Function: a plain object, so autograd
+    does not treat the buffer as an input of the Function (the result is a fresh view of it)."""
+
+    def __init__(self, tensor: torch.Tensor):
+        self.tensor = tensor
+
+
+def typed_linear(x, w, b=None, bounds=None, out: Optional[torch.Tensor] = None):
+    """`out`: write the result into this (non-differentiable) buffer instead of a fresh tensor -- the
+    multi-GPU layers project straight into the head of the table their halo exchange completes."""
+    return TypedLinearFn.apply(x, w, b, bounds, OutBuffer(out) if out is not None else None)
 
 
 class EmbedAllFn(torch.autograd.Function):
