@@ -1,7 +1,7 @@
 """Multi-GPU hypergraph convolution: hyperedge partition + row-sharded node tables (SURVEY.md
 section 8e; the reference itself is single-device).
 
-Partition (host side, numpy -- `PartitionPlan`):
+Partition (`PartitionPlan`: torch ops on the rank's own GPU, or on the CPU in the gloo tests):
   * nodes are row-sharded in contiguous equal ranges *within each node type*, so every rank owns
     U/G users, Q/G queries and I/G items and the slot -> node-type hoisting stays valid;
   * a hyperedge lives on the rank that owns its user, so the user row is always local and at
@@ -16,10 +16,12 @@ Per layer and direction there are two exchange steps, adjoint to each other:
   halo_reduce     ranks send their partial sums of halo rows back; the owner adds its own
                   partial and the received ones in ascending source rank order and applies Dv^-1
                   (all-to-all + one deterministic segmented reduction = reduce-scatter)
-Pack / unpack are the library's row-gather kernels; the ordered sum is ihg_segment_reduce over a
-small CSR built at plan time.  Dense weight gradients are all-reduced.
+With NVLink peer memory (the default) both steps are ONE kernel each: owners write boundary rows straight
+into the readers' tables (`ihg_halo_copy`), and pull + sum the holders' partials in fixed order
+(`ihg_halo_reduce`); over NCCL they are all-to-alls plus the library's gather / segmented-reduce kernels.
+Dense weight gradients are all-reduced.  The sharded step is sync-free and is captured per rank in a CUDA graph.
 
-CUDA only (NCCL).  The planner is pure numpy and is exercised on CPU by tests/test_dist_gloo.py.
+CUDA only (NCCL + symmetric memory).  The planner is exercised on CPU by tests/test_dist_gloo.py.
 """
 from __future__ import annotations
 
@@ -74,7 +76,7 @@ class PartitionPlan:
     numpy copy (host-side tests and the CPU replay of the choreography use those)."""
 
     _TENSORS = ("edge_ids", "i3_local", "row_slot", "send_rows", "reduce_rowptr", "reduce_col", "reduce_entries",
-                "rem_rowptr", "comb_rowptr", "comb_entries", "vertex_degrees_own", "dv_inv_own")
+                "vertex_degrees_own", "dv_inv_own")
 
     def __init__(self, user, query, item, user_count: int, query_count: int, item_count: int,
                  world: int, rank: int, device=None):
@@ -162,17 +164,6 @@ class PartitionPlan:
         peer_slot = src_rank - (src_rank > r).to(torch.int64)              # index among the ranks other than me
         t["reduce_entries"] = torch.stack([peer_slot, order - send_off[src_rank]], 1).to(torch.int32)
 
-        # overlapped form: the remote partials of the n_rem own rows that have any are summed into a compact
-        # buffer T (rem_rowptr over the same entries) while the own rows are still being reduced locally;
-        # a second pass adds T[c] to its own row (comb_rowptr / comb_entries = {0, c})
-        has = counts > 0
-        rem_rows = torch.nonzero(has).view(-1)
-        self.n_rem = int(rem_rows.numel())
-        t["rem_rowptr"] = torch.cat([t["reduce_rowptr"][rem_rows], t["reduce_rowptr"][-1:]])
-        t["comb_rowptr"] = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(has.to(torch.int64), 0)])
-        t["comb_entries"] = torch.stack([torch.zeros(self.n_rem, dtype=torch.int64, device=dev),
-                                         torch.arange(self.n_rem, device=dev)], 1).to(torch.int32)
-
         # ---- global degrees of the rows I own (Graph.py:112,120 on the whole hypergraph)
         deg = torch.cat([deg_u[ub[0]:ub[1]],
                          torch.bincount(query, minlength=query_count)[qb[0]:qb[1]],
@@ -247,20 +238,8 @@ class ShardedHyperGraph:
         self.reduce_rowptr = t("reduce_rowptr", torch.int32)
         self.reduce_csr = CsrPlan(self.reduce_rowptr, t("reduce_col", torch.int32))
         self.reduce_entries = t("reduce_entries", torch.int32)    # (peer slot, row in that peer's chunk) per reduce_col entry
-        # overlap of the NVLink transfers with local work (opt-in, IHG_OVERLAP=1; measured at N = 2 it does not
-        # pay: the extra pass that adds the pulled sums costs more than the hidden transfer): the halo rows of a
-        # local reduction are produced first, the owners pull them on a high-priority side stream while the own
-        # rows are still being reduced, a last pass adds the two
-        self.n_rem = plan.n_rem
-        self.rem_rowptr = t("rem_rowptr", torch.int32)
-        self.comb_rowptr = t("comb_rowptr", torch.int32)
-        self.comb_entries = t("comb_entries", torch.int32)
-        self.plan_own = self.plan_csr.row_range(0, plan.n_own)
-        self.plan_halo = self.plan_csr.row_range(plan.n_own, plan.n_local)
-        self.overlap = os.environ.get("IHG_OVERLAP", "0") == "1"
         # one buffer pair for all call sites when per-site tables (about a dozen per model) would be too large
         self.share_buffers = False
-        self.side = torch.cuda.Stream(device=dev, priority=-1)
         self.p2p = None                                # set by enable_peer_memory()
         # Dv^-1 of every local row (own + halo): exchanged once, the graph is static
         self.dv_inv_local = HaloExchangeFn.apply(self.dv_inv_own.view(-1, 1).expand(-1, 4).contiguous(), self)[:, 0].contiguous()
@@ -299,7 +278,7 @@ class ShardedHyperGraph:
         self._send_off = np.concatenate([[0], np.cumsum(self.send_counts)]).astype(np.int64)
         self._symm = symm_mem
         self._bufs = {}
-        self.share_buffers = (not self.overlap) and self._max_local * 128 * 4 * 14 > (40 << 30)
+        self.share_buffers = self._max_local * 128 * 4 * 14 > (40 << 30)
         # probe once (allocation + rendezvous + barrier); every rank must agree on the outcome
         ok = 1
         try:
@@ -369,9 +348,6 @@ class HaloExchangeFn(torch.autograd.Function):
         dx_local = dx_local.contiguous()
         if g.p2p and key is not None:              # the incoming gradient is an ordinary tensor: stage it
             d = int(dx_local.shape[1])
-            if g.overlap:                          # only the halo tail travels: stage that, add the own rows in place
-                stage = lambda plan, out: out[g.n_own:].copy_(dx_local[g.n_own:])
-                return _halo_reduce_overlapped(g, ("xb", key), d, stage, None, own_rows=dx_local[:g.n_own]), None, None
             buf = reduce_buffer(g, ("xb", key), d, dx_local)
             buf.copy_(dx_local)
             return _halo_reduce(buf, g, None, ("xb", key)), None, None
@@ -390,9 +366,6 @@ class ShardedScatterMeanFn(torch.autograd.Function):
         ctx.g, ctx.key = g, key
         ef = _lib.rows_f32(ef)
         d = int(ef.shape[1])
-        if g.p2p and key is not None and g.overlap:
-            run = lambda plan, out: F_.segment_reduce(plan, ef, d, out=out)
-            return _halo_reduce_overlapped(g, ("sm", key), d, run, g.dv_inv_own)
         s_local = F_.phased_segment_reduce(g.plan_csr, g.EdgeCount, ef, d, out=reduce_buffer(g, ("sm", key), d, ef))
         return _halo_reduce(s_local, g, g.dv_inv_own, ("sm", key) if key is not None else None)
 
@@ -418,9 +391,6 @@ class ShardedTwoHopFn(torch.autograd.Function):
         ctx.g, ctx.key = g, key
         p_local = _lib.rows_f32(p_local)
         d = int(p_local.shape[1])
-        if g.p2p and key is not None and g.overlap:
-            run = lambda plan, out: F_.two_hop_reduce(plan, g.two_hop_nbr, p_local, out=out)
-            return _halo_reduce_overlapped(g, ("sm", key), d, run, g.dv_inv_own)
         s_local = F_.two_hop_reduce(g.plan_csr, g.two_hop_nbr, p_local, out=reduce_buffer(g, ("sm", key), d, p_local))
         return _halo_reduce(s_local, g, g.dv_inv_own, ("sm", key) if key is not None else None)
 
@@ -445,17 +415,6 @@ def _halo_exchange(x_own: torch.Tensor, g: "ShardedHyperGraph", key=None) -> tor
         # ordered by destination rank and holds nothing for myself, so the flat order matches `off`.
         src = (type(own))(*[x_own.data_ptr()] * n)
         x_local = buf[:g.n_local]
-        main = torch.cuda.current_stream()
-        if g.overlap:                               # the NVLink writes run beside the local copy of the own rows
-            g.side.wait_stream(main)
-            with torch.cuda.stream(g.side):
-                _lib.call("ihg_halo_copy", src, chunk, off, n, _lib.ptr(g.send_rows), _lib.ld(x_own), d, d,
-                          _lib.stream_ptr(), tag="halo_push", algo_bytes=g.S * (8 + 8 * d))
-                hdl.barrier(channel=0)              # every rank's pushes have landed
-            if x_own.data_ptr() != x_local.data_ptr():
-                F_.copy_rows_raw(x_own, x_local[:g.n_own])
-            main.wait_stream(g.side)
-            return x_local
         _lib.call("ihg_halo_copy", src, chunk, off, n, _lib.ptr(g.send_rows), _lib.ld(x_own), d, d,
                   _lib.stream_ptr(), tag="halo_push", algo_bytes=g.S * (8 + 8 * d))
         if x_own.data_ptr() != x_local.data_ptr():  # producers may have written the own rows in place (table_head)
@@ -516,16 +475,10 @@ class ShardedFeatureInteractFn(torch.autograd.Function):
                   tag="edge_interact_bwd", algo_bytes=E * (12 + 28 * dim))
         # per-row gradients of the local rows, side by side: [ product-rule part | dP ]
         rkey = ("fib", ctx.key) if ctx.key is not None else None
-        if g.p2p and rkey is not None and g.overlap:
-            def run(plan, out):
-                F_.segment_reduce(plan, slot_grad, dim, src_row_mul=3, row_slot=g.row_slot, out=out[:, :dim])
-                F_.segment_reduce(plan, def_, dim, out=out[:, dim:])
-            own = _halo_reduce_overlapped(g, rkey, 2 * dim, run, None)     # [n_own, 2 dim]
-        else:
-            both = reduce_buffer(g, rkey, 2 * dim, def_)
-            F_.segment_reduce(g.plan_csr, slot_grad, dim, src_row_mul=3, row_slot=g.row_slot, out=both[:, :dim])
-            F_.phased_segment_reduce(g.plan_csr, g.EdgeCount, def_, dim, out=both[:, dim:])
-            own = _halo_reduce(both, g, None, rkey)                        # [n_own, 2 dim]
+        both = reduce_buffer(g, rkey, 2 * dim, def_)
+        F_.segment_reduce(g.plan_csr, slot_grad, dim, src_row_mul=3, row_slot=g.row_slot, out=both[:, :dim])
+        F_.phased_segment_reduce(g.plan_csr, g.EdgeCount, def_, dim, out=both[:, dim:])
+        own = _halo_reduce(both, g, None, rkey)                            # [n_own, 2 dim]
         dxp_hi, dp = own[:, :dim], own[:, dim:]
         dxp = F_.node_linear(dp, w_lo, transpose_w=True, addend=dxp_hi, bounds=g.own_bounds)
         dw_lo, db_lo = F_.node_linear_wgrad(dp, xp_own, 3, g.own_bounds, True)
@@ -556,45 +509,6 @@ def _halo_reduce(s_local: torch.Tensor, g: ShardedHyperGraph, row_scale: Optiona
     recv = torch.empty((g.S, d), dtype=torch.float32, device=s_local.device)
     _all_to_all(recv, s_local[g.n_own:], g.send_counts, g.recv_counts, g.group)
     return F_.segment_reduce(g.reduce_csr, recv, d, row_scale=row_scale, init=s_local[:g.n_own])
-
-
-def _halo_reduce_overlapped(g: ShardedHyperGraph, key, d: int, run, row_scale: Optional[torch.Tensor],
-                            own_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """halo_reduce with the NVLink pull hidden behind local work.  `run(plan_view, out)` performs the local
-    reduction over the rows of a plan view into `out` (absolute local rows).  Order of events:
-      main:  run(halo rows) -> tail of this call site's peer buffer
-      side:  barrier (every rank's halo partials exist) . pull + sum the holders' partials of my rows that
-             have any into T (ascending source rank) . barrier (holders may overwrite)
-      main:  run(own rows) -> own partial                              (concurrently with the side stream)
-      main:  out[v] = row_scale[v] * (own partial[v] + T[v])            (after joining the side stream)
-    `own_rows`: the own partial is already there (an incoming gradient), skip run(own rows).
-    Fixed summation order, hence bitwise reproducible; differs from the serial form only in grouping
-    ((own) + (r0 + r1 + ...) instead of ((own + r0) + r1) + ...)."""
-    from . import _lib
-    buf, hdl, chunk, own, off, n = g.peer_buffer(("s", key), d)
-    s_local = buf[:g.n_local]
-    dev = s_local.device
-    run(g.plan_halo, s_local)
-    tsum = torch.empty((max(g.n_rem, 1), d), dtype=torch.float32, device=dev)
-    out = torch.empty((g.n_own, d), dtype=torch.float32, device=dev)
-    main = torch.cuda.current_stream()
-    g.side.wait_stream(main)
-    with torch.cuda.stream(g.side):
-        hdl.barrier(channel=0)
-        if g.n_rem:
-            _lib.call("ihg_halo_reduce", None, d, _lib.ptr(g.rem_rowptr), _lib.ptr(g.reduce_entries), chunk, n, d,
-                      None, _lib.ptr(tsum), d, g.n_rem, d, _lib.stream_ptr(), tag="halo_pull", algo_bytes=g.S * 4 * d)
-        hdl.barrier(channel=0)
-    if own_rows is None:
-        own_rows = torch.empty((g.n_own, d), dtype=torch.float32, device=dev)
-        run(g.plan_own, own_rows)
-    main.wait_stream(g.side)
-    import ctypes
-    one = (ctypes.c_void_p * 1)(tsum.data_ptr())
-    _lib.call("ihg_halo_reduce", _lib.ptr(own_rows), _lib.ld(own_rows), _lib.ptr(g.comb_rowptr), _lib.ptr(g.comb_entries),
-              one, 1, d, _lib.ptr(row_scale), _lib.ptr(out), d, g.n_own, d, _lib.stream_ptr(),
-              tag="halo_combine", algo_bytes=g.n_own * 8 * d + g.n_rem * 4 * d)
-    return out
 
 
 def halo_exchange(x_own, g, key=None):

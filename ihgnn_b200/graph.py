@@ -68,40 +68,10 @@ class CsrPlan:
         self._nbr = None
         self._phase_plans = {}
 
-    def row_range(self, r0: int, r1: int) -> "CsrPlan":
-        """View of this plan restricted to the rows [r0, r1): same rowptr / col / partial slots (absolute row
-        and incidence numbers), only the work items of those rows -- a reduction over the view writes just
-        those rows of its output.  The multi-GPU layers reduce the halo rows of a local table first (their
-        partial sums travel) and the own rows while the transfer is in flight."""
-        v = object.__new__(CsrPlan)
-        v.__dict__.update(self.__dict__)
-        rows = self.seg[:, 2].contiguous()
-        bounds = torch.tensor([r0, r1], dtype=rows.dtype, device=rows.device)
-        a, b = (int(x) for x in torch.searchsorted(rows, bounds).tolist()) if self.n_seg else (0, 0)
-        v.seg = self.seg[a:b] if b > a else self.seg[:1]
-        v.n_seg = b - a
-        if self.n_split:
-            sa, sb = (int(x) for x in torch.searchsorted(self.split_row[:self.n_split].contiguous(), bounds.to(self.split_row.dtype)).tolist())
-        else:
-            sa = sb = 0
-        v.split_row = self.split_row[sa:sb] if sb > sa else self.split_row[:1]
-        v.split_ptr = self.split_ptr[sa:sb + 1]
-        v.n_split = sb - sa
-        v.struct = _lib.IhgCsr(
-            n_rows=self.n_rows, nnz=self.nnz, rowptr=self.rowptr.data_ptr(),
-            col=self.col.data_ptr() if self.nnz else None, chunk_len=self.chunk_len,
-            n_seg=v.n_seg, n_split=v.n_split, n_part=self.n_part, seg=v.seg.data_ptr(),
-            split_row=v.split_row.data_ptr(), split_ptr=v.split_ptr.data_ptr())
-        v._parent = self                       # shares the partial-sum scratch and the neighbour list
-        return v
-
     def partial(self, dim: int) -> Optional[torch.Tensor]:
         """Scratch for the partial sums of split rows (cached per feature dimension)."""
         if self.n_part == 0:
             return None
-        parent = self.__dict__.get("_parent")
-        if parent is not None:
-            return parent.partial(dim)
         buf = self._partial.get(dim)
         if buf is None:
             buf = torch.empty(self.n_part * dim, dtype=torch.float32, device=self.rowptr.device)
@@ -148,9 +118,6 @@ class CsrPlan:
                     row_slot: Optional[torch.Tensor] = None) -> torch.Tensor:
         """int32 [nnz, 2]: for every incidence (row r, hyperedge col[j]) the two OTHER nodes of that
         hyperedge (`ihg_two_hop_index_build`); built once per plan, the graph is static."""
-        parent = self.__dict__.get("_parent")
-        if parent is not None:
-            return parent.two_hop_nbr(i3, bounds, row_slot)
         if self._nbr is None:
             _lib.require_cuda(i3, row_slot)
             nbr = torch.empty((max(self.nnz, 1), 2), dtype=torch.int32, device=self.rowptr.device)

@@ -57,9 +57,7 @@ typedef struct ihg_csr {
     const int32_t* split_row;  /* [n_split]                                              */
     const int32_t* split_ptr;  /* [n_split+1] range of partial slots of each split row   */
 } ihg_csr;
-/* `seg` / `split_row` / `split_ptr` may be restricted to the work items of a row range (a view of a
- * full plan: same rowptr / col / partial slots, n_rows unchanged): the reductions then touch only
- * those rows of `out`. */
+/* `seg` may list the work items of a subset of the rows: the reductions then touch only those rows of `out`. */
 
 /* ------------------------------------------------------------------------------------
  * a1  PpsHyperGraph.from_interactions            Helpers/Graph.py:94-134

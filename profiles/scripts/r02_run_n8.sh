@@ -10,8 +10,7 @@ run() { # name, env, args...
 (timeout 600 python -m pytest tests/test_gpu_dist.py -x -q 2>&1 | tail -6) > gpurun_out/${T}_tests.log
 run amazon-full IHG_OVERLAP=0 --workload amazon-full
 run cikm IHG_OVERLAP=0 --workload cikm
-run amazon-full_overlap IHG_OVERLAP=1 --workload amazon-full
-run cikm_overlap IHG_OVERLAP=1 --workload cikm
+# (the *_overlap lines of this session came from commit 1bd0c3d's opt-in IHG_OVERLAP=1 path, since removed)
 run scaled IHG_OVERLAP=0 --workload scaled --steps 10 --warmup 3
 run rank IHG_OVERLAP=0 --workload rank
 nvidia-smi --query-gpu=index,memory.used --format=csv > gpurun_out/${T}_mem.log
