@@ -240,8 +240,21 @@ interact_bwd_slot_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
         const uint32_t off0 = sl_stage_off(0, row0, chk);
         int gb = 0;
         uint32_t gph = 0;
-        for (int64_t k = 0; k < my_tiles; ++k) {
+        // the node ids of a tile serve all of its KC units: loaded once per tile, the next tile's ids are
+        // requested before this tile's copies are issued (in-kernel trace: with the ids re-read inside every
+        // unit the gather warps needed ~3 900 cycles to issue one granule and bounded the unit period)
+        auto load_ids = [&](int64_t k, int (&ids)[kSlCopies]) {
             const int64_t k0 = 3 * ((blockIdx.x + k * gridDim.x) * kTileM + row0);
+#pragma unroll
+            for (int jj = 0; jj < kSlCopies; ++jj) {
+                const int64_t kk = k0 + 3 * kRowStep * (jj / 3) + (jj % 3);
+                ids[jj] = (k < my_tiles && kk < 3 * E) ? __ldg(i3 + kk) : -1;
+            }
+        };
+        int ids[kSlCopies], nxt[kSlCopies];
+        load_ids(0, ids);
+        for (int64_t k = 0; k < my_tiles; ++k) {
+            load_ids(k + 1, nxt);
             for (int j = 0; j < KC; ++j) {
                 SL_PROBE(gt == 0, 0, k * KC + j);
                 mbar_wait(smem_u32(&bar_gempty[gb]), gph ^ 1u);
@@ -249,26 +262,17 @@ interact_bwd_slot_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, const f
                 const uint32_t gbuf = gran_base + (uint32_t)gb * kSlGranuleBytes + off0;
                 const float* col = xp + j * kChunkK + 4 * chk;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    int ids[kSlCopies / 2];
-#pragma unroll
-                    for (int x = 0; x < kSlCopies / 2; ++x) {
-                        const int jj = x + half * (kSlCopies / 2);
-                        const int64_t kk = k0 + 3 * kRowStep * (jj / 3) + (jj % 3);
-                        ids[x] = kk < 3 * E ? __ldg(i3 + kk) : -1;
-                    }
-#pragma unroll
-                    for (int x = 0; x < kSlCopies / 2; ++x) {
-                        const int jj = x + half * (kSlCopies / 2);
-                        const bool ok = ids[x] >= 0;
-                        sl_cp16_zfill(gbuf + (uint32_t)(((jj % 3) * kTileM + kRowStep * (jj / 3)) * kChunkBytesPerRow),
-                                      col + (int64_t)(ok ? ids[x] : 0) * xp_ld, ok);
-                    }
+                for (int jj = 0; jj < kSlCopies; ++jj) {
+                    const bool ok = ids[jj] >= 0;
+                    sl_cp16_zfill(gbuf + (uint32_t)(((jj % 3) * kTileM + kRowStep * (jj / 3)) * kChunkBytesPerRow),
+                                  col + (int64_t)(ok ? ids[jj] : 0) * xp_ld, ok);
                 }
                 sl_cp_arrive(smem_u32(&bar_gfull[gb]));
                 SL_PROBE(gt == 0, 0, 4000 + k * KC + j);
                 if (++gb == n_gran) gb = 0, gph ^= 1u;
             }
+#pragma unroll
+            for (int jj = 0; jj < kSlCopies; ++jj) ids[jj] = nxt[jj];
         }
         cp_async_wait_all();
     } else if (warp == kSlLoadWarp) {

@@ -240,32 +240,36 @@ feature_interact_fwd_ts_kernel(const float* __restrict__ xp, int64_t xp_ld, cons
         const uint32_t off0 = stage_off(0, row0, chk);    // (row0 + kRowStep m) % 8 == row0 % 8: same swizzle for all j
         int gb = 0;
         uint32_t gph = 0;
-        for (int64_t t = 0; t < my_tiles; ++t) {
+        // the node ids of a tile serve all of its KC column slices: loaded once per tile, the next tile's ids
+        // are requested before this tile's copies are issued (the id latency -- two dependent global loads per
+        // slice before -- dominated the issue time of a granule)
+        auto load_ids = [&](int64_t t, int (&ids)[kTsCopies]) {
             const int64_t k0 = 3 * ((blockIdx.x + t * gridDim.x) * kTileM + row0);     // offset of i3[e0 + row0][0]
+#pragma unroll
+            for (int jj = 0; jj < kTsCopies; ++jj) {
+                const int64_t k = k0 + 3 * kRowStep * (jj / 3) + (jj % 3);
+                ids[jj] = (t < my_tiles && k < 3 * E) ? __ldg(i3 + k) : -1;
+            }
+        };
+        int ids[kTsCopies], nxt[kTsCopies];
+        load_ids(0, ids);
+        for (int64_t t = 0; t < my_tiles; ++t) {
+            load_ids(t + 1, nxt);
             for (int kc = 0; kc < KC; ++kc) {
                 mbar_wait(smem_u32(&bar_gempty[gb]), gph ^ 1u);
                 const uint32_t gbuf = gran_base + (uint32_t)gb * kTsGranuleBytes + off0;
                 const float* col = xp + kc * kChunkK + 4 * chk;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    int ids[kTsCopies / 2];
-#pragma unroll
-                    for (int j = 0; j < kTsCopies / 2; ++j) {
-                        const int jj = j + half * (kTsCopies / 2);
-                        const int64_t k = k0 + 3 * kRowStep * (jj / 3) + (jj % 3);
-                        ids[j] = k < 3 * E ? __ldg(i3 + k) : -1;
-                    }
-#pragma unroll
-                    for (int j = 0; j < kTsCopies / 2; ++j) {
-                        const int jj = j + half * (kTsCopies / 2);
-                        const bool ok = ids[j] >= 0;
-                        cp_async16_zfill(gbuf + (uint32_t)(((jj % 3) * kTileM + kRowStep * (jj / 3)) * kChunkBytesPerRow),
-                                         col + (int64_t)(ok ? ids[j] : 0) * xp_ld, ok);
-                    }
+                for (int jj = 0; jj < kTsCopies; ++jj) {
+                    const bool ok = ids[jj] >= 0;
+                    cp_async16_zfill(gbuf + (uint32_t)(((jj % 3) * kTileM + kRowStep * (jj / 3)) * kChunkBytesPerRow),
+                                     col + (int64_t)(ok ? ids[jj] : 0) * xp_ld, ok);
                 }
                 cp_async_arrive(smem_u32(&bar_gfull[gb]));
                 if (++gb == n_gran) gb = 0, gph ^= 1u;
             }
+#pragma unroll
+            for (int jj = 0; jj < kTsCopies; ++jj) ids[jj] = nxt[jj];
         }
         cp_async_wait_all();
     } else if (warp == kTsLoadWarp) {

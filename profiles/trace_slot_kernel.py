@@ -23,7 +23,7 @@ buf = np.zeros(1 << 16, dtype=np.int64)
 assert lib.ihg_debug_read_trace_slot(buf.ctypes.data, buf.size) == 0
 T = buf.reshape(8, 8192)
 KC = d // 32
-U = int((T[1, :2000] > 0).sum())
+U = min(int((T[1, :2000] > 0).sum()), 1900 // KC)      # the probe rows hold 2000 entries per phase
 tiles = U // KC
 span = T[5, 2000:2000 + U].max() - T[1, 0]
 print(f"{name} d={d}: block 0: {tiles} tiles, {U} units; span {span/1e3:.0f} kcycles = {span/max(tiles,1):.0f} cycles/tile, {span/max(U,1):.0f} cycles/unit")
