@@ -356,6 +356,56 @@ def gather_rows_multi(table, idxs, offsets):
     return GatherRowsMultiFn.apply(table, tuple(offsets), *idxs)
 
 
+class TapRowsFn(torch.autograd.Function):
+    """`table` passed through unchanged PLUS several row selections out of it (the batch rows RawGnn.py:128-133
+    takes out of every layer's output while the same output feeds the next layer).  Backward adds the few
+    selected-row gradients INTO the dense gradient arriving for the pass-through output (in place, fixed order)
+    instead of building a second dense [N, d] gradient and letting autograd add the two: per layer output that
+    saves one [N, d] zero-fill and one three-operand dense add."""
+
+    @staticmethod
+    def forward(ctx, table, offsets, *idxs):
+        _lib.require_cuda(table, *idxs)
+        src = _lib.rows_f32(table)
+        idxs = tuple(i.to(torch.int64).contiguous() for i in idxs)
+        d = int(src.shape[1])
+        outs = []
+        for idx, off in zip(idxs, offsets):
+            B = int(idx.numel())
+            out = _empty((B, d), src)
+            if B:
+                _lib.call("ihg_gather_rows", _lib.ptr(src), _lib.ld(src), _lib.ptr(idx), int(off), B,
+                          _lib.ptr(out), d, d, _lib.stream_ptr())
+            outs.append(out)
+        ctx.save_for_backward(*idxs)
+        ctx.offsets, ctx.shape = tuple(int(o) for o in offsets), tuple(table.shape)
+        return (table.view_as(table),) + tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_table, *gs):
+        idxs = ctx.saved_tensors
+        d = ctx.shape[1]
+        if g_table is None:
+            dt = torch.zeros(ctx.shape, dtype=_F32, device=idxs[0].device)
+        elif g_table.is_contiguous() and g_table.dtype == _F32 and g_table.data_ptr() % 16 == 0:
+            dt = g_table                       # a temporary produced by the consumer's backward: accumulate in place
+        else:
+            dt = g_table.contiguous().to(_F32).clone()
+        for g, idx, off in zip(gs, idxs, ctx.offsets):
+            if g is None or idx.numel() == 0:
+                continue
+            g = _lib.rows_f32(g)
+            _lib.call("ihg_scatter_add_rows", _lib.ptr(g), _lib.ld(g), _lib.ptr(idx), off,
+                      int(idx.numel()), _lib.ptr(dt), d, d, _lib.stream_ptr())
+        return (dt, None) + (None,) * len(idxs)
+
+
+def tap_rows(table, idxs, offsets):
+    """-> (table, [table[idx_j + offset_j] for j]) with the fused backward of `TapRowsFn`."""
+    out = TapRowsFn.apply(table, tuple(offsets), *idxs)
+    return out[0], out[1:]
+
+
 class HemScoreFn(torch.autograd.Function):
     """HemPredictionLayer.forward, dot-product branch
     (/root/reference/Models/PredictionLayers.py:21-44)."""

@@ -83,10 +83,16 @@ class RawGnn(nn.Module):
             # training: cat(gnn_outputs, 1)[rows] == cat([o[rows] for o in gnn_outputs], 1)  (RawGnn.py:121-133):
             # gather the batch rows out of every layer's table and concatenate the small results -- the
             # [N, d(1+L)] table and its dense gradient are never materialised
-            outs = self.conv_stack(self.embeddings.embed_all())
             idxs = [user_indices, query_indices] + ([item_indices] if item_indices is not None else [])
             offs = [0, ds.query_start_index_in_graph, ds.item_start_index_in_graph][:len(idxs)]
-            picked = [F_.gather_rows_multi(o, idxs, offs) for o in outs]           # one dense gradient per table
+            # every layer output is tapped for the batch rows and passed on to the next layer; the tap's backward
+            # adds the batch-row gradients into the dense gradient coming back from that layer (F_.TapRowsFn)
+            h, rows = F_.tap_rows(self.embeddings.embed_all(), idxs, offs)
+            outs, picked = [h], [rows]
+            for gnn in self.gnns:
+                h, rows = F_.tap_rows(gnn(h), idxs, offs)
+                outs.append(h)
+                picked.append(rows)
             fu = torch.cat([p[0] for p in picked], 1)                                      # :128
             fq = torch.cat([p[1] for p in picked], 1)                                      # :129
             if item_indices is not None:

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--traffic")
     ap.add_argument("--workload", default="amazon-full")
     ap.add_argument("--note", default="")
+    ap.add_argument("--how", default="--set full", help="how the report was collected (goes into the header line)")
     ap.add_argument("--steps-captured", type=int, default=0,
                     help="the report holds exactly this many whole steps: also write dram_bytes_per_step")
     a = ap.parse_args()
@@ -57,7 +58,7 @@ def main():
         for m in METRICS:
             if m in col and r[col[m]] not in ("", "n/a"):
                 d[m].append(float(r[col[m]].replace(",", "")))
-    lines = [f"ncu --set full --clock-control none; per-kernel means over the captured launches. {a.note}".rstrip(), ""]
+    lines = [f"ncu {a.how} --clock-control none; per-kernel means over the captured launches. {a.note}".rstrip(), ""]
     traffic = {}
     total_bytes, total_launches = 0.0, 0
     for k, d in per.items():
