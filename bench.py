@@ -117,6 +117,29 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_tf32_peak():
+    """Dense TF32 tensor throughput in TFLOP/s = half the measured cuBLAS bf16 figure (the tcgen05 kind::tf32
+    rate is half of kind::f16's); the SUSTAINED figure, because the kernels are timed inside a long step."""
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p.get("bf16_tflops_sustained", p["bf16_tflops"])) / 2, \
+            "measured (MEASURED_PEAKS.json bf16_tflops_sustained / 2: tf32 runs at half the bf16 rate)"
+    return 1400.0 / 2, "fallback (B200_PROFILING.md 1.4 PFLOP/s sustained bf16, / 2 for tf32)"
+
+
+def tensor_flops(tag: str, E: int, d: int) -> float:
+    """tf32 flops one call of an order-2/3 interaction kernel EXECUTES: 2 K d^2 per hyperedge and contraction,
+    times the three passes of the 3xTF32 split (a_hi b_hi + a_lo b_hi + a_hi b_lo) that fp32 parity needs.
+    Forward: K = 7 blocks; backward: two contractions (slot gradients, dW_hi) over the 4 product blocks."""
+    if tag == "edge_interact_fwd":
+        return 3.0 * 2 * 7 * d * d * E
+    if tag == "edge_interact_bwd":
+        return 3.0 * 2 * 2 * 4 * d * d * E
+    return 0.0
+
+
 def conv_algorithmic_bytes(E: int, N: int, d: int) -> int:
     """bytes per IHGNN layer, fwd+bwd = E(60+76d) + N(28d+12)."""
     return E * (60 + 76 * d) + N * (28 * d + 12)
@@ -561,6 +584,18 @@ def measure_conv(ctx: Ctx, name: str, with_cpu: bool, profile_step: bool = False
                           "frac": conv_bytes / t_conv / 1e9 / (peak * world),
                           "note": "aggregate over all ranks against n_gpus x the measured single-GPU peak"},
         }
+        # the order-2/3 interaction kernels carry a dense contraction: when its tensor-core time floor exceeds the
+        # HBM floor (d = 128) the kernel is tensor-bound and is reported against the tensor roofline
+        tf32_peak, tf32_src = measured_tf32_peak()
+        flops = tensor_flops(dom_tag, E // world, d)
+        if flops / (tf32_peak * 1e12) > (dom["bytes"] / dom["calls"]) / (peak * 1e9):
+            roofline["hbm_view"] = {"achieved": roofline["achieved"], "peak": peak, "unit": "GB/s", "frac": roofline["frac"]}
+            ach = flops / (dom["avg_ms"] * 1e-3) / 1e12
+            roofline.update({"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                             "frac": ach / tf32_peak, "peak_source": tf32_src,
+                             "flops_per_launch": flops,
+                             "flops_note": "executed tf32 flops: 3 passes (3xTF32 split) x 2 K d^2 per hyperedge and "
+                                           "contraction; fp32-equivalent algorithmic flops are a third of this"})
         if traffic_file and traffic_file.get("dram_bytes_per_step"):
             db = float(traffic_file["dram_bytes_per_step"])
             roofline["dram_step"] = {"bytes": db, "achieved": db / t_conv / 1e9, "frac": db / t_conv / 1e9 / peak,
