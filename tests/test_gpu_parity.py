@@ -423,6 +423,36 @@ def test_medium_graph_vs_oracle(order, dim, layers, two_hop_mode):
     assert not bad, f"beyond {REL_TOL}: {bad}"
 
 
+@pytest.mark.parametrize("order", [2, 3])
+@pytest.mark.parametrize("dim", [32, 64, 96, 128])
+def test_interactor_forward_forms_vs_fp64(order, dim):
+    """Both forward forms of FeatureInteractor (CommonLayers.py:68-85) -- the tensor-core kernel (raw rows as
+    operand blocks) and the hoisted exact-fp32 FFMA kernel -- against the concatenation + Linear written out
+    in fp64; ragged last tile, isolated nodes."""
+    from ihgnn_b200 import layers, synth
+    from ihgnn_b200.dataset import GraphDataset
+    U, Q, I, E, V = 900, 150, 500, 128 * 171 + 37, 200
+    log = synth.make_search_log(U, Q, I, E, V, shape="cikm", seed=dim + order, zipf=1.0)
+    ds = GraphDataset.from_search_log(log, DEV)
+    g = ds.graph
+    torch.manual_seed(dim * 10 + order)
+    fi = layers.FeatureInteractor(ds, order, dim, dim).to(DEV)
+    assert fi._full_supported()
+    x = torch.randn(g.node_count, dim, device=DEV) * 0.7
+    i3 = g.i3.long()
+    xd = x.double()
+    u, q, v = xd[i3[:, 0]], xd[i3[:, 1]], xd[i3[:, 2]]
+    blocks = [u, q, v, u * q, q * v, v * u] + ([u * q * v] if order == 3 else [])
+    ref = torch.cat(blocks, 1) @ fi.aggregation.weight.detach().double().t() + fi.aggregation.bias.detach().double()
+    with torch.no_grad():
+        full = fi(x)
+        p = fi._first_order(x)
+        ffma = layers._EdgeInteractFn.apply(x, p, fi.aggregation.weight[:, 3 * dim:], g, order)
+    assert max_rel(full.cpu().numpy(), ref.cpu().numpy()) <= REL_TOL
+    assert max_rel(ffma.cpu().numpy(), ref.cpu().numpy()) <= REL_TOL
+    assert not torch.equal(full, ffma)                                 # two kernels did run
+
+
 @pytest.mark.parametrize("n_in,n_out", [(32, 16), (32, 32), (64, 64), (128, 128), (64, 48), (128, 16), (96, 80)])
 @pytest.mark.parametrize("typed", [False, True])
 def test_node_linear_tensor_core_path(n_in, n_out, typed):
