@@ -258,59 +258,102 @@ class PpsHyperGraph(PpsGraph):
 
 class Pps2DGraph(PpsGraph):
     """Pairwise user-query-item graph, drop-in for `Helpers.Graph.Pps2DGraph`
-    (/root/reference/Helpers/Graph.py:12-81) with `Gs.graph_completeness == graph_uqi` (the
-    reference default): every positive interaction adds u-q, q-i, i-u in both directions, duplicate
-    pairs summed by `coalesce()`; `VertexDegrees` = [self connection] + 2 x interactions of the node
-    (0 stored as 1e-8 without self connections, Graph.py:35,67-68).
+    (/root/reference/Helpers/Graph.py:12-81).
 
-    The adjacency is never stored: products with it run on the hypergraph incidence (`hyper`, the
-    same device CSR/CSC the IHGNN layers use) through `ihg_two_hop_reduce`.  Reference attributes
-    `Adjacency` (coalesced sparse COO) and `VertexDegrees` are available; `Adjacency` is materialised
-    lazily, only if something reads it.  Interaction flags above 1 are treated as 1, as the reference
-    does by default (`treat_all_1`, Dataset.py:200; SearchLog.py:204-205)."""
+    `Gs.graph_completeness == graph_uqi` with unit flags (the reference default: ArgsParser.py:85, and
+    `treat_all_1` Dataset.py:200 clamps every flag to 1): every positive interaction adds u-q, q-i, i-u in
+    both directions, duplicate pairs summed by `coalesce()`; `VertexDegrees` = [self connection] + 2 x
+    interactions of the node (0 stored as 1e-8 without self connections, Graph.py:35,67-68).  The adjacency
+    is never stored: products with it run on the hypergraph incidence (`hyper`, the same device CSR/CSC the
+    IHGNN layers use) through `ihg_two_hop_reduce`.
+
+    The other branches of Graph.py:40-65 -- `graph_only_uq / ui / qi` (one pair per interaction, degree +1
+    for its two nodes) and interaction flags above 1 (they weight the u-i pair of `graph_uqi`, :44) -- take
+    the *pair form*: the directed pairs are laid out as a device CSR (`pair_plan`, rows by stable sort) and
+    products run through `ihg_segment_reduce`.  Flags are integers (`PosInteraction.interaction: int`,
+    SearchLog.py:193) and enter as multiplicities of the pair, which is what `coalesce()` sums them to.
+
+    Reference attributes `Adjacency` (coalesced sparse COO) and `VertexDegrees` are available; `Adjacency`
+    is materialised lazily, only if something reads it."""
 
     def __init__(self):
         super().__init__()
         self._adjacency = None
+        self.pair_plan: Optional[CsrPlan] = None
 
     @classmethod
     def from_interactions(cls, interactions, node_count: int, user_count: int, query_count: int,
                           use_self_connection: bool, device) -> "Pps2DGraph":
         """Signature of Graph.py:19-26."""
-        hyper = PpsHyperGraph.from_interactions(interactions, node_count, user_count, query_count, device)
-        return cls.from_hypergraph(hyper, use_self_connection)
+        rows, flags = [], []
+        for p in interactions:
+            t = p.uqif() if hasattr(p, "uqif") else tuple(p)
+            if len(t) < 4 or t[3] > 0:                                         # Graph.py:37
+                rows.append(t[:3])
+                flags.append(1 if len(t) < 4 else int(t[3]))
+        arr = np.asarray(rows, dtype=np.int64).reshape(-1, 3)
+        item_count = node_count - user_count - query_count
+        hyper = PpsHyperGraph.from_tensors(torch.from_numpy(arr[:, 0].copy()), torch.from_numpy(arr[:, 1].copy()),
+                                           torch.from_numpy(arr[:, 2].copy()), user_count, query_count,
+                                           item_count, device)
+        fl = np.asarray(flags, dtype=np.int64)
+        return cls.from_hypergraph(hyper, use_self_connection, flags=None if (fl == 1).all() else fl)
 
     @classmethod
-    def from_hypergraph(cls, hyper: PpsHyperGraph, use_self_connection: bool) -> "Pps2DGraph":
+    def from_hypergraph(cls, hyper: PpsHyperGraph, use_self_connection: bool, flags=None) -> "Pps2DGraph":
+        """`flags`: per-hyperedge integer interaction flags in the order of `hyper.i3` (None = all 1)."""
         from .settings import Gs, Gsv
         completeness = getattr(Gs, "graph_completeness", Gsv.graph_uqi)
-        if completeness != Gsv.graph_uqi:                                      # Graph.py:46-65: uq / ui / qi only
-            raise NotImplementedError(f"ihgnn_b200.Pps2DGraph implements graph_completeness == 'uqi' "
-                                      f"(the reference default, ArgsParser.py:85); got {completeness!r}")
+        pairs = {Gsv.graph_uqi: ((0, 1), (1, 2), (2, 0)), Gsv.graph_only_uq: ((0, 1),),
+                 Gsv.graph_only_ui: ((0, 2),), Gsv.graph_only_qi: ((1, 2),)}.get(completeness)
+        if pairs is None:
+            raise ValueError(f"unknown graph_completeness {completeness!r}")           # Graph.py:64-65
         g = cls()
         g.hyper = hyper
         g.use_self_connection = bool(use_self_connection)
-        g.node_count = hyper.node_count
-        counts = (hyper.rowptr[1:] - hyper.rowptr[:-1]).to(torch.float32)
-        deg = 2.0 * counts + (1.0 if use_self_connection else 0.0)            # Graph.py:29,45
+        g.node_count = N = hyper.node_count
+        dev = hyper.i3.device
+        self_deg = 1.0 if use_self_connection else 0.0                                 # Graph.py:29
+        if completeness == Gsv.graph_uqi and flags is None:
+            counts = (hyper.rowptr[1:] - hyper.rowptr[:-1]).to(torch.float32)
+            deg = 2.0 * counts + self_deg                                              # :45
+        else:
+            i3 = hyper.i3.to(torch.int64)
+            a = torch.cat([i3[:, s] for s, _ in pairs] + [i3[:, t] for _, t in pairs])   # both directions
+            b = torch.cat([i3[:, t] for _, t in pairs] + [i3[:, s] for s, _ in pairs])
+            per_node = 2.0 if completeness == Gsv.graph_uqi else 1.0                   # :45 / :50,56,62
+            touched = torch.cat([i3[:, s] for s in sorted({s for pr in pairs for s in pr})])
+            deg = per_node * torch.bincount(touched, minlength=N).to(torch.float32) + self_deg
+            if flags is not None and completeness == Gsv.graph_uqi:                    # :44: the u-i pair carries the flag
+                fl = torch.as_tensor(np.asarray(flags), dtype=torch.int64, device=dev)
+                assert fl.numel() == hyper.EdgeCount and bool((fl >= 1).all())
+                ones = torch.ones_like(fl)
+                mult = torch.cat([fl if set(pr) == {0, 2} else ones for pr in pairs] * 2)
+                a, b = torch.repeat_interleave(a, mult), torch.repeat_interleave(b, mult)
+            g._pair_rows, g._pair_cols = a, b
+            rowptr, _perm, cols = csr_from_keys(a.to(torch.int32), N, values=b.to(torch.int32))
+            g.pair_plan = CsrPlan(rowptr, cols)
         if not use_self_connection:
-            deg = torch.where(deg == 0, torch.full_like(deg, 1e-8), deg)      # :67-68
-        g.VertexDegrees = deg.view(-1, 1)                                     # :80
-        g.dv_inv_sqrt = deg.pow(-0.5)                                         # GnnLayers.py:24
+            deg = torch.where(deg == 0, torch.full_like(deg, 1e-8), deg)               # :67-68
+        g.VertexDegrees = deg.view(-1, 1)                                              # :80
+        g.dv_inv_sqrt = deg.pow(-0.5)                                                  # GnnLayers.py:24
         return g
 
     @property
     def Adjacency(self) -> torch.Tensor:
-        """Coalesced sparse COO adjacency [N,N] (Graph.py:71-77), unit weights summed over duplicates."""
+        """Coalesced sparse COO adjacency [N,N] (Graph.py:71-77), weights summed over duplicates."""
         if self._adjacency is None:
-            i3 = self.hyper.i3.to(torch.int64)
-            u, q, i = i3[:, 0], i3[:, 1], i3[:, 2]
-            rows = torch.cat([u, q, i, i, q, u])                              # Graph.py:42-43
-            cols = torch.cat([q, i, u, q, u, i])
+            if self.pair_plan is not None:
+                rows, cols = self._pair_rows, self._pair_cols
+            else:
+                i3 = self.hyper.i3.to(torch.int64)
+                u, q, i = i3[:, 0], i3[:, 1], i3[:, 2]
+                rows = torch.cat([u, q, i, i, q, u])                          # Graph.py:42-43
+                cols = torch.cat([q, i, u, q, u, i])
             if self.use_self_connection:
-                eye = torch.arange(self.node_count, device=i3.device)
+                eye = torch.arange(self.node_count, device=rows.device)
                 rows, cols = torch.cat([eye, rows]), torch.cat([eye, cols])
-            vals = torch.ones(rows.numel(), dtype=torch.float32, device=i3.device)
+            vals = torch.ones(rows.numel(), dtype=torch.float32, device=rows.device)
             self._adjacency = torch.sparse_coo_tensor(torch.stack([rows, cols]), vals,
                                                       (self.node_count, self.node_count)).coalesce()
         return self._adjacency

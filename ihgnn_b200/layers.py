@@ -198,6 +198,27 @@ class _TwoHopFn(torch.autograd.Function):
         return dh, None, None, None, None, None
 
 
+class _PairAdjFn(torch.autograd.Function):
+    """out = D^-1/2 (A [+ I]) D^-1/2 h over the explicit pair CSR of `Pps2DGraph` (graph_only_* completeness,
+    integer flag weights: Helpers/Graph.py:40-65); A is symmetric, so backward is the same product."""
+
+    @staticmethod
+    def _apply(h, g2):
+        h = _lib.rows_f32(h)
+        s = g2.dv_inv_sqrt
+        init = h * s.view(-1, 1) if g2.use_self_connection else None
+        return F_.segment_reduce(g2.pair_plan, h, int(h.shape[1]), src_scale=s, row_scale=s, init=init)
+
+    @staticmethod
+    def forward(ctx, h, g2):
+        ctx.g2 = g2
+        return _PairAdjFn._apply(h, g2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        return _PairAdjFn._apply(dout, ctx.g2), None
+
+
 def _two_hop_nbr(graph) -> Tensor:
     return graph.plan.two_hop_nbr(graph.i3, graph.type_bounds, getattr(graph, "row_slot", None))
 
@@ -453,6 +474,8 @@ class GCNLayer(nn.Module):
 
     def _propagate(self, h: Tensor) -> Tensor:
         g2 = self.graph2d
+        if g2.pair_plan is not None:            # graph_only_* completeness / flag weights: explicit pair CSR
+            return _PairAdjFn.apply(h, g2)
         own = (0.0, 1.0 if g2.use_self_connection else 0.0)
         return _TwoHopFn.apply(h, g2.hyper, g2.dv_inv_sqrt, 1.0, g2.dv_inv_sqrt, own)
 

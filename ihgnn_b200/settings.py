@@ -15,6 +15,9 @@ except Exception:  # reference not on sys.path: standalone mirror
         activation = "activation"
         rnn = "rnn"
         graph_uqi = "uqi"
+        graph_only_uq = "uq"
+        graph_only_ui = "ui"
+        graph_only_qi = "qi"
 
     class Gs:
         lambda_muq_for_hem = 0.5

@@ -258,6 +258,64 @@ def _make_case(name: str, cfg: dict, outdir: str) -> None:
           f"max degree={np.diff(out['graph.crow']).max()}")
 
 
+def make_graph2d_variants(outdir):
+    """Every branch of the reference's Pps2DGraph.from_interactions (Helpers/Graph.py:19-81): the four
+    graph_completeness values x with / without self connections, on interactions whose flags run over
+    {1, 2, 3} (a flag above 1 weights the u-i pair of graph_uqi, :44) with repeated (u, q, i) triples and
+    isolated nodes; plus the reference GCNLayer (GnnLayers.py:9-45) forward and input / weight gradients on
+    each graph, fp32 and fp64.  -> tests/golden/graph2d/variants.npz"""
+    from Helpers.SearchLog import PosInteraction
+    from Helpers.Graph import Pps2DGraph
+    U, Q, I, E, d_in, d_out = 23, 9, 31, 140, 16, 16
+    rng = np.random.default_rng(41)
+    u = rng.integers(0, U - 2, size=E)                     # the last users / queries / items stay isolated
+    q = rng.integers(0, Q - 1, size=E)
+    i = rng.integers(0, I - 3, size=E)
+    u[5:9], q[5:9], i[5:9] = u[4], q[4], i[4]              # repeated triples: coalesce() sums them
+    fl = rng.integers(1, 4, size=E)
+    inter = [PosInteraction(int(a), int(b), "", int(c), 1, 1, int(f), "") for a, b, c, f in zip(u, q, i, fl)]
+    N = U + Q + I
+    out = {"counts": np.array([U, Q, I, E]), "user": u, "query": q, "item": i, "flags": fl}
+    torch.manual_seed(41)
+    x = torch.randn(N, d_in)
+    w = torch.randn(N, d_out)
+    out["x"], out["w"] = _np(x), _np(w)
+
+    class _DS:
+        pass
+    for comp in (Gsv.graph_uqi, Gsv.graph_only_uq, Gsv.graph_only_ui, Gsv.graph_only_qi):
+        for self_conn in (False, True):
+            Gs.graph_completeness = comp
+            g2 = Pps2DGraph.from_interactions(inter, N, U, Q, self_conn, CPU)
+            key = f"{comp}.{'self' if self_conn else 'noself'}"
+            out[f"{key}.coo_indices"] = _np(g2.Adjacency.indices())
+            out[f"{key}.coo_values"] = _np(g2.Adjacency.values())
+            out[f"{key}.VertexDegrees"] = _np(g2.VertexDegrees)
+            ds = _DS()
+            ds.graph2d = g2
+            torch.manual_seed(7)
+            layer = GCNLayer(CPU, ds, d_in, d_out)
+            if "lin.weight" not in out:
+                out["lin.weight"], out["lin.bias"] = _np(layer.feature_transform.weight), _np(layer.feature_transform.bias)
+            for prefix, dt in (("ref32", torch.float32), ("ref64", torch.float64)):
+                if dt == torch.float64:
+                    layer.double()
+                    layer.Dv_neg_1_slash_2 = layer.Dv_neg_1_slash_2.double()
+                    layer.adjacency = layer.adjacency.to(torch.float64)
+                xx = x.to(dt).clone().requires_grad_(True)
+                layer.zero_grad()
+                y = layer(xx)
+                (y * w.to(dt)).sum().backward()
+                out[f"{key}.{prefix}.out"] = _np(y)
+                out[f"{key}.{prefix}.dx"] = _np(xx.grad)
+                out[f"{key}.{prefix}.dw"] = _np(layer.feature_transform.weight.grad)
+    Gs.graph_completeness = Gsv.graph_uqi
+    os.makedirs(os.path.join(outdir, "graph2d"), exist_ok=True)
+    path = os.path.join(outdir, "graph2d", "variants.npz")
+    np.savez_compressed(path, **out)
+    print(f"graph2d_variants: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def main():
     outdir = os.path.join(REPO, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
@@ -265,6 +323,8 @@ def main():
     for name, cfg in CASES.items():
         if not only or name in only:
             make_case(name, cfg, outdir)
+    if not only or "graph2d_variants" in only:
+        make_graph2d_variants(outdir)
 
 
 if __name__ == "__main__":

@@ -181,27 +181,38 @@ def hgcn_layer(x: torch.Tensor, adjacency: torch.Tensor, adjacency_t: torch.Tens
 
 
 def build_graph2d(user, query, item, user_count: int, query_count: int, item_count: int,
-                  use_self_connection: bool = False):
-    """Pps2DGraph.from_interactions (Helpers/Graph.py:19-81) for graph_completeness == graph_uqi with
-    all flags 1 (treat_all_1, Dataset.py:200): per interaction the six directed pairs u-q, q-i, i-u,
-    i-q, q-u, u-i (:42-44), coalesced (duplicates summed, :71-77); degrees += 2 per interaction per
-    node (:45), 0 -> 1e-8 without self connections (:67-68).  Returns (coalesced COO [N,N] float32,
-    VertexDegrees float32 [N,1])."""
+                  use_self_connection: bool = False, completeness: str = "uqi", flags=None):
+    """Pps2DGraph.from_interactions (Helpers/Graph.py:19-81).  graph_uqi (:40-45): per interaction the six
+    directed pairs u-q, q-i, i-u, i-q, q-u, u-i with values 1, 1, flag, 1, 1, flag, degrees += 2 per node;
+    graph_only_uq / ui / qi (:46-63): the one pair both ways with value 1, degrees += 1 for its two nodes.
+    Coalesced (duplicates summed, :71-77); degree 0 -> 1e-8 without self connections (:67-68).  `flags`
+    None = all 1 (treat_all_1, Dataset.py:200).  Returns (coalesced COO [N,N] float32, VertexDegrees [N,1])."""
     u = torch.as_tensor(np.asarray(user, dtype=np.int64))
     q = torch.as_tensor(np.asarray(query, dtype=np.int64)) + user_count
     i = torch.as_tensor(np.asarray(item, dtype=np.int64)) + user_count + query_count
     n = user_count + query_count + item_count
-    rows = torch.stack([u, q, i, i, q, u], 1).reshape(-1)            # insertion order of :42
-    cols = torch.stack([q, i, u, q, u, i], 1).reshape(-1)            # :43
+    one = torch.ones(u.numel(), dtype=torch.float32)
+    f = one if flags is None else torch.as_tensor(np.asarray(flags), dtype=torch.float32)
+    if completeness == "uqi":
+        rows = torch.stack([u, q, i, i, q, u], 1).reshape(-1)            # insertion order of :42
+        cols = torch.stack([q, i, u, q, u, i], 1).reshape(-1)            # :43
+        vals = torch.stack([one, one, f, one, one, f], 1).reshape(-1)    # :44
+        touched, per_node = [u, q, i], 2.0                               # :45
+    else:
+        a, b = {"uq": (u, q), "ui": (u, i), "qi": (q, i)}[completeness]  # :46-63
+        rows = torch.stack([a, b], 1).reshape(-1)
+        cols = torch.stack([b, a], 1).reshape(-1)
+        vals = torch.ones(rows.numel(), dtype=torch.float32)
+        touched, per_node = [a, b], 1.0
     deg = torch.zeros(n, dtype=torch.float32)
     if use_self_connection:
         eye = torch.arange(n)
-        rows, cols = torch.cat([eye, rows]), torch.cat([eye, cols])  # :28
-        deg += 1                                                     # :29
-    deg += 2 * torch.bincount(torch.cat([u, q, i]), minlength=n).to(torch.float32)   # :45
+        rows, cols = torch.cat([eye, rows]), torch.cat([eye, cols])      # :28
+        vals = torch.cat([torch.ones(n, dtype=torch.float32), vals])
+        deg += 1                                                         # :29
+    deg += per_node * torch.bincount(torch.cat(touched), minlength=n).to(torch.float32)
     if not use_self_connection:
-        deg[deg == 0] = 1e-8                                         # :67-68
-    vals = torch.ones(rows.numel(), dtype=torch.float32)
+        deg[deg == 0] = 1e-8                                             # :67-68
     adj = torch.sparse_coo_tensor(torch.stack([rows, cols]), vals, (n, n)).coalesce()
     return adj, deg.view(-1, 1)
 

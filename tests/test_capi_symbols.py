@@ -99,11 +99,11 @@ def test_product_does_not_import_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
 
 
-def test_pps2dgraph_rejects_partial_completeness(monkeypatch):
-    """--completeness uq / ui / qi (Helpers/Graph.py:46-65) is not implemented: fail loudly instead of
-    silently convolving over the full u-q-i pair set."""
+def test_pps2dgraph_rejects_unknown_completeness(monkeypatch):
+    """graph_completeness outside uqi / uq / ui / qi raises ValueError, as Helpers/Graph.py:64-65 does
+    (the four values themselves are covered on the GPU: test_graph2d_every_branch_matches_reference)."""
     from ihgnn_b200 import settings
     from ihgnn_b200.graph import Pps2DGraph
-    monkeypatch.setattr(settings.Gs, "graph_completeness", "uq", raising=False)
-    with pytest.raises(NotImplementedError):
+    monkeypatch.setattr(settings.Gs, "graph_completeness", "uqx", raising=False)
+    with pytest.raises(ValueError):
         Pps2DGraph.from_hypergraph(None, False)

@@ -76,6 +76,56 @@ def test_graph2d_matches_reference_bit_exact(golden):
     assert torch.equal(g3.VertexDegrees.cpu(), deg)
 
 
+@pytest.mark.parametrize("completeness", ["uqi", "uq", "ui", "qi"])
+@pytest.mark.parametrize("self_conn", [False, True])
+def test_graph2d_every_branch_matches_reference(completeness, self_conn, monkeypatch):
+    """Every branch of Pps2DGraph.from_interactions (Helpers/Graph.py:40-65: the four graph_completeness values,
+    interaction flags 1..3, with / without self connections): adjacency and degrees bit-exact, GCNLayer
+    forward / backward within 1e-5 of the reference's fp64 run (tests/golden/graph2d/variants.npz)."""
+    from test_oracle_golden import load_graph2d_variants
+    from ihgnn_b200 import settings
+    from ihgnn_b200.graph import Pps2DGraph
+    from ihgnn_b200.layers import GCNLayer
+    z = load_graph2d_variants()
+    U, Q, I, E = (int(v) for v in z["counts"])
+    key = f"{completeness}.{'self' if self_conn else 'noself'}"
+    monkeypatch.setattr(settings.Gs, "graph_completeness", completeness, raising=False)
+    inter = list(zip(z["user"].tolist(), z["query"].tolist(), z["item"].tolist(), z["flags"].tolist()))
+    g2 = Pps2DGraph.from_interactions(inter, U + Q + I, U, Q, self_conn, torch.device(DEV))
+    assert g2.pair_plan is not None                                     # flags above 1 / partial completeness
+    assert np.array_equal(g2.Adjacency.indices().cpu().numpy(), z[f"{key}.coo_indices"])
+    assert np.array_equal(g2.Adjacency.values().cpu().numpy(), z[f"{key}.coo_values"])
+    assert np.array_equal(g2.VertexDegrees.cpu().numpy(), z[f"{key}.VertexDegrees"])
+
+    class _DS:
+        graph2d = g2
+    layer = GCNLayer(torch.device(DEV), _DS(), 16, 16).to(DEV)
+    with torch.no_grad():
+        layer.feature_transform.weight.copy_(torch.from_numpy(z["lin.weight"]))
+        layer.feature_transform.bias.copy_(torch.from_numpy(z["lin.bias"]))
+    x = torch.from_numpy(z["x"]).to(DEV).requires_grad_(True)
+    y = layer(x)
+    (y * torch.from_numpy(z["w"]).to(DEV)).sum().backward()
+    assert max_rel(y.detach().cpu().numpy(), z[f"{key}.ref64.out"]) <= REL_TOL
+    assert max_rel(x.grad.cpu().numpy(), z[f"{key}.ref64.dx"]) <= REL_TOL
+    assert max_rel(layer.feature_transform.weight.grad.cpu().numpy(), z[f"{key}.ref64.dw"]) <= REL_TOL
+    if completeness == "uqi":
+        # unit flags take the two-hop form over the hypergraph incidence: same numbers as the pair form
+        unit = [t[:3] for t in inter]
+        g_fast = Pps2DGraph.from_interactions(unit, U + Q + I, U, Q, self_conn, torch.device(DEV))
+        assert g_fast.pair_plan is None
+        g_pair = Pps2DGraph.from_hypergraph(g_fast.hyper, self_conn, flags=np.ones(E, dtype=np.int64))
+        assert g_pair.pair_plan is not None
+        assert torch.equal(g_fast.Adjacency.values(), g_pair.Adjacency.values())
+        outs = []
+        for g in (g_fast, g_pair):
+            _DS.graph2d = g
+            lay = GCNLayer(torch.device(DEV), _DS(), 16, 16).to(DEV)
+            lay.load_state_dict(layer.state_dict())
+            outs.append(lay(x.detach()))
+        assert max_rel(outs[0].detach().cpu().numpy(), outs[1].detach().cpu().numpy()) <= REL_TOL
+
+
 @pytest.mark.parametrize("d_in,d_out,self_conn", [(64, 64, False), (32, 64, True), (128, 48, True)])
 def test_gcn_layer_vs_oracle(d_in, d_out, self_conn):
     """GCNLayer forward / backward (both Linear placements, with and without self connections,

@@ -6,6 +6,7 @@ classes on CPU.  Indices must agree bit-exactly; fp32 values must agree far insi
 parity budget (same ATen ops in the same order), and the fp64 arbiter to ~1e-12.
 """
 import numpy as np
+import pytest
 import torch
 
 from helpers import batch_of, max_rel, oracle_graph, oracle_model, orc
@@ -120,3 +121,38 @@ def test_graph2d_bit_exact(golden):
     assert np.array_equal(adj.indices().numpy(), golden["graph2d.coo_indices"])
     assert np.array_equal(adj.values().numpy(), golden["graph2d.coo_values"])
     assert np.array_equal(deg.numpy(), golden["graph2d.VertexDegrees"])
+
+
+GRAPH2D_VARIANTS = [(c, sc) for c in ("uqi", "uq", "ui", "qi") for sc in (False, True)]
+
+
+def load_graph2d_variants():
+    import os
+    from conftest import GOLDEN_DIR
+    with np.load(os.path.join(GOLDEN_DIR, "graph2d", "variants.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize("completeness,self_conn", GRAPH2D_VARIANTS)
+def test_graph2d_every_branch_bit_exact(completeness, self_conn):
+    """oracle.build_graph2d against every branch of the reference's Pps2DGraph.from_interactions
+    (Graph.py:40-65: four graph_completeness values, flags 1..3, with / without self connections) and
+    oracle.gcn_layer against the reference GCNLayer on each graph (fixture: oracle/gen_golden.py
+    make_graph2d_variants)."""
+    z = load_graph2d_variants()
+    U, Q, I, E = (int(v) for v in z["counts"])
+    key = f"{completeness}.{'self' if self_conn else 'noself'}"
+    adj, deg = orc.build_graph2d(z["user"], z["query"], z["item"], U, Q, I, self_conn, completeness, z["flags"])
+    assert np.array_equal(adj.indices().numpy(), z[f"{key}.coo_indices"])
+    assert np.array_equal(adj.values().numpy(), z[f"{key}.coo_values"])
+    assert np.array_equal(deg.numpy(), z[f"{key}.VertexDegrees"])
+    if completeness == "uqi":
+        assert z[f"{key}.coo_values"].max() > 3                      # flag weights and repeated triples did add up
+    x = torch.from_numpy(z["x"]).double().requires_grad_(True)
+    w = torch.from_numpy(z["lin.weight"]).double().requires_grad_(True)
+    b = torch.from_numpy(z["lin.bias"]).double()
+    y = orc.gcn_layer(x, adj.double(), deg.pow(-0.5).double(), w, b)
+    (y * torch.from_numpy(z["w"]).double()).sum().backward()
+    assert max_rel(y.detach().numpy(), z[f"{key}.ref64.out"]) <= 1e-12
+    assert max_rel(x.grad.numpy(), z[f"{key}.ref64.dx"]) <= 1e-12
+    assert max_rel(w.grad.numpy(), z[f"{key}.ref64.dw"]) <= 1e-12
