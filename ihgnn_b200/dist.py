@@ -366,7 +366,7 @@ class ShardedScatterMeanFn(torch.autograd.Function):
         ctx.g, ctx.key = g, key
         ef = _lib.rows_f32(ef)
         d = int(ef.shape[1])
-        s_local = F_.phased_segment_reduce(g.plan_csr, g.EdgeCount, ef, d, out=reduce_buffer(g, ("sm", key), d, ef))
+        s_local = F_.segment_reduce(g.plan_csr, ef, d, out=reduce_buffer(g, ("sm", key), d, ef))
         return _halo_reduce(s_local, g, g.dv_inv_own, ("sm", key) if key is not None else None)
 
     @staticmethod
@@ -477,7 +477,7 @@ class ShardedFeatureInteractFn(torch.autograd.Function):
         rkey = ("fib", ctx.key) if ctx.key is not None else None
         both = reduce_buffer(g, rkey, 2 * dim, def_)
         F_.segment_reduce(g.plan_csr, slot_grad, dim, src_row_mul=3, row_slot=g.row_slot, out=both[:, :dim])
-        F_.phased_segment_reduce(g.plan_csr, g.EdgeCount, def_, dim, out=both[:, dim:])
+        F_.segment_reduce(g.plan_csr, def_, dim, out=both[:, dim:])
         own = _halo_reduce(both, g, None, rkey)                            # [n_own, 2 dim]
         dxp_hi, dp = own[:, :dim], own[:, dim:]
         dxp = F_.node_linear(dp, w_lo, transpose_w=True, addend=dxp_hi, bounds=g.own_bounds)

@@ -89,25 +89,6 @@ def two_hop_reduce(plan: CsrPlan, nbr: torch.Tensor, src: torch.Tensor, *,
     return out
 
 
-def phased_segment_reduce(plan: CsrPlan, edge_count: int, src: torch.Tensor, dim: int, *,
-                          row_scale: Optional[torch.Tensor] = None,
-                          out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """segment_reduce(plan, src [E, dim]) as a few passes over L2-sized hyperedge ranges.
-    Every hyperedge row is read three times (once per slot); in one pass over all hyperedges the
-    second and third read come from DRAM again (E*dim*4 bytes >> L2).  Restricting a pass to a range
-    of hyperedges whose rows fit in L2 turns them into L2 hits: DRAM reads drop from 3x to ~1x.
-    Falls back to the single pass when the table already fits or would need too many passes."""
-    plans = plan.phase_plans(edge_count, dim)
-    if not plans:
-        return segment_reduce(plan, src, dim, row_scale=row_scale, out=out)
-    src = _lib.rows_f32(src)
-    l2 = os.environ.get("IHG_PHASE_L2_VARIANT", "1") != "0"
-    out = segment_reduce(plans[0], src, dim, row_scale=row_scale, out=out, l2_source=l2)
-    for sub in plans[1:]:
-        segment_reduce(sub, src, dim, row_scale=row_scale, out=out, init=out, accumulate=True, l2_source=l2)
-    return out
-
-
 def edge_gather_sum(src: torch.Tensor, i3: torch.Tensor, *, node_scale: Optional[torch.Tensor] = None,
                     alpha: float = 1.0, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[e] = alpha * sum_s node_scale[i3[e,s]] * src[i3[e,s]] (+ bias)."""

@@ -66,7 +66,6 @@ class CsrPlan:
             split_row=self.split_row.data_ptr(), split_ptr=self.split_ptr.data_ptr())
         self._partial = {}
         self._nbr = None
-        self._phase_plans = {}
 
     def partial(self, dim: int) -> Optional[torch.Tensor]:
         """Scratch for the partial sums of split rows (cached per feature dimension)."""
@@ -80,39 +79,6 @@ class CsrPlan:
 
     def ref(self):
         return ctypes.byref(self.struct)
-
-    # ---- L2-sized hyperedge ranges for the edge -> node reductions -------------------------
-    def phase_plans(self, edge_count: int, dim: int):
-        """CSR plans restricted to consecutive hyperedge ranges whose [range, dim] fp32 rows fit in
-        L2 (`functional.phased_segment_reduce`); None when one pass is already right (table fits, or
-        more than IHG_PHASE_MAX ranges would be needed: every pass also walks all rows).
-        IHG_PHASE_MB sets the range size (default 72 MB of the B200's 126 MB L2).
-        OFF unless IHG_PHASES=1: measured on B200 it loses (amazon-full, two reductions per step: 0.52 ms
-        single pass vs 0.86 ms in 5 ranges of 72 MB, 1.08 ms in 2 ranges of 154 MB with the
-        high-occupancy launch; profiles/r01_bench_phased_rejected.txt) -- the second and third read of
-        a hyperedge row do not become cheap L2 hits, and every pass pays its own launch + row walk."""
-        if os.environ.get("IHG_PHASES", "0") != "1":
-            return None
-        got = self._phase_plans.get(dim)
-        if got is None:
-            budget = float(os.environ.get("IHG_PHASE_MB", "72")) * (1 << 20)
-            k = int(-(-edge_count * dim * 4 // budget))
-            if k < 2 or k > int(os.environ.get("IHG_PHASE_MAX", "6")):
-                got = ()
-            else:
-                per = -(-edge_count // k)
-                counts = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
-                rows = torch.repeat_interleave(torch.arange(self.n_rows, device=self.rowptr.device,
-                                                            dtype=torch.int32), counts)
-                phase = torch.div(self.col, per, rounding_mode="floor")
-                plans = []
-                for p in range(k):
-                    sel = phase == p
-                    rp, _perm, cols = csr_from_keys(rows[sel], self.n_rows, values=self.col[sel])
-                    plans.append(CsrPlan(rp, cols, self.chunk_len, drop_empty_rows=p > 0))
-                got = tuple(plans)
-            self._phase_plans[dim] = got
-        return got or None
 
     def two_hop_nbr(self, i3: torch.Tensor, bounds=(INT64_MAX, INT64_MAX),
                     row_slot: Optional[torch.Tensor] = None) -> torch.Tensor:

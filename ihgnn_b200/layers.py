@@ -303,7 +303,7 @@ class _FeatureInteractFn(torch.autograd.Function):
         nb = 4 if order == 3 else 3
         w_hi = w_agg[:, 3 * dim:]
         w_lo = _split_first_order(w_agg, dim).contiguous()              # [3, dim, dim]
-        dp = F_.phased_segment_reduce(g.plan, g.EdgeCount, def_, dim)
+        dp = F_.segment_reduce(g.plan, def_, dim)
         slot_grad = torch.empty((E, 3, dim), dtype=torch.float32, device=xp.device)
         dw_hi = torch.empty((dim, nb * dim), dtype=torch.float32, device=xp.device)
         ws_bytes = _lib.lib().ihg_edge_interact_bwd_workspace_bytes(dim, order)
@@ -329,7 +329,7 @@ class _ScatterMeanFn(torch.autograd.Function):
     def forward(ctx, ef, graph: PpsHyperGraph, row_scale):
         ctx.graph, ctx.row_scale = graph, row_scale
         ef = _lib.rows_f32(ef)
-        return F_.phased_segment_reduce(graph.plan, graph.EdgeCount, ef, int(ef.shape[1]), row_scale=row_scale)
+        return F_.segment_reduce(graph.plan, ef, int(ef.shape[1]), row_scale=row_scale)
 
     @staticmethod
     def backward(ctx, dout):

@@ -841,44 +841,49 @@ def test_graphed_train_step_equals_eager(golden, with_example):
     assert len(set(losses["eager"])) == 4                             # the parameters do move between steps
 
 
-@pytest.mark.parametrize("dim,mb", [(64, 0.5), (128, 1.0), (32, 0.25)])
-def test_phased_segment_reduce_equals_single_pass(dim, mb, monkeypatch):
-    """The edge -> node reduction run as several passes over L2-sized hyperedge ranges
-    (accumulate mode of ihg_segment_reduce) against the fp64 SpMM and the single pass: every
-    incidence lands in exactly one range plan, isolated rows stay exact zeros, split rows included."""
+@pytest.mark.parametrize("dim,parts", [(64, 3), (128, 2), (32, 5)])
+def test_segment_reduce_accumulate_over_hyperedge_ranges(dim, parts):
+    """IHG_SEG_ACCUMULATE of ihg_segment_reduce: the edge -> node reduction run as several passes, each over
+    a CSR restricted to one range of hyperedges and accumulating into the same output (plans listing only
+    the non-empty rows), against the fp64 SpMM and the single pass; isolated rows stay exact zeros; strided
+    destination."""
     from ihgnn_b200 import functional as F_
     from ihgnn_b200 import synth
-    from ihgnn_b200.graph import PpsHyperGraph
-    monkeypatch.setenv("IHG_PHASE_MB", str(mb))
-    monkeypatch.setenv("IHG_PHASES", "1")                   # opt-in: measured slower than the single pass on B200
+    from ihgnn_b200.graph import CsrPlan, PpsHyperGraph, csr_from_keys
     U, Q, I, E = 400, 30, 200, 9000
     log = synth.make_search_log(U, Q, I, E, 50, shape="cikm", seed=dim + 7, zipf=1.0)
     ref = orc.build_hypergraph(log.pos_user, log.pos_query, log.pos_item, U, Q, I)
     g = PpsHyperGraph.from_tensors(log.pos_user, log.pos_query, log.pos_item, U, Q, I, DEV, chunk_len=64)
-    plans = g.plan.phase_plans(E, dim)
-    assert plans is not None and 2 <= len(plans) <= 6
-    assert sum(p.nnz for p in plans) == 3 * E
-    assert any(p.n_split > 0 for p in plans)
-    per = -(-E // len(plans))
-    for k, p in enumerate(plans):
-        c = p.col.cpu().numpy()
-        assert c.size == 0 or (c.min() >= k * per and c.max() < (k + 1) * per)
+    N = U + Q + I
+    counts = (g.rowptr[1:] - g.rowptr[:-1]).to(torch.int64)
+    rows = torch.repeat_interleave(torch.arange(N, device=DEV, dtype=torch.int32), counts)
+    per = -(-E // parts)
+    plans = []
+    for k in range(parts):
+        sel = torch.div(g.col, per, rounding_mode="floor") == k
+        rp, _perm, cols = csr_from_keys(rows[sel], N, values=g.col[sel])
+        plans.append(CsrPlan(rp, cols, 64, drop_empty_rows=k > 0))
+    assert sum(p.nnz for p in plans) == 3 * E and any(p.n_split > 0 for p in plans)
     gen = torch.Generator().manual_seed(dim)
     ef = torch.randn(E, dim, generator=gen)
-    dv = ref.VertexDegrees.pow(-1)
-    want = (dv.double() * torch.sparse.mm(ref.adjacency(torch.float64), ef.double())).numpy()
-    got = F_.phased_segment_reduce(g.plan, E, ef.to(DEV), dim, row_scale=g.dv_inv).cpu().numpy()
+    efd = ef.to(DEV)
+    want_raw = torch.sparse.mm(ref.adjacency(torch.float64), ef.double()).numpy()
+    want = (ref.VertexDegrees.pow(-1).double().numpy() * want_raw)
+
+    def run(out, row_scale):
+        out = F_.segment_reduce(plans[0], efd, dim, row_scale=row_scale, out=out)
+        for sub in plans[1:]:
+            F_.segment_reduce(sub, efd, dim, row_scale=row_scale, out=out, init=out, accumulate=True)
+        return out
+    got = run(None, g.dv_inv).cpu().numpy()
     assert max_rel(got, want) < 2e-6
     iso = (np.diff(ref.rowptr.numpy()) == 0)
     assert iso.any() and np.all(got[iso] == 0.0)
-    one = F_.segment_reduce(g.plan, ef.to(DEV), dim, row_scale=g.dv_inv).cpu().numpy()
+    one = F_.segment_reduce(g.plan, efd, dim, row_scale=g.dv_inv).cpu().numpy()
     assert max_rel(got, one) < 2e-6
-    again = F_.phased_segment_reduce(g.plan, E, ef.to(DEV), dim, row_scale=g.dv_inv).cpu().numpy()
-    assert np.array_equal(got, again)
-    # a strided destination (the sharded backward writes next to another block of columns)
-    both = torch.zeros(U + Q + I, 2 * dim, device=DEV)
-    F_.phased_segment_reduce(g.plan, E, ef.to(DEV), dim, out=both[:, dim:])
-    want_raw = torch.sparse.mm(ref.adjacency(torch.float64), ef.double()).numpy()
+    assert np.array_equal(got, run(None, g.dv_inv).cpu().numpy())
+    both = torch.zeros(N, 2 * dim, device=DEV)
+    run(both[:, dim:], None)
     assert max_rel(both[:, dim:].cpu().numpy(), want_raw) < 2e-6 and float(both[:, :dim].abs().max()) == 0.0
 
 
