@@ -17,7 +17,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libihgnn_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -56,6 +56,8 @@ SIGNATURES = {
     "ihg_segment_reduce": (c_int32, [POINTER(IhgCsr), P, I64, I32, I64, I64, P, P, I64, P, P, P, P, I64, I32, I32, P]),
     "ihg_two_hop_index_build": (c_int32, [POINTER(IhgCsr), P, I64, I64, P, P, P]),
     "ihg_two_hop_reduce": (c_int32, [POINTER(IhgCsr), P, P, I64, P, F32, F32, F32, P, P, P, I64, I32, P]),
+    "ihg_segment_reduce_routed": (c_int32, [POINTER(IhgCsr), P, I64, I32, I64, I64, P, P, P, P, I32, I64, I32, P]),
+    "ihg_two_hop_reduce_routed": (c_int32, [POINTER(IhgCsr), P, P, I64, P, F32, F32, F32, P, P, P, I32, I64, I32, P]),
     "ihg_edge_gather_sum": (c_int32, [P, I64, P, F32, P, P, I64, P, I64, I32, P]),
     "ihg_edge_interact_fwd_workspace_bytes": (I64, [I32, I32]),
     "ihg_edge_interact_fwd": (c_int32, [P, I64, P, I64, P, I64, I32, P, I64, P, I64, I32, P, I64, P]),

@@ -21,11 +21,29 @@
 
 namespace ihg {
 
+// Routed output (multi-GPU, ihg_*_routed): consecutive row ranges of the result go to different destinations --
+// the own rows to a local matrix, each peer's halo rows straight into that peer's receive buffer over NVLink
+// (posted stores that overlap the kernel's own gathers), so the partial sums need no separate transfer pass.
+constexpr int kMaxRoute = 16;
+struct OutRoute {
+    int32_t n;                        // ranges in use
+    int32_t start[kMaxRoute + 1];     // range g = rows [start[g], start[g+1])
+    float* base[kMaxRoute];           // where row start[g] goes (rows of a range are out_ld floats apart)
+};
+template <bool ROUTED>
+__device__ __forceinline__ float* out_row(const OutRoute& r, float* out, int64_t out_ld, int row) {
+    if (!ROUTED) return out + (int64_t)row * out_ld;
+    int g = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxRoute; ++k) g += (k < r.n && row >= r.start[k]) ? 1 : 0;
+    return r.base[g] + (int64_t)(row - r.start[g]) * out_ld;
+}
+
 constexpr int kSegWarpsPerBlock = 8;
 constexpr int kSegUnroll = 4;        // independent 128-bit row gathers in flight per lane group
 constexpr int kSegPerGroup = 1;      // chunks a lane group walks through (strided)
 
-template <int LPR, int VPL, int UNR, int SEGS, int MINB>
+template <int LPR, int VPL, int UNR, int SEGS, int MINB, bool ROUTED>
 __global__ void __launch_bounds__(kSegWarpsPerBlock * 32, MINB)
 segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src_row_mul,
                       int64_t bound0, int64_t bound1, const int32_t* __restrict__ row_slot,
@@ -34,7 +52,7 @@ segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src
                       const float* __restrict__ row_scale, const int32_t* __restrict__ col,
                       int64_t n_seg, int64_t n_groups, const int4* __restrict__ seg,
                       float* __restrict__ partial, float* __restrict__ out, int64_t out_ld, int dim,
-                      int accumulate) {
+                      int accumulate, const __grid_constant__ OutRoute route) {
     constexpr int G = 32 / LPR;
     constexpr unsigned kFull = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -105,10 +123,11 @@ segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src
             if (part < 0) {
                 const float rs = row_scale ? __ldg(row_scale + row) : 1.0f;
                 if (!accumulate) {
+                    float* dst = out_row<ROUTED>(route, out, out_ld, row);
 #pragma unroll
                     for (int w = 0; w < VPL; ++w) {
                         const int cv = gl + w * LPR;
-                        if (cv < nvec) stg4(out + (int64_t)row * out_ld + 4 * cv, f4_scale(rs, acc[w]));
+                        if (cv < nvec) stg4(dst + 4 * cv, f4_scale(rs, acc[w]));
                     }
                 } else if (end > begin) {
                     // accumulate mode: out[row] = init[row] + rs * sum; rows without incidences stay untouched
@@ -141,13 +160,13 @@ segment_reduce_kernel(const float* __restrict__ src, int64_t src_ld, int32_t src
 // compiler keeps ~4 loads in flight per lane, so parallelism comes from the groups), a fixed
 // shuffle tree combines the groups of a warp and warp 0 adds the 8 warp sums in order:
 //   out[row] = row_scale * sum of partial[p0 .. p1)        (fixed order => deterministic)
-template <int LPR, int VPL>
+template <int LPR, int VPL, bool ROUTED>
 __global__ void __launch_bounds__(kSegWarpsPerBlock * 32)
 segment_fixup_kernel(const float* __restrict__ partial, const int32_t* __restrict__ split_row,
                      const int32_t* __restrict__ split_ptr, int64_t n_split,
                      const float* __restrict__ init, int64_t init_ld,
                      const float* __restrict__ row_scale, float* __restrict__ out, int64_t out_ld,
-                     int dim, int accumulate) {
+                     int dim, int accumulate, const __grid_constant__ OutRoute route) {
     constexpr int G = 32 / LPR;
     __shared__ float4 warp_sum[kSegWarpsPerBlock][LPR * VPL];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -189,7 +208,7 @@ segment_fixup_kernel(const float* __restrict__ partial, const int32_t* __restric
                 float4 t = init ? ldg4(init + (int64_t)row * init_ld + 4 * cv) : f4_zero();
 #pragma unroll
                 for (int k = 0; k < kSegWarpsPerBlock; ++k) f4_add(t, warp_sum[k][cv]);
-                stg4(out + (int64_t)row * out_ld + 4 * cv, f4_scale(rs, t));
+                stg4(out_row<ROUTED>(route, out, out_ld, row) + 4 * cv, f4_scale(rs, t));
             } else {
                 float4 t = f4_zero();
 #pragma unroll
@@ -207,8 +226,9 @@ static int launch_segment_reduce(const ihg_csr* g, const float* src, int64_t src
                                  int64_t b0, int64_t b1, const int32_t* row_slot, const float* init,
                                  int64_t init_ld, const float* src_scale,
                                  const float* row_scale, float* partial, float* out, int64_t out_ld,
-                                 int dim, int accumulate, int l2_source, cudaStream_t st) {
+                                 int dim, int accumulate, int l2_source, const OutRoute* route, cudaStream_t st) {
     constexpr int G = 32 / LPR;
+    static const OutRoute kNoRoute = {};
     // (unroll, chunks per group) = (4, 1) measured best on both bench workloads (profiles/
     // microbench_segment.py): 5.3 TB/s at d=128 (82% of the measured copy bandwidth); at d=64 the
     // 256-byte random rows cap every variant near 3.1 TB/s (DRAM page locality, not the kernel).
@@ -228,18 +248,26 @@ static int launch_segment_reduce(const ihg_csr* g, const float* src, int64_t src
     // resident warps or a shorter unroll (unroll 2 with >= 5/6/8 blocks: 2.3 / 2.7 / 3.2 TB/s vs 3.6-4.0).
     // A source that is L2-resident (the L2-sized hyperedge ranges of the phased reduction) wants the
     // opposite: unroll 2 and >= 5 resident blocks, like the two-hop gathers.
-    if (l2_source)
-        segment_reduce_kernel<LPR, VPL, 2, SEGS, 5><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
+    if (route)
+        segment_reduce_kernel<LPR, VPL, kSegUnroll, SEGS, 0, true><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
             src, src_ld, mul, b0, b1, row_slot, init, init_ld, src_scale, row_scale, g->col, g->n_seg, n_groups,
-            reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim, accumulate);
+            reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim, 0, *route);
+    else if (l2_source)
+        segment_reduce_kernel<LPR, VPL, 2, SEGS, 5, false><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
+            src, src_ld, mul, b0, b1, row_slot, init, init_ld, src_scale, row_scale, g->col, g->n_seg, n_groups,
+            reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim, accumulate, kNoRoute);
     else
-        segment_reduce_kernel<LPR, VPL, kSegUnroll, SEGS, 0><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
+        segment_reduce_kernel<LPR, VPL, kSegUnroll, SEGS, 0, false><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
             src, src_ld, mul, b0, b1, row_slot, init, init_ld, src_scale, row_scale, g->col, g->n_seg, n_groups,
-            reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim, accumulate);
+            reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim, accumulate, kNoRoute);
     IHG_LAUNCH_CHECK();
     if (g->n_split > 0) {
-        segment_fixup_kernel<LPR, VPL><<<(unsigned)g->n_split, kSegWarpsPerBlock * 32, 0, st>>>(
-            partial, g->split_row, g->split_ptr, g->n_split, init, init_ld, row_scale, out, out_ld, dim, accumulate);
+        if (route)
+            segment_fixup_kernel<LPR, VPL, true><<<(unsigned)g->n_split, kSegWarpsPerBlock * 32, 0, st>>>(
+                partial, g->split_row, g->split_ptr, g->n_split, init, init_ld, row_scale, out, out_ld, dim, 0, *route);
+        else
+            segment_fixup_kernel<LPR, VPL, false><<<(unsigned)g->n_split, kSegWarpsPerBlock * 32, 0, st>>>(
+                partial, g->split_row, g->split_ptr, g->n_split, init, init_ld, row_scale, out, out_ld, dim, accumulate, kNoRoute);
         IHG_LAUNCH_CHECK();
     }
     return IHG_OK;
@@ -277,14 +305,14 @@ __global__ void two_hop_index_kernel(const int4* __restrict__ seg, int64_t n_seg
     }
 }
 
-template <int LPR, int VPL, int UNR, int MINB>
+template <int LPR, int VPL, int UNR, int MINB, bool ROUTED>
 __global__ void __launch_bounds__(kSegWarpsPerBlock * 32, MINB)
 two_hop_reduce_kernel(const float* __restrict__ src, int64_t src_ld,
                       const float* __restrict__ node_scale, float alpha, float own_per_inc, float own_const,
                       const float* __restrict__ row_scale, const int2* __restrict__ nbr,
                       const int32_t* __restrict__ rowptr,
                       int64_t n_seg, const int4* __restrict__ seg, float* __restrict__ partial,
-                      float* __restrict__ out, int64_t out_ld, int dim) {
+                      float* __restrict__ out, int64_t out_ld, int dim, const __grid_constant__ OutRoute route) {
     constexpr int G = 32 / LPR;
     constexpr unsigned kFull = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -359,13 +387,13 @@ two_hop_reduce_kernel(const float* __restrict__ src, int64_t src_ld,
     }
     if (live) {
         const float rs = (part < 0 && row_scale) ? alpha * __ldg(row_scale + row) : alpha;
+        float* drow = part < 0 ? out_row<ROUTED>(route, out, out_ld, row) : partial + (int64_t)part * dim;
 #pragma unroll
         for (int w = 0; w < VPL; ++w) {
             const int cv = gl + w * LPR;
             if (cv >= nvec) continue;
             f4_fma(acc[w], own_w, own[w]);
-            float* dst = part < 0 ? out + (int64_t)row * out_ld + 4 * cv : partial + (int64_t)part * dim + 4 * cv;
-            stg4(dst, f4_scale(rs, acc[w]));
+            stg4(drow + 4 * cv, f4_scale(rs, acc[w]));
         }
     }
 }
@@ -374,21 +402,31 @@ template <int LPR, int VPL>
 static int launch_two_hop(const ihg_csr* g, const int32_t* nbr, const float* src, int64_t src_ld,
                           const float* node_scale, float alpha, float own_per_inc, float own_const,
                           const float* row_scale,
-                          float* partial, float* out, int64_t out_ld, int dim, cudaStream_t st) {
+                          float* partial, float* out, int64_t out_ld, int dim, const OutRoute* route, cudaStream_t st) {
     constexpr int G = 32 / LPR;
+    static const OutRoute kNoRoute = {};
     const int64_t groups_per_block = (int64_t)kSegWarpsPerBlock * G;
     int64_t blocks = ceil_div(g->n_seg, groups_per_block);
     if (blocks < 1) blocks = 1;
     // (unroll 2, >= 5 resident blocks = 48 registers) measured best in situ: occupancy beats per-thread
     // ILP for these L2-served gathers (per call 0.274 vs 0.327 ms for unroll 4 / 80 registers at the
     // amazon-full shape, 1.59 vs 1.99 ms at cikm; profiles/r01_bench_twohop_variants.txt)
-    two_hop_reduce_kernel<LPR, VPL, 2, 5><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
-        src, src_ld, node_scale, alpha, own_per_inc, own_const, row_scale, reinterpret_cast<const int2*>(nbr),
-        g->rowptr, g->n_seg, reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim);
+    if (route)
+        two_hop_reduce_kernel<LPR, VPL, 2, 5, true><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
+            src, src_ld, node_scale, alpha, own_per_inc, own_const, row_scale, reinterpret_cast<const int2*>(nbr),
+            g->rowptr, g->n_seg, reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim, *route);
+    else
+        two_hop_reduce_kernel<LPR, VPL, 2, 5, false><<<(unsigned)blocks, kSegWarpsPerBlock * 32, 0, st>>>(
+            src, src_ld, node_scale, alpha, own_per_inc, own_const, row_scale, reinterpret_cast<const int2*>(nbr),
+            g->rowptr, g->n_seg, reinterpret_cast<const int4*>(g->seg), partial, out, out_ld, dim, kNoRoute);
     IHG_LAUNCH_CHECK();
     if (g->n_split > 0) {
-        segment_fixup_kernel<LPR, VPL><<<(unsigned)g->n_split, kSegWarpsPerBlock * 32, 0, st>>>(
-            partial, g->split_row, g->split_ptr, g->n_split, nullptr, 0, row_scale, out, out_ld, dim, 0);
+        if (route)
+            segment_fixup_kernel<LPR, VPL, true><<<(unsigned)g->n_split, kSegWarpsPerBlock * 32, 0, st>>>(
+                partial, g->split_row, g->split_ptr, g->n_split, nullptr, 0, row_scale, out, out_ld, dim, 0, *route);
+        else
+            segment_fixup_kernel<LPR, VPL, false><<<(unsigned)g->n_split, kSegWarpsPerBlock * 32, 0, st>>>(
+                partial, g->split_row, g->split_ptr, g->n_split, nullptr, 0, row_scale, out, out_ld, dim, 0, kNoRoute);
         IHG_LAUNCH_CHECK();
     }
     return IHG_OK;
@@ -398,13 +436,29 @@ static int launch_two_hop(const ihg_csr* g, const int32_t* nbr, const float* src
 
 using namespace ihg;
 
-extern "C" int ihg_segment_reduce(const ihg_csr* g, const float* src, int64_t src_ld,
-                                  int32_t src_row_mul, int64_t bound0, int64_t bound1,
-                                  const int32_t* row_slot, const float* init, int64_t init_ld,
-                                  const float* src_scale, const float* row_scale, float* partial,
-                                  float* out, int64_t out_ld, int32_t dim, int32_t flags,
-                                  void* stream) {
-    IHG_REQUIRE(g && src && out, "segment_reduce: null pointer");
+static int make_route(const char* what, const ihg_csr* g, const int64_t* start, void* const* base, int32_t n,
+                      OutRoute* r) {
+    IHG_REQUIRE(start && base && n >= 1 && n <= kMaxRoute, "%s: needs 1..%d output ranges", what, kMaxRoute);
+    IHG_REQUIRE(start[0] == 0 && start[n] == g->n_rows, "%s: the output ranges must cover rows [0, n_rows)", what);
+    *r = OutRoute{};
+    r->n = n;
+    for (int k = 0; k < n; ++k) {
+        IHG_REQUIRE(start[k] <= start[k + 1], "%s: output ranges must ascend", what);
+        IHG_REQUIRE(base[k] || start[k] == start[k + 1], "%s: null destination of a non-empty range", what);
+        r->start[k] = (int32_t)start[k];
+        r->base[k] = static_cast<float*>(base[k]);
+    }
+    for (int k = n; k <= kMaxRoute; ++k) r->start[k] = (int32_t)start[n];
+    return IHG_OK;
+}
+
+static int segment_reduce_impl(const ihg_csr* g, const float* src, int64_t src_ld,
+                               int32_t src_row_mul, int64_t bound0, int64_t bound1,
+                               const int32_t* row_slot, const float* init, int64_t init_ld,
+                               const float* src_scale, const float* row_scale, float* partial,
+                               float* out, int64_t out_ld, int32_t dim, int32_t flags,
+                               const OutRoute* route, void* stream) {
+    IHG_REQUIRE(g && src && (out || route), "segment_reduce: null pointer");
     const int accumulate = (flags & IHG_SEG_ACCUMULATE) != 0, l2_source = (flags & IHG_SEG_L2_SOURCE) != 0;
     IHG_REQUIRE(!accumulate || init, "segment_reduce: accumulate mode needs init (usually == out)");
     IHG_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 256, "segment_reduce: dim=%d must be a multiple of 4, <= 256", dim);
@@ -422,7 +476,7 @@ extern "C" int ihg_segment_reduce(const ihg_csr* g, const float* src, int64_t sr
     cudaStream_t st = as_stream(stream);
     const int nvec = dim / 4;
 #define IHG_SEG_CASE(L, V) \
-    return launch_segment_reduce<L, V>(g, src, src_ld, src_row_mul, bound0, bound1, row_slot, init, init_ld, src_scale, row_scale, partial, out, out_ld, dim, accumulate, l2_source, st)
+    return launch_segment_reduce<L, V>(g, src, src_ld, src_row_mul, bound0, bound1, row_slot, init, init_ld, src_scale, row_scale, partial, out, out_ld, dim, accumulate, l2_source, route, st)
     if (nvec <= 1) IHG_SEG_CASE(1, 1);
     if (nvec <= 2) IHG_SEG_CASE(2, 1);
     if (nvec <= 4) IHG_SEG_CASE(4, 1);
@@ -431,6 +485,28 @@ extern "C" int ihg_segment_reduce(const ihg_csr* g, const float* src, int64_t sr
     if (nvec <= 32) IHG_SEG_CASE(32, 1);
     IHG_SEG_CASE(32, 2);
 #undef IHG_SEG_CASE
+}
+
+extern "C" int ihg_segment_reduce(const ihg_csr* g, const float* src, int64_t src_ld,
+                                  int32_t src_row_mul, int64_t bound0, int64_t bound1,
+                                  const int32_t* row_slot, const float* init, int64_t init_ld,
+                                  const float* src_scale, const float* row_scale, float* partial,
+                                  float* out, int64_t out_ld, int32_t dim, int32_t flags,
+                                  void* stream) {
+    return segment_reduce_impl(g, src, src_ld, src_row_mul, bound0, bound1, row_slot, init, init_ld, src_scale,
+                               row_scale, partial, out, out_ld, dim, flags, nullptr, stream);
+}
+
+extern "C" int ihg_segment_reduce_routed(const ihg_csr* g, const float* src, int64_t src_ld,
+                                         int32_t src_row_mul, int64_t bound0, int64_t bound1,
+                                         const int32_t* row_slot, float* partial,
+                                         const int64_t* route_start, void* const* route_base,
+                                         int32_t n_route, int64_t out_ld, int32_t dim, void* stream) {
+    IHG_REQUIRE(g, "segment_reduce_routed: null csr");
+    OutRoute route;
+    if (int rc = make_route("segment_reduce_routed", g, route_start, route_base, n_route, &route)) return rc;
+    return segment_reduce_impl(g, src, src_ld, src_row_mul, bound0, bound1, row_slot, nullptr, 0, nullptr, nullptr,
+                               partial, nullptr, out_ld, dim, 0, &route, stream);
 }
 
 extern "C" int ihg_two_hop_index_build(const ihg_csr* g, const int32_t* i3, int64_t bound0,
@@ -448,12 +524,12 @@ extern "C" int ihg_two_hop_index_build(const ihg_csr* g, const int32_t* i3, int6
     return IHG_OK;
 }
 
-extern "C" int ihg_two_hop_reduce(const ihg_csr* g, const int32_t* nbr, const float* src,
-                                  int64_t src_ld, const float* node_scale, float alpha,
-                                  float own_per_incidence, float own_const,
-                                  const float* row_scale, float* partial, float* out,
-                                  int64_t out_ld, int32_t dim, void* stream) {
-    IHG_REQUIRE(g && src && out, "two_hop_reduce: null pointer");
+static int two_hop_reduce_impl(const ihg_csr* g, const int32_t* nbr, const float* src,
+                               int64_t src_ld, const float* node_scale, float alpha,
+                               float own_per_incidence, float own_const,
+                               const float* row_scale, float* partial, float* out,
+                               int64_t out_ld, int32_t dim, const OutRoute* route, void* stream) {
+    IHG_REQUIRE(g && src && (out || route), "two_hop_reduce: null pointer");
     IHG_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 256, "two_hop_reduce: dim=%d must be a multiple of 4, <= 256", dim);
     IHG_REQUIRE(src_ld % 4 == 0 && out_ld % 4 == 0 && src_ld >= dim && out_ld >= dim,
                 "two_hop_reduce: leading dimensions must be multiples of 4 and >= dim");
@@ -465,7 +541,7 @@ extern "C" int ihg_two_hop_reduce(const ihg_csr* g, const int32_t* nbr, const fl
     cudaStream_t st = as_stream(stream);
     const int nvec = dim / 4;
 #define IHG_TH_CASE(L, V) \
-    return launch_two_hop<L, V>(g, nbr, src, src_ld, node_scale, alpha, own_per_incidence, own_const, row_scale, partial, out, out_ld, dim, st)
+    return launch_two_hop<L, V>(g, nbr, src, src_ld, node_scale, alpha, own_per_incidence, own_const, row_scale, partial, out, out_ld, dim, route, st)
     if (nvec <= 1) IHG_TH_CASE(1, 1);
     if (nvec <= 2) IHG_TH_CASE(2, 1);
     if (nvec <= 4) IHG_TH_CASE(4, 1);
@@ -474,4 +550,25 @@ extern "C" int ihg_two_hop_reduce(const ihg_csr* g, const int32_t* nbr, const fl
     if (nvec <= 32) IHG_TH_CASE(32, 1);
     IHG_TH_CASE(32, 2);
 #undef IHG_TH_CASE
+}
+
+extern "C" int ihg_two_hop_reduce(const ihg_csr* g, const int32_t* nbr, const float* src,
+                                  int64_t src_ld, const float* node_scale, float alpha,
+                                  float own_per_incidence, float own_const,
+                                  const float* row_scale, float* partial, float* out,
+                                  int64_t out_ld, int32_t dim, void* stream) {
+    return two_hop_reduce_impl(g, nbr, src, src_ld, node_scale, alpha, own_per_incidence, own_const, row_scale,
+                               partial, out, out_ld, dim, nullptr, stream);
+}
+
+extern "C" int ihg_two_hop_reduce_routed(const ihg_csr* g, const int32_t* nbr, const float* src,
+                                         int64_t src_ld, const float* node_scale, float alpha,
+                                         float own_per_incidence, float own_const, float* partial,
+                                         const int64_t* route_start, void* const* route_base,
+                                         int32_t n_route, int64_t out_ld, int32_t dim, void* stream) {
+    IHG_REQUIRE(g, "two_hop_reduce_routed: null csr");
+    OutRoute route;
+    if (int rc = make_route("two_hop_reduce_routed", g, route_start, route_base, n_route, &route)) return rc;
+    return two_hop_reduce_impl(g, nbr, src, src_ld, node_scale, alpha, own_per_incidence, own_const, nullptr,
+                               partial, nullptr, out_ld, dim, &route, stream);
 }

@@ -229,6 +229,7 @@ class ShardedHyperGraph:
         rowptr, _perm, col = csr_from_keys(self.i3.reshape(-1), plan.n_local, values=edge_of)
         self.rowptr, self.col = rowptr, col
         self.plan_csr = CsrPlan(rowptr, col)
+        self._interleave_halo_work(plan)
         self.row_slot = t("row_slot", torch.int32)     # slot(row) for the per-slot gradient reduce
         self.own_bounds = plan.own_bounds              # node types of the own rows (typed Linear)
         self.dv_inv_own = t("dv_inv_own", torch.float32)
@@ -245,6 +246,28 @@ class ShardedHyperGraph:
         self.dv_inv_local = HaloExchangeFn.apply(self.dv_inv_own.view(-1, 1).expand(-1, 4).contiguous(), self)[:, 0].contiguous()
         if os.environ.get("IHG_P2P", "1") != "0":
             self.enable_peer_memory()
+
+    def _interleave_halo_work(self, plan: PartitionPlan) -> None:
+        """Order of the work items (row chunks) of the local CSR plan: own rows first, then the halo rows
+        round-robin over their owners instead of owner by owner.  The routed reductions write a halo row's
+        partial sum straight into its owner's receive buffer; in row order every rank would write to rank 0
+        first, then to rank 1, ... -- seven writers on one NVLink ingress while the others idle.  The records
+        are independent ({begin, end, row, partial slot}), so any order gives the same bits."""
+        seg = self.plan_csr.seg
+        if plan.world < 3 or seg.shape[0] == 0:
+            return
+        row = seg[:, 2].to(torch.int64)
+        halo = row >= plan.n_own
+        if not bool(halo.any()):
+            return
+        hseg = seg[halo]
+        chunk_end = torch.as_tensor(np.cumsum(plan.recv_counts) + plan.n_own, dtype=torch.int64, device=seg.device)
+        owner = torch.bucketize(hseg[:, 2].to(torch.int64), chunk_end, right=True)
+        first = torch.searchsorted(owner, torch.arange(plan.world, device=seg.device))    # records are in row order
+        within = torch.arange(hseg.shape[0], device=seg.device) - first[owner]
+        order = torch.argsort(within * plan.world + (owner - plan.rank - 1) % plan.world, stable=True)
+        self.plan_csr.seg = torch.cat([seg[~halo], hseg[order]]).contiguous()
+        self.plan_csr.struct.seg = self.plan_csr.seg.data_ptr()
 
     @property
     def two_hop_nbr(self) -> torch.Tensor:
@@ -275,7 +298,16 @@ class ShardedHyperGraph:
         # row where MY chunk starts in peer d's local table (its halo chunks are ordered by source rank)
         self._peer_row = [int(n_own_of[d] + send_of[:rank, d].sum()) for d in range(world)]
         self._max_local = int(meta[:, 1].max())
-        self._send_off = np.concatenate([[0], np.cumsum(self.send_counts)]).astype(np.int64)
+        # routed reduce: the partial sums I hold for owner d land in d's receive buffer [S_d rows, by source rank]
+        # at the row where MY block starts; my local table keeps d's rows in one contiguous chunk
+        self._recv_row = [int(send_of[d, :rank].sum()) for d in range(world)]
+        self._max_send = int(send_of.sum(1).max())
+        self._chunk0 = [int(self.n_own + sum(self.recv_counts[:d])) for d in range(world + 1)]
+        # send_rows in the order the push sweeps its destinations (rank + 1, rank + 2, ... cyclically)
+        so = self._send_off = np.concatenate([[0], np.cumsum(self.send_counts)]).astype(np.int64)
+        self.send_rows_push = torch.cat([self.send_rows[int(so[d]):int(so[d + 1])]
+                                         for d in [(rank + 1 + j) % world for j in range(world - 1)]]).contiguous()
+        self.routed = os.environ.get("IHG_ROUTED_REDUCE", "1") != "0"
         self._symm = symm_mem
         self._bufs = {}
         self.share_buffers = self._max_local * 128 * 4 * 14 > (40 << 30)
@@ -298,6 +330,18 @@ class ShardedHyperGraph:
         if not self.p2p:
             return None
         return self.peer_buffer(("x", key), cols)[0][:self.n_own]
+
+    def reduce_site(self, key, cols: int) -> Optional["_ReduceSite"]:
+        """Routed-reduce buffers of call site `key` (None: routed mode off -> the pull path).  Allocation is a
+        collective (symmetric memory): every rank reaches the sites in the same order."""
+        if not (self.p2p and self.routed) or key is None:
+            return None
+        if self.share_buffers:
+            key = "shared"
+        k = ("route", key, cols)
+        if k not in self._bufs:
+            self._bufs[k] = _ReduceSite(self, key, cols)
+        return self._bufs[k]
 
     def peer_buffer(self, key, cols: int):
         """Persistent symmetric [max n_local, cols] fp32 buffer for call site `key` (allocated and
@@ -323,8 +367,37 @@ class ShardedHyperGraph:
             chunk = (ctypes.c_void_p * n)(*[base[d] + self._peer_row[d] * row_bytes for d in peers])   # my chunk in d's table
             own = (ctypes.c_void_p * n)(*[buf.data_ptr()] * n)
             off = (ctypes.c_int64 * (n + 1))(*([0] + list(np.cumsum([self.send_counts[d] for d in peers]))))
-            self._bufs[k] = (buf, hdl, chunk, own, off, n)
+            # the push sweeps its destinations starting with the next rank (every rank a different one at a time)
+            rot = [(rank + 1 + j) % world for j in range(n)]
+            push_chunk = (ctypes.c_void_p * n)(*[base[d] + self._peer_row[d] * row_bytes for d in rot])
+            push_off = (ctypes.c_int64 * (n + 1))(*([0] + list(np.cumsum([self.send_counts[d] for d in rot]))))
+            self._bufs[k] = (buf, hdl, chunk, own, off, n, push_chunk, push_off)
         return self._bufs[k]
+
+
+class _ReduceSite:
+    """Buffers of one reduce call site in routed mode: `own` [n_own, cols] (this rank's partial sums of its own
+    rows), `recv` [S, cols] (symmetric: the partials the other ranks hold for my rows, written by THEIR reduction
+    kernels, blocks by source rank), and the `route` my reduction kernels write through."""
+
+    def __init__(self, g: "ShardedHyperGraph", key, cols: int):
+        from . import functional as F_
+        world, rank = g.plan.world, g.plan.rank
+        buf = g._symm.empty((max(g._max_send, 1), cols), dtype=torch.float32, device=g.device)
+        self.hdl = g._symm.rendezvous(buf, group=g.group if g.group is not None else torch.distributed.group.WORLD)
+        self.recv_full, self.recv = buf, buf[:g.S]
+        self.own = torch.empty((g.n_own, cols), dtype=torch.float32, device=g.device)
+        base = [int(p) for p in self.hdl.buffer_ptrs]
+        row_bytes = cols * 4
+        starts, bases = [0], [self.own.data_ptr()]
+        for d in range(world):
+            if d == rank or g.recv_counts[d] == 0:
+                continue
+            starts.append(g._chunk0[d])
+            bases.append(base[d] + g._recv_row[d] * row_bytes)
+        starts.append(g.n_local)
+        assert all(a <= b for a, b in zip(starts, starts[1:])) and (len(starts) == 2 or starts[1] == g.n_own)
+        self.route = F_.OutRoute(starts, bases, cols, keep=(buf, self.own))
 
 
 def _all_to_all(out: torch.Tensor, inp: torch.Tensor, out_counts, in_counts, group) -> None:
@@ -366,6 +439,10 @@ class ShardedScatterMeanFn(torch.autograd.Function):
         ctx.g, ctx.key = g, key
         ef = _lib.rows_f32(ef)
         d = int(ef.shape[1])
+        site = g.reduce_site(("sm", key) if key is not None else None, d)
+        if site is not None:
+            F_.segment_reduce_routed(g.plan_csr, ef, d, site.route)
+            return _finish_routed(site, g, g.dv_inv_own)
         s_local = F_.segment_reduce(g.plan_csr, ef, d, out=reduce_buffer(g, ("sm", key), d, ef))
         return _halo_reduce(s_local, g, g.dv_inv_own, ("sm", key) if key is not None else None)
 
@@ -379,27 +456,35 @@ class ShardedScatterMeanFn(torch.autograd.Function):
 
 class ShardedTwoHopFn(torch.autograd.Function):
     """Order-1 round trip over a partitioned hypergraph without the [E_local, d] intermediate:
-    p_local [n_local, d] -> Dv^-1 * H H^T p for the own rows.  One two-hop pass over the local table
-    (`ihg_two_hop_reduce`) replaces gather-sum + segmented sum; then halo_reduce.  Backward: halo_exchange
-    of the gradient, the same two-hop pass with Dv^-1 as the node scale; the result is the gradient of
-    the LOCAL table (its halo part travels back through HaloExchangeFn.backward)."""
+    p_own [n_own, d] -> Dv^-1 * H H^T p for the own rows: halo_exchange, one two-hop pass over the local table
+    (`ihg_two_hop_reduce`: replaces gather-sum + segmented sum), halo_reduce.  H H^T is symmetric, so backward
+    is the same three steps with the scales swapped (Dv^-1 as the node scale, none on the rows)."""
 
     @staticmethod
-    def forward(ctx, p_local, g: "ShardedHyperGraph", key=None):
+    def _round_trip(x_own, g: "ShardedHyperGraph", key, node_scale, row_scale, tag: str):
         from . import _lib
         from . import functional as F_
+        x_own = _lib.rows_f32(x_own)
+        d = int(x_own.shape[1])
+        x_local = _halo_exchange(x_own, g, (tag + "x", key) if key is not None else None)
+        rkey = (tag + "s", key) if key is not None else None
+        site = g.reduce_site(rkey, d)
+        if site is not None:
+            F_.two_hop_reduce_routed(g.plan_csr, g.two_hop_nbr, x_local, site.route, node_scale=node_scale)
+            return _finish_routed(site, g, row_scale)
+        s_local = F_.two_hop_reduce(g.plan_csr, g.two_hop_nbr, x_local, node_scale=node_scale,
+                                    out=reduce_buffer(g, rkey, d, x_local))
+        return _halo_reduce(s_local, g, row_scale, rkey)
+
+    @staticmethod
+    def forward(ctx, p_own, g: "ShardedHyperGraph", key=None):
         ctx.g, ctx.key = g, key
-        p_local = _lib.rows_f32(p_local)
-        d = int(p_local.shape[1])
-        s_local = F_.two_hop_reduce(g.plan_csr, g.two_hop_nbr, p_local, out=reduce_buffer(g, ("sm", key), d, p_local))
-        return _halo_reduce(s_local, g, g.dv_inv_own, ("sm", key) if key is not None else None)
+        return ShardedTwoHopFn._round_trip(p_own, g, key, None, g.dv_inv_own, "f")
 
     @staticmethod
     def backward(ctx, dout_own):
-        from . import functional as F_
         g, key = ctx.g, ctx.key
-        g_local = _halo_exchange(dout_own.contiguous(), g, ("smb", key) if key is not None else None)
-        return F_.two_hop_reduce(g.plan_csr, g.two_hop_nbr, g_local, node_scale=g.dv_inv_local), None, None
+        return ShardedTwoHopFn._round_trip(dout_own.contiguous(), g, key, g.dv_inv_local, None, "b"), None, None
 
 
 def _halo_exchange(x_own: torch.Tensor, g: "ShardedHyperGraph", key=None) -> torch.Tensor:
@@ -409,13 +494,13 @@ def _halo_exchange(x_own: torch.Tensor, g: "ShardedHyperGraph", key=None) -> tor
     from . import _lib
     d = int(x_own.shape[1])
     if g.p2p and key is not None:
-        buf, hdl, chunk, own, off, n = g.peer_buffer(("x", key), d)
+        buf, hdl, _chunk, own, _off, n, chunk, off = g.peer_buffer(("x", key), d)
         x_own = _lib.rows_f32(x_own)
         # push: row send_rows[r] of my table -> my chunk in the reader's local table.  send_rows is
         # ordered by destination rank and holds nothing for myself, so the flat order matches `off`.
         src = (type(own))(*[x_own.data_ptr()] * n)
         x_local = buf[:g.n_local]
-        _lib.call("ihg_halo_copy", src, chunk, off, n, _lib.ptr(g.send_rows), _lib.ld(x_own), d, d,
+        _lib.call("ihg_halo_copy", src, chunk, off, n, _lib.ptr(g.send_rows_push), _lib.ld(x_own), d, d,
                   _lib.stream_ptr(), tag="halo_push", algo_bytes=g.S * (8 + 8 * d))
         if x_own.data_ptr() != x_local.data_ptr():  # producers may have written the own rows in place (table_head)
             F_.copy_rows_raw(x_own, x_local[:g.n_own])
@@ -475,10 +560,16 @@ class ShardedFeatureInteractFn(torch.autograd.Function):
                   tag="edge_interact_bwd", algo_bytes=E * (12 + 28 * dim))
         # per-row gradients of the local rows, side by side: [ product-rule part | dP ]
         rkey = ("fib", ctx.key) if ctx.key is not None else None
-        both = reduce_buffer(g, rkey, 2 * dim, def_)
-        F_.segment_reduce(g.plan_csr, slot_grad, dim, src_row_mul=3, row_slot=g.row_slot, out=both[:, :dim])
-        F_.segment_reduce(g.plan_csr, def_, dim, out=both[:, dim:])
-        own = _halo_reduce(both, g, None, rkey)                            # [n_own, 2 dim]
+        site = g.reduce_site(rkey, 2 * dim)
+        if site is not None:
+            F_.segment_reduce_routed(g.plan_csr, slot_grad, dim, site.route, src_row_mul=3, row_slot=g.row_slot)
+            F_.segment_reduce_routed(g.plan_csr, def_, dim, site.route.shifted(4 * dim))
+            own = _finish_routed(site, g, None)                            # [n_own, 2 dim]
+        else:
+            both = reduce_buffer(g, rkey, 2 * dim, def_)
+            F_.segment_reduce(g.plan_csr, slot_grad, dim, src_row_mul=3, row_slot=g.row_slot, out=both[:, :dim])
+            F_.segment_reduce(g.plan_csr, def_, dim, out=both[:, dim:])
+            own = _halo_reduce(both, g, None, rkey)                        # [n_own, 2 dim]
         dxp_hi, dp = own[:, :dim], own[:, dim:]
         dxp = F_.node_linear(dp, w_lo, transpose_w=True, addend=dxp_hi, bounds=g.own_bounds)
         dw_lo, db_lo = F_.node_linear_wgrad(dp, xp_own, 3, g.own_bounds, True)
@@ -495,7 +586,7 @@ def _halo_reduce(s_local: torch.Tensor, g: ShardedHyperGraph, row_scale: Optiona
     from . import _lib
     d = int(s_local.shape[1])
     if g.p2p and key is not None:
-        buf, hdl, chunk, own, off, n = g.peer_buffer(("s", key), d)
+        buf, hdl, chunk, own, off, n = g.peer_buffer(("s", key), d)[:6]
         assert s_local.data_ptr() == buf.data_ptr(), "halo_reduce: s_local must be the call site's peer buffer"
         out = torch.empty((g.n_own, d), dtype=torch.float32, device=s_local.device)
         hdl.barrier(channel=0)                      # every rank's partial sums are complete
@@ -509,6 +600,20 @@ def _halo_reduce(s_local: torch.Tensor, g: ShardedHyperGraph, row_scale: Optiona
     recv = torch.empty((g.S, d), dtype=torch.float32, device=s_local.device)
     _all_to_all(recv, s_local[g.n_own:], g.send_counts, g.recv_counts, g.group)
     return F_.segment_reduce(g.reduce_csr, recv, d, row_scale=row_scale, init=s_local[:g.n_own])
+
+
+def _finish_routed(site: "_ReduceSite", g: ShardedHyperGraph, row_scale: Optional[torch.Tensor]) -> torch.Tensor:
+    """Second half of a routed reduce: every rank's reduction kernel has written its partial sums of my rows
+    into `site.recv` (posted NVLink stores); after the barrier the owner adds its own partial and the received
+    ones in ascending source rank (`reduce_csr` over the flat receive layout), applies `row_scale`."""
+    from . import functional as F_
+    d = int(site.own.shape[1])
+    site.hdl.barrier(channel=0)                     # all ranks' partial sums have landed
+    out = F_.segment_reduce(g.reduce_csr, site.recv, d, row_scale=row_scale, init=site.own) if g.S else \
+        (site.own * row_scale.view(-1, 1) if row_scale is not None else site.own.clone())
+    if g.share_buffers:
+        site.hdl.barrier(channel=0)                 # the one shared receive buffer is written again by the next site
+    return out
 
 
 def halo_exchange(x_own, g, key=None):
@@ -569,10 +674,11 @@ class ShardedIHGNNLayer(torch.nn.Module):
         if self.order == 1:
             w_f = torch.matmul(w_lo, wt)
             b_f = torch.matmul(w_lo, bt) + torch.stack([fi.aggregation.bias, zeros, zeros])
+            if F_.two_hop_enabled(g.n_local, d):
+                p_own = F_.typed_linear(x_own, w_f, b_f, g.own_bounds, out=g.table_head(("fx", self.uid), d))
+                return ShardedTwoHopFn.apply(p_own, g, self.uid)
             p_own = F_.typed_linear(x_own, w_f, b_f, g.own_bounds, out=g.table_head((self.uid, "p"), d))
             p = halo_exchange(p_own, g, (self.uid, "p"))
-            if F_.two_hop_enabled(g.n_local, d):
-                return ShardedTwoHopFn.apply(p, g, self.uid)
             ef = _EdgeGatherSumFn.apply(p, self.view, None, 1.0, None)
         else:
             from . import _lib

@@ -89,6 +89,58 @@ def two_hop_reduce(plan: CsrPlan, nbr: torch.Tensor, src: torch.Tensor, *,
     return out
 
 
+class OutRoute:
+    """Destinations of consecutive row ranges of a routed reduction (`ihg_*_routed`): range k = rows
+    [starts[k], starts[k+1]) goes to device address bases[k] (+ row stride `ld` floats).  Host arrays,
+    built once per call site; `keep` holds the tensors the addresses point into."""
+
+    def __init__(self, starts, bases, ld: int, keep=()):
+        import ctypes
+        n = len(bases)
+        assert len(starts) == n + 1 and 1 <= n <= 16
+        self.n, self.ld, self.keep = n, int(ld), tuple(keep)
+        self.starts = (ctypes.c_int64 * (n + 1))(*[int(x) for x in starts])
+        self.bases = (ctypes.c_void_p * n)(*[int(b) if b else None for b in bases])
+
+    def shifted(self, byte_offset: int) -> "OutRoute":
+        """The same ranges `byte_offset` bytes further (a column block of the destination rows)."""
+        r = OutRoute.__new__(OutRoute)
+        r.n, r.ld, r.keep, r.starts = self.n, self.ld, self.keep, self.starts
+        import ctypes
+        r.bases = (ctypes.c_void_p * self.n)(*[(b + byte_offset) if b else None for b in self.bases])
+        return r
+
+
+def segment_reduce_routed(plan: CsrPlan, src: torch.Tensor, dim: int, route: OutRoute, *, src_row_mul: int = 1,
+                          bounds: Tuple[int, int] = (INT64_MAX, INT64_MAX),
+                          row_slot: Optional[torch.Tensor] = None) -> None:
+    """`segment_reduce` (no init / scales) whose result rows go where `route` says."""
+    _lib.require_cuda(src, row_slot)
+    if src_row_mul == 1:
+        src = _lib.rows_f32(src)
+        src_ld = _lib.ld(src)
+    else:
+        assert src.is_contiguous() and src.dtype == _F32
+        src_ld = dim
+    _lib.call("ihg_segment_reduce_routed", plan.ref(), _lib.ptr(src), src_ld, src_row_mul, bounds[0], bounds[1],
+              _lib.ptr(row_slot), _lib.ptr(plan.partial(dim)), route.starts, route.bases, route.n, route.ld, dim,
+              _lib.stream_ptr(), tag="segment_reduce",
+              algo_bytes=plan.nnz * (4 + 4 * dim) + plan.n_rows * (4 * dim + 16))
+
+
+def two_hop_reduce_routed(plan: CsrPlan, nbr: torch.Tensor, src: torch.Tensor, route: OutRoute, *,
+                          node_scale: Optional[torch.Tensor] = None, alpha: float = 1.0, own=(1.0, 0.0)) -> None:
+    """`two_hop_reduce` (no row scale) whose result rows go where `route` says."""
+    _lib.require_cuda(src, nbr, node_scale)
+    src = _lib.rows_f32(src)
+    dim = int(src.shape[1])
+    assert src.shape[0] == plan.n_rows, (src.shape, plan.n_rows)
+    _lib.call("ihg_two_hop_reduce_routed", plan.ref(), _lib.ptr(nbr), _lib.ptr(src), _lib.ld(src),
+              _lib.ptr(node_scale), float(alpha), float(own[0]), float(own[1]), _lib.ptr(plan.partial(dim)),
+              route.starts, route.bases, route.n, route.ld, dim, _lib.stream_ptr(), tag="two_hop_reduce",
+              algo_bytes=(plan.nnz // 3) * (12 + 16 * dim) + plan.nnz * (4 + 4 * dim) + plan.n_rows * (4 * dim + 16))
+
+
 def edge_gather_sum(src: torch.Tensor, i3: torch.Tensor, *, node_scale: Optional[torch.Tensor] = None,
                     alpha: float = 1.0, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[e] = alpha * sum_s node_scale[i3[e,s]] * src[i3[e,s]] (+ bias)."""

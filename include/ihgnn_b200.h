@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define IHG_ABI_VERSION 3   /* 3: ihg_adam_step; 2: ihg_segment_reduce gained `flags`, two-hop / ranking / sampler */
+#define IHG_ABI_VERSION 4   /* 4: ihg_segment_reduce_routed / ihg_two_hop_reduce_routed; 3: ihg_adam_step; 2: ihg_segment_reduce gained `flags`, two-hop / ranking / sampler */
 
 #define IHG_OK 0
 #define IHG_ERR_INVALID_ARGUMENT 1   /* bad shape / null pointer / unsupported dimension   */
@@ -148,6 +148,30 @@ int ihg_two_hop_reduce(const ihg_csr* csr_host, const int32_t* nbr, const float*
                        int64_t src_ld, const float* node_scale, float alpha,
                        float own_per_incidence, float own_const, const float* row_scale,
                        float* partial, float* out, int64_t out_ld, int32_t dim, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (e) multi-GPU reduce-scatter of node partial sums (SURVEY.md section 8e "Collectives per layer":
+ *     local partials over owned + halo rows, then the cross-GPU reduce), fused into the producer:
+ * the same reductions as ihg_segment_reduce / ihg_two_hop_reduce (no init / row scale / flags), but
+ * consecutive row ranges of the result go to different destinations: range k = rows
+ * [route_start[k], route_start[k+1]) is written to route_base[k] + (row - route_start[k]) * out_ld.
+ * The sharded layers route the own rows to a local matrix and every peer's halo rows straight into
+ * that peer's receive buffer over NVLink (peer-mapped pointers): the partial sums travel as posted
+ * stores while the kernel is still gathering, and the owner finishes with a local ordered sum
+ * (ihg_segment_reduce over its receive buffer).  route_start (n_route + 1 entries, route_start[0] == 0,
+ * route_start[n_route] == csr->n_rows, ascending) and route_base (n_route entries) are HOST arrays;
+ * 1 <= n_route <= 16.  Deterministic like the un-routed calls.
+ * ------------------------------------------------------------------------------------ */
+int ihg_segment_reduce_routed(const ihg_csr* csr_host, const float* src, int64_t src_ld,
+                              int32_t src_row_mul, int64_t bound0, int64_t bound1,
+                              const int32_t* row_slot, float* partial,
+                              const int64_t* route_start, void* const* route_base, int32_t n_route,
+                              int64_t out_ld, int32_t dim, void* stream);
+int ihg_two_hop_reduce_routed(const ihg_csr* csr_host, const int32_t* nbr, const float* src,
+                              int64_t src_ld, const float* node_scale, float alpha,
+                              float own_per_incidence, float own_const, float* partial,
+                              const int64_t* route_start, void* const* route_base, int32_t n_route,
+                              int64_t out_ld, int32_t dim, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * a6/a8  node -> hyperedge gather-sum.

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_error_channel(lib):
-    assert lib.ihg_abi_version() == 3
+    assert lib.ihg_abi_version() == 4
     assert lib.ihg_last_error() is not None
     # argument validation happens before any CUDA call, so it can be exercised without a GPU
     rc = lib.ihg_node_linear(None, 0, None, 1, 64, 64, 0, None, None, 0, 10, 0, 0, None, 0, None)
@@ -70,6 +70,17 @@ def test_new_entry_points_validate_arguments(lib):
     # accumulate mode without an init row
     rc = lib.ihg_segment_reduce(ctypes.byref(csr), 1, 64, 1, 0, 0, None, None, 0, None, None, None, 1, 64, 64, 1, None)
     assert rc == 1 and b"accumulate" in lib.ihg_last_error()
+    # routed reductions (multi-GPU): the output ranges must cover [0, n_rows), ascending, non-null where non-empty
+    starts = (ctypes.c_int64 * 3)(0, 2, 3)
+    bases = (ctypes.c_void_p * 2)(1, 1)
+    rc = lib.ihg_segment_reduce_routed(ctypes.byref(csr), 1, 64, 1, 0, 0, None, None, starts, bases, 2, 64, 64, None)
+    assert rc == 1 and b"cover rows" in lib.ihg_last_error()
+    starts = (ctypes.c_int64 * 3)(0, 2, 4)
+    bases = (ctypes.c_void_p * 2)(1, None)
+    rc = lib.ihg_two_hop_reduce_routed(ctypes.byref(csr), 1, 1, 64, None, 1.0, 1.0, 0.0, None, starts, bases, 2, 64, 64, None)
+    assert rc == 1 and b"null destination" in lib.ihg_last_error()
+    rc = lib.ihg_two_hop_reduce_routed(ctypes.byref(csr), 1, 1, 64, None, 1.0, 1.0, 0.0, None, starts, bases, 17, 64, 64, None)
+    assert rc == 1 and b"output ranges" in lib.ihg_last_error()
 
 
 def test_workspace_queries_are_pure(lib):

@@ -21,8 +21,9 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _worker(rank: int, world: int, port: int, dim: int, ret):
+def _worker(rank: int, world: int, port: int, dim: int, routed: str, ret):
     sys.path.insert(0, REPO)
+    os.environ["IHG_ROUTED_REDUCE"] = routed
     import torch.distributed as dist
     from ihgnn_b200 import synth
     from ihgnn_b200.dataset import GraphDataset
@@ -89,14 +90,17 @@ def _worker(rank: int, world: int, port: int, dim: int, ret):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("routed", ["1", "0"], ids=["routed-reduce", "pull-reduce"])
 @pytest.mark.parametrize("dim", [64, 16])
-def test_sharded_stack_matches_single_gpu(dim):
+def test_sharded_stack_matches_single_gpu(dim, routed):
+    """routed: the reduction kernels write the halo partial sums straight into their owners' receive buffers
+    (`ihg_*_routed`); pull: the owners read them out of the holders' tables (`ihg_halo_reduce`)."""
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     port = _free_port()
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, port, dim, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, dim, routed, ret), nprocs=world, join=True)
     assert len(ret) == world
     errs = [v[0] for v in ret.values()]
     assert max(errs) < 5e-6, dict(ret)       # different (but fixed) summation order across ranks

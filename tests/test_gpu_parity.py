@@ -37,7 +37,7 @@ def _model(golden, ds=None):
 
 def test_library_loaded():
     from ihgnn_b200 import _lib
-    assert _lib.lib().ihg_abi_version() == _lib.ABI_VERSION == 3
+    assert _lib.lib().ihg_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_graph_build_matches_reference_bit_exact(golden):
@@ -885,6 +885,49 @@ def test_segment_reduce_accumulate_over_hyperedge_ranges(dim, parts):
     both = torch.zeros(N, 2 * dim, device=DEV)
     run(both[:, dim:], None)
     assert max_rel(both[:, dim:].cpu().numpy(), want_raw) < 2e-6 and float(both[:, :dim].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dim", [16, 64, 128, 256])
+def test_routed_reductions_equal_the_plain_ones(dim):
+    """ihg_segment_reduce_routed / ihg_two_hop_reduce_routed (the multi-GPU reductions that write every peer's
+    halo rows straight into that peer's receive buffer) with all destinations local: consecutive row ranges
+    land in separate matrices (one of them a column block of a wider matrix), bitwise equal to the plain
+    calls -- split rows (fix-up kernel), empty ranges and the per-slot [E,3,d] source included."""
+    from ihgnn_b200 import functional as F_
+    from ihgnn_b200 import synth
+    from ihgnn_b200.graph import PpsHyperGraph
+    U, Q, I, E = 500, 40, 300, 12_000
+    log = synth.make_search_log(U, Q, I, E, 50, shape="cikm", seed=dim + 3, zipf=1.0)
+    g = PpsHyperGraph.from_tensors(log.pos_user, log.pos_query, log.pos_item, U, Q, I, DEV, chunk_len=64)
+    assert g.plan.n_split > 0
+    N = U + Q + I
+    gen = torch.Generator(device=DEV).manual_seed(dim)
+    ef = torch.randn(E, dim, device=DEV, generator=gen)
+    slot_grad = torch.randn(E, 3, dim, device=DEV, generator=gen)
+    x = torch.randn(N, dim, device=DEV, generator=gen)
+    ns = torch.rand(N, device=DEV, generator=gen) + 0.5
+    cuts = [0, U - 7, U - 7, U + Q + 11, N]                     # four ranges, one empty; range 2 is a column block
+    wide = torch.full((cuts[3] - cuts[2], 2 * dim + 8), -7.0, device=DEV)
+
+    def routed(fn):
+        parts = [torch.full((cuts[k + 1] - cuts[k], 2 * dim + 8), -7.0, device=DEV) for k in range(4)]
+        parts[2] = wide
+        bases = [p.data_ptr() + 4 * (dim + 8) if p.numel() else 0 for p in parts]
+        route = F_.OutRoute(cuts, bases, 2 * dim + 8, keep=parts)
+        fn(route)
+        torch.cuda.synchronize()
+        for p in parts:                                         # nothing outside the destination column block
+            assert p.numel() == 0 or (float(p[:, :dim + 8].min()) == -7.0 and float(p[:, :dim + 8].max()) == -7.0)
+        return torch.cat([p[:, dim + 8:] for p in parts])
+
+    plain = F_.segment_reduce(g.plan, ef, dim)
+    assert torch.equal(routed(lambda r: F_.segment_reduce_routed(g.plan, ef, dim, r)), plain)
+    plain3 = F_.segment_reduce(g.plan, slot_grad, dim, src_row_mul=3, bounds=g.type_bounds)
+    assert torch.equal(routed(lambda r: F_.segment_reduce_routed(g.plan, slot_grad, dim, r, src_row_mul=3,
+                                                                 bounds=g.type_bounds)), plain3)
+    nbr = g.plan.two_hop_nbr(g.i3, g.type_bounds)
+    plain2 = F_.two_hop_reduce(g.plan, nbr, x, node_scale=ns)
+    assert torch.equal(routed(lambda r: F_.two_hop_reduce_routed(g.plan, nbr, x, r, node_scale=ns)), plain2)
 
 
 @pytest.mark.parametrize("B,rows,dim", [(1100, 300, 64), (2048, 50, 192), (5000, 700, 128), (7, 3, 8), (3000, 1, 512)])
