@@ -16,9 +16,15 @@ Per layer and direction there are two exchange steps, adjoint to each other:
   halo_reduce     ranks send their partial sums of halo rows back; the owner adds its own
                   partial and the received ones in ascending source rank order and applies Dv^-1
                   (all-to-all + one deterministic segmented reduction = reduce-scatter)
-With NVLink peer memory (the default) both steps are ONE kernel each: owners write boundary rows straight
-into the readers' tables (`ihg_halo_copy`), and pull + sum the holders' partials in fixed order
-(`ihg_halo_reduce`); over NCCL they are all-to-alls plus the library's gather / segmented-reduce kernels.
+With NVLink peer memory (the default): owners write boundary rows straight into the readers' tables
+(`ihg_halo_copy`, every rank sweeping its destinations from a different start), and the reduction kernels
+that produce the halo partial sums write them straight into their owners' receive buffers
+(`ihg_segment_reduce_routed` / `ihg_two_hop_reduce_routed`: posted NVLink stores under the kernel's own gathers,
+the halo work items interleaved across owners so that no NVLink ingress is hit by every rank at once); the owner
+then adds its own partial and the received ones in fixed order with a local `ihg_segment_reduce`.
+`IHG_ROUTED_REDUCE=0` (and graphs large enough to share one table pair between all call sites) keeps the pull
+form: the owner reads the holders' partials over NVLink and sums them in one kernel (`ihg_halo_reduce`).  Over
+NCCL the steps are all-to-alls plus the library's gather / segmented-reduce kernels.
 Dense weight gradients are all-reduced.  The sharded step is sync-free and is captured per rank in a CUDA graph.
 
 CUDA only (NCCL + symmetric memory).  The planner is exercised on CPU by tests/test_dist_gloo.py.
@@ -307,10 +313,12 @@ class ShardedHyperGraph:
         so = self._send_off = np.concatenate([[0], np.cumsum(self.send_counts)]).astype(np.int64)
         self.send_rows_push = torch.cat([self.send_rows[int(so[d]):int(so[d + 1])]
                                          for d in [(rank + 1 + j) % world for j in range(world - 1)]]).contiguous()
-        self.routed = os.environ.get("IHG_ROUTED_REDUCE", "1") != "0"
+        self.share_buffers = self._max_local * 128 * 4 * 14 > (40 << 30)
+        # routed reduce needs a receive buffer per call site; with the single shared table pair of very large
+        # graphs the (validated) pull path stays
+        self.routed = os.environ.get("IHG_ROUTED_REDUCE", "1") != "0" and not self.share_buffers
         self._symm = symm_mem
         self._bufs = {}
-        self.share_buffers = self._max_local * 128 * 4 * 14 > (40 << 30)
         # probe once (allocation + rendezvous + barrier); every rank must agree on the outcome
         ok = 1
         try:
@@ -336,8 +344,6 @@ class ShardedHyperGraph:
         collective (symmetric memory): every rank reaches the sites in the same order."""
         if not (self.p2p and self.routed) or key is None:
             return None
-        if self.share_buffers:
-            key = "shared"
         k = ("route", key, cols)
         if k not in self._bufs:
             self._bufs[k] = _ReduceSite(self, key, cols)
@@ -609,11 +615,10 @@ def _finish_routed(site: "_ReduceSite", g: ShardedHyperGraph, row_scale: Optiona
     from . import functional as F_
     d = int(site.own.shape[1])
     site.hdl.barrier(channel=0)                     # all ranks' partial sums have landed
-    out = F_.segment_reduce(g.reduce_csr, site.recv, d, row_scale=row_scale, init=site.own) if g.S else \
-        (site.own * row_scale.view(-1, 1) if row_scale is not None else site.own.clone())
-    if g.share_buffers:
-        site.hdl.barrier(channel=0)                 # the one shared receive buffer is written again by the next site
-    return out
+    if g.S == 0:
+        return site.own * row_scale.view(-1, 1) if row_scale is not None else site.own.clone()
+    # a per-site receive buffer is next written a whole step -- many barriers -- later: no second barrier
+    return F_.segment_reduce(g.reduce_csr, site.recv, d, row_scale=row_scale, init=site.own)
 
 
 def halo_exchange(x_own, g, key=None):
