@@ -7,8 +7,21 @@ import sys
 
 def main(path):
     with open(path) as f:
-        lines = [l for l in f if l.startswith('"')]
+        text = f.read()
     agg = collections.OrderedDict()
+    if text.startswith("id,kernel,duration("):
+        # compact list written by profiles/scripts/r02_run_ncu.sh: id,kernel,duration(<unit>)
+        unit = text[text.index("(") + 1:text.index(")")]
+        scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit.replace("second", "s"), 1.0)
+        for line in text.splitlines()[1:]:
+            _id, rest = line.split(",", 1)
+            name, dur = rest.rsplit(",", 1)
+            a = agg.setdefault(name.replace("ihg::", "").replace("<unnamed>::", ""), [0, 0.0])
+            a[0] += 1
+            a[1] += float(dur) * scale
+        lines = []
+    else:
+        lines = [l for l in text.splitlines(True) if l.startswith('"')]
     for row in csv.DictReader(lines):
         name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("void ", "")
         v = float(row["Metric Value"].replace(",", ""))
