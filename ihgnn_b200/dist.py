@@ -213,6 +213,25 @@ class PartitionPlan:
                                self.U + self.Q + np.arange(self.ib[r], self.ib[r + 1])])
 
 
+def halo_work_order(rows: torch.Tensor, n_own: int, recv_counts, world: int, rank: int) -> torch.Tensor:
+    """Processing order of the work items of a local table (`rows[k]` = local row of item k, ascending): the
+    own rows first, then the halo rows round-robin over their owners -- starting with rank + 1 -- instead of
+    owner by owner.  The routed reductions store a halo row's partial sum straight into its owner's receive
+    buffer; in row order every rank would write to rank 0 first, then rank 1, ...: seven writers on one NVLink
+    ingress while the others idle.  Returns a permutation of arange(len(rows))."""
+    idx = torch.arange(rows.numel(), device=rows.device)
+    halo = rows >= n_own
+    if not bool(halo.any()):
+        return idx
+    chunk_end = torch.as_tensor(np.cumsum(np.asarray(recv_counts)) + n_own, dtype=torch.int64, device=rows.device)
+    hidx = idx[halo]
+    owner = torch.bucketize(rows[halo], chunk_end, right=True)                 # ascending: rows are
+    first = torch.searchsorted(owner, torch.arange(world, device=rows.device))
+    within = torch.arange(hidx.numel(), device=rows.device) - first[owner]
+    order = torch.argsort(within * world + (owner - rank - 1) % world, stable=True)
+    return torch.cat([idx[~halo], hidx[order]])
+
+
 # ----------------------------------------------------------------------------------------
 # device side (CUDA + NCCL)
 # ----------------------------------------------------------------------------------------
@@ -254,25 +273,13 @@ class ShardedHyperGraph:
             self.enable_peer_memory()
 
     def _interleave_halo_work(self, plan: PartitionPlan) -> None:
-        """Order of the work items (row chunks) of the local CSR plan: own rows first, then the halo rows
-        round-robin over their owners instead of owner by owner.  The routed reductions write a halo row's
-        partial sum straight into its owner's receive buffer; in row order every rank would write to rank 0
-        first, then to rank 1, ... -- seven writers on one NVLink ingress while the others idle.  The records
-        are independent ({begin, end, row, partial slot}), so any order gives the same bits."""
+        """Reorder the work items (row chunks) of the local CSR plan with `halo_work_order`.  The records are
+        independent ({begin, end, row, partial slot}), so any order gives the same bits."""
         seg = self.plan_csr.seg
         if plan.world < 3 or seg.shape[0] == 0:
             return
-        row = seg[:, 2].to(torch.int64)
-        halo = row >= plan.n_own
-        if not bool(halo.any()):
-            return
-        hseg = seg[halo]
-        chunk_end = torch.as_tensor(np.cumsum(plan.recv_counts) + plan.n_own, dtype=torch.int64, device=seg.device)
-        owner = torch.bucketize(hseg[:, 2].to(torch.int64), chunk_end, right=True)
-        first = torch.searchsorted(owner, torch.arange(plan.world, device=seg.device))    # records are in row order
-        within = torch.arange(hseg.shape[0], device=seg.device) - first[owner]
-        order = torch.argsort(within * plan.world + (owner - plan.rank - 1) % plan.world, stable=True)
-        self.plan_csr.seg = torch.cat([seg[~halo], hseg[order]]).contiguous()
+        order = halo_work_order(seg[:, 2].to(torch.int64), plan.n_own, plan.recv_counts, plan.world, plan.rank)
+        self.plan_csr.seg = seg[order].contiguous()
         self.plan_csr.struct.seg = self.plan_csr.seg.data_ptr()
 
     @property

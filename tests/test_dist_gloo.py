@@ -157,3 +157,69 @@ def test_fixed_shape_batch_row_fetch(world):
     ret = mp.Manager().dict()
     mp.spawn(_fetch_worker, args=(world, port, ret), nprocs=world, join=True)
     assert len(ret) == world and all(all(v) for v in ret.values()), dict(ret)
+
+
+@pytest.mark.parametrize("world", [3, 5])
+def test_routed_reduce_layout_and_work_order(world):
+    """Host side of the routed reduce (ihgnn_b200.dist, `ihg_*_routed`): a holder h stores its partial sums of
+    the rows owner p owns -- one contiguous chunk of h's local table -- at row send_of[p][:h].sum() of p's
+    receive buffer; p's ordered sum (reduce_rowptr / reduce_col over the flat [S rows, by source rank] layout)
+    must then see exactly the rows it expects.  Replayed in numpy over the plans of all ranks against the
+    global sum; plus the interleaved processing order of the halo work items."""
+    from ihgnn_b200 import synth
+    from ihgnn_b200.dist import PartitionPlan, halo_work_order
+    U, Q, I, E, d = 83, 17, 59, 1500, 4
+    log = synth.make_search_log(U, Q, I, E, 30, shape="cikm", seed=8, zipf=0.9)
+    plans = [PartitionPlan(log.pos_user, log.pos_query, log.pos_item, U, Q, I, world, r) for r in range(world)]
+    N = U + Q + I
+    send_of = np.stack([p.send_counts for p in plans])                   # send_of[s][d]
+    rng = np.random.default_rng(0)
+    # every rank's partial sums over its local rows; global ids of the local rows
+    glob = []
+    for h, p in enumerate(plans):
+        own = p.own_global_ids()
+        ids = np.full(p.n_local, -1, dtype=np.int64)
+        ids[:p.n_own] = own
+        i3g = np.stack([log.pos_user, U + log.pos_query, U + Q + log.pos_item], 1)[p.edge_ids]
+        ids[p.i3_local.reshape(-1)] = i3g.reshape(-1)                    # halo rows get their global id from the edges
+        assert (ids >= 0).all()
+        glob.append(ids)
+    part = [rng.standard_normal((p.n_local, d)) for p in plans]
+    want = np.zeros((N, d))
+    for ids, t in zip(glob, part):
+        np.add.at(want, ids, t)
+    for pr, p in enumerate(plans):
+        recv = np.full((p.S, d), np.nan)
+        recv_ids = np.full(p.S, -1, dtype=np.int64)
+        for h, q in enumerate(plans):
+            if h == pr:
+                continue
+            c0 = q.n_own + int(q.recv_counts[:pr].sum())                 # h's chunk of rows owned by pr
+            n = int(q.recv_counts[pr])
+            assert n == send_of[pr][h]
+            at = int(send_of[pr][:h].sum())                              # where h's block starts in pr's buffer
+            recv[at:at + n] = part[h][c0:c0 + n]
+            recv_ids[at:at + n] = glob[h][c0:c0 + n]
+        assert not np.isnan(recv).any()
+        own_ids = p.own_global_ids()
+        assert np.array_equal(recv_ids, own_ids[p.send_rows])           # the flat receive layout IS the send order
+        out = part[pr][:p.n_own].copy()
+        rp, rc = p.reduce_rowptr, p.reduce_col
+        for v in range(p.n_own):
+            for j in rc[rp[v]:rp[v + 1]]:
+                out[v] += recv[j]
+        assert np.allclose(out, want[own_ids], rtol=0, atol=1e-12)
+        # work order: a permutation, own rows first and untouched, halo items cycling over the owners
+        rows = torch.from_numpy(np.sort(np.concatenate([np.arange(p.n_local), rng.integers(0, p.n_local, 40)])))
+        order = halo_work_order(rows, p.n_own, p.recv_counts, world, pr).numpy()
+        assert np.array_equal(np.sort(order), np.arange(rows.numel()))
+        r = rows.numpy()[order]
+        n_own_items = int((rows.numpy() < p.n_own).sum())
+        assert np.array_equal(order[:n_own_items], np.arange(n_own_items))
+        ends = np.cumsum(p.recv_counts) + p.n_own
+        owners = np.searchsorted(ends, r[n_own_items:], side="right")
+        k = int(min(np.bincount(owners, minlength=world)[[o for o in range(world) if o != pr and p.recv_counts[o] > 0]]))
+        live = [o for o in range(world) if o != pr and p.recv_counts[o] > 0]
+        first = owners[:k * len(live)].reshape(k, len(live))
+        expect = sorted(live, key=lambda o: (o - pr - 1) % world)
+        assert (first == np.array(expect)).all()
