@@ -13,7 +13,6 @@ import hashlib
 import os
 import shutil
 import subprocess
-import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(PKG)

@@ -32,7 +32,7 @@ CUDA only (NCCL + symmetric memory).  The planner is exercised on CPU by tests/t
 from __future__ import annotations
 
 import os
-from typing import List, Optional
+from typing import Optional
 
 import numpy as np
 import torch

@@ -11,7 +11,6 @@ Main.py:252-262 load into either optimizer.  The update is bit-identical with to
 hence the step is CUDA-graph capturable without a `capturable=` switch.  CUDA only, no fallback."""
 from __future__ import annotations
 
-import ctypes
 from typing import Iterable
 
 import torch

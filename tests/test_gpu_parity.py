@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import REL_TOL, batch_of, max_rel, oracle_model, orc, state_of
+from helpers import REL_TOL, batch_of, max_rel, orc, state_of
 
 pytestmark = pytest.mark.gpu
 
